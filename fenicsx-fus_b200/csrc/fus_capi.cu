@@ -1,0 +1,957 @@
+// fus_capi.cu -- C ABI (include/fus_b200.h) on top of the sm_100a kernels in fus_kernels.cuh.
+//
+// One fus_ctx per GPU/process; all launches of a context go to one stream and are
+// stream-ordered.  There is no CPU fallback: without a usable device every compute entry
+// point returns FUS_ERR_CUDA.
+#include "fus_halo.hpp"
+#include "fus_internal.hpp"
+#include "fus_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace fus {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+#define FUS_CUDA(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      fus::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));       \
+      return FUS_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+#define FUS_TRY(call)                                                                              \
+  do {                                                                                             \
+    int r__ = (call);                                                                              \
+    if (r__ != FUS_OK)                                                                             \
+      return r__;                                                                                  \
+  } while (0)
+
+#define FUS_LAUNCHED()                                                                             \
+  do {                                                                                             \
+    fus::g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
+    FUS_CUDA(cudaGetLastError());                                                                  \
+  } while (0)
+
+static inline int grid_for(long long n, int block, int max_blocks) {
+  long long g = (n + block - 1) / block;
+  if (g < 1)
+    g = 1;
+  if (g > max_blocks)
+    g = max_blocks;
+  return (int)g;
+}
+
+} // namespace fus
+
+using namespace fus;
+
+struct fus_ctx {
+  int P = 0, N = 0, Nd = 0;
+  int64_t ncells = 0, ndofs = 0, nowned = 0;
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int32_t* d_dofmap = nullptr;
+  double2* d_G2 = nullptr;
+  double* d_detJ = nullptr;
+  double dphi[64];
+  int variant = 0; // 0 column kernel, 1 point kernel
+  int col_blocks_per_sm = 0;
+  Halo* halo = nullptr;
+};
+
+struct fus_model {
+  fus_ctx* ctx = nullptr;
+  int kind = 0;
+  double freq = 0, p0 = 0, s0 = 0, w0 = 0, period = 0, window_length = 4.0;
+  // per-cell operator coefficients
+  double *d_lin = nullptr, *d_att = nullptr;
+  // per-dof
+  double *d_m = nullptr, *d_dnl = nullptr;
+  // compacted boundary lists
+  int64_t nb = 0;
+  int32_t* d_bidx = nullptr;
+  double *d_bsrc = nullptr, *d_bdsrc = nullptr, *d_babs = nullptr;
+  // state (u0,v0 double as u_n,v_n) and work vectors
+  double *d_u0 = nullptr, *d_v0 = nullptr, *d_ua = nullptr, *d_va = nullptr, *d_un = nullptr,
+         *d_vn = nullptr, *d_b = nullptr;
+};
+
+namespace {
+
+int select_device(fus_ctx* c) {
+  FUS_CUDA(cudaSetDevice(c->device));
+  return FUS_OK;
+}
+
+// ---- per-degree dispatch ---------------------------------------------------------------------
+
+template <int N>
+int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const double* coeff,
+                       const double* coeff2, double* y, long long cb, long long ce,
+                       cudaStream_t st) {
+  if (ce <= cb)
+    return FUS_OK;
+  DMat<N> D;
+  std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
+  const bool fuse = (x2 != nullptr);
+  if (c->variant == 1) {
+    const int blocks = (int)std::min<long long>(ce - cb, (long long)c->num_sms * 16);
+    if (fuse)
+      stiffness_point_kernel<N, true><<<blocks, N * N * N, 0, st>>>(
+          x, x2, y, c->d_dofmap, c->d_G2, coeff, coeff2, cb, ce, D);
+    else
+      stiffness_point_kernel<N, false><<<blocks, N * N * N, 0, st>>>(
+          x, x2, y, c->d_dofmap, c->d_G2, coeff, coeff2, cb, ce, D);
+    FUS_LAUNCHED();
+    return FUS_OK;
+  }
+  using C = ColCfg<N>;
+  static bool configured = false;
+  static int bps_plain = 1, bps_fuse = 1;
+  if (!configured) {
+    FUS_CUDA(cudaFuncSetAttribute(stiffness_col_kernel<N, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FUS_CUDA(cudaFuncSetAttribute(stiffness_col_kernel<N, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &bps_plain, stiffness_col_kernel<N, false>, C::THREADS, C::SMEM_BYTES));
+    FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &bps_fuse, stiffness_col_kernel<N, true>, C::THREADS, C::SMEM_BYTES));
+    if (bps_plain < 1 || bps_fuse < 1) {
+      set_error("stiffness_col_kernel<N=%d> does not fit on an SM", N);
+      return FUS_ERR_CUDA;
+    }
+    configured = true;
+  }
+  int bps = fuse ? bps_fuse : bps_plain;
+  if (c->col_blocks_per_sm > 0)
+    bps = std::min(bps, c->col_blocks_per_sm);
+  const long long want = (ce - cb + C::CPB - 1) / C::CPB;
+  const int blocks = (int)std::min<long long>(want, (long long)c->num_sms * bps);
+  if (fuse)
+    stiffness_col_kernel<N, true><<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(
+        x, x2, y, c->d_dofmap, c->d_G2, coeff, coeff2, cb, ce, D);
+  else
+    stiffness_col_kernel<N, false><<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(
+        x, x2, y, c->d_dofmap, c->d_G2, coeff, coeff2, cb, ce, D);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
+int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double* coeff,
+                     const double* coeff2, double* y, long long cb, long long ce,
+                     cudaStream_t st) {
+  if (!c->d_G2) {
+    set_error("context was created without G: stiffness operator unavailable");
+    return FUS_ERR_STATE;
+  }
+  switch (c->N) {
+  case 2: return launch_stiffness_n<2>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  case 3: return launch_stiffness_n<3>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  case 4: return launch_stiffness_n<4>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  case 5: return launch_stiffness_n<5>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  case 6: return launch_stiffness_n<6>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  case 7: return launch_stiffness_n<7>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  case 8: return launch_stiffness_n<8>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  }
+  set_error("unsupported degree P=%d", c->P);
+  return FUS_ERR_UNSUPPORTED;
+}
+
+int launch_mass(fus_ctx* c, const double* x, const double* coeff, double* y, long long cb,
+                long long ce, cudaStream_t st) {
+  if (!c->d_detJ) {
+    set_error("context was created without detJ: mass operator unavailable");
+    return FUS_ERR_STATE;
+  }
+  if (ce <= cb)
+    return FUS_OK;
+  // the kernel indexes points from 0: shift the per-point arrays, keep coeff indexed by cell
+  const long long np = (ce - cb) * c->Nd;
+  mass_kernel<<<grid_for(np, 256, c->num_sms * 8), 256, 0, st>>>(
+      x, y, c->d_dofmap + cb * c->Nd, c->d_detJ + cb * c->Nd, coeff + cb, np, c->Nd);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
+template <int N>
+int launch_geometry_n(fus_ctx* c, const double* d_xg, const int32_t* d_xd, bool want_G,
+                      bool want_detJ) {
+  Rule1D<N> R;
+  FUS_TRY(gll(N - 1, R.pts, R.wts));
+  geometry_kernel<N><<<grid_for(c->ncells * c->Nd, 128, c->num_sms * 16), 128, 0, c->stream>>>(
+      d_xg, d_xd, c->ncells, want_G ? c->d_G2 : nullptr, want_detJ ? c->d_detJ : nullptr, R);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
+template <int N>
+int g_upload_n(fus_ctx* c, const double* G) {
+  // stream the reference-layout G through a bounded staging buffer
+  const long long chunk_cells = std::max<long long>(1, (64ll << 20) / (c->Nd * 48));
+  double* d_stage = nullptr;
+  FUS_CUDA(cudaMalloc(&d_stage, (size_t)chunk_cells * c->Nd * 48));
+  for (long long c0 = 0; c0 < c->ncells; c0 += chunk_cells) {
+    const long long nc = std::min<long long>(chunk_cells, c->ncells - c0);
+    FUS_CUDA(cudaMemcpyAsync(d_stage, G + c0 * c->Nd * 6, (size_t)nc * c->Nd * 48,
+                             cudaMemcpyHostToDevice, c->stream));
+    g_to_device_layout_kernel<N><<<grid_for(nc * c->Nd, 256, c->num_sms * 8), 256, 0,
+                                   c->stream>>>(d_stage, nc, c->d_G2 + c0 * (3 * c->Nd));
+    FUS_LAUNCHED();
+  }
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  FUS_CUDA(cudaFree(d_stage));
+  return FUS_OK;
+}
+
+template <int N>
+int g_download_n(fus_ctx* c, double* G) {
+  const long long chunk_cells = std::max<long long>(1, (64ll << 20) / (c->Nd * 48));
+  double* d_stage = nullptr;
+  FUS_CUDA(cudaMalloc(&d_stage, (size_t)chunk_cells * c->Nd * 48));
+  for (long long c0 = 0; c0 < c->ncells; c0 += chunk_cells) {
+    const long long nc = std::min<long long>(chunk_cells, c->ncells - c0);
+    g_from_device_layout_kernel<N><<<grid_for(nc * c->Nd, 256, c->num_sms * 8), 256, 0,
+                                     c->stream>>>(c->d_G2 + c0 * (3 * c->Nd), nc, d_stage);
+    FUS_LAUNCHED();
+    FUS_CUDA(cudaMemcpyAsync(G + c0 * c->Nd * 6, d_stage, (size_t)nc * c->Nd * 48,
+                             cudaMemcpyDeviceToHost, c->stream));
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  FUS_CUDA(cudaFree(d_stage));
+  return FUS_OK;
+}
+
+#define FUS_DISPATCH_N(c, fn, ...)                                                                 \
+  [&]() -> int {                                                                                   \
+    switch ((c)->N) {                                                                              \
+    case 2: return fn<2>(__VA_ARGS__);                                                             \
+    case 3: return fn<3>(__VA_ARGS__);                                                             \
+    case 4: return fn<4>(__VA_ARGS__);                                                             \
+    case 5: return fn<5>(__VA_ARGS__);                                                             \
+    case 6: return fn<6>(__VA_ARGS__);                                                             \
+    case 7: return fn<7>(__VA_ARGS__);                                                             \
+    case 8: return fn<8>(__VA_ARGS__);                                                             \
+    }                                                                                              \
+    set_error("unsupported degree P=%d", (c)->P);                                                  \
+    return FUS_ERR_UNSUPPORTED;                                                                    \
+  }()
+
+int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32_t* dm,
+               int device, bool want_G, bool want_detJ, fus_ctx** out) {
+  if (!out || !dm || ncells < 1 || ndofs < 1 || nowned < 0 || nowned > ndofs) {
+    set_error("fus_ctx_create: bad argument");
+    return FUS_ERR_ARG;
+  }
+  if (P < 1 || P > 7) {
+    set_error("unsupported degree P=%d (supported: 1..7)", P);
+    return FUS_ERR_UNSUPPORTED;
+  }
+  if (ndofs > INT32_MAX) {
+    set_error("local dof count exceeds int32 (the reference dofmap is int32 too)");
+    return FUS_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device >= ndev) {
+    set_error("no usable CUDA device (requested %d of %d); there is no CPU fallback", device, ndev);
+    return FUS_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  FUS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+              prop.minor);
+    return FUS_ERR_CUDA;
+  }
+  fus_ctx* c = new fus_ctx();
+  c->P = P;
+  c->N = P + 1;
+  c->Nd = c->N * c->N * c->N;
+  c->ncells = ncells;
+  c->ndofs = ndofs;
+  c->nowned = nowned;
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  FUS_CUDA(cudaSetDevice(device));
+  FUS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  // validate the dofmap on the host: every index inside [0, ndofs)
+  const int64_t nent = ncells * c->Nd;
+  for (int64_t i = 0; i < nent; ++i)
+    if (dm[i] < 0 || dm[i] >= ndofs) {
+      set_error("tensor_dofmap[%lld] = %d outside [0,%lld)", (long long)i, dm[i],
+                (long long)ndofs);
+      return FUS_ERR_ARG;
+    }
+  FUS_CUDA(cudaMalloc(&c->d_dofmap, sizeof(int32_t) * nent));
+  FUS_CUDA(cudaMemcpyAsync(c->d_dofmap, dm, sizeof(int32_t) * nent, cudaMemcpyHostToDevice,
+                           c->stream));
+  if (want_G)
+    FUS_CUDA(cudaMalloc(&c->d_G2, sizeof(double2) * 3 * nent));
+  if (want_detJ)
+    FUS_CUDA(cudaMalloc(&c->d_detJ, sizeof(double) * nent));
+  return FUS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* fus_last_error(void) { return g_err.c_str(); }
+int fus_version(void) { return 100; }
+int64_t fus_launch_count(void) { return g_launches.load(); }
+
+int fus_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major >= 10)
+      ++ok;
+  }
+  return ok;
+}
+
+// ---- host setup ---------------------------------------------------------------------------------
+int fus_gll(int P, double* pts, double* wts) { return gll(P, pts, wts); }
+int fus_tabulate_dphi(int P, double* dphi) { return tabulate_dphi(P, dphi); }
+int fus_box_mesh(const int n[3], const double lo[3], const double hi[3], double* xg,
+                 int32_t* xdofmap) {
+  return box_mesh(n, lo, hi, xg, xdofmap);
+}
+int fus_box_dofmap(int P, const int n[3], int numbering, int32_t* dm) {
+  return box_dofmap(P, n, numbering, dm);
+}
+int64_t fus_box_num_dofs(int P, const int n[3]) { return box_num_dofs(P, n); }
+int64_t fus_box_facets(const int n[3], int32_t* facets) { return box_facets(n, facets); }
+int fus_boundary_vectors(int kind, int P, int64_t ncells, int64_t ndofs, const double* xg,
+                         const int32_t* xdofmap, const int32_t* tensor_dofmap, int64_t nfacets,
+                         const int32_t* facets, const double* c0, const double* rho0,
+                         const double* delta0, double* src, double* dsrc, double* absb,
+                         double* bmass) {
+  return boundary_vectors(kind, P, ncells, ndofs, xg, xdofmap, tensor_dofmap, nfacets, facets, c0,
+                          rho0, delta0, src, dsrc, absb, bmass);
+}
+
+// ---- context ----------------------------------------------------------------------------------
+int fus_ctx_create(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                   const int32_t* tensor_dofmap, const double* G, const double* detJ,
+                   const double* dphi, int device, fus_ctx** out) {
+  if (!dphi || (!G && !detJ)) {
+    set_error("fus_ctx_create: dphi and at least one of G, detJ are required");
+    return FUS_ERR_ARG;
+  }
+  int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, G != nullptr,
+                     detJ != nullptr, out);
+  if (r != FUS_OK) {
+    if (out && *out) {
+      fus_ctx_destroy(*out);
+      *out = nullptr;
+    }
+    return r;
+  }
+  fus_ctx* c = *out;
+  std::memcpy(c->dphi, dphi, sizeof(double) * c->N * c->N);
+  if (detJ)
+    FUS_CUDA(cudaMemcpyAsync(c->d_detJ, detJ, sizeof(double) * ncells * c->Nd,
+                             cudaMemcpyHostToDevice, c->stream));
+  if (G)
+    FUS_TRY(FUS_DISPATCH_N(c, g_upload_n, c, G));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                             const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                             const int32_t* xdofmap, int device, fus_ctx** out) {
+  if (!xg || !xdofmap || nverts < 8) {
+    set_error("fus_ctx_create_from_mesh: mesh geometry required");
+    return FUS_ERR_ARG;
+  }
+  for (int64_t i = 0; i < ncells * 8; ++i)
+    if (xdofmap[i] < 0 || xdofmap[i] >= nverts) {
+      set_error("xdofmap[%lld] = %d outside [0,%lld)", (long long)i, xdofmap[i],
+                (long long)nverts);
+      return FUS_ERR_ARG;
+    }
+  int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, true, true, out);
+  if (r != FUS_OK) {
+    if (out && *out) {
+      fus_ctx_destroy(*out);
+      *out = nullptr;
+    }
+    return r;
+  }
+  fus_ctx* c = *out;
+  FUS_TRY(tabulate_dphi(P, c->dphi));
+  double* d_xg = nullptr;
+  int32_t* d_xd = nullptr;
+  FUS_CUDA(cudaMalloc(&d_xg, sizeof(double) * 3 * nverts));
+  FUS_CUDA(cudaMalloc(&d_xd, sizeof(int32_t) * 8 * ncells));
+  FUS_CUDA(cudaMemcpyAsync(d_xg, xg, sizeof(double) * 3 * nverts, cudaMemcpyHostToDevice,
+                           c->stream));
+  FUS_CUDA(cudaMemcpyAsync(d_xd, xdofmap, sizeof(int32_t) * 8 * ncells, cudaMemcpyHostToDevice,
+                           c->stream));
+  FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_n, c, d_xg, d_xd, true, true));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  FUS_CUDA(cudaFree(d_xg));
+  FUS_CUDA(cudaFree(d_xd));
+  return FUS_OK;
+}
+
+int fus_ctx_destroy(fus_ctx* c) {
+  if (!c)
+    return FUS_OK;
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  if (c->halo)
+    halo_destroy(c->halo);
+  cudaFree(c->d_dofmap);
+  cudaFree(c->d_G2);
+  cudaFree(c->d_detJ);
+  if (c->own_stream && c->stream)
+    cudaStreamDestroy(c->stream);
+  delete c;
+  return FUS_OK;
+}
+
+int fus_ctx_set_stream(fus_ctx* c, void* s) {
+  if (!c)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->own_stream && c->stream)
+    FUS_CUDA(cudaStreamDestroy(c->stream));
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return FUS_OK;
+}
+
+int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
+  if (!c || !name)
+    return FUS_ERR_ARG;
+  if (!std::strcmp(name, "stiffness_variant")) {
+    if (value < 0 || value > 1)
+      return FUS_ERR_ARG;
+    c->variant = value;
+    return FUS_OK;
+  }
+  if (!std::strcmp(name, "col_blocks_per_sm")) {
+    c->col_blocks_per_sm = value;
+    return FUS_OK;
+  }
+  if (!std::strcmp(name, "halo_overlap") && c->halo) {
+    halo_set_overlap(c->halo, value);
+    return FUS_OK;
+  }
+  set_error("unknown option %s", name);
+  return FUS_ERR_ARG;
+}
+
+int fus_ctx_sync(fus_ctx* c) {
+  if (!c)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+int fus_ctx_get_geometry(fus_ctx* c, double* G, double* detJ) {
+  if (!c)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  if (G) {
+    if (!c->d_G2)
+      return FUS_ERR_STATE;
+    FUS_TRY(FUS_DISPATCH_N(c, g_download_n, c, G));
+  }
+  if (detJ) {
+    if (!c->d_detJ)
+      return FUS_ERR_STATE;
+    FUS_CUDA(cudaMemcpyAsync(detJ, c->d_detJ, sizeof(double) * c->ncells * c->Nd,
+                             cudaMemcpyDeviceToHost, c->stream));
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return FUS_OK;
+}
+
+// ---- operators --------------------------------------------------------------------------------
+int fus_stiffness_apply_dev(fus_ctx* c, const double* x, const double* coeffs, double* y) {
+  if (!c || !x || !coeffs || !y)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  return launch_stiffness(c, x, nullptr, coeffs, nullptr, y, 0, c->ncells, c->stream);
+}
+
+int fus_mass_apply_dev(fus_ctx* c, const double* x, const double* coeffs, double* y) {
+  if (!c || !x || !coeffs || !y)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  return launch_mass(c, x, coeffs, y, 0, c->ncells, c->stream);
+}
+
+static int apply_host(fus_ctx* c, const double* x, const double* coeffs, double* y, bool stiff) {
+  if (!c || !x || !coeffs || !y)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  double *dx = nullptr, *dy = nullptr, *dc = nullptr;
+  const size_t vb = sizeof(double) * c->ndofs, cbytes = sizeof(double) * c->ncells;
+  FUS_CUDA(cudaMalloc(&dx, vb));
+  FUS_CUDA(cudaMalloc(&dy, vb));
+  FUS_CUDA(cudaMalloc(&dc, cbytes));
+  FUS_CUDA(cudaMemcpyAsync(dx, x, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(dy, y, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(dc, coeffs, cbytes, cudaMemcpyHostToDevice, c->stream));
+  int r = stiff ? launch_stiffness(c, dx, nullptr, dc, nullptr, dy, 0, c->ncells, c->stream)
+                : launch_mass(c, dx, dc, dy, 0, c->ncells, c->stream);
+  if (r == FUS_OK) {
+    FUS_CUDA(cudaMemcpyAsync(y, dy, vb, cudaMemcpyDeviceToHost, c->stream));
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(dx);
+  cudaFree(dy);
+  cudaFree(dc);
+  return r;
+}
+
+int fus_stiffness_apply_host(fus_ctx* c, const double* x, const double* coeffs, double* y) {
+  return apply_host(c, x, coeffs, y, true);
+}
+int fus_mass_apply_host(fus_ctx* c, const double* x, const double* coeffs, double* y) {
+  return apply_host(c, x, coeffs, y, false);
+}
+
+// ---- device memory helpers ----------------------------------------------------------------------
+int fus_dev_alloc(fus_ctx* c, size_t bytes, void** p) {
+  if (!c || !p)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaMalloc(p, bytes ? bytes : 8));
+  return FUS_OK;
+}
+int fus_dev_free(fus_ctx* c, void* p) {
+  if (!c)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  FUS_CUDA(cudaFree(p));
+  return FUS_OK;
+}
+int fus_dev_upload(fus_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+int fus_dev_download(fus_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+int fus_dev_memset(fus_ctx* c, void* dst, int value, size_t bytes) {
+  if (!c)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaMemsetAsync(dst, value, bytes, c->stream));
+  return FUS_OK;
+}
+
+// ---- models -------------------------------------------------------------------------------------
+static int model_alloc_vec(fus_ctx* c, double** p) {
+  FUS_CUDA(cudaMalloc(p, sizeof(double) * c->ndofs));
+  FUS_CUDA(cudaMemsetAsync(*p, 0, sizeof(double) * c->ndofs, c->stream));
+  return FUS_OK;
+}
+
+int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
+                     const double* delta0, const double* beta0, const double* src,
+                     const double* dsrc, const double* absb, const double* bmass, double freq,
+                     double p0, double s0, fus_model** out) {
+  if (!c || !out || !c0 || !rho0 || kind < 0 || kind > 2) {
+    set_error("fus_model_create: bad argument");
+    return FUS_ERR_ARG;
+  }
+  if ((kind >= FUS_LOSSY && !delta0) || (kind == FUS_WESTERVELT && !beta0)) {
+    set_error("fus_model_create: delta0/beta0 required for this model kind");
+    return FUS_ERR_ARG;
+  }
+  if (!c->d_G2 || !c->d_detJ) {
+    set_error("fus_model_create: context needs both G and detJ");
+    return FUS_ERR_STATE;
+  }
+  FUS_TRY(select_device(c));
+  fus_model* m = new fus_model();
+  *out = m;
+  m->ctx = c;
+  m->kind = kind;
+  m->freq = freq;
+  m->p0 = p0;
+  m->s0 = s0;
+  m->w0 = 2 * M_PI * freq;
+  m->period = 1.0 / freq;
+  m->window_length = 4.0;
+  const int64_t nc = c->ncells, nd = c->ndofs;
+  // operator coefficients (Linear.hpp:148-155, Lossy.hpp:166-169, Westervelt.hpp:182-187)
+  std::vector<double> lin(nc), att(nc, 0.0), mco(nc), nl2(nc, 0.0);
+  for (int64_t i = 0; i < nc; ++i) {
+    lin[i] = -1.0 / rho0[i];
+    if (kind >= FUS_LOSSY)
+      att[i] = -delta0[i] / rho0[i] / c0[i] / c0[i];
+    if (kind == FUS_WESTERVELT)
+      nl2[i] = 2.0 * beta0[i] / rho0[i] / rho0[i] / c0[i] / c0[i] / c0[i] / c0[i];
+    mco[i] = 1.0 / rho0[i] / c0[i] / c0[i];
+  }
+  const size_t cb = sizeof(double) * nc;
+  double *d_mco = nullptr, *d_nl2 = nullptr;
+  FUS_CUDA(cudaMalloc(&m->d_lin, cb));
+  FUS_CUDA(cudaMalloc(&m->d_att, cb));
+  FUS_CUDA(cudaMalloc(&d_mco, cb));
+  FUS_CUDA(cudaMemcpyAsync(m->d_lin, lin.data(), cb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(m->d_att, att.data(), cb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(d_mco, mco.data(), cb, cudaMemcpyHostToDevice, c->stream));
+  for (double** v : {&m->d_m, &m->d_u0, &m->d_v0, &m->d_ua, &m->d_va, &m->d_un, &m->d_vn, &m->d_b})
+    FUS_TRY(model_alloc_vec(c, v));
+  // lumped mass: the form `a` assembled with u == 1 (Linear.hpp:127-134), + facet mass term
+  std::vector<double> ones(nd, 1.0);
+  FUS_CUDA(cudaMemcpyAsync(m->d_un, ones.data(), sizeof(double) * nd, cudaMemcpyHostToDevice,
+                           c->stream));
+  FUS_TRY(launch_mass(c, m->d_un, d_mco, m->d_m, 0, nc, c->stream));
+  if (bmass) {
+    FUS_CUDA(cudaMemcpyAsync(m->d_vn, bmass, sizeof(double) * nd, cudaMemcpyHostToDevice,
+                             c->stream));
+    add_kernel<<<grid_for(nd, 256, 1 << 30), 256, 0, c->stream>>>(m->d_m, m->d_vn, nd);
+    FUS_LAUNCHED();
+  }
+  if (kind == FUS_WESTERVELT) {
+    FUS_CUDA(cudaMalloc(&d_nl2, cb));
+    FUS_CUDA(cudaMemcpyAsync(d_nl2, nl2.data(), cb, cudaMemcpyHostToDevice, c->stream));
+    FUS_TRY(model_alloc_vec(c, &m->d_dnl));
+    FUS_TRY(launch_mass(c, m->d_un, d_nl2, m->d_dnl, 0, nc, c->stream));
+  }
+  if (c->halo) { // sum the per-rank partial sums on the owners, once (Linear.hpp:134)
+    FUS_TRY(halo_reverse(c->halo, m->d_m, nullptr, c->stream));
+    if (m->d_dnl)
+      FUS_TRY(halo_reverse(c->halo, m->d_dnl, nullptr, c->stream));
+  }
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  FUS_CUDA(cudaMemsetAsync(m->d_un, 0, sizeof(double) * nd, c->stream));
+  FUS_CUDA(cudaMemsetAsync(m->d_vn, 0, sizeof(double) * nd, c->stream));
+  cudaFree(d_mco);
+  cudaFree(d_nl2);
+  // compact the boundary vectors
+  std::vector<int32_t> bidx;
+  std::vector<double> bs, bd, ba;
+  for (int64_t i = 0; i < nd; ++i) {
+    const double a = src ? src[i] : 0.0, b = dsrc ? dsrc[i] : 0.0, e = absb ? absb[i] : 0.0;
+    if (a != 0.0 || b != 0.0 || e != 0.0) {
+      bidx.push_back((int32_t)i);
+      bs.push_back(a);
+      bd.push_back(b);
+      ba.push_back(e);
+    }
+  }
+  m->nb = (int64_t)bidx.size();
+  if (m->nb) {
+    FUS_CUDA(cudaMalloc(&m->d_bidx, sizeof(int32_t) * m->nb));
+    FUS_CUDA(cudaMalloc(&m->d_bsrc, sizeof(double) * m->nb));
+    FUS_CUDA(cudaMalloc(&m->d_bdsrc, sizeof(double) * m->nb));
+    FUS_CUDA(cudaMalloc(&m->d_babs, sizeof(double) * m->nb));
+    FUS_CUDA(cudaMemcpy(m->d_bidx, bidx.data(), sizeof(int32_t) * m->nb, cudaMemcpyHostToDevice));
+    FUS_CUDA(cudaMemcpy(m->d_bsrc, bs.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
+    FUS_CUDA(cudaMemcpy(m->d_bdsrc, bd.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
+    FUS_CUDA(cudaMemcpy(m->d_babs, ba.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
+  }
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+int fus_model_destroy(fus_model* m) {
+  if (!m)
+    return FUS_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (void* p : {(void*)m->d_lin, (void*)m->d_att, (void*)m->d_m, (void*)m->d_dnl,
+                  (void*)m->d_bidx, (void*)m->d_bsrc, (void*)m->d_bdsrc, (void*)m->d_babs,
+                  (void*)m->d_u0, (void*)m->d_v0, (void*)m->d_ua, (void*)m->d_va, (void*)m->d_un,
+                  (void*)m->d_vn, (void*)m->d_b})
+    cudaFree(p);
+  delete m;
+  return FUS_OK;
+}
+
+int fus_model_set_state(fus_model* m, const double* u, const double* v) {
+  if (!m)
+    return FUS_ERR_ARG;
+  fus_ctx* c = m->ctx;
+  FUS_TRY(select_device(c));
+  const size_t vb = sizeof(double) * c->ndofs;
+  if (u)
+    FUS_CUDA(cudaMemcpyAsync(m->d_u0, u, vb, cudaMemcpyHostToDevice, c->stream));
+  else
+    FUS_CUDA(cudaMemsetAsync(m->d_u0, 0, vb, c->stream));
+  if (v)
+    FUS_CUDA(cudaMemcpyAsync(m->d_v0, v, vb, cudaMemcpyHostToDevice, c->stream));
+  else
+    FUS_CUDA(cudaMemsetAsync(m->d_v0, 0, vb, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+int fus_model_get_state(fus_model* m, double* u, double* v) {
+  if (!m)
+    return FUS_ERR_ARG;
+  fus_ctx* c = m->ctx;
+  FUS_TRY(select_device(c));
+  const size_t vb = sizeof(double) * c->ndofs;
+  if (u)
+    FUS_CUDA(cudaMemcpyAsync(u, m->d_u0, vb, cudaMemcpyDeviceToHost, c->stream));
+  if (v)
+    FUS_CUDA(cudaMemcpyAsync(v, m->d_v0, vb, cudaMemcpyDeviceToHost, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+int fus_model_state_dev(fus_model* m, double** u, double** v) {
+  if (!m)
+    return FUS_ERR_ARG;
+  if (u)
+    *u = m->d_u0;
+  if (v)
+    *v = m->d_v0;
+  return FUS_OK;
+}
+
+int fus_model_get_mass(fus_model* m, double* mass) {
+  if (!m || !mass)
+    return FUS_ERR_ARG;
+  fus_ctx* c = m->ctx;
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaMemcpyAsync(mass, m->d_m, sizeof(double) * c->ndofs, cudaMemcpyDeviceToHost,
+                           c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+// Source scalars at time t (Linear.hpp:185-192, Lossy.hpp:199-220, Westervelt.hpp:220-240)
+static void source_scalars(const fus_model* m, double t, double* g, double* dg) {
+  double window, dwindow;
+  if (t < m->period * m->window_length) {
+    window = 0.5 * (1.0 - cos(m->freq * M_PI * t / m->window_length));
+    dwindow = 0.5 * M_PI * m->freq / m->window_length * sin(m->freq * M_PI * t / m->window_length);
+  } else {
+    window = 1.0;
+    dwindow = 0.0;
+  }
+  if (m->kind == FUS_LINEAR) {
+    *g = window * m->p0 * m->w0 / m->s0 * cos(m->w0 * t);
+    *dg = 0.0;
+  } else {
+    *g = window * 2.0 * m->p0 * m->w0 / m->s0 * cos(m->w0 * t);
+    *dg = dwindow * 2.0 * m->p0 * m->w0 / m->s0 * cos(m->w0 * t)
+          - window * 2.0 * m->p0 * m->w0 * m->w0 / m->s0 * sin(m->w0 * t);
+  }
+}
+
+// b += K(lin) u [+ K(att) v] + boundary terms, with the halo exchange around it when partitioned:
+// the right-hand side assembly of f1 (Linear.hpp:203-206, Lossy.hpp:229-234, Westervelt.hpp:260-265).
+// u, v must have fresh ghosts on entry.
+static int assemble_rhs(fus_model* m, double t, const double* u, const double* v) {
+  fus_ctx* c = m->ctx;
+  double g, dg;
+  source_scalars(m, t, &g, &dg);
+  const double* x2 = (m->kind >= FUS_LOSSY) ? v : nullptr;
+  const double* c2 = (m->kind >= FUS_LOSSY) ? m->d_att : nullptr;
+  auto boundary = [&]() -> int {
+    if (m->nb) {
+      boundary_kernel<<<grid_for(m->nb, 256, 1 << 30), 256, 0, c->stream>>>(
+          m->d_b, v, m->d_bidx, m->d_bsrc, m->d_bdsrc, m->d_babs, m->nb, g, dg);
+      FUS_LAUNCHED();
+    }
+    return FUS_OK;
+  };
+  if (!c->halo) {
+    FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, c->ncells, c->stream));
+    return boundary();
+  }
+  // partitioned: interface cells and boundary terms first, then the reverse exchange of the
+  // ghost partial sums overlaps with the interior cells.
+  const long long ni = halo_interface_cells(c->halo);
+  FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, ni, c->stream));
+  FUS_TRY(boundary());
+  FUS_TRY(halo_reverse_begin(c->halo, m->d_b, c->stream));
+  FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, c->ncells, c->stream));
+  FUS_TRY(halo_reverse_end(c->halo, m->d_b, c->stream));
+  return FUS_OK;
+}
+
+int fus_model_f1(fus_model* m, double t, const double* u, const double* v, double* result) {
+  if (!m || !u || !v || !result)
+    return FUS_ERR_ARG;
+  fus_ctx* c = m->ctx;
+  FUS_TRY(select_device(c));
+  const int64_t nd = c->ndofs;
+  const size_t vb = sizeof(double) * nd;
+  FUS_CUDA(cudaMemcpyAsync(m->d_un, u, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(m->d_vn, v, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemsetAsync(m->d_b, 0, vb, c->stream));
+  if (c->halo)
+    FUS_TRY(halo_forward(c->halo, m->d_un, m->d_vn, c->stream));
+  FUS_TRY(assemble_rhs(m, t, m->d_un, m->d_vn));
+  const int grid = grid_for(nd, 256, 1 << 30);
+  if (m->kind == FUS_WESTERVELT)
+    f1_finish_kernel<true><<<grid, 256, 0, c->stream>>>(m->d_b, m->d_m, m->d_dnl, m->d_un,
+                                                        m->d_vn, m->d_ua, nd);
+  else
+    f1_finish_kernel<false><<<grid, 256, 0, c->stream>>>(m->d_b, m->d_m, nullptr, m->d_un,
+                                                         m->d_vn, m->d_ua, nd);
+  FUS_LAUNCHED();
+  FUS_CUDA(cudaMemcpyAsync(result, m->d_ua, vb, cudaMemcpyDeviceToHost, c->stream));
+  FUS_CUDA(cudaMemsetAsync(m->d_b, 0, vb, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+} // extern "C"
+
+template <int STAGE>
+static int launch_stage(fus_model* m, const StageArgs& A) {
+  fus_ctx* c = m->ctx;
+  const int grid = grid_for(A.ntotal, 256, c->num_sms * 8);
+  if (m->kind == FUS_WESTERVELT)
+    rk4_stage_kernel<STAGE, true><<<grid, 256, 0, c->stream>>>(A);
+  else
+    rk4_stage_kernel<STAGE, false><<<grid, 256, 0, c->stream>>>(A);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
+extern "C" {
+
+int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeStep,
+                  int* nsteps) {
+  if (!m || !(timeStep > 0.0)) {
+    set_error("fus_model_rk4: bad argument");
+    return FUS_ERR_ARG;
+  }
+  fus_ctx* c = m->ctx;
+  FUS_TRY(select_device(c));
+  // Same host-side time arithmetic as the reference loop (Linear.hpp:231-298).
+  double t = startTime, tf = finalTime, dt = timeStep;
+  int step = 0;
+  const double a_runge[4] = {0.0, 0.5, 0.5, 1.0};
+  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  const double c_runge[4] = {0.0, 0.5, 0.5, 1.0};
+  StageArgs A;
+  A.b = m->d_b;
+  A.m = m->d_m;
+  A.dnl = m->d_dnl;
+  A.u0 = m->d_u0;
+  A.v0 = m->d_v0;
+  A.ua = m->d_ua;
+  A.va = m->d_va;
+  A.un = m->d_un;
+  A.vn = m->d_vn;
+  A.nowned = c->nowned;
+  A.ntotal = c->ndofs;
+  FUS_CUDA(cudaMemsetAsync(m->d_b, 0, sizeof(double) * c->ndofs, c->stream));
+  if (c->halo)
+    FUS_TRY(halo_forward(c->halo, m->d_u0, m->d_v0, c->stream));
+  while (t < tf) {
+    dt = std::min(dt, tf - t);
+    for (int i = 0; i < 4; ++i) {
+      const double tn = t + c_runge[i] * dt;
+      const double* u_in = (i == 0) ? m->d_u0 : m->d_un;
+      const double* v_in = (i == 0) ? m->d_v0 : m->d_vn;
+      FUS_TRY(assemble_rhs(m, tn, u_in, v_in));
+      A.bw_dt = dt * b_runge[i];
+      A.a_next_dt = (i < 3) ? dt * a_runge[i + 1] : 0.0;
+      switch (i) {
+      case 0: FUS_TRY(launch_stage<0>(m, A)); break;
+      case 1: FUS_TRY(launch_stage<1>(m, A)); break;
+      case 2: FUS_TRY(launch_stage<2>(m, A)); break;
+      case 3: FUS_TRY(launch_stage<3>(m, A)); break;
+      }
+      if (c->halo) // scatter_fwd of the next stage input (Linear.hpp:196-199)
+        FUS_TRY(halo_forward(c->halo, (i < 3) ? m->d_un : m->d_u0, (i < 3) ? m->d_vn : m->d_v0,
+                             c->stream));
+    }
+    t += dt;
+    step += 1;
+  }
+  if (nsteps)
+    *nsteps = step;
+  return FUS_OK;
+}
+
+// ---- halo ---------------------------------------------------------------------------------------
+int fus_comm_unique_id(void* id128) { return halo_unique_id(id128); }
+
+int fus_halo_setup(fus_ctx* c, int rank, int nranks, const void* uid, int nneigh, const int* neigh,
+                   const int64_t* send_off, const int32_t* send_idx, const int64_t* recv_off,
+                   const int32_t* recv_idx, int64_t ninterface_cells) {
+  if (!c || nranks < 1 || rank < 0 || rank >= nranks || nneigh < 0 || ninterface_cells < 0
+      || ninterface_cells > c->ncells) {
+    set_error("fus_halo_setup: bad argument");
+    return FUS_ERR_ARG;
+  }
+  FUS_TRY(select_device(c));
+  if (c->halo) {
+    halo_destroy(c->halo);
+    c->halo = nullptr;
+  }
+  return halo_create(&c->halo, c->device, rank, nranks, uid, nneigh, neigh, send_off, send_idx,
+                     recv_off, recv_idx, c->nowned, c->ndofs, ninterface_cells);
+}
+
+int fus_scatter_fwd_dev(fus_ctx* c, double* x) {
+  if (!c || !x)
+    return FUS_ERR_ARG;
+  if (!c->halo)
+    return FUS_OK;
+  FUS_TRY(select_device(c));
+  return halo_forward(c->halo, x, nullptr, c->stream);
+}
+
+int fus_scatter_rev_dev(fus_ctx* c, double* x) {
+  if (!c || !x)
+    return FUS_ERR_ARG;
+  if (!c->halo)
+    return FUS_OK;
+  FUS_TRY(select_device(c));
+  return halo_reverse(c->halo, x, nullptr, c->stream);
+}
+
+} // extern "C"

@@ -1,0 +1,343 @@
+// fus_halo.cu -- halo exchange over NCCL point-to-point (NVLink 5 / NVSwitch on an 8xB200 box).
+//
+// The exchange is a neighbour halo, not a reduction over all ranks: per neighbour one grouped
+// ncclSend + ncclRecv of the packed interface values.  NCCL is resolved at run time from the
+// libnccl.so.2 already loaded in the process (torch's) or found by the loader, so that the
+// single-GPU path has no NCCL dependency.
+#include "fus_halo.hpp"
+#include "fus_internal.hpp"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace fus {
+
+namespace {
+// Minimal NCCL surface (ABI-stable since NCCL 2.7)
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+constexpr int kNcclFloat64 = 8;
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.lib)
+    return FUS_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h)
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h)
+    h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    set_error("cannot load libnccl.so.2: %s", dlerror());
+    return FUS_ERR_COMM;
+  }
+  auto sym = [&](const char* n) { return dlsym(h, n); };
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+  g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+  g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.GroupStart || !g_nccl.GroupEnd
+      || !g_nccl.Send || !g_nccl.Recv) {
+    set_error("libnccl.so.2 lacks a required symbol");
+    return FUS_ERR_COMM;
+  }
+  g_nccl.lib = h;
+  return FUS_OK;
+}
+
+#define FUS_NCCL(call)                                                                             \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != 0) {                                                                                \
+      set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                                      \
+                g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error");                \
+      return FUS_ERR_COMM;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+#define FUS_CUDA_H(call)                                                                           \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));            \
+      return FUS_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+inline int blocks_for(long long n) { return (int)std::max<long long>(1, (n + 255) / 256); }
+} // namespace
+
+struct Halo {
+  int device = 0, rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  std::vector<int> neigh;
+  std::vector<int64_t> send_off, recv_off; // per neighbour, in entries
+  int64_t nsend = 0, nrecv = 0;
+  int32_t *d_send_idx = nullptr, *d_recv_idx = nullptr;
+  double *d_sbuf = nullptr, *d_rbuf = nullptr; // 2 vectors deep
+  int64_t nowned = 0, ndofs = 0, ninterface = 0;
+  int overlap = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+};
+
+int halo_unique_id(void* id128) {
+  if (!id128)
+    return FUS_ERR_ARG;
+  int r = load_nccl();
+  if (r != FUS_OK)
+    return r;
+  ncclUniqueId id;
+  FUS_NCCL(g_nccl.GetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
+  return FUS_OK;
+}
+
+int halo_create(Halo** out, int device, int rank, int nranks, const void* uid, int nneigh,
+                const int* neigh, const int64_t* send_off, const int32_t* send_idx,
+                const int64_t* recv_off, const int32_t* recv_idx, int64_t nowned, int64_t ndofs,
+                int64_t ninterface_cells) {
+  int r = load_nccl();
+  if (r != FUS_OK)
+    return r;
+  if (!uid || (nneigh > 0 && (!neigh || !send_off || !recv_off))) {
+    set_error("halo_create: bad argument");
+    return FUS_ERR_ARG;
+  }
+  Halo* h = new Halo();
+  *out = h;
+  h->device = device;
+  h->rank = rank;
+  h->nranks = nranks;
+  h->nowned = nowned;
+  h->ndofs = ndofs;
+  h->ninterface = ninterface_cells;
+  h->neigh.assign(neigh, neigh + nneigh);
+  h->send_off.assign(send_off, send_off + nneigh + 1);
+  h->recv_off.assign(recv_off, recv_off + nneigh + 1);
+  h->nsend = nneigh ? send_off[nneigh] : 0;
+  h->nrecv = nneigh ? recv_off[nneigh] : 0;
+  for (int64_t i = 0; i < h->nsend; ++i)
+    if (send_idx[i] < 0 || send_idx[i] >= nowned) {
+      set_error("halo_create: send index %d is not an owned dof", send_idx[i]);
+      return FUS_ERR_ARG;
+    }
+  for (int64_t i = 0; i < h->nrecv; ++i)
+    if (recv_idx[i] < nowned || recv_idx[i] >= ndofs) {
+      set_error("halo_create: recv index %d is not a ghost dof", recv_idx[i]);
+      return FUS_ERR_ARG;
+    }
+  FUS_CUDA_H(cudaSetDevice(device));
+  FUS_CUDA_H(cudaMalloc(&h->d_send_idx, sizeof(int32_t) * std::max<int64_t>(1, h->nsend)));
+  FUS_CUDA_H(cudaMalloc(&h->d_recv_idx, sizeof(int32_t) * std::max<int64_t>(1, h->nrecv)));
+  const int64_t nb = std::max<int64_t>(1, std::max(h->nsend, h->nrecv));
+  FUS_CUDA_H(cudaMalloc(&h->d_sbuf, sizeof(double) * 2 * nb));
+  FUS_CUDA_H(cudaMalloc(&h->d_rbuf, sizeof(double) * 2 * nb));
+  if (h->nsend)
+    FUS_CUDA_H(cudaMemcpy(h->d_send_idx, send_idx, sizeof(int32_t) * h->nsend,
+                          cudaMemcpyHostToDevice));
+  if (h->nrecv)
+    FUS_CUDA_H(cudaMemcpy(h->d_recv_idx, recv_idx, sizeof(int32_t) * h->nrecv,
+                          cudaMemcpyHostToDevice));
+  FUS_CUDA_H(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  ncclUniqueId id;
+  std::memcpy(&id, uid, sizeof(id));
+  FUS_NCCL(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+  return FUS_OK;
+}
+
+void halo_destroy(Halo* h) {
+  if (!h)
+    return;
+  cudaSetDevice(h->device);
+  if (h->comm_stream)
+    cudaStreamSynchronize(h->comm_stream);
+  if (h->comm && g_nccl.CommDestroy)
+    g_nccl.CommDestroy(h->comm);
+  cudaFree(h->d_send_idx);
+  cudaFree(h->d_recv_idx);
+  cudaFree(h->d_sbuf);
+  cudaFree(h->d_rbuf);
+  if (h->ev_ready)
+    cudaEventDestroy(h->ev_ready);
+  if (h->ev_done)
+    cudaEventDestroy(h->ev_done);
+  if (h->comm_stream)
+    cudaStreamDestroy(h->comm_stream);
+  delete h;
+}
+
+void halo_set_overlap(Halo* h, int on) { h->overlap = on; }
+long long halo_interface_cells(const Halo* h) { return h->overlap ? h->ninterface : 0; }
+
+// One grouped exchange.  `fwd`: owners send send_idx entries, ghosts receive; otherwise reversed.
+// nv vectors are concatenated per neighbour: [neighbour k][vector][entry].
+static int exchange(Halo* h, bool fwd, int nv, cudaStream_t st) {
+  const std::vector<int64_t>& soff = fwd ? h->send_off : h->recv_off;
+  const std::vector<int64_t>& roff = fwd ? h->recv_off : h->send_off;
+  FUS_NCCL(g_nccl.GroupStart());
+  for (size_t k = 0; k < h->neigh.size(); ++k) {
+    const int64_t ns = soff[k + 1] - soff[k], nr = roff[k + 1] - roff[k];
+    if (ns)
+      FUS_NCCL(g_nccl.Send(h->d_sbuf + nv * soff[k], (size_t)(nv * ns), kNcclFloat64, h->neigh[k],
+                           h->comm, st));
+    if (nr)
+      FUS_NCCL(g_nccl.Recv(h->d_rbuf + nv * roff[k], (size_t)(nv * nr), kNcclFloat64, h->neigh[k],
+                           h->comm, st));
+  }
+  FUS_NCCL(g_nccl.GroupEnd());
+  return FUS_OK;
+}
+
+// pack/unpack with the per-neighbour [vector][entry] interleave
+__global__ void __launch_bounds__(256)
+    halo_pack_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                     const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
+                     double* __restrict__ buf, long long n, int nv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int k = 0;
+  while (k + 1 < nneigh && i >= off[k + 1])
+    ++k;
+  const long long base = nv * off[k], len = off[k + 1] - off[k], j = i - off[k];
+  const int d = idx[i];
+  buf[base + j] = a[d];
+  if (nv == 2)
+    buf[base + len + j] = b[d];
+}
+
+template <bool ADD>
+__global__ void __launch_bounds__(256)
+    halo_unpack_kernel(double* __restrict__ a, double* __restrict__ b,
+                       const int32_t* __restrict__ idx, const int64_t* __restrict__ off,
+                       int nneigh, const double* __restrict__ buf, long long n, int nv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int k = 0;
+  while (k + 1 < nneigh && i >= off[k + 1])
+    ++k;
+  const long long base = nv * off[k], len = off[k + 1] - off[k], j = i - off[k];
+  const int d = idx[i];
+  if (ADD) {
+    atomicAdd(a + d, buf[base + j]); // an owned dof may be a ghost on several neighbours
+    if (nv == 2)
+      atomicAdd(b + d, buf[base + len + j]);
+  } else {
+    a[d] = buf[base + j];
+    if (nv == 2)
+      b[d] = buf[base + len + j];
+  }
+}
+
+namespace {
+// device copies of the offset tables, created lazily
+struct OffTables {
+  int64_t *d_soff = nullptr, *d_roff = nullptr;
+};
+OffTables& tables(Halo* h) {
+  static std::vector<std::pair<Halo*, OffTables>> all;
+  for (auto& p : all)
+    if (p.first == h)
+      return p.second;
+  OffTables t;
+  const size_t nb = sizeof(int64_t) * h->send_off.size();
+  cudaMalloc(&t.d_soff, nb);
+  cudaMalloc(&t.d_roff, nb);
+  cudaMemcpy(t.d_soff, h->send_off.data(), nb, cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_roff, h->recv_off.data(), nb, cudaMemcpyHostToDevice);
+  all.push_back({h, t});
+  return all.back().second;
+}
+} // namespace
+
+int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
+  if (h->neigh.empty())
+    return FUS_OK;
+  const int nv = b ? 2 : 1, nn = (int)h->neigh.size();
+  OffTables& T = tables(h);
+  if (h->nsend)
+    halo_pack_kernel<<<blocks_for(h->nsend), 256, 0, st>>>(a, b, h->d_send_idx, T.d_soff, nn,
+                                                          h->d_sbuf, h->nsend, nv);
+  int r = exchange(h, true, nv, st);
+  if (r != FUS_OK)
+    return r;
+  if (h->nrecv)
+    halo_unpack_kernel<false><<<blocks_for(h->nrecv), 256, 0, st>>>(
+        a, b, h->d_recv_idx, T.d_roff, nn, h->d_rbuf, h->nrecv, nv);
+  FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
+static int reverse_on(Halo* h, double* a, double* b, cudaStream_t st) {
+  const int nv = b ? 2 : 1, nn = (int)h->neigh.size();
+  OffTables& T = tables(h);
+  if (h->nrecv)
+    halo_pack_kernel<<<blocks_for(h->nrecv), 256, 0, st>>>(a, b, h->d_recv_idx, T.d_roff, nn,
+                                                          h->d_sbuf, h->nrecv, nv);
+  int r = exchange(h, false, nv, st);
+  if (r != FUS_OK)
+    return r;
+  if (h->nsend)
+    halo_unpack_kernel<true><<<blocks_for(h->nsend), 256, 0, st>>>(
+        a, b, h->d_send_idx, T.d_soff, nn, h->d_rbuf, h->nsend, nv);
+  FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
+int halo_reverse(Halo* h, double* a, double* b, cudaStream_t st) {
+  if (h->neigh.empty())
+    return FUS_OK;
+  return reverse_on(h, a, b, st);
+}
+
+int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
+  if (h->neigh.empty())
+    return FUS_OK;
+  if (!h->overlap)
+    return FUS_OK; // whole exchange happens in _end, after all cells
+  FUS_CUDA_H(cudaEventRecord(h->ev_ready, st));
+  FUS_CUDA_H(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  int r = reverse_on(h, a, nullptr, h->comm_stream);
+  if (r != FUS_OK)
+    return r;
+  FUS_CUDA_H(cudaEventRecord(h->ev_done, h->comm_stream));
+  return FUS_OK;
+}
+
+int halo_reverse_end(Halo* h, double* a, cudaStream_t st) {
+  if (h->neigh.empty())
+    return FUS_OK;
+  if (!h->overlap)
+    return reverse_on(h, a, nullptr, st);
+  FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_done, 0));
+  return FUS_OK;
+}
+
+} // namespace fus

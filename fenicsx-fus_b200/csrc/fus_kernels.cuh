@@ -1,0 +1,562 @@
+// fus_kernels.cuh -- hand-written sm_100a kernels of the sum-factorised operator + RK4 path.
+//
+// FP64 on the CUDA cores (no tensor cores: the 1-D contractions are (P+1)x(P+1) and the path is
+// HBM-bound).  References are to cpp/fenicsx-sf/common/ of adeebkor/fenicsx-fus.
+//
+// Device layout of the geometric factor (DESIGN.md "data layout"):
+//   G2[cell][i0][p][t]  (double2),  p = 0..2 holding (G00,G01) (G02,G11) (G12,G22),
+//   t = i1*N + i2, i.e. for one cell and one i0-level the N*N points of a component pair are
+//   contiguous: a thread column (i1,i2) streams its 3*N double2 with 16-byte coalesced loads.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace fus {
+
+template <int N>
+struct DMat {
+  double d[N * N]; // d[q*N+k] = phi_k'(xi_q)
+};
+
+template <int N>
+struct Rule1D {
+  double pts[N];
+  double wts[N];
+};
+
+// Streaming 16-byte load for data that is used exactly once (G): read-only path, do not keep
+// the line in L1 so that L1 stays available for the gathered dofs.
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+  double2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stiffness operator, "column" kernel (kernels (1)(2)(3) of the north star in one pass):
+//   y[dof] += sum_cells B^T (coeff_c G_c) B x[dof]        StiffnessSpectral3D::operator(),
+//                                                         spectral_op.hpp:173-243
+// One thread owns the column (i1,i2) of a cell and keeps the N values along i0 in registers:
+//   - gather  x[dofmap]                                   (:185-186)
+//   - direction-0 contraction in registers with dphi as immediate constant-bank operands
+//   - direction-1/2 contractions through shared memory    (:194-210)
+//   - G transform with G streamed straight to registers   (:113-130, :213-214)
+//   - transposed contractions                             (:221-238)
+//   - scatter-add with FP64 RED atomics                   (:240-241)
+// The geometric factors of the NEXT cell are loaded into the registers the current cell has just
+// consumed (level by level), and the next cell's dofs are gathered as soon as the current ones
+// have been staged, so a warp always has one whole cell (~7 KB at P=4) of HBM requests in flight.
+// For N*N <= 32 a cell (or several) lives inside one warp and only __syncwarp is needed.
+// FUSE2: x := coeff[c]*x + coeff2[c]*x2 at gather time and the transform coefficient is 1 --
+// the lossy model's K(-1/rho) u + K(-delta/rho c^2) v in a single application (Lossy.hpp:230-232).
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct ColCfg {
+  static constexpr int NN = N * N;
+  static constexpr bool WARP = (NN <= 32);
+  static constexpr int CPW = WARP ? 32 / NN : 0; // cells per warp
+  static constexpr int WPB = 4;                  // warps per block in WARP mode
+  static constexpr int CPB = WARP ? CPW * WPB : (N == 6 ? 8 : 4); // cells per block
+  static constexpr int THREADS = WARP ? 32 * WPB : ((CPB * NN + 31) / 32) * 32;
+  static constexpr int NS = N | 1;                  // padded row length (doubles), odd
+  static constexpr int PL = N * NS;                 // plane stride
+  static constexpr int CS = ((N * PL + 7) / 8) * 8 + 8; // cell stride of one buffer (doubles)
+  static constexpr int SMEM_BYTES = CPB * 3 * CS * (int)sizeof(double);
+};
+
+template <int N, bool FUSE2>
+__global__ void __launch_bounds__(ColCfg<N>::THREADS)
+    stiffness_col_kernel(const double* __restrict__ x, const double* __restrict__ x2,
+                         double* __restrict__ y, const int32_t* __restrict__ dofmap,
+                         const double2* __restrict__ G2, const double* __restrict__ coeff,
+                         const double* __restrict__ coeff2, long long cell_begin,
+                         long long cell_end, const __grid_constant__ DMat<N> D) {
+  using C = ColCfg<N>;
+  constexpr int NN = C::NN, NS = C::NS, PL = C::PL;
+  extern __shared__ double smem[];
+
+  const int tid = threadIdx.x;
+  int slot, t;
+  bool lane_ok;
+  if constexpr (C::WARP) {
+    const int lane = tid & 31, w = tid >> 5;
+    const int cw = lane / NN;
+    t = lane - cw * NN;
+    lane_ok = cw < C::CPW;
+    slot = w * C::CPW + (lane_ok ? cw : 0);
+  } else {
+    slot = tid / NN;
+    t = tid - slot * NN;
+    lane_ok = slot < C::CPB;
+    if (!lane_ok)
+      slot = 0;
+  }
+  const int i1 = t / N, i2 = t - i1 * N;
+  double* xs = smem + slot * (3 * C::CS);
+  double* s1 = xs + C::CS;
+  double* s2 = s1 + C::CS;
+
+  // thread-dependent rows/columns of dphi (direction 1 and 2), kept in registers
+  double D1[N], D2[N], DT1[N], DT2[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    D1[k] = D.d[i1 * N + k];
+    D2[k] = D.d[i2 * N + k];
+    DT1[k] = D.d[k * N + i1];
+    DT2[k] = D.d[k * N + i2];
+  }
+
+  const long long stride = (long long)gridDim.x * C::CPB;
+  const long long ncell = cell_end - cell_begin;
+  const int niter = (int)((ncell + stride - 1) / stride); // uniform over the block
+  long long c = cell_begin + (long long)blockIdx.x * C::CPB + slot;
+
+  int idx[N], idxn[N];
+  double xv[N];
+  double2 g[N][3];
+  double cf = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    idx[k] = 0;
+    idxn[k] = 0;
+    xv[k] = 0.0;
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      g[k][p] = make_double2(0.0, 0.0);
+  }
+
+  // ---- prologue: everything for the first cell, dof indices for the second ----
+  bool valid = lane_ok && (c < cell_end);
+  if (valid) {
+    const int32_t* dm = dofmap + c * (N * NN) + t;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      idx[k] = __ldg(dm + k * NN);
+    if constexpr (FUSE2) {
+      const double ca = __ldg(coeff + c), cb = __ldg(coeff2 + c);
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        xv[k] = ca * __ldg(x + idx[k]) + cb * __ldg(x2 + idx[k]);
+      cf = 1.0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        xv[k] = __ldg(x + idx[k]);
+      cf = __ldg(coeff + c);
+    }
+    const double2* gp = G2 + c * (3 * N * NN) + t;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        g[k][p] = ld_stream(gp + (k * 3 + p) * NN);
+  }
+  long long cn = c + stride;
+  bool validn = lane_ok && (cn < cell_end);
+  if (validn) {
+    const int32_t* dm = dofmap + cn * (N * NN) + t;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      idxn[k] = __ldg(dm + k * NN);
+  }
+
+  for (int it = 0; it < niter; ++it) {
+    // (a) stage the column, direction-0 contraction in registers
+    if (lane_ok) {
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        xs[k * PL + i1 * NS + i2] = xv[k];
+    }
+    double f0[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        s = fma(D.d[q * N + k], xv[k], s);
+      f0[q] = s;
+    }
+    const double cfc = cf;
+    // gather the next cell's dofs now that xv has been consumed
+    if (validn) {
+      if constexpr (FUSE2) {
+        const double ca = __ldg(coeff + cn), cb = __ldg(coeff2 + cn);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          xv[k] = ca * __ldg(x + idxn[k]) + cb * __ldg(x2 + idxn[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          xv[k] = __ldg(x + idxn[k]);
+        cf = __ldg(coeff + cn);
+      }
+    }
+    if constexpr (C::WARP)
+      __syncwarp();
+    else
+      __syncthreads();
+
+    // (b) per i0-level: directions 1,2 from shared memory, G transform, transposed direction 0
+    double yv[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m)
+      yv[m] = 0.0;
+    const double2* gpn = G2 + cn * (3 * N * NN) + t;
+#pragma unroll
+    for (int i0 = 0; i0 < N; ++i0) {
+      double f1 = 0.0, f2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        f1 = fma(D1[k], xs[i0 * PL + k * NS + i2], f1);
+        f2 = fma(D2[k], xs[i0 * PL + i1 * NS + k], f2);
+      }
+      const double2 ga = g[i0][0], gb = g[i0][1], gc = g[i0][2];
+      // stiffness::transform (spectral_op.hpp:113-130)
+      const double t0 = cfc * (ga.x * f0[i0] + ga.y * f1 + gb.x * f2);
+      const double t1 = cfc * (ga.y * f0[i0] + gb.y * f1 + gc.x * f2);
+      const double t2 = cfc * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
+      // refill this level's registers with the next cell's factors
+      if (validn) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          g[i0][p] = ld_stream(gpn + (i0 * 3 + p) * NN);
+      }
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+        yv[m] = fma(D.d[i0 * N + m], t0, yv[m]);
+      if (lane_ok) { // padding lanes alias slot 0 and must not write
+        s1[i0 * PL + i1 * NS + i2] = t1;
+        s2[i0 * PL + i1 * NS + i2] = t2;
+      }
+    }
+    if constexpr (C::WARP)
+      __syncwarp();
+    else
+      __syncthreads();
+
+    // (c) transposed directions 1,2 and scatter-add
+#pragma unroll
+    for (int j0 = 0; j0 < N; ++j0) {
+      double acc = yv[j0];
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        acc = fma(DT1[q], s1[j0 * PL + q * NS + i2], acc);
+        acc = fma(DT2[q], s2[j0 * PL + i1 * NS + q], acc);
+      }
+      if (valid)
+        atomicAdd(y + idx[j0], acc);
+    }
+
+    // rotate the pipeline
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      idx[k] = idxn[k];
+    valid = validn;
+    c = cn;
+    cn += stride;
+    validn = lane_ok && (cn < cell_end);
+    if (validn) {
+      const int32_t* dm = dofmap + cn * (N * NN) + t;
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        idxn[k] = __ldg(dm + k * NN);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stiffness operator, "point" kernel: one thread per quadrature point, one cell per block pass.
+// Deliberately plain; kept as the on-device cross-check of the column kernel.
+// ------------------------------------------------------------------------------------------------
+template <int N, bool FUSE2>
+__global__ void __launch_bounds__(N* N* N)
+    stiffness_point_kernel(const double* __restrict__ x, const double* __restrict__ x2,
+                           double* __restrict__ y, const int32_t* __restrict__ dofmap,
+                           const double2* __restrict__ G2, const double* __restrict__ coeff,
+                           const double* __restrict__ coeff2, long long cell_begin,
+                           long long cell_end, const __grid_constant__ DMat<N> D) {
+  constexpr int NN = N * N, Nd = N * N * N;
+  __shared__ double xs[Nd], s0[Nd], s1[Nd], s2[Nd];
+  __shared__ double Ds[NN];
+  const int q = threadIdx.x;
+  const int i0 = q / NN, t = q - i0 * NN, i1 = t / N, i2 = t - i1 * N;
+  if (q < NN)
+    Ds[q] = D.d[q];
+  for (long long c = cell_begin + blockIdx.x; c < cell_end; c += gridDim.x) {
+    const int dof = dofmap[c * Nd + q];
+    double cf;
+    if constexpr (FUSE2) {
+      xs[q] = coeff[c] * x[dof] + coeff2[c] * x2[dof];
+      cf = 1.0;
+    } else {
+      xs[q] = x[dof];
+      cf = coeff[c];
+    }
+    __syncthreads();
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      f0 = fma(Ds[i0 * N + k], xs[k * NN + i1 * N + i2], f0);
+      f1 = fma(Ds[i1 * N + k], xs[i0 * NN + k * N + i2], f1);
+      f2 = fma(Ds[i2 * N + k], xs[i0 * NN + i1 * N + k], f2);
+    }
+    const double2* gp = G2 + (c * N + i0) * (3 * NN) + t;
+    const double2 ga = gp[0], gb = gp[NN], gc = gp[2 * NN];
+    s0[q] = cf * (ga.x * f0 + ga.y * f1 + gb.x * f2);
+    s1[q] = cf * (ga.y * f0 + gb.y * f1 + gc.x * f2);
+    s2[q] = cf * (gb.x * f0 + gc.x * f1 + gc.y * f2);
+    __syncthreads();
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      acc = fma(Ds[k * N + i0], s0[k * NN + i1 * N + i2], acc);
+      acc = fma(Ds[k * N + i1], s1[i0 * NN + k * N + i2], acc);
+      acc = fma(Ds[k * N + i2], s2[i0 * NN + i1 * N + k], acc);
+    }
+    atomicAdd(y + dof, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mass operator: y[dof] += coeff_c * detJ[c][q] * x[dof]   MassSpectral3D::operator(),
+// spectral_op.hpp:69-86 with mass::transform :19-26.  One thread per quadrature point.
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+    mass_kernel(const double* __restrict__ x, double* __restrict__ y,
+                const int32_t* __restrict__ dofmap, const double* __restrict__ detJ,
+                const double* __restrict__ coeff, long long npoints, int Nd) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npoints; p += stride) {
+    const long long c = p / Nd;
+    const int dof = __ldg(dofmap + p);
+    const double v = __ldg(coeff + c) * __ldg(x + dof) * __ldg(detJ + p);
+    atomicAdd(y + dof, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Geometry setup on the device (runs once): per cell and quadrature point
+//   J = sum_v x_v (x) grad phi_v^{Q1}(xi_q),  K = J^-1,  G = K K^T,
+//   detJ[c][q] = |det J| w_q,  G2 <- |det J| w_q {G00,G01,G02,G11,G12,G22}
+// compute_scaled_jacobian_determinant / compute_scaled_geometrical_factor, precompute.hpp:33-213.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128)
+    geometry_kernel(const double* __restrict__ xg, const int32_t* __restrict__ xdofmap,
+                    long long ncells, double2* __restrict__ G2, double* __restrict__ detJ,
+                    const __grid_constant__ Rule1D<N> R) {
+  constexpr int NN = N * N, Nd = N * N * N;
+  const long long total = ncells * Nd;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += stride) {
+    const long long c = gid / Nd;
+    const int q = (int)(gid - c * Nd);
+    const int q0 = q / NN, t = q - q0 * NN, q1 = t / N, q2 = t - q1 * N;
+    const double xi[3] = {R.pts[q0], R.pts[q1], R.pts[q2]};
+    const double w = R.wts[q0] * R.wts[q1] * R.wts[q2];
+    double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const int a = v & 1, b = (v >> 1) & 1, cc = (v >> 2) & 1;
+      const double l0 = a ? xi[0] : 1.0 - xi[0], l1 = b ? xi[1] : 1.0 - xi[1],
+                   l2 = cc ? xi[2] : 1.0 - xi[2];
+      const double d0 = a ? 1.0 : -1.0, d1 = b ? 1.0 : -1.0, d2 = cc ? 1.0 : -1.0;
+      const double gr[3] = {d0 * l1 * l2, l0 * d1 * l2, l0 * l1 * d2};
+      const double* X = xg + 3 * (long long)__ldg(xdofmap + 8 * c + v);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          J[i][j] += X[i] * gr[j];
+    }
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+    const double dj = fabs(det) * w;
+    if (detJ)
+      detJ[gid] = dj;
+    if (G2) {
+      const double id = 1.0 / det;
+      // K = adj(J)/det, row a of K
+      const double K[3][3]
+          = {{c00 * id, (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id,
+              (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id},
+             {c01 * id, (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id,
+              (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id},
+             {c02 * id, (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id,
+              (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id}};
+      double Gm[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+          Gm[a][b] = K[a][0] * K[b][0] + K[a][1] * K[b][1] + K[a][2] * K[b][2];
+      double2* o = G2 + (c * N + q0) * (3 * NN) + t;
+      o[0] = make_double2(dj * Gm[0][0], dj * Gm[0][1]);
+      o[NN] = make_double2(dj * Gm[0][2], dj * Gm[1][1]);
+      o[2 * NN] = make_double2(dj * Gm[1][2], dj * Gm[2][2]);
+    }
+  }
+}
+
+// Reference layout G[c][q][6] (a chunk of cells already on the device) -> G2, and back.
+template <int N>
+__global__ void __launch_bounds__(256)
+    g_to_device_layout_kernel(const double* __restrict__ Gref, long long ncells_chunk,
+                              double2* __restrict__ G2_chunk) {
+  constexpr int NN = N * N, Nd = N * N * N;
+  const long long total = ncells_chunk * Nd;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += stride) {
+    const long long c = gid / Nd;
+    const int q = (int)(gid - c * Nd);
+    const int q0 = q / NN, t = q - q0 * NN;
+    const double* s = Gref + gid * 6;
+    double2* o = G2_chunk + (c * N + q0) * (3 * NN) + t;
+    o[0] = make_double2(s[0], s[1]);
+    o[NN] = make_double2(s[2], s[3]);
+    o[2 * NN] = make_double2(s[4], s[5]);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+    g_from_device_layout_kernel(const double2* __restrict__ G2_chunk, long long ncells_chunk,
+                                double* __restrict__ Gref) {
+  constexpr int NN = N * N, Nd = N * N * N;
+  const long long total = ncells_chunk * Nd;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += stride) {
+    const long long c = gid / Nd;
+    const int q = (int)(gid - c * Nd);
+    const int q0 = q / NN, t = q - q0 * NN;
+    const double2* s = G2_chunk + (c * N + q0) * (3 * NN) + t;
+    double* o = Gref + gid * 6;
+    const double2 a = s[0], b = s[NN], cc = s[2 * NN];
+    o[0] = a.x;
+    o[1] = a.y;
+    o[2] = b.x;
+    o[3] = b.y;
+    o[4] = cc.x;
+    o[5] = cc.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Boundary terms of the right-hand side over the compacted list of boundary dofs:
+//   b[d] += g * src[k] + dg * dsrc[k] - absb[k] * v[d]
+// -- fem::assemble_vector(b_, *L) with the collocated `ds` forms (Linear.hpp:205, forms.py).
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+    boundary_kernel(double* __restrict__ b, const double* __restrict__ v,
+                    const int32_t* __restrict__ bidx, const double* __restrict__ bsrc,
+                    const double* __restrict__ bdsrc, const double* __restrict__ babs,
+                    long long nb, double g, double dg) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nb) {
+    const int d = bidx[k];
+    b[d] += g * bsrc[k] + dg * bdsrc[k] - babs[k] * v[d];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused RK4 stage epilogue (kernels (4)(5) of the north star).  After the operator has
+// accumulated b = K(un[,vn]) + boundary terms, one pass does, per owned dof,
+//     kv     = b / m                                   (Linear.hpp:212-221; Westervelt: m = m0 - dnl*un,
+//                                                       b += dnl*vn^2, Westervelt.hpp:249-265)
+//     ku     = vn                                      (f0, Linear.hpp:171-174)
+//     uacc  += bw*dt*ku ; vacc += bw*dt*kv             (:293-294)
+//     un'    = u0 + a'*dt*ku ; vn' = v0 + a'*dt*kv     (:279-283 of the NEXT stage)
+//     b      = 0                                       (:203 of the NEXT stage)
+// STAGE 0: the stage input is (u0,v0) itself and uacc/vacc are written, not read-modified.
+// STAGE 3: the new state is written straight into (u0,v0), which is also the next step's stage-0
+//          input, so no un'/vn' are produced.
+// Every vector crosses HBM at most once per stage: 9 / 12 / 12 / 8 passes for stages 0..3.
+// ------------------------------------------------------------------------------------------------
+struct StageArgs {
+  double* b;         // rhs accumulator, zeroed on exit (owned + ghosts)
+  const double* m;   // lumped mass (m0 for Westervelt)
+  const double* dnl; // Westervelt: D^(2 beta / rho^2 c^4) assembled; else nullptr
+  double* u0;        // state at step start (stage-3 output)
+  double* v0;
+  double* ua; // accumulators
+  double* va;
+  double* un; // stage inputs of stages 1..3 (read as ku = vn, rewritten for the next stage)
+  double* vn;
+  long long nowned;
+  long long ntotal;
+  double a_next_dt; // a_{i+1} * dt
+  double bw_dt;     // b_i * dt
+};
+
+template <int STAGE, bool WESTERVELT>
+__global__ void __launch_bounds__(256) rk4_stage_kernel(const StageArgs A) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = i0; i < A.nowned; i += stride) {
+    double b = A.b[i];
+    const double u0 = (STAGE < 3) ? A.u0[i] : 0.0;
+    const double v0 = (STAGE < 3) ? A.v0[i] : 0.0;
+    const double vn = (STAGE == 0) ? v0 : A.vn[i];
+    double m = A.m[i];
+    if constexpr (WESTERVELT) {
+      const double un = (STAGE == 0) ? u0 : A.un[i];
+      const double d = A.dnl[i];
+      m = m - d * un;
+      b = b + d * (vn * vn);
+    }
+    const double kv = b / m;
+    double ua, va;
+    if constexpr (STAGE == 0) {
+      ua = fma(vn, A.bw_dt, u0);
+      va = fma(kv, A.bw_dt, v0);
+    } else {
+      ua = fma(vn, A.bw_dt, A.ua[i]);
+      va = fma(kv, A.bw_dt, A.va[i]);
+    }
+    if constexpr (STAGE < 3) {
+      A.ua[i] = ua;
+      A.va[i] = va;
+      A.un[i] = fma(vn, A.a_next_dt, u0);
+      A.vn[i] = fma(kv, A.a_next_dt, v0);
+    } else {
+      A.u0[i] = ua;
+      A.v0[i] = va;
+    }
+    A.b[i] = 0.0;
+  }
+  for (long long i = A.nowned + i0; i < A.ntotal; i += stride)
+    A.b[i] = 0.0; // ghost partial sums have been sent to their owners
+}
+
+// out = b / m (Westervelt: with the solution-dependent terms) -- single f1 evaluation for tests
+template <bool WESTERVELT>
+__global__ void __launch_bounds__(256)
+    f1_finish_kernel(const double* __restrict__ b, const double* __restrict__ m,
+                     const double* __restrict__ dnl, const double* __restrict__ un,
+                     const double* __restrict__ vn, double* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double bb = b[i], mm = m[i];
+    if constexpr (WESTERVELT) {
+      mm = mm - dnl[i] * un[i];
+      bb = bb + dnl[i] * (vn[i] * vn[i]);
+    }
+    out[i] = bb / mm;
+  }
+}
+
+// y[i] += a[i]
+static __global__ void __launch_bounds__(256)
+    add_kernel(double* __restrict__ y, const double* __restrict__ a, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    y[i] += a[i];
+}
+
+} // namespace fus

@@ -1,0 +1,192 @@
+/*
+ * fus_b200.h -- C ABI of the B200-native sum-factorised acoustic operator + RK4 path.
+ *
+ * This is the drop-in boundary for the hot path of adeebkor/fenicsx-fus
+ * (cpp/fenicsx-sf/common/).  Plain pointers and sizes only; no C++/torch types.
+ * Each entry point names the reference interface it stands in for (paths relative to
+ * cpp/fenicsx-sf/common/ of the reference).  All functions return FUS_OK (0) or a
+ * negative error code and never throw; fus_last_error() gives the message.
+ *
+ * There is NO CPU fallback: every compute entry point fails with FUS_ERR_CUDA when no
+ * sm_100 device is usable.
+ *
+ * Conventions:
+ *   N = P+1 nodes/points per direction, Nd = N^3, tensor index i = i0*N*N + i1*N + i2 with i0 <->
+ *   reference direction 0; 1-D node order [0, 1, interior ascending] (Basix);
+ *   dphi[q*N+i] = phi_i'(xi_q);  G[c][q][6] = {G00,G01,G02,G11,G12,G22} * |detJ| * w_q;
+ *   local vectors hold `nowned` owned entries first, then ghosts.
+ */
+#ifndef FUS_B200_H
+#define FUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FUS_OK 0
+#define FUS_ERR_ARG (-1)
+#define FUS_ERR_CUDA (-2)
+#define FUS_ERR_UNSUPPORTED (-3)
+#define FUS_ERR_STATE (-4)
+#define FUS_ERR_COMM (-5)
+
+#define FUS_LINEAR 0     /* LinearSpectral3D      (Linear.hpp:52)      */
+#define FUS_LOSSY 1      /* LossySpectral3D       (Lossy.hpp:54)       */
+#define FUS_WESTERVELT 2 /* WesterveltSpectral3D  (Westervelt.hpp:56)  */
+
+typedef struct fus_ctx fus_ctx;     /* what the operator constructors build (spectral_op.hpp:135-171) */
+typedef struct fus_model fus_model; /* what the solver constructors build   (Linear.hpp:55-158)       */
+
+const char* fus_last_error(void);
+int fus_version(void);
+/* number of usable sm_100 devices (0 when none; never an error) */
+int fus_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side setup (CPU, runs once): the Basix / DOLFINx calls of the reference constructors.
+ * ---------------------------------------------------------------------------------------- */
+
+/* GLL rule with P+1 points on [0,1], Basix order.
+   Replaces basix::quadrature::make_quadrature(gll, interval, Qdegree[P]) (spectral_op.hpp:35-59). */
+int fus_gll(int P, double* pts, double* wts);
+
+/* Derivative block of tabulate_1d (precompute.hpp:217-234, spectral_op.hpp:168-170): dphi[N*N]. */
+int fus_tabulate_dphi(int P, double* dphi);
+
+/* Structured hexahedral box [lo,hi] with n[3] cells: vertex coordinates xg[nverts][3] and the
+   cell->vertex map xdofmap[ncells][8] in DOLFINx tensor vertex order (x fastest).
+   Replaces dolfinx::mesh::create_box (experiments/measure_fraction_of_peak_performance/main.cpp:61-65). */
+int fus_box_mesh(const int n[3], const double lo[3], const double hi[3], double* xg,
+                 int32_t* xdofmap);
+
+/* Tensor-product dofmap of degree P on that box: tensor_dofmap[ncells][Nd].
+   Replaces create_functionspace + reorder_dofmap (permute.hpp:15-42).
+   numbering 0: lexicographic (x slowest); 1: cell-blocked (dofs of one cell contiguous). */
+int fus_box_dofmap(int P, const int n[3], int numbering, int32_t* tensor_dofmap);
+int64_t fus_box_num_dofs(int P, const int n[3]);
+
+/* Exterior facets of the box as {cell, local facet, tag} triplets; tag 1 on x=lo, 2 on x=hi,
+   0 elsewhere.  facets may be NULL to query the count.  Returns the count (>=0) or an error. */
+int64_t fus_box_facets(const int n[3], int32_t* facets);
+
+/* Facet-lumped boundary vectors for a model kind.  With GLL quadrature the FFCx `ds` kernels of
+   forms.py are collocated, so each boundary term is a diagonal vector times a nodal value
+   (benchmarks/PH1/BM7-SC1/forms.py:37-42; fenicsx-sf-naive/benchmarks/PH1/SC2-BM1/forms.py:35-38).
+   Inputs: mesh geometry, tensor dofmap, facets {cell, lf, tag}, per-cell c0/rho0/delta0 (delta0 may
+   be NULL for FUS_LINEAR).  Outputs are dense over the local dofs (ndofs each, zero off-boundary):
+     src   multiplies g(t):   S^(1/rho)(tag 1)
+     dsrc  multiplies dg(t):  S^(delta/rho c^2)(tag 1)             [lossy, westervelt]
+     absb  multiplies -v:     S^(1/rho c)(tag 2)  for linear,  S^(1/rho c)(all exterior) otherwise
+     bmass added to the lumped mass: S^(delta/rho c^3)(all exterior) [lossy, westervelt] */
+int fus_boundary_vectors(int kind, int P, int64_t ncells, int64_t ndofs, const double* xg,
+                         const int32_t* xdofmap, const int32_t* tensor_dofmap, int64_t nfacets,
+                         const int32_t* facets, const double* c0, const double* rho0,
+                         const double* delta0, double* src, double* dsrc, double* absb,
+                         double* bmass);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator context (device).  Owns device copies of the cell data; host arrays are only
+ * borrowed during the call.
+ * ---------------------------------------------------------------------------------------- */
+
+/* From precomputed host arrays in the reference's layouts -- the members the reference operator
+   classes hold (spectral_op.hpp:256-264): tensor_dofmap[ncells*Nd], G[ncells*Nd*6] (may be NULL if
+   only the mass operator is needed), detJ[ncells*Nd] (may be NULL if only stiffness), dphi[N*N]. */
+int fus_ctx_create(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                   const int32_t* tensor_dofmap, const double* G, const double* detJ,
+                   const double* dphi, int device, fus_ctx** out);
+
+/* From the mesh: G and detJ are evaluated on the device from the trilinear geometry
+   (compute_scaled_geometrical_factor / compute_scaled_jacobian_determinant, precompute.hpp:33-213)
+   and the 1-D tables are generated internally (fus_gll / fus_tabulate_dphi). */
+int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                             const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                             const int32_t* xdofmap, int device, fus_ctx** out);
+
+int fus_ctx_destroy(fus_ctx* ctx);
+
+/* Launch all work of this context on the given cudaStream_t (default: a private stream). */
+int fus_ctx_set_stream(fus_ctx* ctx, void* cuda_stream);
+/* Tuning/diagnostic knobs: "stiffness_variant" (0 = column kernel, 1 = per-point kernel). */
+int fus_ctx_set_option(fus_ctx* ctx, const char* name, int value);
+int fus_ctx_sync(fus_ctx* ctx);
+
+/* Read the device cell data back in the reference layouts (tests; G or detJ may be NULL). */
+int fus_ctx_get_geometry(fus_ctx* ctx, double* G, double* detJ);
+
+/* y += K(coeffs) x  -- StiffnessSpectral3D::operator() (spectral_op.hpp:173-243).
+   Accumulates into y (caller zero-fills, Linear.hpp:203); loops local cells only; x must hold
+   fresh ghosts; coeffs indexed by local cell.  *_dev take device pointers and are stream-ordered;
+   *_host take host buffers of ndofs / ncells entries and include the copies. */
+int fus_stiffness_apply_dev(fus_ctx* ctx, const double* x, const double* coeffs, double* y);
+int fus_stiffness_apply_host(fus_ctx* ctx, const double* x, const double* coeffs, double* y);
+
+/* y += M(coeffs) x  -- MassSpectral3D::operator() (spectral_op.hpp:69-86). */
+int fus_mass_apply_dev(fus_ctx* ctx, const double* x, const double* coeffs, double* y);
+int fus_mass_apply_host(fus_ctx* ctx, const double* x, const double* coeffs, double* y);
+
+/* Device buffers for callers without a CUDA runtime of their own (C, ctypes). */
+int fus_dev_alloc(fus_ctx* ctx, size_t bytes, void** ptr);
+int fus_dev_free(fus_ctx* ctx, void* ptr);
+int fus_dev_upload(fus_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int fus_dev_download(fus_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int fus_dev_memset(fus_ctx* ctx, void* dst_dev, int value, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Models: {Linear,Lossy,Westervelt}Spectral3D (Linear.hpp:52-347, Lossy.hpp:54-373,
+ * Westervelt.hpp:56-406).  Per-cell material arrays are host arrays of ncells entries; the
+ * boundary vectors are the dense outputs of fus_boundary_vectors (NULL = all zero).
+ * The lumped mass m = M(1/rho c^2) 1 + bmass is assembled on the device (Linear.hpp:127-134).
+ * ---------------------------------------------------------------------------------------- */
+int fus_model_create(fus_ctx* ctx, int kind, const double* c0, const double* rho0,
+                     const double* delta0, const double* beta0, const double* src,
+                     const double* dsrc, const double* absb, const double* bmass, double freq,
+                     double p0, double s0, fus_model** out);
+int fus_model_destroy(fus_model* m);
+
+/* init() (Linear.hpp:161-164) when u,v are NULL; otherwise sets u_n, v_n from host arrays. */
+int fus_model_set_state(fus_model* m, const double* u, const double* v);
+/* u_sol() (Linear.hpp:316): copies u_n (and v_n) back; either may be NULL. */
+int fus_model_get_state(fus_model* m, double* u, double* v);
+/* Device pointers to u_n / v_n (ndofs doubles each). */
+int fus_model_state_dev(fus_model* m, double** u, double** v);
+/* The assembled lumped mass (m, or m0 for Westervelt), ndofs entries. */
+int fus_model_get_mass(fus_model* m, double* mass);
+
+/* kv = f1(t, u, v) for host u, v (Linear.hpp:181-222); a single stage evaluation, for tests. */
+int fus_model_f1(fus_model* m, double t, const double* u, const double* v, double* result);
+
+/* rk4(startTime, finalTime, timeStep) (Linear.hpp:228-314): runs entirely on the device from the
+   current state; same host-side time arithmetic as the reference loop.  nsteps (may be NULL)
+   receives the number of steps taken.  Asynchronous on the context stream until the state is read. */
+int fus_model_rk4(fus_model* m, double t0, double tf, double dt, int* nsteps);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t fus_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU halo exchange: replaces la::Vector::scatter_fwd / scatter_rev(std::plus)
+ * (call sites Linear.hpp:196,199,206; Westervelt.hpp:243,246,257,265) with NCCL send/recv.
+ * One context per GPU/process.  Neighbour k exchanges send_idx[send_off[k]:send_off[k+1]] (local
+ * indices of OWNED dofs that are ghosts on rank neigh[k]) and recv_idx[recv_off[k]:...] (local
+ * indices of GHOST dofs owned by neigh[k]), in matching order on both sides.
+ * `nccl_unique_id` is the 128-byte ncclUniqueId made by fus_comm_unique_id on rank 0 and
+ * distributed by the caller (e.g. torch.distributed broadcast).
+ * `ninterface_cells`: cells [0, ninterface_cells) touch shared dofs and are applied first so that
+ * the reverse exchange overlaps with the remaining interior cells.
+ * ---------------------------------------------------------------------------------------- */
+int fus_comm_unique_id(void* id128);
+int fus_halo_setup(fus_ctx* ctx, int rank, int nranks, const void* nccl_unique_id, int nneigh,
+                   const int* neigh, const int64_t* send_off, const int32_t* send_idx,
+                   const int64_t* recv_off, const int32_t* recv_idx, int64_t ninterface_cells);
+/* Stand-alone collectives on device vectors (tests): owner -> ghost, ghost -> owner (+=). */
+int fus_scatter_fwd_dev(fus_ctx* ctx, double* x);
+int fus_scatter_rev_dev(fus_ctx* ctx, double* x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUS_B200_H */

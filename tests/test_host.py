@@ -1,0 +1,124 @@
+"""CPU tests of the product's host side: set-up arithmetic vs the oracle, the C-ABI surface, and
+loud failure without a GPU.  No device compute here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2, warp_vertices
+
+
+def test_capi_exports_every_declared_symbol(fus):
+    """include/fus_b200.h and the built library agree symbol for symbol."""
+    hdr = open(os.path.join(ROOT, "include", "fus_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fus_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    from fenicsx_fus_b200 import capi
+    lib = capi.load()
+    for name in declared:
+        assert hasattr(lib, name), f"library lacks {name}"
+    assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
+    assert lib.fus_version() >= 100
+
+
+@pytest.mark.parametrize("P", range(1, 8))
+def test_tables_vs_oracle(fus, orc, P):
+    p, w = fus.gll(P)
+    po, wo = orc.gll(P + 1)
+    assert np.allclose(p, po, rtol=0, atol=2e-16) and np.allclose(w, wo, rtol=0, atol=2e-16)
+    d, do = fus.tabulate_dphi(P), orc.dphi(P)
+    assert np.allclose(d, do, rtol=0, atol=5e-15 * np.abs(do).max())
+
+
+@pytest.mark.parametrize("n,P,mode", [((1, 1, 1), 2, 0), ((3, 2, 4), 3, 0), ((3, 2, 4), 3, 1),
+                                      ((2, 2, 2), 7, 1), ((5, 1, 2), 1, 1)])
+def test_box_mesh_and_dofmap_bit_exact(fus, orc, n, P, mode):
+    m = fus.BoxMesh(n, (0.1, 0.0, -1.0), (1.0, 2.0, 3.0))
+    xg, xd = orc.box_mesh(n, (0.1, 0.0, -1.0), (1.0, 2.0, 3.0))
+    assert np.array_equal(m.x, xg) and np.array_equal(m.xdofmap, xd)
+    assert np.array_equal(m.facets, orc.box_facets(n))
+    V = fus.FunctionSpace(m, P, numbering=mode)
+    dm = orc.box_dofmap(P, n, mode)
+    assert np.array_equal(V.dofmap, dm)                     # gather/scatter indices: bit-exact
+    assert V.ndofs == dm.max() + 1 == len(np.unique(dm))
+    # collocation: node i of a cell sits at quadrature point i
+    X = V.tabulate_dof_coordinates()
+    pts, _ = orc.gll(P + 1)
+    h = (np.array([1.0, 2.0, 3.0]) - np.array([0.1, 0.0, -1.0])) / np.array(n)
+    c = 0
+    i0, i1, i2 = 1, min(2, P), 0
+    node = dm[c, (i0 * (P + 1) + i1) * (P + 1) + i2]
+    assert np.allclose(X[node], np.array([0.1, 0.0, -1.0]) + h * np.array([pts[i0], pts[i1], pts[i2]]))
+
+
+@pytest.mark.parametrize("kind", ["linear", "lossy", "westervelt"])
+def test_boundary_vectors_vs_oracle_facet_assembly(fus, orc, kind):
+    """The lumped vectors reproduce the oracle's facet-by-facet assembly of L and of the facet
+    part of a (forms.py)."""
+    from fenicsx_fus_b200 import capi
+    P, n = 3, (3, 2, 2)
+    m = fus.BoxMesh(n, (0, 0, 0), (0.3, 0.2, 0.2), warp=lambda x: warp_vertices(x, 0.07, 5))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    nc, nd = m.ncells, V.ndofs
+    rng = np.random.default_rng(3)
+    c0, rho0 = rng.uniform(1400, 2500, nc), rng.uniform(900, 1900, nc)
+    delta0, beta0 = rng.uniform(1e-3, 5e-3, nc), rng.uniform(3, 5, nc)
+    src, dsrc, absb, bmass = (np.zeros(nd) for _ in range(4))
+    lib = capi.load()
+    rc = lib.fus_boundary_vectors(capi.KINDS[kind], P, nc, nd, m.x, m.xdofmap, V.dofmap,
+                                  m.facets.shape[0], m.facets, c0, rho0, capi.optional(delta0),
+                                  capi.optional(src), capi.optional(dsrc), capi.optional(absb),
+                                  capi.optional(bmass))
+    assert rc == 0
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    mdl = orc.model(kind, P, nd, V.dofmap, G, dJ, orc.dphi(P), c0, rho0, delta0, beta0, m.facets,
+                    fn, fs, 0.5e6, 1e5, 1500.0)
+    # mass: oracle's assembled m minus the volume part = facet mass
+    vol = orc.mass_apply(P, V.dofmap, dJ, 1 / rho0 / c0 ** 2, np.ones(nd), np.zeros(nd))
+    assert rel_l2(vol + bmass, mdl.mass()) < 1e-14
+    if kind == "linear":
+        assert not bmass.any() and not dsrc.any()
+    # L: with K u removed (u = 0) f1*m = g*src + dg*dsrc - absb*v
+    t = 0.7e-6
+    v = rng.uniform(-1, 1, nd)
+    b = mdl.f1(t, np.zeros(nd), v) * mdl.mass()
+    if kind == "westervelt":
+        pytest.skip("westervelt f1 has the solution-dependent mass; covered by linear/lossy here")
+    f, p0, s0, w0 = 0.5e6, 1e5, 1500.0, 2 * np.pi * 0.5e6
+    win = 0.5 * (1 - np.cos(f * np.pi * t / 4))
+    dwin = 0.5 * np.pi * f / 4 * np.sin(f * np.pi * t / 4)
+    if kind == "linear":
+        g, dg = win * p0 * w0 / s0 * np.cos(w0 * t), 0.0
+        kv = np.zeros(nd)
+    else:
+        g = win * 2 * p0 * w0 / s0 * np.cos(w0 * t)
+        dg = dwin * 2 * p0 * w0 / s0 * np.cos(w0 * t) - win * 2 * p0 * w0 * w0 / s0 * np.sin(w0 * t)
+        kv = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), -delta0 / rho0 / c0 ** 2, v, np.zeros(nd))
+    assert rel_l2(g * src + dg * dsrc - absb * v + kv, b) < 1e-13
+
+
+def test_compute_paths_fail_loudly_without_gpu(fus):
+    """No CPU fallback: creating a context without a usable device is an error."""
+    if fus.device_count() > 0:
+        pytest.skip("a GPU is present")
+    m = fus.BoxMesh((1, 1, 1))
+    V = fus.FunctionSpace(m, 2)
+    with pytest.raises(fus.FusError, match="no usable CUDA device|CUDA"):
+        V.context()
+
+
+def test_bad_arguments_are_errors_not_crashes(fus):
+    from fenicsx_fus_b200 import capi
+    lib = capi.load()
+    assert lib.fus_gll(0, np.zeros(4), np.zeros(4)) < 0
+    assert lib.fus_box_dofmap(2, np.array([1, 0, 1], dtype=np.int32), 0, np.zeros(27, dtype=np.int32)) < 0
+    h = C.c_void_p()
+    # degree outside 1..7 -> FUS_ERR_UNSUPPORTED (the reference silently maps unknown P to Qdegree 0,
+    # spectral_op.hpp:59)
+    rc = lib.fus_ctx_create(9, 1, 1000, 1000, np.zeros(1000, dtype=np.int32), None, None,
+                            np.zeros(100), 0, C.byref(h))
+    assert rc < 0 and lib.fus_last_error()
