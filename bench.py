@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (see DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json metric "FP64 DOF-updates/sec (operator+RK4)"): LinearSpectral3D RK4 on the
+P=4 GLL hex box of 54^3 cells per GPU (10.2 M dofs; SURVEY.md section 8d config 1 at the config-2
+size); one "step" is one RK4 time step = 4 fused stages (operator + epilogue).  For N > 1 the mesh
+is the union of Px x Py x Pz such boxes (weak scaling), partitioned one box per GPU with an NCCL
+halo exchange per stage.
+
+Prints ONE JSON line on rank 0.  `value` is device-resident throughput, `e2e` the same metric
+through the host-facing call sequence init(u,v) -> rk4 -> u_sol() with host buffers and the copies
+inside the timed region, `roofline` the dominant kernel (stiffness operator) against the measured
+HBM peak, `cpu_baseline` the reference kernels (oracle/_ref) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_BENCH = 4
+N_BENCH = 54               # cells per direction per GPU
+BOX_LEN = 0.12             # m (SC2-BM1/main.cpp:41)
+C0, RHO0 = 1500.0, 1000.0  # water (SC2-BM1/main.cpp:37-38)
+FREQ, P0 = 0.5e6, 60000.0
+CFL = 0.65
+METRIC = "FP64 DOF-updates/sec (operator+RK4)"
+UNIT = "DOF-updates/s"
+PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def timestep(P, h_edge, c):
+    """Time step of every reference driver (BM7-SC1/main.cpp:112-118): CFL on the cell diameter,
+    snapped to an integer number of steps per period."""
+    dt0 = CFL * (np.sqrt(3.0) * h_edge) / (c * P * P)
+    steps_per_period = int((1.0 / FREQ) / dt0) + 1
+    return (1.0 / FREQ) / steps_per_period
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU side: the reference kernels on the host cores (oracle/_ref)
+# --------------------------------------------------------------------------------------------
+def cpu_linear_rk4(n_cells, steps, warmup, threads=None, budget_s=None):
+    """LinearSpectral3D RK4 on a P=4 box of n_cells^3 cells, with the cell loops running on the
+    reference's own sum_factorisation.hpp (oracle/_ref), one OpenMP thread per contiguous cell
+    range.  Returns (dof_updates_per_s, cores, steps_done, ndofs, kind)."""
+    from oracle.oracle import Oracle, ref_available
+    use_ref = ref_available() or os.path.isdir("/root/reference/cpp/fenicsx-sf/common")
+    orc = Oracle(ref=use_ref)
+    kind = "reference" if use_ref else "port"
+    cores = os.cpu_count() or 1
+    if threads:
+        cores = threads
+    if use_ref:
+        orc.lib.fr_set_threads(cores)
+    else:
+        cores = 1
+    P, n = P_BENCH, (n_cells,) * 3
+    h = BOX_LEN / N_BENCH                      # same cell size as the GPU workload
+    xg, xd = orc.box_mesh(n, (0, 0, 0), (h * n_cells,) * 3)
+    dm = orc.box_dofmap(P, n, 0)
+    nd = int(dm.max()) + 1
+    G, dJ = orc.geometry(P, xg, xd)
+    facets = orc.box_facets(n)
+    fn, fs = orc.facet_data(P, xg, xd, facets)
+    nc = dm.shape[0]
+    mdl = orc.model("linear", P, nd, dm, G, dJ, orc.dphi(P), np.full(nc, C0), np.full(nc, RHO0),
+                    None, None, facets, fn, fs, FREQ, P0, C0, use_ref_kernels=use_ref)
+    dt = timestep(P, h, C0)
+    u, v = np.zeros(nd), np.zeros(nd)
+    t = 0.0
+    if warmup:
+        mdl.rk4(t, t + (warmup - 0.5) * dt, dt, u, v)
+        t += warmup * dt
+    t0 = time.perf_counter()
+    done = 0
+    if budget_s is None:
+        done = mdl.rk4(t, t + (steps - 0.5) * dt, dt, u, v)
+    else:
+        while done < steps and (time.perf_counter() - t0) < budget_s:
+            done += mdl.rk4(t, t + 0.5 * dt, dt, u, v)
+            t += dt
+    el = time.perf_counter() - t0
+    assert np.isfinite(u).all()
+    return nd * done / el, cores, done, nd, kind, el
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU path for the same metric/config on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # full workload if it fits a few minutes, else a bounded sample of it
+    n_cells = N_BENCH
+    probe, cores, _, _, kind, _ = cpu_linear_rk4(18, 2, 1)
+    est = (N_BENCH * P_BENCH + 1) ** 3 * (args.steps + args.warmup) / probe
+    if est > 150.0:
+        n_cells = 27
+    val, cores, done, nd, kind, el = cpu_linear_rk4(n_cells, args.steps, args.warmup)
+    sample = (f"LinearSpectral3D RK4, P={P_BENCH}, box {n_cells}^3 cells ({nd} dofs), {done} steps, "
+              f"{cores} OpenMP threads as ranks, cell loops on the reference's sum_factorisation.hpp")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"linear_rk4_P{P_BENCH}_box{n_cells}", "dofs": nd,
+                   "full_size": n_cells == N_BENCH},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import fenicsx_fus_b200 as fus
+    from fenicsx_fus_b200 import partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    if fus.device_count() < 1:
+        raise SystemExit("bench.py: no B200 visible and there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    P = P_BENCH
+    pg = PGRID[world]
+    h = BOX_LEN / N_BENCH
+    n_global = tuple(N_BENCH * p for p in pg)
+    # local part of the global box, local dof numbering (owned first, then ghosts), halo lists
+    part = partition.BoxPartition(P, n_global, pg, rank, lo=(0.0, 0.0, 0.0),
+                                  hi=tuple(h * n for n in n_global))
+    V = part.function_space(device=local_rank)
+    ctx = V.context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        part.setup_halo(ctx, dist)
+    mdl = fus.LinearSpectral3D(V, C0, RHO0, FREQ, P0, C0, facets=part.facets, device=local_rank)
+    dt = timestep(P, h, C0)
+    ndofs_global = part.ndofs_global
+    K, W = args.steps, max(args.warmup, 0)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------
+    mdl.init()
+    t = 0.0
+    if W:
+        assert mdl.rk4(t, t + (W - 0.5) * dt, dt) == W
+        t += W * dt
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.set_option("profile_kernels", 1)
+    launches0 = fus.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    done = mdl.rk4(t, t + (K - 0.5) * dt, dt)
+    ev1.record(stream)
+    sync_all()
+    launches = fus.launch_count() - launches0
+    ctx.set_option("profile_kernels", 0)
+    clocks = sampler.stop() if rank == 0 else None
+    assert done == K, (done, K)
+    t += K * dt
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = ndofs_global * K / (ms_total * 1e-3)
+    n_st, ms_st = ctx.profile("stiffness")
+    n_ep, ms_ep = ctx.profile("stage")
+    u_probe = mdl.u_sol()
+    assert np.isfinite(u_probe).all() and np.abs(u_probe).max() > 0.0
+
+    # ---- end to end through the host-facing calls, host buffers, copies timed --------------
+    nloc = V.ndofs
+    u_host = torch.zeros(nloc, dtype=torch.float64).pin_memory()
+    v_host = torch.zeros(nloc, dtype=torch.float64).pin_memory()
+    u_host.numpy()[:] = u_probe
+    v_host.numpy()[:] = mdl.v_sol()
+    uh, vh = u_host.numpy(), v_host.numpy()
+    sync_all()
+    t_e0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    mdl.init(uh, vh)                                   # H2D of the state (2 vectors)
+    done = mdl.rk4(t, t + (K - 0.5) * dt, dt)          # K steps on the device
+    fus.check(mdl.lib.fus_model_get_state(mdl.h, uh.ctypes.data, vh.ctypes.data), "get_state")
+    e1.record(stream)                                  # D2H of the result (2 vectors) done
+    sync_all()
+    wall_e2e = time.perf_counter() - t_e0
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = max(float(ms2.item()), 0.0)
+    e2e_value = ndofs_global * K / (ms_e2e * 1e-3)
+    bytes_state = 2 * 8 * nloc
+
+    # ---- step with a host round trip of the state around EVERY step (extra information) ----
+    kr = min(K, 5)
+    sync_all()
+    t_r0 = time.perf_counter()
+    for _ in range(kr):
+        mdl.init(uh, vh)
+        mdl.rk4(t, t + 0.5 * dt, dt)
+        fus.check(mdl.lib.fus_model_get_state(mdl.h, uh.ctypes.data, vh.ctypes.data), "get_state")
+    sync_all()
+    roundtrip_value = ndofs_global * kr / (time.perf_counter() - t_r0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (stiffness operator) -------------------------------
+    peak, peak_src = measured_peaks()
+    npts_loc = part.ncells * (P + 1) ** 3
+    alg_bytes = 52.0 * npts_loc + 16.0 * nloc       # 48 B G + 4 B dofmap per point; x read, y write
+    avg_ms = ms_st / max(n_st, 1)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    # whole-step algorithmic bytes: 4 * (52 r + 112) per dof
+    step_bytes = 4.0 * (52.0 * npts_loc + 112.0 * nloc)
+    step_gbs = step_bytes * K / (ms_total * 1e-3) / 1e9
+
+    # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            val, cores, sdone, snd, kind, el = cpu_linear_rk4(30, 50, 1, budget_s=12.0)
+            cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": (f"same model on a P=4 box of 30^3 cells ({snd} dofs), {sdone} steps in "
+                              f"{el:.1f} s, {cores} OpenMP threads as ranks")}
+        except Exception as ex:  # the baseline must never sink the GPU measurement
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable",
+                   "sample": repr(ex)[:200]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"linear_rk4_P{P}_box{N_BENCH}_per_gpu", "degree": P,
+                   "cells_per_gpu": part.ncells, "dofs_global": ndofs_global,
+                   "process_grid": list(pg), "dt": dt,
+                   "l2": "inputs_exceed_l2 (945 MB of geometric factors streamed per stage)",
+                   "parallelism": f"mesh partition {pg[0]}x{pg[1]}x{pg[2]}, NCCL halo"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state / K,
+                "d2h_bytes_per_step": bytes_state / K,
+                "note": ("init(u,v) from pinned host + rk4(K steps) + u_sol()/v_sol() to host, all "
+                         "inside the timed region; the state stays resident across steps as in the "
+                         "reference's rk4 loop"),
+                "wall_s": wall_e2e,
+                "roundtrip_every_step_value": roundtrip_value},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "stiffness_col_kernel<5,false>",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "launches": int(n_st),
+                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "stage_epilogue_avg_ms": ms_ep / max(n_ep, 1),
+                     "step_algorithmic_gbs": step_gbs, "step_frac": step_gbs / peak},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus not in PGRID:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

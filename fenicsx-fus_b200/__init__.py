@@ -157,6 +157,13 @@ class Context:
     def sync(self):
         check(self.lib.fus_ctx_sync(self.h), "fus_ctx_sync")
 
+    def profile(self, kernel):
+        """(launches, total device ms) of one kernel family since option profile_kernels=1."""
+        n, ms = C.c_int64(0), C.c_double(0.0)
+        check(self.lib.fus_ctx_profile(self.h, kernel.encode(), C.byref(n), C.byref(ms)),
+              "fus_ctx_profile")
+        return n.value, ms.value
+
     def geometry(self, want_G=True, want_detJ=True):
         Nd = (self.P + 1) ** 3
         G = np.zeros((self.ncells, Nd, 6)) if want_G else None

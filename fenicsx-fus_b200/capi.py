@@ -63,6 +63,7 @@ SIGNATURES = {
     "fus_model_f1": (_int, [_p, _dbl, _f64, _f64, _f64]),
     "fus_model_rk4": (_int, [_p, _dbl, _dbl, _dbl, C.POINTER(_int)]),
     "fus_launch_count": (_ll, []),
+    "fus_ctx_profile": (_int, [_p, C.c_char_p, C.POINTER(_ll), C.POINTER(_dbl)]),
     "fus_comm_unique_id": (_int, [_p]),
     "fus_halo_setup": (_int, [_p, _int, _int, _p, _int, _p, _p, _p, _p, _p, _ll]),
     "fus_scatter_fwd_dev": (_int, [_p, _p]),

@@ -79,7 +79,39 @@ struct fus_ctx {
   int variant = 0; // 0 column kernel, 1 point kernel
   int col_blocks_per_sm = 0;
   Halo* halo = nullptr;
+  // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];
+  size_t prof_used[3] = {0, 0, 0};
 };
+
+namespace {
+// RAII event bracket around one launch; a no-op unless profiling is on.
+struct ProfScope {
+  fus_ctx* c;
+  int fam;
+  cudaStream_t st;
+  cudaEvent_t stop = nullptr;
+  ProfScope(fus_ctx* c_, int fam_, cudaStream_t st_) : c(c_), fam(fam_), st(st_) {
+    if (!c->profile)
+      return;
+    auto& ev = c->prof_events[fam];
+    if (c->prof_used[fam] == ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess)
+        return;
+      ev.push_back({a, b});
+    }
+    auto& pr = ev[c->prof_used[fam]++];
+    cudaEventRecord(pr.first, st);
+    stop = pr.second;
+  }
+  ~ProfScope() {
+    if (stop)
+      cudaEventRecord(stop, st);
+  }
+};
+} // namespace
 
 struct fus_model {
   fus_ctx* ctx = nullptr;
@@ -117,6 +149,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
   const bool fuse = (x2 != nullptr);
   if (c->variant == 1) {
+    ProfScope prof(c, 0, st);
     const int blocks = (int)std::min<long long>(ce - cb, (long long)c->num_sms * 16);
     if (fuse)
       stiffness_point_kernel<N, true><<<blocks, N * N * N, 0, st>>>(
@@ -145,6 +178,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     }
     configured = true;
   }
+  ProfScope prof(c, 0, st);
   int bps = fuse ? bps_fuse : bps_plain;
   if (c->col_blocks_per_sm > 0)
     bps = std::min(bps, c->col_blocks_per_sm);
@@ -434,6 +468,11 @@ int fus_ctx_destroy(fus_ctx* c) {
     cudaStreamSynchronize(c->stream);
   if (c->halo)
     halo_destroy(c->halo);
+  for (auto& fam : c->prof_events)
+    for (auto& pr : fam) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
   cudaFree(c->d_dofmap);
   cudaFree(c->d_G2);
   cudaFree(c->d_detJ);
@@ -464,6 +503,13 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
     c->variant = value;
     return FUS_OK;
   }
+  if (!std::strcmp(name, "profile_kernels")) {
+    c->profile = value != 0;
+    if (value)
+      for (int f = 0; f < 3; ++f)
+        c->prof_used[f] = 0;
+    return FUS_OK;
+  }
   if (!std::strcmp(name, "col_blocks_per_sm")) {
     c->col_blocks_per_sm = value;
     return FUS_OK;
@@ -481,6 +527,33 @@ int fus_ctx_sync(fus_ctx* c) {
     return FUS_ERR_ARG;
   FUS_TRY(select_device(c));
   FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+int fus_ctx_profile(fus_ctx* c, const char* kernel, int64_t* launches, double* total_ms) {
+  if (!c || !kernel || !launches || !total_ms)
+    return FUS_ERR_ARG;
+  int fam = -1;
+  if (!std::strcmp(kernel, "stiffness"))
+    fam = 0;
+  else if (!std::strcmp(kernel, "stage"))
+    fam = 1;
+  else if (!std::strcmp(kernel, "boundary"))
+    fam = 2;
+  if (fam < 0) {
+    set_error("unknown kernel family %s", kernel);
+    return FUS_ERR_ARG;
+  }
+  FUS_TRY(select_device(c));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i < c->prof_used[fam]; ++i) {
+    float ms = 0.f;
+    FUS_CUDA(cudaEventElapsedTime(&ms, c->prof_events[fam][i].first, c->prof_events[fam][i].second));
+    tot += ms;
+  }
+  *launches = (int64_t)c->prof_used[fam];
+  *total_ms = tot;
   return FUS_OK;
 }
 
@@ -796,6 +869,7 @@ static int assemble_rhs(fus_model* m, double t, const double* u, const double* v
   const double* c2 = (m->kind >= FUS_LOSSY) ? m->d_att : nullptr;
   auto boundary = [&]() -> int {
     if (m->nb) {
+      ProfScope prof(c, 2, c->stream);
       boundary_kernel<<<grid_for(m->nb, 256, 1 << 30), 256, 0, c->stream>>>(
           m->d_b, v, m->d_bidx, m->d_bsrc, m->d_bdsrc, m->d_babs, m->nb, g, dg);
       FUS_LAUNCHED();
@@ -849,6 +923,7 @@ int fus_model_f1(fus_model* m, double t, const double* u, const double* v, doubl
 template <int STAGE>
 static int launch_stage(fus_model* m, const StageArgs& A) {
   fus_ctx* c = m->ctx;
+  ProfScope prof(c, 1, c->stream);
   const int grid = grid_for(A.ntotal, 256, c->num_sms * 8);
   if (m->kind == FUS_WESTERVELT)
     rk4_stage_kernel<STAGE, true><<<grid, 256, 0, c->stream>>>(A);

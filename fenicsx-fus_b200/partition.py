@@ -1,0 +1,250 @@
+"""Mesh partition of a structured box over a Px x Py x Pz process grid (one block per GPU).
+
+Mirrors the reference's distributed model: cells are partitioned without
+ghost cells (GhostMode::none, BM7-SC1/main.cpp:58-59), a dof on a partition interface is owned by
+exactly one rank and ghosted on the others, local vectors hold the owned entries first and the
+ghosts after them (relied on by kernels::axpy, Linear.hpp:35), and each operator application is
+preceded by an owner->ghost update and followed by a ghost->owner sum
+(scatter_fwd / scatter_rev, Linear.hpp:196-206).
+
+Ownership rule: an interface node belongs to the block with the lowest grid coordinates among
+those sharing it, so the ghosts of a block sit on its lower faces.
+Cells that touch a shared dof ("interface cells") are ordered first so that the reverse exchange
+can overlap with the remaining interior cells.
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+
+from . import capi
+
+
+def _split(n, parts, r):
+    """Balanced contiguous split of n cells in `parts`: [start, end) of part r."""
+    base, rem = divmod(n, parts)
+    start = r * base + min(r, rem)
+    return start, start + base + (1 if r < rem else 0)
+
+
+class BoxPartition:
+    def __init__(self, P, n_global, pgrid, rank, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0),
+                 numbering=1):
+        lib = capi.load()
+        self.P, self.N = int(P), int(P) + 1
+        self.n_global = tuple(int(v) for v in n_global)
+        self.pgrid = tuple(int(v) for v in pgrid)
+        self.rank = int(rank)
+        self.nranks = int(np.prod(self.pgrid))
+        Px, Py, Pz = self.pgrid
+        self.rcoord = (rank // (Py * Pz), (rank // Pz) % Py, rank % Pz)
+        rng = [_split(self.n_global[d], self.pgrid[d], self.rcoord[d]) for d in range(3)]
+        self.cell_lo = np.array([r[0] for r in rng])
+        self.n_local = np.array([r[1] - r[0] for r in rng], dtype=np.int32)
+        if np.any(self.n_local < 1):
+            raise ValueError("a rank has no cells")
+        nl = self.n_local
+        P_, N = self.P, self.N
+        lo, hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+        self.has_lower = [self.rcoord[d] > 0 for d in range(3)]
+        self.has_upper = [self.rcoord[d] < self.pgrid[d] - 1 for d in range(3)]
+        M = [self.n_global[d] * P_ + 1 for d in range(3)]          # global node grid
+        self.ndofs_global = int(M[0]) * int(M[1]) * int(M[2])
+
+        # ---- local geometry: vertex coordinates from the GLOBAL formula (bitwise identical to the
+        # unpartitioned box) -------------------------------------------------------------------
+        nv = nl + 1
+        ax = [lo[d] + (hi[d] - lo[d]) * (self.cell_lo[d] + np.arange(nv[d])) / self.n_global[d]
+              for d in range(3)]
+        X, Y, Z = np.meshgrid(*ax, indexing="ij")
+        self.x = np.ascontiguousarray(np.stack([X, Y, Z], -1).reshape(-1, 3))
+        xd = np.zeros((int(nl.prod()), 8), dtype=np.int32)
+        dummy = np.zeros_like(self.x)
+        capi.check(lib.fus_box_mesh(nl, np.zeros(3), np.ones(3), dummy, xd), "fus_box_mesh")
+
+        # ---- raw local dofmap (cell-blocked numbering of the local node grid) ---------------
+        ncl = int(nl.prod())
+        Nd = N ** 3
+        raw = np.zeros((ncl, Nd), dtype=np.int32)
+        capi.check(lib.fus_box_dofmap(P_, nl, numbering, raw), "fus_box_dofmap")
+        nraw = int(lib.fus_box_num_dofs(P_, nl))
+        # local grid coordinates of every raw dof
+        pos = np.array([0, P_] + list(range(1, P_)), dtype=np.int64)   # Basix node -> offset
+        cz, cy, cx = np.meshgrid(np.arange(nl[2]), np.arange(nl[1]), np.arange(nl[0]),
+                                 indexing="ij")
+        # cell index c = (cx*ny + cy)*nz + cz  -> arrays in that order
+        cxs, cys, czs = (np.arange(ncl) // (nl[1] * nl[2]), (np.arange(ncl) // nl[2]) % nl[1],
+                         np.arange(ncl) % nl[2])
+        del cz, cy, cx
+        i0, i1, i2 = np.meshgrid(pos, pos, pos, indexing="ij")
+        g = [np.zeros(nraw, dtype=np.int64) for _ in range(3)]
+        for d, (cc, ii) in enumerate(((cxs, i0), (cys, i1), (czs, i2))):
+            gd = (cc[:, None] * P_ + ii.reshape(1, -1)).reshape(-1)
+            g[d][raw.reshape(-1)] = gd
+        top = [int(nl[d]) * P_ for d in range(3)]
+        ghost = np.zeros(nraw, dtype=bool)
+        owner = np.zeros((nraw, 3), dtype=np.int64)
+        for d in range(3):
+            on_low = (g[d] == 0) & self.has_lower[d]
+            ghost |= on_low
+            owner[:, d] = self.rcoord[d] - on_low.astype(np.int64)
+        owner_rank = (owner[:, 0] * Py + owner[:, 1]) * Pz + owner[:, 2]
+        key = ((g[0] + self.cell_lo[0] * P_) * M[1] + (g[1] + self.cell_lo[1] * P_)) * M[2] \
+            + (g[2] + self.cell_lo[2] * P_)                          # global node id
+
+        # ---- local numbering: owned (raw order), then ghosts grouped by owner, by global key --
+        owned_raw = np.flatnonzero(~ghost)
+        ghost_raw = np.flatnonzero(ghost)
+        order = np.lexsort((key[ghost_raw], owner_rank[ghost_raw]))
+        ghost_raw = ghost_raw[order]
+        self.nowned = int(owned_raw.size)
+        self.ndofs = nraw
+        new_of_raw = np.empty(nraw, dtype=np.int32)
+        new_of_raw[owned_raw] = np.arange(self.nowned, dtype=np.int32)
+        new_of_raw[ghost_raw] = self.nowned + np.arange(ghost_raw.size, dtype=np.int32)
+        self.global_key = np.empty(nraw, dtype=np.int64)
+        self.global_key[new_of_raw] = key
+        dofmap = new_of_raw[raw]
+
+        # ---- halo lists ------------------------------------------------------------------------
+        # recv: ghosts, already grouped by owner rank and sorted by key
+        g_owner = owner_rank[ghost_raw]
+        neigh = {}
+        for q in np.unique(g_owner):
+            sel = np.flatnonzero(g_owner == q)
+            neigh.setdefault(int(q), {})["recv"] = (self.nowned + sel).astype(np.int32)
+        # send: for every upper neighbour r+delta, my owned nodes on the top planes of delta
+        owned_mask_new = np.zeros(nraw, dtype=bool)
+        owned_mask_new[:self.nowned] = True
+        gn = [np.empty(nraw, dtype=np.int64) for _ in range(3)]
+        for d in range(3):
+            gn[d][new_of_raw] = g[d]
+        for delta in itertools.product((0, 1), repeat=3):
+            if not any(delta):
+                continue
+            if any(delta[d] and not self.has_upper[d] for d in range(3)):
+                continue
+            q = ((self.rcoord[0] + delta[0]) * Py + self.rcoord[1] + delta[1]) * Pz \
+                + self.rcoord[2] + delta[2]
+            m = owned_mask_new.copy()
+            for d in range(3):
+                if delta[d]:
+                    m &= gn[d] == top[d]
+            idx = np.flatnonzero(m)
+            idx = idx[np.argsort(self.global_key[idx], kind="stable")]
+            neigh.setdefault(int(q), {})["send"] = idx.astype(np.int32)
+        self.neigh = sorted(neigh)
+        e = np.zeros(0, dtype=np.int32)
+        self.send_lists = [neigh[q].get("send", e) for q in self.neigh]
+        self.recv_lists = [neigh[q].get("recv", e) for q in self.neigh]
+
+        # ---- interface cells first ------------------------------------------------------------
+        shared = np.zeros(nraw, dtype=bool)
+        shared[self.nowned:] = True
+        for s in self.send_lists:
+            shared[s] = True
+        is_iface = shared[dofmap].any(axis=1)
+        perm = np.concatenate([np.flatnonzero(is_iface), np.flatnonzero(~is_iface)])
+        self.ninterface_cells = int(is_iface.sum())
+        self.dofmap = np.ascontiguousarray(dofmap[perm])
+        self.xdofmap = np.ascontiguousarray(xd[perm])
+        self.ncells = ncl
+        gcx, gcy, gcz = cxs + self.cell_lo[0], cys + self.cell_lo[1], czs + self.cell_lo[2]
+        self.cell_global = (((gcx * self.n_global[1]) + gcy) * self.n_global[2] + gcz)[perm]
+        inv = np.empty(ncl, dtype=np.int64)
+        inv[perm] = np.arange(ncl)
+
+        # ---- exterior facets of the GLOBAL box that belong to local cells ----------------------
+        nf = lib.fus_box_facets(nl, None)
+        f = np.zeros((nf, 3), dtype=np.int32)
+        lib.fus_box_facets(nl, f.ctypes.data_as(C.c_void_p))
+        fdir = np.array([2, 1, 0, 0, 1, 2])[f[:, 1]]
+        fside = np.array([0, 0, 0, 1, 1, 1])[f[:, 1]]
+        keep = np.ones(nf, dtype=bool)
+        for d in range(3):
+            keep &= ~((fdir == d) & (fside == 0) & self.has_lower[d])
+            keep &= ~((fdir == d) & (fside == 1) & self.has_upper[d])
+        f = f[keep]
+        f[:, 0] = inv[f[:, 0]]
+        self.facets = np.ascontiguousarray(f)
+
+    # -------------------------------------------------------------------------------------------
+    def function_space(self, device=0):
+        """FunctionSpace-like object over the local block for the operator/model classes."""
+        import types
+
+        from . import Context
+        mesh = types.SimpleNamespace(x=self.x, xdofmap=self.xdofmap, facets=self.facets,
+                                     ncells=self.ncells, n=self.n_local)
+        V = types.SimpleNamespace(mesh=mesh, P=self.P, N=self.N, ndofs=self.ndofs,
+                                  nowned=self.nowned, dofmap=self.dofmap, _ctx=None)
+
+        def context(dev=device):
+            if V._ctx is None:
+                V._ctx = Context.from_mesh(V, dev, nowned=self.nowned)
+            return V._ctx
+        V.context = context
+        return V
+
+    def halo_arrays(self):
+        nn = len(self.neigh)
+        neigh = np.array(self.neigh, dtype=np.int32)
+        soff = np.zeros(nn + 1, dtype=np.int64)
+        roff = np.zeros(nn + 1, dtype=np.int64)
+        for k in range(nn):
+            soff[k + 1] = soff[k] + self.send_lists[k].size
+            roff[k + 1] = roff[k] + self.recv_lists[k].size
+        sidx = np.concatenate(self.send_lists) if nn else np.zeros(0, np.int32)
+        ridx = np.concatenate(self.recv_lists) if nn else np.zeros(0, np.int32)
+        return (neigh, soff, np.ascontiguousarray(sidx, dtype=np.int32), roff,
+                np.ascontiguousarray(ridx, dtype=np.int32))
+
+    def setup_halo(self, ctx, dist):
+        """Create the NCCL communicator of the context: rank 0 makes the unique id, it is
+        broadcast with torch.distributed, every rank calls fus_halo_setup."""
+        import torch
+        lib = capi.load()
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            capi.check(lib.fus_comm_unique_id(uid.ctypes.data_as(C.c_void_p)), "fus_comm_unique_id")
+        t = torch.from_numpy(uid).cuda() if dist.get_backend() == "nccl" else torch.from_numpy(uid)
+        dist.broadcast(t, src=0)
+        uid = t.cpu().numpy().copy()
+        neigh, soff, sidx, roff, ridx = self.halo_arrays()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        capi.check(lib.fus_halo_setup(ctx.h, self.rank, self.nranks, p(uid), len(self.neigh),
+                                      p(neigh), p(soff), p(sidx), p(roff), p(ridx),
+                                      self.ninterface_cells), "fus_halo_setup")
+
+    # ---- host-side halo (CPU tests over gloo; the device path is fus_halo.cu) -----------------
+    def scatter_fwd_host(self, dist, x):
+        import torch
+        ops, bufs = [], []
+        for q, s, r in zip(self.neigh, self.send_lists, self.recv_lists):
+            if s.size:
+                ops.append(dist.P2POp(dist.isend, torch.from_numpy(x[s].copy()), q))
+            if r.size:
+                b = torch.zeros(r.size, dtype=torch.float64)
+                bufs.append((r, b))
+                ops.append(dist.P2POp(dist.irecv, b, q))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for r, b in bufs:
+            x[r] = b.numpy()
+
+    def scatter_rev_host(self, dist, x):
+        import torch
+        ops, bufs = [], []
+        for q, s, r in zip(self.neigh, self.send_lists, self.recv_lists):
+            if r.size:
+                ops.append(dist.P2POp(dist.isend, torch.from_numpy(x[r].copy()), q))
+            if s.size:
+                b = torch.zeros(s.size, dtype=torch.float64)
+                bufs.append((s, b))
+                ops.append(dist.P2POp(dist.irecv, b, q))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for s, b in bufs:
+            np.add.at(x, s, b.numpy())

@@ -167,6 +167,12 @@ int fus_model_rk4(fus_model* m, double t0, double tf, double dt, int* nsteps);
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t fus_launch_count(void);
 
+/* Per-kernel device timing with CUDA events recorded on the context stream around each launch
+   (option "profile_kernels" = 1 to start, 0 to stop).  fus_ctx_profile synchronises, then returns
+   the number of launches and the summed device time of one kernel family since profiling was
+   enabled: "stiffness" (operator), "stage" (fused RK4 epilogue), "boundary". */
+int fus_ctx_profile(fus_ctx* ctx, const char* kernel, int64_t* launches, double* total_ms);
+
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU halo exchange: replaces la::Vector::scatter_fwd / scatter_rev(std::plus)
  * (call sites Linear.hpp:196,199,206; Westervelt.hpp:243,246,257,265) with NCCL send/recv.

@@ -1,0 +1,262 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI,
+against the CPU oracle on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): gather/scatter indexing bit-exact; one operator application
+<= 1e-12 relative L2; fields after N steps <= 1e-10 relative L2.
+"""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2, warp_vertices
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_APPLY = 1e-12
+TOL_STEPS = 1e-10
+REPORT = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _report():
+    yield
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def note(key, val):
+    REPORT[key] = float(val)
+
+
+def make_case(fus, orc, P, n, mode, warp=True, hi=(1.0, 1.0, 1.0)):
+    m = fus.BoxMesh(n, (0, 0, 0), hi, warp=(lambda x: warp_vertices(x, 0.08, 3)) if warp else None)
+    V = fus.FunctionSpace(m, P, numbering=mode)
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    return m, V, G, dJ
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_device_geometry_vs_oracle(fus, orc, gpu, P):
+    m, V, G, dJ = make_case(fus, orc, P, (3, 2, 2), 1)
+    Gd, dJd = V.context().geometry()
+    note(f"geometry_G_P{P}", rel_l2(Gd, G))
+    assert rel_l2(Gd, G) < 1e-13 and rel_l2(dJd, dJ) < 1e-13
+    assert np.abs(Gd - G).max() <= 1e-12 * np.abs(G).max()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_stiffness_apply_vs_oracle(fus, orc, gpu, P, variant):
+    # 5x3x2 = 30 cells: not a multiple of any cells-per-block packing; warped (all six G entries)
+    m, V, G, dJ = make_case(fus, orc, P, (5, 3, 2), P % 2)
+    ctx = V.context()
+    ctx.set_option("stiffness_variant", variant)
+    rng = np.random.default_rng(12345)
+    x = rng.uniform(-1, 1, V.ndofs)
+    coeffs = rng.uniform(0.5, 2.0, m.ncells)
+    y0 = rng.uniform(-1, 1, V.ndofs)
+    K = fus.StiffnessSpectral3D(V)
+    y = K(x, coeffs, y0.copy())                              # accumulates (spectral_op.hpp:240-241)
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, y0.copy())
+    e = rel_l2(y - y0, yo - y0)
+    note(f"stiffness_P{P}_variant{variant}", e)
+    assert e < TOL_APPLY
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("P", [2, 3, 4, 5])
+def test_stiffness_golden(fus, gpu, P, variant):
+    """Fixture produced by the reference's own contract<>/transpose<> (oracle/_ref); the context is
+    built from the stored reference-layout arrays, i.e. through fus_ctx_create."""
+    g = np.load(os.path.join(GOLD, f"stiffness_P{P}.npz"))
+    nd = g["x"].shape[0]
+    ctx = fus.Context.from_arrays(P, g["dofmap"], nd, g["G"], g["detJ"], g["dphi"])
+    ctx.set_option("stiffness_variant", variant)
+    y = fus.StiffnessSpectral3D(ctx)(g["x"], g["coeffs"], g["y0"].copy())
+    e = rel_l2(y - g["y0"], g["y"] - g["y0"])
+    note(f"stiffness_golden_P{P}_variant{variant}", e)
+    assert e < TOL_APPLY
+    Gd, dJd = ctx.geometry()
+    assert np.array_equal(Gd, g["G"]) and np.array_equal(dJd, g["detJ"])   # layout round trip
+    ym = fus.MassSpectral3D(ctx)(g["x"], g["coeffs"], g["y0"].copy())
+    gm = np.load(os.path.join(GOLD, f"mass_P{P}.npz"))
+    assert rel_l2(ym - g["y0"], gm["y"] - gm["y0"]) < TOL_APPLY
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_gather_scatter_bit_exact(fus, orc, gpu, P, variant):
+    """Integer-valued tables and data: every product and partial sum is an exactly representable
+    integer, so the result is independent of summation order (atomics) and of FMA contraction.
+    Any indexing error in gather, contraction plumbing or scatter changes the integers."""
+    n = (4, 3, 3)
+    mode = (P + 1) % 2
+    dm = orc.box_dofmap(P, n, mode)
+    nc, Nd = dm.shape
+    nd = dm.max() + 1
+    rng = np.random.default_rng(99 + P)
+    G = rng.integers(-3, 4, (nc, Nd, 6)).astype(np.float64)
+    dJ = rng.integers(1, 5, (nc, Nd)).astype(np.float64)
+    dphi = rng.integers(-2, 3, (P + 1) ** 2).astype(np.float64)
+    x = rng.integers(-4, 5, nd).astype(np.float64)
+    coeffs = rng.integers(1, 4, nc).astype(np.float64)
+    y0 = rng.integers(-9, 10, nd).astype(np.float64)
+    ctx = fus.Context.from_arrays(P, dm, nd, G, dJ, dphi)
+    ctx.set_option("stiffness_variant", variant)
+    y = fus.StiffnessSpectral3D(ctx)(x, coeffs, y0.copy())
+    yo = orc.stiffness_apply(P, dm, G, dphi, coeffs, x, y0.copy())
+    assert np.array_equal(y, yo)
+    ym = fus.MassSpectral3D(ctx)(x, coeffs, y0.copy())
+    assert np.array_equal(ym, orc.mass_apply(P, dm, dJ, coeffs, x, y0.copy()))
+
+
+@pytest.mark.parametrize("n", [(1, 1, 1), (1, 1, 2), (17, 1, 1), (2, 3, 11)])
+def test_ragged_cell_counts(fus, orc, gpu, n):
+    """One cell, fewer cells than one block packs, and counts that leave a partial last block."""
+    for P in (2, 4, 5, 6):
+        m, V, G, dJ = make_case(fus, orc, P, n, 1)
+        rng = np.random.default_rng(5)
+        x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2.0, m.ncells)
+        y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+        yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(V.ndofs))
+        assert rel_l2(y, yo) < TOL_APPLY
+        ym = fus.MassSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+        assert rel_l2(ym, orc.mass_apply(P, V.dofmap, dJ, coeffs, x, np.zeros(V.ndofs))) < TOL_APPLY
+
+
+def _golden_space(fus, g):
+    """FunctionSpace-like view of a golden fixture (arrays only, no mesh generator)."""
+    P = int(g["P"])
+    nd = g["u"].shape[0]
+    mesh = types.SimpleNamespace(x=np.ascontiguousarray(g["xg"]), xdofmap=np.ascontiguousarray(g["xd"]),
+                                 facets=np.ascontiguousarray(g["facets"]), ncells=g["xd"].shape[0])
+    ctx = fus.Context.from_arrays(P, g["dofmap"], nd, g["G"], g["detJ"], g["dphi"])
+    return types.SimpleNamespace(mesh=mesh, P=P, N=P + 1, ndofs=nd, nowned=nd,
+                                 dofmap=np.ascontiguousarray(g["dofmap"]), context=lambda device=0: ctx)
+
+
+def _make_model(fus, kind, V, g):
+    f, p0, s0 = float(g["freq"]), float(g["p0"]), float(g["s0"])
+    if kind == "linear":
+        return fus.LinearSpectral3D(V, g["c0"], g["rho0"], f, p0, s0)
+    if kind == "lossy":
+        return fus.LossySpectral3D(V, g["c0"], g["rho0"], g["delta0"], f, p0, s0)
+    return fus.WesterveltSpectral3D(V, g["c0"], g["rho0"], g["delta0"], g["beta0"], f, p0, s0)
+
+
+@pytest.mark.parametrize("kind", ["linear", "lossy", "westervelt"])
+def test_models_golden(fus, gpu, kind):
+    g = np.load(os.path.join(GOLD, f"rk4_{kind}.npz"))
+    V = _golden_space(fus, g)
+    mdl = _make_model(fus, kind, V, g)
+    e = rel_l2(mdl.mass(), g["mass"])
+    note(f"mass_{kind}", e)
+    assert e < TOL_APPLY
+    kv = mdl.f1(float(g["f1_t"]), g["u_init"].copy(), g["v_init"].copy())
+    e = rel_l2(kv, g["f1"])
+    note(f"f1_{kind}", e)
+    assert e < TOL_APPLY
+    mdl.init(g["u_init"].copy(), g["v_init"].copy())
+    steps = mdl.rk4(float(g["t0"]), float(g["tf"]), float(g["dt"]))
+    assert steps == int(g["steps"])                          # same host-side time arithmetic
+    eu, ev = rel_l2(mdl.u_sol(), g["u"]), rel_l2(mdl.v_sol(), g["v"])
+    note(f"rk4_u_{kind}", eu)
+    note(f"rk4_v_{kind}", ev)
+    assert eu < TOL_STEPS and ev < TOL_STEPS
+
+
+@pytest.mark.parametrize("kind,P", [("linear", 4), ("lossy", 2), ("westervelt", 5), ("linear", 6)])
+def test_models_vs_oracle_from_rest(fus, orc, gpu, kind, P):
+    """init() then rk4 from rest with the source switched on, 20 steps, heterogeneous media,
+    lexicographic numbering, device-computed geometry: the pressure field agrees to 1e-10."""
+    n = (4, 3, 2)
+    h = 0.002
+    hi = (n[0] * h, n[1] * h, n[2] * h)
+    m = fus.BoxMesh(n, (0, 0, 0), hi, warp=lambda x: warp_vertices(x, 0.05, 21))
+    V = fus.FunctionSpace(m, P, numbering=0)
+    nc, nd = m.ncells, V.ndofs
+    c0 = np.where(np.arange(nc) % 3 == 0, 2800.0, 1500.0)
+    rho0 = np.where(np.arange(nc) % 3 == 0, 1850.0, 1000.0)
+    f, p0, s0 = 0.5e6, 6.0e4, 1500.0
+    w0 = 2 * np.pi * f
+    delta0 = np.full(nc, fus.compute_diffusivity_of_sound(w0, 1500.0, 5.0))
+    beta0 = np.full(nc, 3.5)
+    dt = 0.3 * 0.65 * np.sqrt(3) * h / (2800.0 * P * P)
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    om = orc.model(kind, P, nd, V.dofmap, G, dJ, orc.dphi(P), c0, rho0, delta0, beta0, m.facets, fn,
+                   fs, f, p0, s0)
+    gold = dict(c0=c0, rho0=rho0, delta0=delta0, beta0=beta0, freq=f, p0=p0, s0=s0)
+    mdl = _make_model(fus, kind, V, gold)
+    mdl.init()
+    t0, tf = 0.2e-6, 0.2e-6 + 20 * dt
+    steps = mdl.rk4(t0, tf, dt)
+    u, v = np.zeros(nd), np.zeros(nd)
+    assert om.rk4(t0, tf, dt, u, v) == steps
+    assert np.linalg.norm(u) > 0
+    eu, ev = rel_l2(mdl.u_sol(), u), rel_l2(mdl.v_sol(), v)
+    note(f"rest_rk4_u_{kind}_P{P}", eu)
+    assert eu < TOL_STEPS and ev < TOL_STEPS
+
+
+def test_full_size_properties(fus, gpu):
+    """BASELINE config (P=4, 54^3 cells, 10.2 M dofs): size-independent properties of the operator
+    on the device -- K 1 = 0, symmetry, linearity, accumulate -- since the oracle would take minutes."""
+    import torch
+    P, n = 4, (54, 54, 54)
+    m = fus.BoxMesh(n)
+    V = fus.FunctionSpace(m, P, numbering=1)
+    assert V.ndofs == 10218313
+    ctx = V.context()
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    K = fus.StiffnessSpectral3D(V)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(V.ndofs, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    z = torch.rand(V.ndofs, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    coeffs = torch.full((m.ncells,), -1.0 / 1000.0, dtype=torch.float64, device="cuda")
+    one = torch.ones_like(x)
+    k1 = K(one, coeffs, torch.zeros_like(x))
+    kx = K(x, coeffs, torch.zeros_like(x))
+    kz = K(z, coeffs, torch.zeros_like(x))
+    torch.cuda.synchronize()
+    scale = kx.abs().max().item()
+    assert k1.abs().max().item() < 1e-12 * scale
+    a, b = torch.dot(z, kx).item(), torch.dot(x, kz).item()
+    assert abs(a - b) < 1e-11 * abs(a)
+    kxz = K(2.0 * x - 3.0 * z, coeffs, torch.zeros_like(x))
+    assert (torch.linalg.norm(kxz - (2.0 * kx - 3.0 * kz)) / torch.linalg.norm(kxz)).item() < 1e-13
+    acc = K(x, coeffs, z.clone())
+    assert (torch.linalg.norm(acc - (z + kx)) / torch.linalg.norm(acc)).item() < 1e-15
+    # affine cells: interior rows of K x for a quadratic field equal -coeff * h-weighted Laplacian = const
+    # (checked on the small meshes against the oracle; here only finiteness)
+    assert torch.isfinite(kx).all()
+    # second variant agrees with the first at full size
+    ctx.set_option("stiffness_variant", 1)
+    kx1 = K(x, coeffs, torch.zeros_like(x))
+    ctx.set_option("stiffness_variant", 0)
+    assert (torch.linalg.norm(kx1 - kx) / torch.linalg.norm(kx)).item() < 1e-13
+
+
+def test_full_size_rk4_linearity(fus, gpu):
+    """Source off (p0 = 0): the RK4 map is linear in the state; 3 steps at 10.2 M dofs."""
+    P, n = 4, (54, 54, 54)
+    m = fus.BoxMesh(n, (0, 0, 0), (0.12, 0.12, 0.12))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    mdl = fus.LinearSpectral3D(V, 1500.0, 1000.0, 0.5e6, 0.0, 1500.0)
+    h = 0.12 / 54
+    dt = 0.65 * np.sqrt(3) * h / (1500.0 * 16)
+    rng = np.random.default_rng(0)
+    X = V.tabulate_dof_coordinates()
+    ua = np.sin(40 * X[:, 0]) * np.cos(30 * X[:, 1])
+    ub = np.cos(25 * X[:, 2]) + X[:, 0]
+    outs = []
+    for u0 in (ua, ub, 2 * ua - ub):
+        mdl.init(u0.copy(), 1e6 * u0)
+        assert mdl.rk4(0.0, 3 * dt, dt) == 3
+        outs.append(mdl.u_sol())
+    assert rel_l2(2 * outs[0] - outs[1], outs[2]) < 1e-12
+    assert np.isfinite(outs[2]).all() and np.linalg.norm(outs[2] - (2 * ua - ub)) > 0

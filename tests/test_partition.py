@@ -1,0 +1,130 @@
+"""CPU tests of the multi-GPU host logic: ownership, halo lists, interface-first ordering, and a
+world_size-2 gloo run of the distributed operator algorithm (oracle kernels stand in for the GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+
+
+def _parts(P, n, pg):
+    from fenicsx_fus_b200.partition import BoxPartition
+    nr = int(np.prod(pg))
+    return [BoxPartition(P, n, pg, r, lo=(0, 0, 0), hi=(1.0, 0.7, 0.9)) for r in range(nr)]
+
+
+@pytest.mark.parametrize("P,n,pg", [(2, (4, 4, 4), (2, 2, 2)), (3, (5, 3, 2), (2, 1, 1)),
+                                    (4, (4, 6, 2), (2, 2, 1)), (1, (3, 3, 3), (3, 1, 3))])
+def test_ownership_and_halo_lists(fus, P, n, pg):
+    parts = _parts(P, n, pg)
+    nglob = np.prod([n[d] * P + 1 for d in range(3)])
+    owned = np.concatenate([p.global_key[:p.nowned] for p in parts])
+    # every global dof is owned exactly once
+    assert owned.size == nglob and np.array_equal(np.sort(owned), np.arange(nglob))
+    for p in parts:
+        assert p.ndofs_global == nglob
+        assert len(np.unique(p.global_key)) == p.ndofs          # local numbering is a bijection
+        assert sorted(np.unique(p.dofmap)) == list(range(p.ndofs))
+        for q, s, r in zip(p.neigh, p.send_lists, p.recv_lists):
+            o = parts[q]
+            k = o.neigh.index(p.rank)
+            # what I send is exactly what q expects from me, in the same order, and vice versa
+            assert np.array_equal(p.global_key[s], o.global_key[o.recv_lists[k]])
+            assert np.array_equal(p.global_key[r], o.global_key[o.send_lists[k]])
+            assert np.all(s < p.nowned) and np.all(r >= p.nowned)
+        # every ghost is received exactly once
+        rec = np.concatenate(p.recv_lists) if p.neigh else np.zeros(0, int)
+        assert np.array_equal(np.sort(rec), np.arange(p.nowned, p.ndofs))
+        # interior cells touch no shared dof
+        shared = np.zeros(p.ndofs, bool)
+        shared[p.nowned:] = True
+        for s in p.send_lists:
+            shared[s] = True
+        touch = shared[p.dofmap].any(1)
+        assert touch[:p.ninterface_cells].all() and not touch[p.ninterface_cells:].any()
+    # cells: a partition of the global cells
+    cells = np.concatenate([p.cell_global for p in parts])
+    assert np.array_equal(np.sort(cells), np.arange(np.prod(n)))
+    # exterior facets: a partition of the global exterior facets
+    nf = sum(p.facets.shape[0] for p in parts)
+    assert nf == 2 * (n[0] * n[1] + n[1] * n[2] + n[0] * n[2])
+
+
+def test_single_rank_partition_is_trivial(fus, orc):
+    from fenicsx_fus_b200.partition import BoxPartition
+    p = BoxPartition(3, (3, 2, 2), (1, 1, 1), 0)
+    assert p.nowned == p.ndofs and not p.neigh and p.ninterface_cells == 0
+    assert np.array_equal(p.dofmap, orc.box_dofmap(3, (3, 2, 2), 1))
+    xg, xd = orc.box_mesh((3, 2, 2))
+    assert np.array_equal(p.x, xg) and np.array_equal(p.xdofmap, xd)
+    assert np.array_equal(p.facets, orc.box_facets((3, 2, 2)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, P, n, pg, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fenicsx_fus_b200.partition import BoxPartition
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    hi = (1.0, 0.7, 0.9)
+    p = BoxPartition(P, n, pg, rank, lo=(0, 0, 0), hi=hi)
+    G, dJ = orc.geometry(P, p.x, p.xdofmap)
+    dphi = orc.dphi(P)
+    # global field and per-cell coefficient defined through global ids
+    x = np.zeros(p.ndofs)
+    x[:p.nowned] = np.sin(0.37 * p.global_key[:p.nowned]) + 0.1
+    p.scatter_fwd_host(dist, x)                                  # owner -> ghost
+    assert np.allclose(x, np.sin(0.37 * p.global_key) + 0.1, rtol=0, atol=0)
+    coeffs = 1.0 + 0.01 * (p.cell_global % 7)
+    y = np.zeros(p.ndofs)
+    # interface cells, then interior (two launches on the GPU); reverse exchange in between
+    ni = p.ninterface_cells
+    orc.stiffness_apply(P, p.dofmap[:ni], G[:ni], dphi, coeffs[:ni], x, y)
+    orc.stiffness_apply(P, p.dofmap[ni:], G[ni:], dphi, coeffs[ni:], x, y)
+    m = np.zeros(p.ndofs)
+    orc.mass_apply(P, p.dofmap, dJ, coeffs, np.ones(p.ndofs), m)
+    p.scatter_rev_host(dist, y)                                  # ghost -> owner (+=)
+    p.scatter_rev_host(dist, m)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), key=p.global_key[:p.nowned],
+             y=y[:p.nowned], m=m[:p.nowned])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P,n,pg", [(3, (4, 3, 2), (2, 1, 1)), (2, (3, 4, 3), (1, 2, 1))])
+def test_distributed_operator_gloo_world2(fus, orc, tmp_path, P, n, pg):
+    """Two processes over gloo run the partitioned algorithm (scatter_fwd, local cells with the
+    interface cells first, scatter_rev) and reproduce the single-domain operator."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, P, n, pg, str(tmp_path)), nprocs=2, join=True)
+    hi = (1.0, 0.7, 0.9)
+    xg, xd = orc.box_mesh(n, (0, 0, 0), hi)
+    dm = orc.box_dofmap(P, n, 0)                                   # lexicographic: dof id == global key
+    nd = dm.max() + 1
+    G, dJ = orc.geometry(P, xg, xd)
+    x = np.sin(0.37 * np.arange(nd)) + 0.1
+    coeffs = 1.0 + 0.01 * (np.arange(dm.shape[0]) % 7)
+    y = orc.stiffness_apply(P, dm, G, orc.dphi(P), coeffs, x, np.zeros(nd))
+    m = orc.mass_apply(P, dm, dJ, coeffs, np.ones(nd), np.zeros(nd))
+    got_y, got_m = np.full(nd, np.nan), np.full(nd, np.nan)
+    for r in range(2):
+        d = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        got_y[d["key"]] = d["y"]
+        got_m[d["key"]] = d["m"]
+    assert rel_l2(got_y, y) < 1e-14 and rel_l2(got_m, m) < 1e-14
