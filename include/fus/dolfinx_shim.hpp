@@ -1,0 +1,291 @@
+// dolfinx_shim.hpp -- the slice of the DOLFINx / Basix API that the hot path touches.
+//
+// DOLFINx, Basix and FFCx are not installed in this image, so the C++ mirror of the reference's
+// operator and solver classes (fus/spectral_op.hpp, fus/Linear.hpp, ...) is written against this
+// shim: same namespaces, class names and member names as DOLFINx for everything the reference's
+// cpp/fenicsx-sf/common/*.hpp uses, backed by this repository's own structured-box mesh and dofmap
+// generator (C ABI in fus_b200.h).  Members that exist only here are marked [shim].
+#pragma once
+
+#include "../fus_b200.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <memory>
+#include <numeric>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace fus {
+inline void check(int rc, const char* what) {
+  if (rc != FUS_OK)
+    throw std::runtime_error(std::string(what) + ": " + fus_last_error());
+}
+
+/// Minimal row-major 2-D view with the mdspan members the reference uses
+/// (`extent`, `operator()`, `size`, `data_handle`).
+template <typename T>
+class View2D {
+public:
+  View2D() = default;
+  View2D(T* p, std::size_t n0, std::size_t n1) : _p(p), _n0(n0), _n1(n1) {}
+  std::size_t extent(int i) const { return i == 0 ? _n0 : _n1; }
+  std::size_t size() const { return _n0 * _n1; }
+  T& operator()(std::size_t i, std::size_t j) const { return _p[i * _n1 + j]; }
+  T* data_handle() const { return _p; }
+
+private:
+  T* _p = nullptr;
+  std::size_t _n0 = 0, _n1 = 0;
+};
+} // namespace fus
+
+namespace basix {
+namespace cell {
+enum class type { interval, quadrilateral, hexahedron };
+}
+namespace element {
+enum class family { P };
+enum class lagrange_variant { gll_warped };
+enum class dpc_variant { unset };
+} // namespace element
+
+/// basix::FiniteElement<T>: only the degree is consumed by the hot path.
+template <typename T>
+class FiniteElement {
+public:
+  explicit FiniteElement(int degree) : _degree(degree) {}
+  int degree() const { return _degree; }
+
+private:
+  int _degree;
+};
+
+template <typename T>
+FiniteElement<T> create_element(element::family, cell::type, int degree, element::lagrange_variant,
+                                element::dpc_variant, bool) {
+  return FiniteElement<T>(degree);
+}
+} // namespace basix
+
+namespace dolfinx {
+
+namespace common {
+/// common::IndexMap: owned entries first, then ghosts.
+class IndexMap {
+public:
+  IndexMap(std::int64_t size_local, std::int64_t num_ghosts, std::int64_t size_global)
+      : _local(size_local), _ghosts(num_ghosts), _global(size_global) {}
+  std::int32_t size_local() const { return (std::int32_t)_local; }
+  std::int32_t num_ghosts() const { return (std::int32_t)_ghosts; }
+  std::int64_t size_global() const { return _global; }
+
+private:
+  std::int64_t _local, _ghosts, _global;
+};
+} // namespace common
+
+namespace la {
+/// la::Vector<T>: host array of owned + ghost entries (single rank: no ghosts, scatters are no-ops).
+template <typename T, typename Alloc = std::allocator<T>>
+class Vector {
+public:
+  Vector(std::shared_ptr<const common::IndexMap> map, int bs)
+      : _map(std::move(map)), _bs(bs), _x((_map->size_local() + _map->num_ghosts()) * bs, T(0)) {}
+  std::span<const T> array() const { return std::span<const T>(_x.data(), _x.size()); }
+  std::span<T> mutable_array() { return std::span<T>(_x.data(), _x.size()); }
+  std::shared_ptr<const common::IndexMap> index_map() const { return _map; }
+  int bs() const { return _bs; }
+  void set(T v) { std::fill(_x.begin(), _x.end(), v); }
+  void scatter_fwd() {}
+  template <typename Op>
+  void scatter_rev(Op) {}
+
+private:
+  std::shared_ptr<const common::IndexMap> _map;
+  int _bs;
+  std::vector<T, Alloc> _x;
+};
+} // namespace la
+
+namespace mesh {
+enum class CellType { hexahedron };
+enum class GhostMode { none };
+
+class Topology {
+public:
+  Topology(std::int64_t ncells) : _cells(std::make_shared<common::IndexMap>(ncells, 0, ncells)) {}
+  int dim() const { return 3; }
+  std::shared_ptr<const common::IndexMap> index_map(int) const { return _cells; }
+
+private:
+  std::shared_ptr<const common::IndexMap> _cells;
+};
+
+template <typename T>
+class Geometry {
+public:
+  Geometry(std::vector<T> x, std::vector<std::int32_t> dofmap)
+      : _x(std::move(x)), _dofmap(std::move(dofmap)) {}
+  int dim() const { return 3; }
+  std::span<const T> x() const { return std::span<const T>(_x.data(), _x.size()); }
+  fus::View2D<const std::int32_t> dofmap() const {
+    return fus::View2D<const std::int32_t>(_dofmap.data(), _dofmap.size() / 8, 8);
+  }
+
+private:
+  std::vector<T> _x;
+  std::vector<std::int32_t> _dofmap;
+};
+
+template <typename T>
+class Mesh {
+public:
+  Mesh(std::array<int, 3> n, Geometry<T> g, std::vector<std::int32_t> exterior_facets)
+      : _n(n), _geometry(std::move(g)),
+        _topology(std::make_shared<Topology>((std::int64_t)n[0] * n[1] * n[2])),
+        _ext(std::move(exterior_facets)) {}
+  const Geometry<T>& geometry() const { return _geometry; }
+  std::shared_ptr<Topology> topology() const { return _topology; }
+  std::shared_ptr<Topology> topology_mutable() const { return _topology; }
+  /// [shim] cells per direction of the structured box
+  const std::array<int, 3>& box_cells() const { return _n; }
+  /// [shim] exterior facets as {cell, local facet, box tag} triplets
+  const std::vector<std::int32_t>& exterior_facets() const { return _ext; }
+
+private:
+  std::array<int, 3> _n;
+  Geometry<T> _geometry;
+  std::shared_ptr<Topology> _topology;
+  std::vector<std::int32_t> _ext;
+};
+
+/// mesh::create_box (experiments/measure_fraction_of_peak_performance/main.cpp:61-65)
+template <typename T>
+Mesh<T> create_box(std::array<std::array<T, 3>, 2> p, std::array<std::size_t, 3> n, CellType) {
+  static_assert(std::is_same_v<T, double>, "the B200 path is FP64 only");
+  const int nn[3] = {(int)n[0], (int)n[1], (int)n[2]};
+  const std::int64_t nv = (std::int64_t)(nn[0] + 1) * (nn[1] + 1) * (nn[2] + 1);
+  const std::int64_t nc = (std::int64_t)nn[0] * nn[1] * nn[2];
+  std::vector<T> x(3 * nv);
+  std::vector<std::int32_t> xd(8 * nc);
+  fus::check(fus_box_mesh(nn, p[0].data(), p[1].data(), x.data(), xd.data()), "fus_box_mesh");
+  const std::int64_t nf = fus_box_facets(nn, nullptr);
+  std::vector<std::int32_t> f(3 * nf);
+  fus_box_facets(nn, f.data());
+  return Mesh<T>({nn[0], nn[1], nn[2]}, Geometry<T>(std::move(x), std::move(xd)), std::move(f));
+}
+
+/// mesh::MeshTags<int32_t> over exterior facets.  [shim] a facet "index" is cell*6 + local facet.
+template <typename V>
+class MeshTags {
+public:
+  MeshTags(std::vector<std::int32_t> indices, std::vector<V> values)
+      : _indices(std::move(indices)), _values(std::move(values)) {}
+  std::span<const std::int32_t> indices() const { return _indices; }
+  std::span<const V> values() const { return _values; }
+  std::vector<std::int32_t> find(V value) const {
+    std::vector<std::int32_t> out;
+    for (std::size_t i = 0; i < _values.size(); ++i)
+      if (_values[i] == value)
+        out.push_back(_indices[i]);
+    return out;
+  }
+
+private:
+  std::vector<std::int32_t> _indices;
+  std::vector<V> _values;
+};
+
+/// [shim] facet tags of the box: 1 on x = lo, 2 on x = hi
+template <typename T>
+MeshTags<std::int32_t> box_facet_tags(const Mesh<T>& mesh) {
+  std::vector<std::int32_t> idx, val;
+  const auto& f = mesh.exterior_facets();
+  for (std::size_t k = 0; k < f.size() / 3; ++k)
+    if (f[3 * k + 2] != 0) {
+      idx.push_back(f[3 * k] * 6 + f[3 * k + 1]);
+      val.push_back(f[3 * k + 2]);
+    }
+  return MeshTags<std::int32_t>(std::move(idx), std::move(val));
+}
+} // namespace mesh
+
+namespace fem {
+class DofMap {
+public:
+  DofMap(std::vector<std::int32_t> tensor_map, int nd, std::shared_ptr<const common::IndexMap> im)
+      : index_map(std::move(im)), _map(std::move(tensor_map)), _nd(nd) {}
+  /// [shim] the map is already in tensor-product order (reorder_dofmap is the identity)
+  fus::View2D<const std::int32_t> map() const {
+    return fus::View2D<const std::int32_t>(_map.data(), _map.size() / _nd, _nd);
+  }
+  int index_map_bs() const { return 1; }
+  std::shared_ptr<const common::IndexMap> index_map;
+
+private:
+  std::vector<std::int32_t> _map;
+  int _nd;
+};
+
+template <typename T>
+class FunctionSpace {
+public:
+  FunctionSpace(std::shared_ptr<mesh::Mesh<T>> mesh, int degree, std::shared_ptr<DofMap> dm)
+      : _mesh(std::move(mesh)), _degree(degree), _dofmap(std::move(dm)) {}
+  std::shared_ptr<const mesh::Mesh<T>> mesh() const { return _mesh; }
+  std::shared_ptr<const DofMap> dofmap() const { return _dofmap; }
+  int degree() const { return _degree; }
+
+private:
+  std::shared_ptr<mesh::Mesh<T>> _mesh;
+  int _degree;
+  std::shared_ptr<DofMap> _dofmap;
+};
+
+/// fem::create_functionspace(mesh, element) (Linear.hpp:82-83).  degree 0 gives the DG0 space
+/// of per-cell coefficients.
+template <typename T>
+FunctionSpace<T> create_functionspace(std::shared_ptr<mesh::Mesh<T>> mesh,
+                                      const basix::FiniteElement<T>& e) {
+  const auto& n = mesh->box_cells();
+  const int nn[3] = {n[0], n[1], n[2]};
+  const std::int64_t nc = (std::int64_t)n[0] * n[1] * n[2];
+  const int P = e.degree();
+  if (P == 0) {
+    std::vector<std::int32_t> dm(nc);
+    std::iota(dm.begin(), dm.end(), 0);
+    auto im = std::make_shared<common::IndexMap>(nc, 0, nc);
+    return FunctionSpace<T>(mesh, 0, std::make_shared<DofMap>(std::move(dm), 1, im));
+  }
+  const int Nd = (P + 1) * (P + 1) * (P + 1);
+  std::vector<std::int32_t> dm((std::size_t)nc * Nd);
+  fus::check(fus_box_dofmap(P, nn, 1, dm.data()), "fus_box_dofmap");
+  const std::int64_t nd = fus_box_num_dofs(P, nn);
+  auto im = std::make_shared<common::IndexMap>(nd, 0, nd);
+  return FunctionSpace<T>(mesh, P, std::make_shared<DofMap>(std::move(dm), Nd, im));
+}
+
+template <typename T>
+class Function {
+public:
+  explicit Function(std::shared_ptr<const FunctionSpace<T>> V)
+      : _V(std::move(V)),
+        _x(std::make_shared<la::Vector<T>>(_V->dofmap()->index_map, _V->dofmap()->index_map_bs())) {}
+  std::shared_ptr<la::Vector<T>> x() { return _x; }
+  std::shared_ptr<const la::Vector<T>> x() const { return _x; }
+  std::shared_ptr<const FunctionSpace<T>> function_space() const { return _V; }
+
+private:
+  std::shared_ptr<const FunctionSpace<T>> _V;
+  std::shared_ptr<la::Vector<T>> _x;
+};
+} // namespace fem
+
+} // namespace dolfinx

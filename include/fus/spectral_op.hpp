@@ -1,0 +1,91 @@
+// fus/spectral_op.hpp -- drop-in for cpp/fenicsx-sf/common/spectral_op.hpp of the reference.
+//
+// Same class names, template parameters and call signatures:
+//   MassSpectral3D<T,P>(std::shared_ptr<fem::FunctionSpace<T>>& V)            (spectral_op.hpp:29-32)
+//   StiffnessSpectral3D<T,P>(std::shared_ptr<fem::FunctionSpace<T>>& V)       (spectral_op.hpp:132-135)
+//   void operator()(const la::Vector<T,Alloc>& x, std::span<T> coeffs, la::Vector<T,Alloc>& y)
+//                                                                             (:69-70, :173-174)
+// with the same semantics: y += A(coeffs) x over the local cells, no communication, the caller
+// zero-fills y and refreshes the ghosts of x.  The arithmetic runs in the CUDA library through the
+// C ABI (fus_b200.h); T must be double.  Construction uploads the cell data once (the reference
+// precomputes G / detJ in its constructor too); each call moves x, coeffs and y across PCIe --
+// the solver classes (fus/Linear.hpp, ...) keep everything resident instead.
+#pragma once
+
+#include "dolfinx_shim.hpp"
+
+namespace fus::detail {
+/// One device context per function space, shared by the operators built on it.
+template <typename T>
+class SpaceContext {
+public:
+  explicit SpaceContext(const dolfinx::fem::FunctionSpace<T>& V, int device = 0) {
+    static_assert(std::is_same_v<T, double>, "the B200 path is FP64 only");
+    auto mesh = V.mesh();
+    auto dm = V.dofmap()->map();
+    auto im = V.dofmap()->index_map;
+    auto xd = mesh->geometry().dofmap();
+    auto x = mesh->geometry().x();
+    check(fus_ctx_create_from_mesh(V.degree(), (std::int64_t)dm.extent(0),
+                                   im->size_local() + im->num_ghosts(), im->size_local(),
+                                   dm.data_handle(), (std::int64_t)x.size() / 3, x.data(),
+                                   xd.data_handle(), device, &_ctx),
+          "fus_ctx_create_from_mesh");
+  }
+  ~SpaceContext() { fus_ctx_destroy(_ctx); }
+  SpaceContext(const SpaceContext&) = delete;
+  SpaceContext& operator=(const SpaceContext&) = delete;
+  fus_ctx* get() const { return _ctx; }
+
+private:
+  fus_ctx* _ctx = nullptr;
+};
+} // namespace fus::detail
+
+using namespace dolfinx;
+
+/// 3D Spectral Mass operator (spectral_op.hpp:28-107)
+template <typename T, int P>
+class MassSpectral3D {
+public:
+  MassSpectral3D(std::shared_ptr<fem::FunctionSpace<T>>& V)
+      : _ctx(std::make_shared<fus::detail::SpaceContext<T>>(*V)) {
+    static_assert(P >= 1 && P <= 7, "supported degrees: 1..7");
+    if (V->degree() != P)
+      throw std::runtime_error("MassSpectral3D: function space degree != P");
+  }
+
+  /// Operator y += M x
+  template <typename Alloc>
+  void operator()(const la::Vector<T, Alloc>& x, std::span<T> coeffs, la::Vector<T, Alloc>& y) {
+    fus::check(fus_mass_apply_host(_ctx->get(), x.array().data(), coeffs.data(),
+                                   y.mutable_array().data()),
+               "fus_mass_apply_host");
+  }
+
+private:
+  std::shared_ptr<fus::detail::SpaceContext<T>> _ctx;
+};
+
+/// 3D Spectral Stiffness operator (spectral_op.hpp:132-284)
+template <typename T, int P>
+class StiffnessSpectral3D {
+public:
+  StiffnessSpectral3D(std::shared_ptr<fem::FunctionSpace<T>>& V)
+      : _ctx(std::make_shared<fus::detail::SpaceContext<T>>(*V)) {
+    static_assert(P >= 1 && P <= 7, "supported degrees: 1..7");
+    if (V->degree() != P)
+      throw std::runtime_error("StiffnessSpectral3D: function space degree != P");
+  }
+
+  /// Operator y += K x
+  template <typename Alloc>
+  void operator()(const la::Vector<T, Alloc>& x, std::span<T> coeffs, la::Vector<T, Alloc>& y) {
+    fus::check(fus_stiffness_apply_host(_ctx->get(), x.array().data(), coeffs.data(),
+                                        y.mutable_array().data()),
+               "fus_stiffness_apply_host");
+  }
+
+private:
+  std::shared_ptr<fus::detail::SpaceContext<T>> _ctx;
+};

@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the headline bench line): BASELINE.json configs 2-4 on one GPU.
+
+  * config 2: degree sweep P=2..7, single stiffness apply on a ~10 M-dof box
+    (cpp/fenicsx-sf/experiments/measure_fraction_of_peak_performance/main.cpp:44-116):
+    time = min over repeats, reported as Gdof/s and as fraction of the HBM roofline with the
+    algorithmic bytes 52 r + 16 per dof;
+  * config 3/4: RK4 steps of the heterogeneous linear, lossy and Westervelt models at P=4.
+Writes one JSON object per line to stdout.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SWEEP = {2: 107, 3: 71, 4: 54, 5: 43, 6: 36, 7: 31}
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def main():
+    import torch
+
+    import fenicsx_fus_b200 as fus
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--degrees", default="2,3,4,5,6,7")
+    ap.add_argument("--repeats", type=int, default=20)
+    ap.add_argument("--models", default="linear_het,lossy,westervelt")
+    ap.add_argument("--variants", default="0")
+    ap.add_argument("--numbering", type=int, default=1)
+    args = ap.parse_args()
+    pk = peak()
+    stream = torch.cuda.current_stream()
+    for P in [int(s) for s in args.degrees.split(",") if s]:
+        n = SWEEP[P]
+        m = fus.BoxMesh((n, n, n))
+        V = fus.FunctionSpace(m, P, numbering=args.numbering)
+        ctx = V.context()
+        ctx.set_stream(stream.cuda_stream)
+        X = None
+        x = torch.rand(V.ndofs, dtype=torch.float64, device="cuda")
+        y = torch.zeros_like(x)
+        coeffs = torch.full((m.ncells,), -1.0 / 1000.0, dtype=torch.float64, device="cuda")
+        K = fus.StiffnessSpectral3D(V)
+        for variant in [int(s) for s in args.variants.split(",")]:
+            ctx.set_option("stiffness_variant", variant)
+            for _ in range(3):
+                K(x, coeffs, y)
+            times = []
+            for _ in range(args.repeats):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                K(x, coeffs, y)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+            tmin, tmed = min(times), float(np.median(times))
+            npts = m.ncells * (P + 1) ** 3
+            alg = 52.0 * npts + 16.0 * V.ndofs
+            print(json.dumps({"config": "degree_sweep", "P": P, "n": n, "dofs": V.ndofs,
+                              "variant": variant, "numbering": args.numbering,
+                              "ms_min": tmin, "ms_median": tmed,
+                              "gdof_per_s": V.ndofs / (tmin * 1e-3) / 1e9,
+                              "alg_gbs_min": alg / (tmin * 1e-3) / 1e9,
+                              "alg_gbs_median": alg / (tmed * 1e-3) / 1e9,
+                              "frac_of_measured_peak": alg / (tmed * 1e-3) / 1e9 / pk}), flush=True)
+        ctx.set_option("stiffness_variant", 0)
+        del K, x, y, coeffs
+        V._ctx = None
+        ctx.destroy()
+        torch.cuda.empty_cache()
+
+    # ---- models at P=4 on the 54^3 box ----------------------------------------------------
+    P, n, L = 4, 54, 0.12
+    h = L / n
+    models = [s for s in args.models.split(",") if s]
+    if models:
+        m = fus.BoxMesh((n, n, n), (0, 0, 0), (L, L, L))
+        V = fus.FunctionSpace(m, P, numbering=args.numbering)
+        ctx = V.context()
+        ctx.set_stream(stream.cuda_stream)
+        nc = m.ncells
+        cx = np.arange(nc) // (n * n)                   # layers along x by cell index
+        # water / skin / cortical / trabecular / brain
+        # (cpp/fenicsx-sf/experiments/measure_vector_assembly_speed/main.cpp:43-83)
+        lay = np.minimum(cx * 5 // n, 4)
+        c_tab = np.array([1500.0, 1610.0, 2800.0, 2300.0, 1560.0])
+        r_tab = np.array([1000.0, 1090.0, 1850.0, 1700.0, 1040.0])
+        f0 = 0.5e6
+        for name in models:
+            if name == "linear_het":
+                c0, rho0 = c_tab[lay], r_tab[lay]
+                mdl = fus.LinearSpectral3D(V, c0, rho0, f0, 6e4, 1500.0)
+                cmax, cfl = 2800.0, 0.65
+            elif name == "lossy":
+                c0, rho0 = c_tab[lay], r_tab[lay]
+                delta = fus.compute_diffusivity_of_sound(2 * np.pi * f0, c0, 5.0)
+                mdl = fus.LossySpectral3D(V, c0, rho0, delta, f0, 6e4, 1500.0)
+                cmax, cfl = 2800.0, 0.2      # `ds` absorbs on every facet: see DESIGN.md (stability)
+            else:
+                f0 = 1.1e6                    # HITU/W-H131-WATER/main.cpp:33-46
+                c0, rho0 = np.full(nc, 1480.0), np.full(nc, 1000.0)
+                alpha = 0.2 / 20 * np.log(10)   # 0.2 dB/m in Np/m
+                delta = np.full(nc, fus.compute_diffusivity_of_sound(2 * np.pi * f0, 1480.0, alpha))
+                mdl = fus.WesterveltSpectral3D(V, c0, rho0, delta, np.full(nc, 3.5), f0,
+                                               1000.0 * 1480.0 * 0.2726428, 1480.0)
+                cmax, cfl = 1480.0, 0.2
+            dt = cfl * np.sqrt(3) * h / (cmax * P * P)
+            mdl.init()
+            mdl.rk4(0.0, 2.5 * dt, dt)
+            torch.cuda.synchronize()
+            K = 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            done = mdl.rk4(3 * dt, 3 * dt + (K - 0.5) * dt, dt)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            u = mdl.u_sol()
+            print(json.dumps({"config": "model_rk4", "model": name, "P": P, "dofs": V.ndofs,
+                              "steps": done, "ms_per_step": ms / done,
+                              "dof_updates_per_s": V.ndofs * done / (ms * 1e-3),
+                              "finite": bool(np.isfinite(u).all()),
+                              "u_norm": float(np.linalg.norm(u))}), flush=True)
+            mdl.destroy()
+
+
+if __name__ == "__main__":
+    main()

@@ -260,3 +260,31 @@ def test_full_size_rk4_linearity(fus, gpu):
         outs.append(mdl.u_sol())
     assert rel_l2(2 * outs[0] - outs[1], outs[2]) < 1e-12
     assert np.isfinite(outs[2]).all() and np.linalg.norm(outs[2] - (2 * ua - ub)) > 0
+
+
+def test_cpp_dropin_driver(fus, gpu):
+    """examples/linear_box.cpp is a reference-style driver written against include/fus/*.hpp
+    (same class names, constructor arguments and methods as cpp/fenicsx-sf/common/Linear.hpp and
+    spectral_op.hpp).  Its fields must equal the Python mirror's on the same problem."""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "linear_box")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_cpp_example()
+    n, steps = 6, 10
+    res = subprocess.run([exe, str(n), str(steps)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    vals = {ln.split(":")[0]: ln.split(":")[1].strip() for ln in res.stdout.splitlines() if ":" in ln}
+    L = 0.12 * n / 54.0
+    m = fus.BoxMesh((n, n, n), (0, 0, 0), (L, L, L))
+    V = fus.FunctionSpace(m, 4, numbering=1)
+    assert int(vals["Degrees of freedom"]) == V.ndofs
+    dt = float(vals["Time step size"])
+    mdl = fus.LinearSpectral3D(V, 1500.0, 1000.0, 0.5e6, 60000.0, 1500.0)
+    mdl.init()
+    assert mdl.rk4(0.0, (steps - 0.5) * dt, dt) == int(vals["Number of steps"]) == steps
+    u = mdl.u_sol()
+    assert abs(np.linalg.norm(u) - float(vals["u_l2"])) < 1e-11 * np.linalg.norm(u)
+    x = np.sin(0.001 * np.arange(V.ndofs))
+    y = fus.StiffnessSpectral3D(V)(x, np.full(m.ncells, -1e-3), np.zeros(V.ndofs))
+    assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
