@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -76,7 +77,7 @@ struct fus_ctx {
   double2* d_G2 = nullptr;
   double* d_detJ = nullptr;
   double dphi[64];
-  int variant = 0; // 0 column kernel, 1 point kernel
+  int variant = 0; // 0 column kernel, 1 point kernel, 2 line kernel
   int col_blocks_per_sm = 0;
   Halo* halo = nullptr;
   // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
@@ -160,38 +161,51 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     FUS_LAUNCHED();
     return FUS_OK;
   }
+  // variant 0: column kernel, variant 2: line kernel (same launch geometry rules)
+  auto launch = [&](auto kern_plain, auto kern_fuse, int threads, int smem_bytes, int cpb,
+                    bool& configured, int& bps_plain, int& bps_fuse) -> int {
+    if (!configured) {
+      FUS_CUDA(cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem_bytes));
+      FUS_CUDA(cudaFuncSetAttribute(kern_fuse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem_bytes));
+      FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_plain, kern_plain, threads,
+                                                            smem_bytes));
+      FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_fuse, kern_fuse, threads,
+                                                            smem_bytes));
+      if (bps_plain < 1 || bps_fuse < 1) {
+        set_error("stiffness kernel <N=%d> does not fit on an SM", N);
+        return FUS_ERR_CUDA;
+      }
+      configured = true;
+    }
+    ProfScope prof(c, 0, st);
+    int bps = fuse ? bps_fuse : bps_plain;
+    if (c->col_blocks_per_sm > 0)
+      bps = std::min(bps, c->col_blocks_per_sm);
+    const long long want = (ce - cb + cpb - 1) / cpb;
+    const int blocks = (int)std::min<long long>(want, (long long)c->num_sms * bps);
+    if (fuse)
+      kern_fuse<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, c->d_G2, coeff,
+                                                     coeff2, cb, ce, D);
+    else
+      kern_plain<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, c->d_G2, coeff,
+                                                      coeff2, cb, ce, D);
+    FUS_LAUNCHED();
+    return FUS_OK;
+  };
+  if (c->variant == 2) {
+    using L = LineCfg<N>;
+    static bool configured = false;
+    static int bp = 1, bf = 1;
+    return launch(stiffness_line_kernel<N, false>, stiffness_line_kernel<N, true>, L::THREADS,
+                  L::SMEM_BYTES, L::CPB, configured, bp, bf);
+  }
   using C = ColCfg<N>;
   static bool configured = false;
-  static int bps_plain = 1, bps_fuse = 1;
-  if (!configured) {
-    FUS_CUDA(cudaFuncSetAttribute(stiffness_col_kernel<N, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    FUS_CUDA(cudaFuncSetAttribute(stiffness_col_kernel<N, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &bps_plain, stiffness_col_kernel<N, false>, C::THREADS, C::SMEM_BYTES));
-    FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &bps_fuse, stiffness_col_kernel<N, true>, C::THREADS, C::SMEM_BYTES));
-    if (bps_plain < 1 || bps_fuse < 1) {
-      set_error("stiffness_col_kernel<N=%d> does not fit on an SM", N);
-      return FUS_ERR_CUDA;
-    }
-    configured = true;
-  }
-  ProfScope prof(c, 0, st);
-  int bps = fuse ? bps_fuse : bps_plain;
-  if (c->col_blocks_per_sm > 0)
-    bps = std::min(bps, c->col_blocks_per_sm);
-  const long long want = (ce - cb + C::CPB - 1) / C::CPB;
-  const int blocks = (int)std::min<long long>(want, (long long)c->num_sms * bps);
-  if (fuse)
-    stiffness_col_kernel<N, true><<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(
-        x, x2, y, c->d_dofmap, c->d_G2, coeff, coeff2, cb, ce, D);
-  else
-    stiffness_col_kernel<N, false><<<blocks, C::THREADS, C::SMEM_BYTES, st>>>(
-        x, x2, y, c->d_dofmap, c->d_G2, coeff, coeff2, cb, ce, D);
-  FUS_LAUNCHED();
-  return FUS_OK;
+  static int bp = 1, bf = 1;
+  return launch(stiffness_col_kernel<N, false>, stiffness_col_kernel<N, true>, C::THREADS,
+                C::SMEM_BYTES, C::CPB, configured, bp, bf);
 }
 
 int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double* coeff,
@@ -328,6 +342,11 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   c->nowned = nowned;
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  if (const char* e = std::getenv("FUS_STIFFNESS_VARIANT")) { // A/B runs of bench.py
+    const int v = std::atoi(e);
+    if (v >= 0 && v <= 2)
+      c->variant = v;
+  }
   *out = c;
   FUS_CUDA(cudaSetDevice(device));
   FUS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -498,7 +517,7 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   if (!c || !name)
     return FUS_ERR_ARG;
   if (!std::strcmp(name, "stiffness_variant")) {
-    if (value < 0 || value > 1)
+    if (value < 0 || value > 2)
       return FUS_ERR_ARG;
     c->variant = value;
     return FUS_OK;

@@ -266,6 +266,293 @@ __global__ void __launch_bounds__(ColCfg<N>::THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stiffness operator, "line" kernel: same work split as the column kernel (N*N threads per cell, G
+// streamed to registers with whole-cell look-ahead, RED scatter) but every contraction runs in
+// registers.  Thread (a,b) owns one line of the cell in each of three layouts
+//     A: (k,a,b) along i0      B: (a,k,b) along i1      C: (a,b,k) along i2
+// and the tensors are re-laid-out through shared memory between the phases, so a thread moves
+// 7N stores + 8N loads of distinct data per cell instead of N + 2N stores and 4N*N broadcast
+// loads (each 64-bit shared access costs two wavefronts whether or not lanes share addresses,
+// and L1TEX wavefronts are what bounds the column kernel).  dphi is a constant-bank operand in
+// all six contractions, which also frees the 4N registers of per-thread dphi rows.
+// Buffer strides are chosen per access-pattern pair (conflict-free for N = 5):
+//     Sx (written A, read B and C), S1 (A and B only), S2 (A and C only).
+// GPF = look-ahead depth of the G stream in i0-levels (a divisor of N; N = whole cell).
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct LineCfg {
+  static constexpr int NN = N * N;
+  static constexpr bool WARP = (NN <= 32);
+  static constexpr int CPW = WARP ? 32 / NN : 0;
+  static constexpr int WPB = 4;
+  static constexpr int CPB = WARP ? CPW * WPB : (N == 6 ? 8 : 4);
+  static constexpr int THREADS = WARP ? 32 * WPB : ((CPB * NN + 31) / 32) * 32;
+  // strides in doubles: element (i0,i1,i2) of buffer Z at i0*Z_S0 + i1*Z_S1 + i2
+  static constexpr int X_S1 = N, X_S0 = N * N;
+  static constexpr int B1_S1 = N, B1_S0 = (N == 5) ? 37 : (N * N + ((N % 2) ? 0 : 1));
+  static constexpr int B2_S1 = N, B2_S0 = N * N;
+  static constexpr int X_SZ = N * X_S0, B1_SZ = N * B1_S0, B2_SZ = N * B2_S0;
+  static constexpr int CS = ((X_SZ + B1_SZ + B2_SZ + 7) / 8) * 8 + 8; // all three buffers of a cell
+  static constexpr int SMEM_BYTES = CPB * CS * (int)sizeof(double);
+  static constexpr int GPF = (N <= 7) ? N : N / 2;
+};
+
+template <int N, bool FUSE2>
+__global__ void __launch_bounds__(LineCfg<N>::THREADS)
+    stiffness_line_kernel(const double* __restrict__ x, const double* __restrict__ x2,
+                          double* __restrict__ y, const int32_t* __restrict__ dofmap,
+                          const double2* __restrict__ G2, const double* __restrict__ coeff,
+                          const double* __restrict__ coeff2, long long cell_begin,
+                          long long cell_end, const __grid_constant__ DMat<N> D) {
+  using C = LineCfg<N>;
+  constexpr int NN = C::NN, GPF = C::GPF;
+  static_assert(N % GPF == 0, "G look-ahead depth must divide N");
+  extern __shared__ double smem[];
+
+  const int tid = threadIdx.x;
+  int slot, t;
+  bool lane_ok;
+  if constexpr (C::WARP) {
+    const int lane = tid & 31, w = tid >> 5;
+    const int cw = lane / NN;
+    t = lane - cw * NN;
+    lane_ok = cw < C::CPW;
+    slot = w * C::CPW + (lane_ok ? cw : 0);
+  } else {
+    slot = tid / NN;
+    t = tid - slot * NN;
+    lane_ok = slot < C::CPB;
+    if (!lane_ok)
+      slot = 0;
+  }
+  const int a = t / N, b = t - a * N;
+  double* Sx = smem + slot * C::CS;
+  double* S1 = Sx + C::X_SZ;
+  double* S2 = S1 + C::B1_SZ;
+  // per-thread base offsets of the three access patterns
+  double* SxA = Sx + a * C::X_S1 + b;   // + k*X_S0
+  double* SxB = Sx + a * C::X_S0 + b;   // + k*X_S1
+  double* SxC = Sx + a * C::X_S0 + b * C::X_S1; // + k
+  double* S1A = S1 + a * C::B1_S1 + b;  // + k*B1_S0
+  double* S1B = S1 + a * C::B1_S0 + b;  // + k*B1_S1
+  double* S2A = S2 + a * C::B2_S1 + b;  // + k*B2_S0
+  double* S2C = S2 + a * C::B2_S0 + b * C::B2_S1; // + k
+
+  auto sync = [] {
+    if constexpr (C::WARP)
+      __syncwarp();
+    else
+      __syncthreads();
+  };
+
+  const long long stride = (long long)gridDim.x * C::CPB;
+  const long long ncell = cell_end - cell_begin;
+  const int niter = (int)((ncell + stride - 1) / stride);
+  long long c = cell_begin + (long long)blockIdx.x * C::CPB + slot;
+
+  int idx[N], idxn[N];
+  double xv[N];
+  double2 g[GPF][3];
+  double cf = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    idx[k] = 0;
+    idxn[k] = 0;
+    xv[k] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < GPF; ++k)
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      g[k][p] = make_double2(0.0, 0.0);
+
+  bool valid = lane_ok && (c < cell_end);
+  if (valid) {
+    const int32_t* dm = dofmap + c * (N * NN) + t;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      idx[k] = __ldg(dm + k * NN);
+    if constexpr (FUSE2) {
+      const double ca = __ldg(coeff + c), cb = __ldg(coeff2 + c);
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        xv[k] = ca * __ldg(x + idx[k]) + cb * __ldg(x2 + idx[k]);
+      cf = 1.0;
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        xv[k] = __ldg(x + idx[k]);
+      cf = __ldg(coeff + c);
+    }
+    const double2* gp = G2 + c * (3 * N * NN) + t;
+#pragma unroll
+    for (int k = 0; k < GPF; ++k)
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        g[k][p] = ld_stream(gp + (k * 3 + p) * NN);
+  }
+  long long cn = c + stride;
+  bool validn = lane_ok && (cn < cell_end);
+  if (validn) {
+    const int32_t* dm = dofmap + cn * (N * NN) + t;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      idxn[k] = __ldg(dm + k * NN);
+  }
+
+  for (int it = 0; it < niter; ++it) {
+    // (1) stage x in layout A; direction-0 derivative in registers
+    if (lane_ok) {
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        SxA[k * C::X_S0] = xv[k];
+    }
+    double f0[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        s = fma(D.d[q * N + k], xv[k], s);
+      f0[q] = s;
+    }
+    const double cfc = cf;
+    if (validn) {
+      if constexpr (FUSE2) {
+        const double ca = __ldg(coeff + cn), cb = __ldg(coeff2 + cn);
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          xv[k] = ca * __ldg(x + idxn[k]) + cb * __ldg(x2 + idxn[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          xv[k] = __ldg(x + idxn[k]);
+        cf = __ldg(coeff + cn);
+      }
+    }
+    sync();
+
+    // (2) direction-1 and direction-2 derivatives along the thread's own lines (layouts B, C)
+    {
+      double l[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        l[k] = SxB[k * C::X_S1];
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          s = fma(D.d[q * N + k], l[k], s);
+        if (lane_ok)
+          S1B[q * C::B1_S1] = s;
+      }
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        l[k] = SxC[k];
+#pragma unroll
+      for (int q = 0; q < N; ++q) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          s = fma(D.d[q * N + k], l[k], s);
+        if (lane_ok)
+          S2C[q] = s;
+      }
+    }
+    sync();
+
+    // (3) back in layout A: G transform per level, transposed direction 0 in registers
+    double yv[N];
+#pragma unroll
+    for (int m = 0; m < N; ++m)
+      yv[m] = 0.0;
+    const double2* gpc = G2 + c * (3 * N * NN) + t;
+    const double2* gpn = G2 + cn * (3 * N * NN) + t;
+#pragma unroll
+    for (int i0 = 0; i0 < N; ++i0) {
+      const double f1 = S1A[i0 * C::B1_S0], f2 = S2A[i0 * C::B2_S0];
+      const double2 ga = g[i0 % GPF][0], gb = g[i0 % GPF][1], gc = g[i0 % GPF][2];
+      const double t0 = cfc * (ga.x * f0[i0] + ga.y * f1 + gb.x * f2);
+      const double t1 = cfc * (ga.y * f0[i0] + gb.y * f1 + gc.x * f2);
+      const double t2 = cfc * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
+      // refill the ring slot: level i0+GPF of this cell, or of the next cell once past the top
+      if (i0 + GPF < N) {
+        if (valid) {
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+            g[i0 % GPF][p] = ld_stream(gpc + ((i0 + GPF) * 3 + p) * NN);
+        }
+      } else if (validn) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          g[i0 % GPF][p] = ld_stream(gpn + ((i0 + GPF - N) * 3 + p) * NN);
+      }
+#pragma unroll
+      for (int m = 0; m < N; ++m)
+        yv[m] = fma(D.d[i0 * N + m], t0, yv[m]);
+      if (lane_ok) { // same addresses this thread has just read
+        S1A[i0 * C::B1_S0] = t1;
+        S2A[i0 * C::B2_S0] = t2;
+      }
+    }
+    sync();
+
+    // (4) transposed direction 1 and 2 along the thread's own lines, results back in place
+    {
+      double l[N];
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        l[q] = S1B[q * C::B1_S1];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < N; ++q)
+          s = fma(D.d[q * N + j], l[q], s);
+        if (lane_ok)
+          S1B[j * C::B1_S1] = s;
+      }
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        l[q] = S2C[q];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < N; ++q)
+          s = fma(D.d[q * N + j], l[q], s);
+        if (lane_ok)
+          S2C[j] = s;
+      }
+    }
+    sync();
+
+    // (5) sum the three contributions in layout A and scatter-add
+#pragma unroll
+    for (int j0 = 0; j0 < N; ++j0) {
+      const double acc = yv[j0] + S1A[j0 * C::B1_S0] + S2A[j0 * C::B2_S0];
+      if (valid)
+        atomicAdd(y + idx[j0], acc);
+    }
+
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+      idx[k] = idxn[k];
+    valid = validn;
+    c = cn;
+    cn += stride;
+    validn = lane_ok && (cn < cell_end);
+    if (validn) {
+      const int32_t* dm = dofmap + cn * (N * NN) + t;
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        idxn[k] = __ldg(dm + k * NN);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stiffness operator, "point" kernel: one thread per quadrature point, one cell per block pass.
 // Deliberately plain; kept as the on-device cross-check of the column kernel.
 // ------------------------------------------------------------------------------------------------

@@ -48,7 +48,7 @@ def test_device_geometry_vs_oracle(fus, orc, gpu, P):
     assert np.abs(Gd - G).max() <= 1e-12 * np.abs(G).max()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
 def test_stiffness_apply_vs_oracle(fus, orc, gpu, P, variant):
     # 5x3x2 = 30 cells: not a multiple of any cells-per-block packing; warped (all six G entries)
@@ -67,7 +67,7 @@ def test_stiffness_apply_vs_oracle(fus, orc, gpu, P, variant):
     assert e < TOL_APPLY
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("P", [2, 3, 4, 5])
 def test_stiffness_golden(fus, gpu, P, variant):
     """Fixture produced by the reference's own contract<>/transpose<> (oracle/_ref); the context is
@@ -87,7 +87,7 @@ def test_stiffness_golden(fus, gpu, P, variant):
     assert rel_l2(ym - g["y0"], gm["y"] - gm["y0"]) < TOL_APPLY
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
 def test_gather_scatter_bit_exact(fus, orc, gpu, P, variant):
     """Integer-valued tables and data: every product and partial sum is an exactly representable
