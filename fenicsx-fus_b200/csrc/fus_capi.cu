@@ -77,7 +77,9 @@ struct fus_ctx {
   double2* d_G2 = nullptr;
   double* d_detJ = nullptr;
   double dphi[64];
-  int variant = 0; // 0 column kernel, 1 point kernel, 2 line kernel
+  // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
+  // profiles/), 0 column kernel, 1 point kernel, 2 line kernel
+  int variant = -1;
   int col_blocks_per_sm = 0;
   Halo* halo = nullptr;
   // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
@@ -149,7 +151,8 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   DMat<N> D;
   std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
   const bool fuse = (x2 != nullptr);
-  if (c->variant == 1) {
+  const int variant = (c->variant >= 0) ? c->variant : (N >= 5 ? 2 : 0);
+  if (variant == 1) {
     ProfScope prof(c, 0, st);
     const int blocks = (int)std::min<long long>(ce - cb, (long long)c->num_sms * 16);
     if (fuse)
@@ -194,7 +197,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     FUS_LAUNCHED();
     return FUS_OK;
   };
-  if (c->variant == 2) {
+  if (variant == 2) {
     using L = LineCfg<N>;
     static bool configured = false;
     static int bp = 1, bf = 1;
@@ -344,7 +347,7 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   c->num_sms = prop.multiProcessorCount;
   if (const char* e = std::getenv("FUS_STIFFNESS_VARIANT")) { // A/B runs of bench.py
     const int v = std::atoi(e);
-    if (v >= 0 && v <= 2)
+    if (v >= -1 && v <= 2)
       c->variant = v;
   }
   *out = c;
@@ -517,7 +520,7 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   if (!c || !name)
     return FUS_ERR_ARG;
   if (!std::strcmp(name, "stiffness_variant")) {
-    if (value < 0 || value > 2)
+    if (value < -1 || value > 2)
       return FUS_ERR_ARG;
     c->variant = value;
     return FUS_OK;

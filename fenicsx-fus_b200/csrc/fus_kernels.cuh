@@ -283,10 +283,13 @@ template <int N>
 struct LineCfg {
   static constexpr int NN = N * N;
   static constexpr bool WARP = (NN <= 32);
-  static constexpr int CPW = WARP ? 32 / NN : 0;
-  static constexpr int WPB = 4;
-  static constexpr int CPB = WARP ? CPW * WPB : (N == 6 ? 8 : 4);
-  static constexpr int THREADS = WARP ? 32 * WPB : ((CPB * NN + 31) / 32) * 32;
+  // A "group" of GW warps works on GC cells and synchronises on its own: a warp (__syncwarp) when a
+  // cell fits in one, else a named barrier per group, so groups of a block never wait on each other.
+  static constexpr int GW = WARP ? 1 : (N == 6 ? 3 : 2);
+  static constexpr int GC = WARP ? 32 / NN : (N == 6 ? 2 : 1);
+  static constexpr int GROUPS = WARP ? 4 : (N == 6 ? 2 : 4); // sized so the register file fills
+  static constexpr int CPB = GROUPS * GC;
+  static constexpr int THREADS = GROUPS * GW * 32;
   // strides in doubles: element (i0,i1,i2) of buffer Z at i0*Z_S0 + i1*Z_S1 + i2
   static constexpr int X_S1 = N, X_S0 = N * N;
   static constexpr int B1_S1 = N, B1_S0 = (N == 5) ? 37 : (N * N + ((N % 2) ? 0 : 1));
@@ -310,21 +313,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
   extern __shared__ double smem[];
 
   const int tid = threadIdx.x;
-  int slot, t;
-  bool lane_ok;
-  if constexpr (C::WARP) {
-    const int lane = tid & 31, w = tid >> 5;
-    const int cw = lane / NN;
-    t = lane - cw * NN;
-    lane_ok = cw < C::CPW;
-    slot = w * C::CPW + (lane_ok ? cw : 0);
-  } else {
-    slot = tid / NN;
-    t = tid - slot * NN;
-    lane_ok = slot < C::CPB;
-    if (!lane_ok)
-      slot = 0;
-  }
+  const int group = tid / (C::GW * 32), lg = tid - group * (C::GW * 32);
+  const int cg = lg / NN;
+  const int t = lg - cg * NN;
+  const bool lane_ok = cg < C::GC;
+  const int slot = group * C::GC + (lane_ok ? cg : 0);
   const int a = t / N, b = t - a * N;
   double* Sx = smem + slot * C::CS;
   double* S1 = Sx + C::X_SZ;
@@ -338,11 +331,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
   double* S2A = S2 + a * C::B2_S1 + b;  // + k*B2_S0
   double* S2C = S2 + a * C::B2_S0 + b * C::B2_S1; // + k
 
-  auto sync = [] {
+  auto sync = [group] {
     if constexpr (C::WARP)
       __syncwarp();
     else
-      __syncthreads();
+      asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(C::GW * 32) : "memory");
   };
 
   const long long stride = (long long)gridDim.x * C::CPB;
