@@ -81,6 +81,8 @@ struct fus_ctx {
   // profiles/), 0 column kernel, 1 point kernel, 2 line kernel
   int variant = -1;
   int col_blocks_per_sm = 0;
+  int reserve_sms = 0;      // SMs left free for the halo kernels while cells overlap with them
+  int halo_reserve = 4;     // value of reserve_sms used inside a partitioned stage
   Halo* halo = nullptr;
   // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
   bool profile = false;
@@ -187,7 +189,8 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     if (c->col_blocks_per_sm > 0)
       bps = std::min(bps, c->col_blocks_per_sm);
     const long long want = (ce - cb + cpb - 1) / cpb;
-    const int blocks = (int)std::min<long long>(want, (long long)c->num_sms * bps);
+    const int sms = std::max(1, c->num_sms - c->reserve_sms);
+    const int blocks = (int)std::min<long long>(want, (long long)sms * bps);
     if (fuse)
       kern_fuse<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, c->d_G2, coeff,
                                                      coeff2, cb, ce, D);
@@ -534,6 +537,12 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   }
   if (!std::strcmp(name, "col_blocks_per_sm")) {
     c->col_blocks_per_sm = value;
+    return FUS_OK;
+  }
+  if (!std::strcmp(name, "halo_reserve_sms")) {
+    if (value < 0 || value >= c->num_sms)
+      return FUS_ERR_ARG;
+    c->halo_reserve = value;
     return FUS_OK;
   }
   if (!std::strcmp(name, "halo_overlap") && c->halo) {
@@ -883,7 +892,8 @@ static void source_scalars(const fus_model* m, double t, double* g, double* dg) 
 // b += K(lin) u [+ K(att) v] + boundary terms, with the halo exchange around it when partitioned:
 // the right-hand side assembly of f1 (Linear.hpp:203-206, Lossy.hpp:229-234, Westervelt.hpp:260-265).
 // u, v must have fresh ghosts on entry.
-static int assemble_rhs(fus_model* m, double t, const double* u, const double* v) {
+static int assemble_rhs(fus_model* m, double t, const double* u, const double* v,
+                        bool fwd_pending) {
   fus_ctx* c = m->ctx;
   double g, dg;
   source_scalars(m, t, &g, &dg);
@@ -902,15 +912,31 @@ static int assemble_rhs(fus_model* m, double t, const double* u, const double* v
     FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, c->ncells, c->stream));
     return boundary();
   }
-  // partitioned: interface cells and boundary terms first, then the reverse exchange of the
-  // ghost partial sums overlaps with the interior cells.
+  // Partitioned stage.  Cells are ordered [interface | interior]; the interior is split in two so
+  // that BOTH exchanges hide behind cells that touch no shared dof:
+  //   interior A  ||  owner->ghost update of (u,v) started by the caller (halo_forward_begin)
+  //   interface cells + boundary terms (need the fresh ghosts)
+  //   interior B  ||  ghost->owner sum of b
+  // A few SMs are left free so that the exchange kernels can start while a cell kernel runs.
+  const bool ov = halo_overlap(c->halo) != 0;
   const long long ni = halo_interface_cells(c->halo);
-  FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, ni, c->stream));
-  FUS_TRY(boundary());
-  FUS_TRY(halo_reverse_begin(c->halo, m->d_b, c->stream));
-  FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, c->ncells, c->stream));
-  FUS_TRY(halo_reverse_end(c->halo, m->d_b, c->stream));
-  return FUS_OK;
+  const long long mid = ov ? ni + (c->ncells - ni) / 2 : c->ncells;
+  c->reserve_sms = ov ? c->halo_reserve : 0;
+  int rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, mid, c->stream);
+  if (rc == FUS_OK && fwd_pending)
+    rc = halo_forward_end(c->halo, c->stream);
+  if (rc == FUS_OK)
+    rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, ni, c->stream);
+  if (rc == FUS_OK)
+    rc = boundary();
+  if (rc == FUS_OK)
+    rc = halo_reverse_begin(c->halo, m->d_b, c->stream);
+  if (rc == FUS_OK)
+    rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, mid, c->ncells, c->stream);
+  c->reserve_sms = 0;
+  if (rc == FUS_OK)
+    rc = halo_reverse_end(c->halo, m->d_b, c->stream);
+  return rc;
 }
 
 int fus_model_f1(fus_model* m, double t, const double* u, const double* v, double* result) {
@@ -925,7 +951,7 @@ int fus_model_f1(fus_model* m, double t, const double* u, const double* v, doubl
   FUS_CUDA(cudaMemsetAsync(m->d_b, 0, vb, c->stream));
   if (c->halo)
     FUS_TRY(halo_forward(c->halo, m->d_un, m->d_vn, c->stream));
-  FUS_TRY(assemble_rhs(m, t, m->d_un, m->d_vn));
+  FUS_TRY(assemble_rhs(m, t, m->d_un, m->d_vn, false));
   const int grid = grid_for(nd, 256, 1 << 30);
   if (m->kind == FUS_WESTERVELT)
     f1_finish_kernel<true><<<grid, 256, 0, c->stream>>>(m->d_b, m->d_m, m->d_dnl, m->d_un,
@@ -985,14 +1011,14 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   A.ntotal = c->ndofs;
   FUS_CUDA(cudaMemsetAsync(m->d_b, 0, sizeof(double) * c->ndofs, c->stream));
   if (c->halo)
-    FUS_TRY(halo_forward(c->halo, m->d_u0, m->d_v0, c->stream));
+    FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
   while (t < tf) {
     dt = std::min(dt, tf - t);
     for (int i = 0; i < 4; ++i) {
       const double tn = t + c_runge[i] * dt;
       const double* u_in = (i == 0) ? m->d_u0 : m->d_un;
       const double* v_in = (i == 0) ? m->d_v0 : m->d_vn;
-      FUS_TRY(assemble_rhs(m, tn, u_in, v_in));
+      FUS_TRY(assemble_rhs(m, tn, u_in, v_in, true));
       A.bw_dt = dt * b_runge[i];
       A.a_next_dt = (i < 3) ? dt * a_runge[i + 1] : 0.0;
       switch (i) {
@@ -1001,13 +1027,15 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
       case 2: FUS_TRY(launch_stage<2>(m, A)); break;
       case 3: FUS_TRY(launch_stage<3>(m, A)); break;
       }
-      if (c->halo) // scatter_fwd of the next stage input (Linear.hpp:196-199)
-        FUS_TRY(halo_forward(c->halo, (i < 3) ? m->d_un : m->d_u0, (i < 3) ? m->d_vn : m->d_v0,
-                             c->stream));
+      if (c->halo) // scatter_fwd of the next stage input (Linear.hpp:196-199), joined inside it
+        FUS_TRY(halo_forward_begin(c->halo, (i < 3) ? m->d_un : m->d_u0,
+                                   (i < 3) ? m->d_vn : m->d_v0, c->stream));
     }
     t += dt;
     step += 1;
   }
+  if (c->halo) // u_n, v_n leave with fresh ghosts (Linear.hpp:312-313)
+    FUS_TRY(halo_forward_end(c->halo, c->stream));
   if (nsteps)
     *nsteps = step;
   return FUS_OK;

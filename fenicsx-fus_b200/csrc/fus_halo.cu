@@ -101,7 +101,7 @@ struct Halo {
   int64_t nowned = 0, ndofs = 0, ninterface = 0;
   int overlap = 1;
   cudaStream_t comm_stream = nullptr;
-  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_fwd_ready = nullptr, ev_fwd_done = nullptr;
 };
 
 int halo_unique_id(void* id128) {
@@ -162,9 +162,13 @@ int halo_create(Halo** out, int device, int rank, int nranks, const void* uid, i
   if (h->nrecv)
     FUS_CUDA_H(cudaMemcpy(h->d_recv_idx, recv_idx, sizeof(int32_t) * h->nrecv,
                           cudaMemcpyHostToDevice));
-  FUS_CUDA_H(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  FUS_CUDA_H(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  FUS_CUDA_H(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
   FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_fwd_ready, cudaEventDisableTiming));
+  FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_fwd_done, cudaEventDisableTiming));
   ncclUniqueId id;
   std::memcpy(&id, uid, sizeof(id));
   FUS_NCCL(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
@@ -187,12 +191,17 @@ void halo_destroy(Halo* h) {
     cudaEventDestroy(h->ev_ready);
   if (h->ev_done)
     cudaEventDestroy(h->ev_done);
+  if (h->ev_fwd_ready)
+    cudaEventDestroy(h->ev_fwd_ready);
+  if (h->ev_fwd_done)
+    cudaEventDestroy(h->ev_fwd_done);
   if (h->comm_stream)
     cudaStreamDestroy(h->comm_stream);
   delete h;
 }
 
 void halo_set_overlap(Halo* h, int on) { h->overlap = on; }
+int halo_overlap(const Halo* h) { return h->overlap; }
 long long halo_interface_cells(const Halo* h) { return h->overlap ? h->ninterface : 0; }
 
 // One grouped exchange.  `fwd`: owners send send_idx entries, ghosts receive; otherwise reversed.
@@ -292,6 +301,27 @@ int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
     halo_unpack_kernel<false><<<blocks_for(h->nrecv), 256, 0, st>>>(
         a, b, h->d_recv_idx, T.d_roff, nn, h->d_rbuf, h->nrecv, nv);
   FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
+int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
+  if (h->neigh.empty())
+    return FUS_OK;
+  if (!h->overlap)
+    return halo_forward(h, a, b, st);
+  FUS_CUDA_H(cudaEventRecord(h->ev_fwd_ready, st));
+  FUS_CUDA_H(cudaStreamWaitEvent(h->comm_stream, h->ev_fwd_ready, 0));
+  int r = halo_forward(h, a, b, h->comm_stream);
+  if (r != FUS_OK)
+    return r;
+  FUS_CUDA_H(cudaEventRecord(h->ev_fwd_done, h->comm_stream));
+  return FUS_OK;
+}
+
+int halo_forward_end(Halo* h, cudaStream_t st) {
+  if (h->neigh.empty() || !h->overlap)
+    return FUS_OK;
+  FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_fwd_done, 0));
   return FUS_OK;
 }
 

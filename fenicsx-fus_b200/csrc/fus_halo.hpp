@@ -22,6 +22,11 @@ long long halo_interface_cells(const Halo* h);
 int halo_forward(Halo* h, double* a, double* b, cudaStream_t st);
 // ghost -> owner (add) for one or two vectors; complete in stream order on `st`
 int halo_reverse(Halo* h, double* a, double* b, cudaStream_t st);
+// split forward update: begin after the producer of a/b on `st`; the exchange runs on the halo's
+// own high-priority stream while `st` continues with cells that touch no shared dof; end joins.
+int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st);
+int halo_forward_end(Halo* h, cudaStream_t st);
+int halo_overlap(const Halo* h);
 // split form: begin after the interface cells have been applied on `st`; the exchange runs on the
 // halo's own stream while `st` continues with interior cells; end joins it back into `st`.
 int halo_reverse_begin(Halo* h, double* a, cudaStream_t st);
