@@ -22,7 +22,7 @@ if [ $BRC -eq 0 ] && [ "${SKIP_NCU:-0}" != "1" ]; then
       --log-file $OUT/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_list_${TAG}.log 2>&1
   echo "ncu list exit $?"
   echo "== ncu full (stiffness kernel)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:stiffness_col -s 4 -c 2 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:stiffness_line -s 4 -c 2 \
       -f -o $OUT/prof_stiffness_${TAG} python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_${TAG}.log 2>&1
   echo "ncu full exit $?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:rk4_stage -s 4 -c 2 \
