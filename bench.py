@@ -56,55 +56,60 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region, polled through NVML every ~2 ms from
+    a thread (nvidia-smi's own loop is too coarse for a 30 ms region); falls back to one
+    nvidia-smi query when NVML is unavailable."""
+    HW, HW_THERM, SW_THERM, SW_POWER = 0x8, 0x40, 0x20, 0x4
 
     def __init__(self, index=0):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reason_bits = index, [], 0
+        self.stop_flag = threading.Event()
+        self.thread, self.h, self.nv, self.max_mhz = None, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-less boxes: local index == NVML index on the gpurun pods
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+        except Exception:
+            self.nv = None
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [s.strip() for s in ln.split(",")]
-            if len(f) < 7:
-                continue
+        if self.nv is None:
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}",
+                     "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1,
+                        "reasons": [], "source": "nvidia-smi after the timed region (NVML unavailable)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0,
+                        "reasons": ["clock query unavailable"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        reasons = [nm for nm, bit in (("hw_slowdown", self.HW), ("hw_thermal_slowdown", self.HW_THERM),
+                                      ("sw_thermal_slowdown", self.SW_THERM),
+                                      ("sw_power_cap", self.SW_POWER)) if self.reason_bits & bit]
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(self.samples), "reasons": reasons,
+                "source": "NVML polled every 2 ms during the timed region"}
 
 
 # --------------------------------------------------------------------------------------------

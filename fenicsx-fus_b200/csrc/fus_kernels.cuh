@@ -206,10 +206,12 @@ __global__ void __launch_bounds__(ColCfg<N>::THREADS)
 #pragma unroll
     for (int i0 = 0; i0 < N; ++i0) {
       double f1 = 0.0, f2 = 0.0;
+      if (lane_ok) { // padding lanes must not load either: aliased addresses cost bank conflicts
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        f1 = fma(D1[k], xs[i0 * PL + k * NS + i2], f1);
-        f2 = fma(D2[k], xs[i0 * PL + i1 * NS + k], f2);
+        for (int k = 0; k < N; ++k) {
+          f1 = fma(D1[k], xs[i0 * PL + k * NS + i2], f1);
+          f2 = fma(D2[k], xs[i0 * PL + i1 * NS + k], f2);
+        }
       }
       const double2 ga = g[i0][0], gb = g[i0][1], gc = g[i0][2];
       // stiffness::transform (spectral_op.hpp:113-130)
@@ -238,14 +240,15 @@ __global__ void __launch_bounds__(ColCfg<N>::THREADS)
     // (c) transposed directions 1,2 and scatter-add
 #pragma unroll
     for (int j0 = 0; j0 < N; ++j0) {
-      double acc = yv[j0];
+      if (valid) {
+        double acc = yv[j0];
 #pragma unroll
-      for (int q = 0; q < N; ++q) {
-        acc = fma(DT1[q], s1[j0 * PL + q * NS + i2], acc);
-        acc = fma(DT2[q], s2[j0 * PL + i1 * NS + q], acc);
-      }
-      if (valid)
+        for (int q = 0; q < N; ++q) {
+          acc = fma(DT1[q], s1[j0 * PL + q * NS + i2], acc);
+          acc = fma(DT2[q], s2[j0 * PL + i1 * NS + q], acc);
+        }
         atomicAdd(y + idx[j0], acc);
+      }
     }
 
     // rotate the pipeline
@@ -425,8 +428,10 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     }
     sync();
 
-    // (2) direction-1 and direction-2 derivatives along the thread's own lines (layouts B, C)
-    {
+    // (2) direction-1 and direction-2 derivatives along the thread's own lines (layouts B, C).
+    // Padding lanes are predicated off for loads too: their aliased addresses would add bank
+    // conflicts (ncu: 3-4 wavefronts per LDS.64 instead of 2).
+    if (lane_ok) {
       double l[N];
 #pragma unroll
       for (int k = 0; k < N; ++k)
@@ -437,8 +442,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 #pragma unroll
         for (int k = 0; k < N; ++k)
           s = fma(D.d[q * N + k], l[k], s);
-        if (lane_ok)
-          S1B[q * C::B1_S1] = s;
+        S1B[q * C::B1_S1] = s;
       }
 #pragma unroll
       for (int k = 0; k < N; ++k)
@@ -449,8 +453,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 #pragma unroll
         for (int k = 0; k < N; ++k)
           s = fma(D.d[q * N + k], l[k], s);
-        if (lane_ok)
-          S2C[q] = s;
+        S2C[q] = s;
       }
     }
     sync();
@@ -464,7 +467,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     const double2* gpn = G2 + cn * (3 * N * NN) + t;
 #pragma unroll
     for (int i0 = 0; i0 < N; ++i0) {
-      const double f1 = S1A[i0 * C::B1_S0], f2 = S2A[i0 * C::B2_S0];
+      double f1 = 0.0, f2 = 0.0;
+      if (lane_ok) {
+        f1 = S1A[i0 * C::B1_S0];
+        f2 = S2A[i0 * C::B2_S0];
+      }
       const double2 ga = g[i0 % GPF][0], gb = g[i0 % GPF][1], gc = g[i0 % GPF][2];
       const double t0 = cfc * (ga.x * f0[i0] + ga.y * f1 + gb.x * f2);
       const double t1 = cfc * (ga.y * f0[i0] + gb.y * f1 + gc.x * f2);
@@ -492,7 +499,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     sync();
 
     // (4) transposed direction 1 and 2 along the thread's own lines, results back in place
-    {
+    if (lane_ok) {
       double l[N];
 #pragma unroll
       for (int q = 0; q < N; ++q)
@@ -503,8 +510,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 #pragma unroll
         for (int q = 0; q < N; ++q)
           s = fma(D.d[q * N + j], l[q], s);
-        if (lane_ok)
-          S1B[j * C::B1_S1] = s;
+        S1B[j * C::B1_S1] = s;
       }
 #pragma unroll
       for (int q = 0; q < N; ++q)
@@ -515,8 +521,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 #pragma unroll
         for (int q = 0; q < N; ++q)
           s = fma(D.d[q * N + j], l[q], s);
-        if (lane_ok)
-          S2C[j] = s;
+        S2C[j] = s;
       }
     }
     sync();
@@ -524,9 +529,10 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     // (5) sum the three contributions in layout A and scatter-add
 #pragma unroll
     for (int j0 = 0; j0 < N; ++j0) {
-      const double acc = yv[j0] + S1A[j0 * C::B1_S0] + S2A[j0 * C::B2_S0];
-      if (valid)
+      if (valid) {
+        const double acc = yv[j0] + S1A[j0 * C::B1_S0] + S2A[j0 * C::B2_S0];
         atomicAdd(y + idx[j0], acc);
+      }
     }
 
 #pragma unroll
