@@ -83,6 +83,7 @@ struct fus_ctx {
   int col_blocks_per_sm = 0;
   int reserve_sms = 0;      // SMs left free for the halo kernels while cells overlap with them
   int halo_reserve = 4;     // value of reserve_sms used inside a partitioned stage
+  int l2_persist = 0;       // keep the rhs accumulator b resident in L2 during rk4 (option)
   Halo* halo = nullptr;
   // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
   bool profile = false;
@@ -353,6 +354,8 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
     if (v >= -1 && v <= 2)
       c->variant = v;
   }
+  if (const char* e = std::getenv("FUS_L2_PERSIST"))
+    c->l2_persist = std::atoi(e) != 0;
   *out = c;
   FUS_CUDA(cudaSetDevice(device));
   FUS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -537,6 +540,10 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   }
   if (!std::strcmp(name, "col_blocks_per_sm")) {
     c->col_blocks_per_sm = value;
+    return FUS_OK;
+  }
+  if (!std::strcmp(name, "l2_persist")) {
+    c->l2_persist = value != 0;
     return FUS_OK;
   }
   if (!std::strcmp(name, "halo_reserve_sms")) {
@@ -1010,6 +1017,28 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   A.nowned = c->nowned;
   A.ntotal = c->ndofs;
   FUS_CUDA(cudaMemsetAsync(m->d_b, 0, sizeof(double) * c->ndofs, c->stream));
+  // Optional: pin b in the persisting part of the 126 MB L2.  b is RED-accumulated by the operator,
+  // read and zeroed by the epilogue, 4x per step; resident, it never crosses HBM.
+  bool l2_window = false;
+  if (c->l2_persist) {
+    cudaDeviceProp prop;
+    FUS_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    const size_t want = sizeof(double) * (size_t)c->ndofs;
+    const size_t set_aside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, want);
+    const size_t window = std::min<size_t>((size_t)prop.accessPolicyMaxWindowSize, want);
+    if (set_aside > 0 && window > 0) {
+      FUS_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+      cudaStreamAttrValue av;
+      std::memset(&av, 0, sizeof(av));
+      av.accessPolicyWindow.base_ptr = m->d_b;
+      av.accessPolicyWindow.num_bytes = window;
+      av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)window);
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      FUS_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+      l2_window = true;
+    }
+  }
   if (c->halo)
     FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
   while (t < tf) {
@@ -1036,6 +1065,12 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   }
   if (c->halo) // u_n, v_n leave with fresh ghosts (Linear.hpp:312-313)
     FUS_TRY(halo_forward_end(c->halo, c->stream));
+  if (l2_window) {
+    cudaStreamAttrValue av;
+    std::memset(&av, 0, sizeof(av));
+    FUS_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    FUS_CUDA(cudaCtxResetPersistingL2Cache());
+  }
   if (nsteps)
     *nsteps = step;
   return FUS_OK;
