@@ -224,8 +224,12 @@ def run_gpu_arm(args):
     ctx = V.context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    transport = "none"
     if world > 1:
         part.setup_halo(ctx, dist)
+        transport = "nccl send/recv"
+        if os.environ.get("FUS_HALO_TRANSPORT", "peer") == "peer" and part.connect_peers(ctx, dist):
+            transport = "peer-direct puts over NVLink (CUDA IPC), NCCL for set-up reductions"
     mdl = fus.LinearSpectral3D(V, C0, RHO0, FREQ, P0, C0, facets=part.facets, device=local_rank)
     dt = timestep(P, h, C0)
     ndofs_global = part.ndofs_global
@@ -251,7 +255,9 @@ def run_gpu_arm(args):
     launches0 = fus.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    t_enq0 = time.perf_counter()
     done = mdl.rk4(t, t + (K - 0.5) * dt, dt)
+    host_enqueue_ms = 1e3 * (time.perf_counter() - t_enq0)
     ev1.record(stream)
     sync_all()
     launches = fus.launch_count() - launches0
@@ -350,7 +356,7 @@ def run_gpu_arm(args):
                    "cells_per_gpu": part.ncells, "dofs_global": ndofs_global,
                    "process_grid": list(pg), "dt": dt,
                    "l2": f"inputs_exceed_l2 ({48e-6 * npts_loc:.0f} MB of geometric factors streamed per stage)",
-                   "parallelism": f"mesh partition {pg[0]}x{pg[1]}x{pg[2]}, NCCL halo"},
+                   "parallelism": f"mesh partition {pg[0]}x{pg[1]}x{pg[2]}", "halo": transport},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state / K,
                 "d2h_bytes_per_step": bytes_state / K,
@@ -359,7 +365,7 @@ def run_gpu_arm(args):
                          "reference's rk4 loop"),
                 "wall_s": wall_e2e,
                 "roundtrip_every_step_value": roundtrip_value},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms / K,
         "roofline": {"bound": "hbm", "kernel": f"stiffness_line_kernel<{P + 1},false>",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "launches": int(n_st),

@@ -66,6 +66,8 @@ SIGNATURES = {
     "fus_ctx_profile": (_int, [_p, C.c_char_p, C.POINTER(_ll), C.POINTER(_dbl)]),
     "fus_comm_unique_id": (_int, [_p]),
     "fus_halo_setup": (_int, [_p, _int, _int, _p, _int, _p, _p, _p, _p, _p, _ll]),
+    "fus_halo_peer_export": (_int, [_p, _p, _p]),
+    "fus_halo_peer_connect": (_int, [_p, _p, _p]),
     "fus_scatter_fwd_dev": (_int, [_p, _p]),
     "fus_scatter_rev_dev": (_int, [_p, _p]),
 }

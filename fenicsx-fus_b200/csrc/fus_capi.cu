@@ -560,12 +560,20 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   return FUS_ERR_ARG;
 }
 
+static int check_peer_error(fus_ctx* c) {
+  if (c->halo && halo_peer_error(c->halo)) {
+    set_error("halo exchange timed out waiting for a neighbour (peer transport)");
+    return FUS_ERR_COMM;
+  }
+  return FUS_OK;
+}
+
 int fus_ctx_sync(fus_ctx* c) {
   if (!c)
     return FUS_ERR_ARG;
   FUS_TRY(select_device(c));
   FUS_CUDA(cudaStreamSynchronize(c->stream));
-  return FUS_OK;
+  return check_peer_error(c);
 }
 
 int fus_ctx_profile(fus_ctx* c, const char* kernel, int64_t* launches, double* total_ms) {
@@ -852,7 +860,7 @@ int fus_model_get_state(fus_model* m, double* u, double* v) {
   if (v)
     FUS_CUDA(cudaMemcpyAsync(v, m->d_v0, vb, cudaMemcpyDeviceToHost, c->stream));
   FUS_CUDA(cudaStreamSynchronize(c->stream));
-  return FUS_OK;
+  return check_peer_error(c);
 }
 
 int fus_model_state_dev(fus_model* m, double** u, double** v) {
@@ -928,10 +936,10 @@ static int assemble_rhs(fus_model* m, double t, const double* u, const double* v
   const bool ov = halo_overlap(c->halo) != 0;
   const long long ni = halo_interface_cells(c->halo);
   const long long mid = ov ? ni + (c->ncells - ni) / 2 : c->ncells;
-  c->reserve_sms = ov ? c->halo_reserve : 0;
+  c->reserve_sms = (halo_mode(c->halo) == 1) ? c->halo_reserve : 0;
   int rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, mid, c->stream);
   if (rc == FUS_OK && fwd_pending)
-    rc = halo_forward_end(c->halo, c->stream);
+    rc = halo_forward_end(c->halo, const_cast<double*>(u), const_cast<double*>(v), c->stream);
   if (rc == FUS_OK)
     rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, ni, c->stream);
   if (rc == FUS_OK)
@@ -1064,7 +1072,7 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
     step += 1;
   }
   if (c->halo) // u_n, v_n leave with fresh ghosts (Linear.hpp:312-313)
-    FUS_TRY(halo_forward_end(c->halo, c->stream));
+    FUS_TRY(halo_forward_end(c->halo, m->d_u0, m->d_v0, c->stream));
   if (l2_window) {
     cudaStreamAttrValue av;
     std::memset(&av, 0, sizeof(av));
@@ -1092,8 +1100,31 @@ int fus_halo_setup(fus_ctx* c, int rank, int nranks, const void* uid, int nneigh
     halo_destroy(c->halo);
     c->halo = nullptr;
   }
-  return halo_create(&c->halo, c->device, rank, nranks, uid, nneigh, neigh, send_off, send_idx,
-                     recv_off, recv_idx, c->nowned, c->ndofs, ninterface_cells);
+  int rc = halo_create(&c->halo, c->device, rank, nranks, uid, nneigh, neigh, send_off, send_idx,
+                       recv_off, recv_idx, c->nowned, c->ndofs, ninterface_cells);
+  if (rc == FUS_OK) { // experiment knobs
+    if (const char* e = std::getenv("FUS_HALO_OVERLAP"))
+      halo_set_overlap(c->halo, std::atoi(e));
+    if (const char* e = std::getenv("FUS_HALO_RESERVE"))
+      c->halo_reserve = std::max(0, std::min(c->num_sms - 1, std::atoi(e)));
+  }
+  return rc;
+}
+
+int fus_halo_peer_export(fus_ctx* c, void* ipc_handle64, int64_t* layout3) {
+  if (!c || !c->halo) {
+    set_error("fus_halo_peer_export: call fus_halo_setup first");
+    return FUS_ERR_STATE;
+  }
+  FUS_TRY(select_device(c));
+  return halo_peer_export(c->halo, ipc_handle64, layout3);
+}
+
+int fus_halo_peer_connect(fus_ctx* c, const void* handles, const int64_t* byte_off) {
+  if (!c || !c->halo)
+    return FUS_ERR_STATE;
+  FUS_TRY(select_device(c));
+  return halo_peer_connect(c->halo, handles, byte_off);
 }
 
 int fus_scatter_fwd_dev(fus_ctx* c, double* x) {

@@ -99,9 +99,27 @@ struct Halo {
   int32_t *d_send_idx = nullptr, *d_recv_idx = nullptr;
   double *d_sbuf = nullptr, *d_rbuf = nullptr; // 2 vectors deep
   int64_t nowned = 0, ndofs = 0, ninterface = 0;
-  int overlap = 1;
+  int overlap = 0; // NCCL on a side stream: measured slower than in-order beyond 2 ranks (profiles/)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_fwd_ready = nullptr, ev_fwd_done = nullptr;
+  // ---- peer-direct transport: one-sided puts into the neighbours' mailboxes over NVLink ----
+  // mailbox = [fwd data: 2*nrecv doubles][rev data: nsend doubles][fwd flags][rev flags]
+  bool peer = false;
+  char* d_mbox = nullptr;
+  size_t off_rev = 0, off_fflag = 0, off_rflag = 0, mbox_bytes = 0;
+  std::vector<void*> peer_base;              // opened mailboxes (one per neighbour)
+  struct PeerTable* d_tab = nullptr;         // device copy of the per-neighbour destination table
+  unsigned int* d_counter = nullptr;         // block-completion counters (fwd, rev)
+  int* d_error = nullptr;
+  unsigned long long epoch_fwd = 0, epoch_rev = 0;
+};
+
+constexpr int kMaxNeigh = 26;
+struct PeerTable {
+  double* fwd_dst[kMaxNeigh];               // where my packed owner values go on neighbour k
+  double* rev_dst[kMaxNeigh];               // where my ghost partial sums go on neighbour k
+  unsigned long long* fwd_flag[kMaxNeigh];  // flag on neighbour k that I raise after a forward put
+  unsigned long long* rev_flag[kMaxNeigh];
 };
 
 int halo_unique_id(void* id128) {
@@ -183,6 +201,13 @@ void halo_destroy(Halo* h) {
     cudaStreamSynchronize(h->comm_stream);
   if (h->comm && g_nccl.CommDestroy)
     g_nccl.CommDestroy(h->comm);
+  for (void* pb : h->peer_base)
+    if (pb)
+      cudaIpcCloseMemHandle(pb);
+  cudaFree(h->d_mbox);
+  cudaFree(h->d_tab);
+  cudaFree(h->d_counter);
+  cudaFree(h->d_error);
   cudaFree(h->d_send_idx);
   cudaFree(h->d_recv_idx);
   cudaFree(h->d_sbuf);
@@ -201,8 +226,11 @@ void halo_destroy(Halo* h) {
 }
 
 void halo_set_overlap(Halo* h, int on) { h->overlap = on; }
-int halo_overlap(const Halo* h) { return h->overlap; }
-long long halo_interface_cells(const Halo* h) { return h->overlap ? h->ninterface : 0; }
+int halo_overlap(const Halo* h) { return h->overlap || h->peer; }
+int halo_mode(const Halo* h) { return h->peer ? 2 : (h->overlap ? 1 : 0); }
+long long halo_interface_cells(const Halo* h) {
+  return (h->overlap || h->peer) ? h->ninterface : 0;
+}
 
 // One grouped exchange.  `fwd`: owners send send_idx entries, ghosts receive; otherwise reversed.
 // nv vectors are concatenated per neighbour: [neighbour k][vector][entry].
@@ -304,9 +332,214 @@ int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
   return FUS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-direct transport.  A put kernel gathers the interface values and stores them straight into
+// the neighbours' mailboxes (IPC-mapped peer memory, NVLink); the last block to finish raises one
+// epoch flag per neighbour with system-scope release ordering.  The receiving side's wait kernel
+// spins on its own flags (acquire, bounded), then unpacks with L1-bypassing loads.
+// Puts are one-sided, so they are issued as early as possible and the waits as late as possible:
+// the cells that touch no shared dof run in between on the same stream.
+// A mailbox segment is never overwritten before it is consumed because every exchanging pair
+// alternates forward (owner -> ghost) and reverse (ghost -> owner) messages: the owner cannot put
+// stage s+1 before it has received the reverse message of stage s, which the ghost side only
+// sends after it has unpacked the forward message of stage s (and symmetrically).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+    peer_put_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                    const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
+                    long long n, int nv, const PeerTable* __restrict__ tab, int forward,
+                    unsigned int* counter, unsigned long long epoch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int k = 0;
+    while (k + 1 < nneigh && i >= off[k + 1])
+      ++k;
+    const long long len = off[k + 1] - off[k], j = i - off[k];
+    double* dst = forward ? tab->fwd_dst[k] : tab->rev_dst[k];
+    const int d = idx[i];
+    dst[j] = a[d];
+    if (nv == 2)
+      dst[len + j] = b[d];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) { // every block's stores are fenced before its increment
+      *counter = 0;
+      __threadfence_system();
+      for (int k = 0; k < nneigh; ++k)
+        if (off[k + 1] > off[k])
+          st_release_sys(forward ? tab->fwd_flag[k] : tab->rev_flag[k], epoch);
+    }
+  }
+}
+
+template <bool ADD>
+__global__ void __launch_bounds__(256)
+    peer_wait_kernel(double* __restrict__ a, double* __restrict__ b,
+                     const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
+                     long long n, int nv, const double* mbox_data,
+                     const unsigned long long* flags, unsigned long long epoch, int* error) {
+  if (threadIdx.x < nneigh && off[threadIdx.x + 1] > off[threadIdx.x]) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+      if (clock64() - t0 > 4000000000ll) { // ~2 s: a peer died; report instead of hanging the GPU
+        atomicExch(error, 1);
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  int k = 0;
+  while (k + 1 < nneigh && i >= off[k + 1])
+    ++k;
+  const long long base = nv * off[k], len = off[k + 1] - off[k], j = i - off[k];
+  const int d = idx[i];
+  const double va = __ldcg(mbox_data + base + j); // written by a peer: never trust L1
+  if (ADD) {
+    atomicAdd(a + d, va);
+  } else {
+    a[d] = va;
+    if (nv == 2)
+      b[d] = __ldcg(mbox_data + base + len + j);
+  }
+}
+
+static int peer_put(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
+  if (fwd && !b) {
+    set_error("peer transport: the forward update always carries two vectors");
+    return FUS_ERR_ARG;
+  }
+  const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
+  OffTables& T = tables(h);
+  const long long n = fwd ? h->nsend : h->nrecv;
+  unsigned long long& epoch = fwd ? h->epoch_fwd : h->epoch_rev;
+  ++epoch;
+  if (n == 0)
+    return FUS_OK;
+  peer_put_kernel<<<blocks_for(n), 256, 0, st>>>(a, b, fwd ? h->d_send_idx : h->d_recv_idx,
+                                                 fwd ? T.d_soff : T.d_roff, nn, n, nv, h->d_tab,
+                                                 fwd ? 1 : 0, h->d_counter + (fwd ? 0 : 1), epoch);
+  FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
+static int peer_wait(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
+  const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
+  OffTables& T = tables(h);
+  const long long n = fwd ? h->nrecv : h->nsend;
+  const unsigned long long epoch = fwd ? h->epoch_fwd : h->epoch_rev;
+  if (n == 0)
+    return FUS_OK;
+  const double* data = (const double*)(h->d_mbox + (fwd ? 0 : h->off_rev));
+  const unsigned long long* flags
+      = (const unsigned long long*)(h->d_mbox + (fwd ? h->off_fflag : h->off_rflag));
+  if (fwd)
+    peer_wait_kernel<false><<<blocks_for(n), 256, 0, st>>>(a, b, h->d_recv_idx, T.d_roff, nn, n,
+                                                           nv, data, flags, epoch, h->d_error);
+  else
+    peer_wait_kernel<true><<<blocks_for(n), 256, 0, st>>>(a, nullptr, h->d_send_idx, T.d_soff, nn,
+                                                          n, 1, data, flags, epoch, h->d_error);
+  FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
+int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3) {
+  if (!h || !ipc_handle64 || !layout3)
+    return FUS_ERR_ARG;
+  if ((int)h->neigh.size() > kMaxNeigh) {
+    set_error("peer transport supports at most %d neighbours", kMaxNeigh);
+    return FUS_ERR_UNSUPPORTED;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  FUS_CUDA_H(cudaSetDevice(h->device));
+  if (!h->d_mbox) {
+    const size_t nn = std::max<size_t>(1, h->neigh.size());
+    h->off_rev = sizeof(double) * 2 * (size_t)std::max<int64_t>(1, h->nrecv);
+    h->off_fflag = h->off_rev + sizeof(double) * (size_t)std::max<int64_t>(1, h->nsend);
+    h->off_rflag = h->off_fflag + sizeof(unsigned long long) * nn;
+    h->mbox_bytes = h->off_rflag + sizeof(unsigned long long) * nn;
+    FUS_CUDA_H(cudaMalloc(&h->d_mbox, h->mbox_bytes));
+    FUS_CUDA_H(cudaMemset(h->d_mbox, 0, h->mbox_bytes));
+    FUS_CUDA_H(cudaMalloc(&h->d_counter, 2 * sizeof(unsigned int)));
+    FUS_CUDA_H(cudaMemset(h->d_counter, 0, 2 * sizeof(unsigned int)));
+    FUS_CUDA_H(cudaMalloc(&h->d_error, sizeof(int)));
+    FUS_CUDA_H(cudaMemset(h->d_error, 0, sizeof(int)));
+    FUS_CUDA_H(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t hd;
+  FUS_CUDA_H(cudaIpcGetMemHandle(&hd, h->d_mbox));
+  std::memcpy(ipc_handle64, &hd, sizeof(hd));
+  layout3[0] = (int64_t)h->off_rev;
+  layout3[1] = (int64_t)h->off_fflag;
+  layout3[2] = (int64_t)h->off_rflag;
+  return FUS_OK;
+}
+
+// handles: one 64-byte IPC handle per neighbour (same order as the neighbour list);
+// byte_off[k][4]: byte offsets inside neighbour k's mailbox of {my forward data segment, my forward
+// flag, my reverse data segment, my reverse flag}.  The caller derives them from the layout triple
+// that halo_peer_export returned on that neighbour and from its offset tables:
+//   fwd data  = 8 * 2 * recv_off_q[j]            fwd flag = off_fflag_q + 8 * j
+//   rev data  = off_rev_q + 8 * send_off_q[j]    rev flag = off_rflag_q + 8 * j
+// with j = this rank's position in neighbour q's neighbour list.
+int halo_peer_connect(Halo* h, const void* handles, const int64_t* byte_off) {
+  if (!h || !h->d_mbox || (!h->neigh.empty() && (!handles || !byte_off))) {
+    set_error("halo_peer_connect: export first, then pass the neighbours' handles and offsets");
+    return FUS_ERR_ARG;
+  }
+  FUS_CUDA_H(cudaSetDevice(h->device));
+  const size_t nn = h->neigh.size();
+  PeerTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  h->peer_base.assign(nn, nullptr);
+  for (size_t k = 0; k < nn; ++k) {
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, (const char*)handles + 64 * k, sizeof(hd));
+    void* base = nullptr;
+    FUS_CUDA_H(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_base[k] = base;
+    char* cb = (char*)base;
+    tab.fwd_dst[k] = (double*)(cb + byte_off[4 * k + 0]);
+    tab.fwd_flag[k] = (unsigned long long*)(cb + byte_off[4 * k + 1]);
+    tab.rev_dst[k] = (double*)(cb + byte_off[4 * k + 2]);
+    tab.rev_flag[k] = (unsigned long long*)(cb + byte_off[4 * k + 3]);
+  }
+  if (!h->d_tab)
+    FUS_CUDA_H(cudaMalloc(&h->d_tab, sizeof(PeerTable)));
+  FUS_CUDA_H(cudaMemcpy(h->d_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice));
+  h->peer = true;
+  return FUS_OK;
+}
+
+int halo_peer_error(Halo* h) {
+  if (!h || !h->d_error)
+    return 0;
+  int e = 0;
+  if (cudaMemcpy(&e, h->d_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return 1;
+  return e;
+}
+
 int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
   if (h->neigh.empty())
     return FUS_OK;
+  if (h->peer)
+    return peer_put(h, true, a, b, st);
   if (!h->overlap)
     return halo_forward(h, a, b, st);
   FUS_CUDA_H(cudaEventRecord(h->ev_fwd_ready, st));
@@ -318,8 +551,12 @@ int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
   return FUS_OK;
 }
 
-int halo_forward_end(Halo* h, cudaStream_t st) {
-  if (h->neigh.empty() || !h->overlap)
+int halo_forward_end(Halo* h, double* a, double* b, cudaStream_t st) {
+  if (h->neigh.empty())
+    return FUS_OK;
+  if (h->peer)
+    return peer_wait(h, true, a, b, st);
+  if (!h->overlap)
     return FUS_OK;
   FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_fwd_done, 0));
   return FUS_OK;
@@ -350,6 +587,8 @@ int halo_reverse(Halo* h, double* a, double* b, cudaStream_t st) {
 int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
   if (h->neigh.empty())
     return FUS_OK;
+  if (h->peer)
+    return peer_put(h, false, a, nullptr, st);
   if (!h->overlap)
     return FUS_OK; // whole exchange happens in _end, after all cells
   FUS_CUDA_H(cudaEventRecord(h->ev_ready, st));
@@ -364,6 +603,8 @@ int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
 int halo_reverse_end(Halo* h, double* a, cudaStream_t st) {
   if (h->neigh.empty())
     return FUS_OK;
+  if (h->peer)
+    return peer_wait(h, false, a, nullptr, st);
   if (!h->overlap)
     return reverse_on(h, a, nullptr, st);
   FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_done, 0));

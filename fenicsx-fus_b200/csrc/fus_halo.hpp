@@ -25,8 +25,15 @@ int halo_reverse(Halo* h, double* a, double* b, cudaStream_t st);
 // split forward update: begin after the producer of a/b on `st`; the exchange runs on the halo's
 // own high-priority stream while `st` continues with cells that touch no shared dof; end joins.
 int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st);
-int halo_forward_end(Halo* h, cudaStream_t st);
+int halo_forward_end(Halo* h, double* a, double* b, cudaStream_t st);
 int halo_overlap(const Halo* h);
+// modes: 0 NCCL in stream order, 1 NCCL on a side stream (overlapped), 2 peer-direct one-sided puts
+int halo_mode(const Halo* h);
+// peer-direct transport: export this rank's mailbox, then connect to the neighbours' mailboxes
+int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3);
+int halo_peer_connect(Halo* h, const void* handles, const int64_t* byte_off);
+// 0 when no peer wait has timed out since creation
+int halo_peer_error(Halo* h);
 // split form: begin after the interface cells have been applied on `st`; the exchange runs on the
 // halo's own stream while `st` continues with interior cells; end joins it back into `st`.
 int halo_reverse_begin(Halo* h, double* a, cudaStream_t st);

@@ -216,6 +216,40 @@ class BoxPartition:
                                       p(neigh), p(soff), p(sidx), p(roff), p(ridx),
                                       self.ninterface_cells), "fus_halo_setup")
 
+    def connect_peers(self, ctx, dist):
+        """Switch the context's in-loop exchanges to the peer-direct transport: every rank exports
+        its mailbox (CUDA IPC handle + layout), all ranks gather them, each rank opens its
+        neighbours' mailboxes.  Returns False (and leaves NCCL in place) if IPC is unavailable."""
+        lib = capi.load()
+        handle = np.zeros(64, dtype=np.uint8)
+        layout = np.zeros(3, dtype=np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = lib.fus_halo_peer_export(ctx.h, p(handle), p(layout))
+        neigh, soff, _, roff, _ = self.halo_arrays()
+        mine = dict(ok=(rc == 0), handle=handle.tobytes(), layout=layout.tolist(),
+                    neigh=[int(q) for q in neigh], soff=soff.tolist(), roff=roff.tolist())
+        allinfo = [None] * self.nranks
+        dist.all_gather_object(allinfo, mine)
+        if not all(i["ok"] for i in allinfo):
+            return False
+        nn = len(self.neigh)
+        handles = np.zeros((max(nn, 1), 64), dtype=np.uint8)
+        boff = np.zeros((max(nn, 1), 4), dtype=np.int64)
+        for k, q in enumerate(self.neigh):
+            info = allinfo[q]
+            j = info["neigh"].index(self.rank)
+            off_rev, off_fflag, off_rflag = info["layout"]
+            handles[k] = np.frombuffer(info["handle"], dtype=np.uint8)
+            boff[k] = (8 * 2 * info["roff"][j], off_fflag + 8 * j,
+                       off_rev + 8 * info["soff"][j], off_rflag + 8 * j)
+        rc = lib.fus_halo_peer_connect(ctx.h, p(handles), p(boff))
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, rc == 0)
+        if not all(flags):
+            raise capi.FusError("peer transport connected on some ranks only: "
+                                + lib.fus_last_error().decode(errors="replace"))
+        return True
+
     # ---- host-side halo (CPU tests over gloo; the device path is fus_halo.cu) -----------------
     def scatter_fwd_host(self, dist, x):
         import torch

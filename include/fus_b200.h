@@ -188,6 +188,16 @@ int fus_comm_unique_id(void* id128);
 int fus_halo_setup(fus_ctx* ctx, int rank, int nranks, const void* nccl_unique_id, int nneigh,
                    const int* neigh, const int64_t* send_off, const int32_t* send_idx,
                    const int64_t* recv_off, const int32_t* recv_idx, int64_t ninterface_cells);
+/* Optional peer-direct transport for the exchanges inside fus_model_rk4 (after fus_halo_setup):
+ * one-sided stores into the neighbours' mailboxes over NVLink peer memory instead of NCCL
+ * send/recv.  Export this rank's mailbox (64-byte cudaIpcMemHandle_t + its layout triple
+ * {off_rev, off_fflag, off_rflag} in bytes), distribute both, then connect with one handle per
+ * neighbour and byte_off[nneigh][4] = offsets inside neighbour q's mailbox of
+ *   {8*2*recv_off_q[j], off_fflag_q + 8*j, off_rev_q + 8*send_off_q[j], off_rflag_q + 8*j}
+ * where j is this rank's position in q's neighbour list. */
+int fus_halo_peer_export(fus_ctx* ctx, void* ipc_handle64, int64_t* layout3);
+int fus_halo_peer_connect(fus_ctx* ctx, const void* handles, const int64_t* byte_off);
+
 /* Stand-alone collectives on device vectors (tests): owner -> ghost, ghost -> owner (+=). */
 int fus_scatter_fwd_dev(fus_ctx* ctx, double* x);
 int fus_scatter_rev_dev(fus_ctx* ctx, double* x);

@@ -77,8 +77,14 @@ def main():
     u0 = 1e5 * np.sin(0.013 * key) + 3.0
     v0 = 1e11 * np.cos(0.007 * key)
     results = {}
-    for overlap in (1, 0):
-        ctx.set_option("halo_overlap", overlap)
+    for overlap in (1, 0, "peer"):
+        if overlap == "peer":
+            # one-sided puts into the neighbours' mailboxes (CUDA IPC peer memory)
+            report["peer_connected"] = bool(part.connect_peers(ctx, dist))
+            if not report["peer_connected"]:
+                break
+        else:
+            ctx.set_option("halo_overlap", overlap)
         for kind in ("linear", "lossy", "westervelt"):
             if kind == "linear":
                 mdl = fus.LinearSpectral3D(V, c0, rho0, f, p0, s0, facets=part.facets, device=local)
@@ -118,7 +124,9 @@ def main():
                            f, p0, s0)
             u, v = 1e5 * np.sin(0.013 * keyg) + 3.0, 1e11 * np.cos(0.007 * keyg)
             steps = om.rk4(0.0, 10 * dt - 0.3 * dt, dt, u, v)
-            for overlap in (1, 0):
+            for overlap in (1, 0, "peer"):
+                if (kind, overlap) not in gathered[0][1]:
+                    continue
                 gu, gv, gm = np.zeros(nd), np.zeros(nd), np.zeros(nd)
                 for keys, res, _ in gathered:
                     st, uu, vv, mm = res[(kind, overlap)]
@@ -131,6 +139,8 @@ def main():
                 if not (eu < 1e-10 and ev < 1e-10 and em < 1e-12):
                     status = 1
         if not all(s["scatter_fwd_exact"] and s["scatter_rev_exact"] for s in out["scatter"]):
+            status = 1
+        if not all(s.get("peer_connected") for s in out["scatter"]):
             status = 1
         out["status"] = "ok" if status == 0 else "FAILED"
         print(json.dumps(out), flush=True)
