@@ -313,6 +313,8 @@ def run_gpu_arm(args):
     roundtrip_value = ndofs_global * kr / (time.perf_counter() - t_r0)
 
     if rank != 0:
+        mdl.destroy()
+        ctx.destroy()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -376,6 +378,8 @@ def run_gpu_arm(args):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+    mdl.destroy()
+    ctx.destroy()
     if world > 1:
         dist.destroy_process_group()
     return 0

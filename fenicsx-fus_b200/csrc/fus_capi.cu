@@ -936,7 +936,7 @@ static int assemble_rhs(fus_model* m, double t, const double* u, const double* v
   const bool ov = halo_overlap(c->halo) != 0;
   const long long ni = halo_interface_cells(c->halo);
   const long long mid = ov ? ni + (c->ncells - ni) / 2 : c->ncells;
-  c->reserve_sms = (halo_mode(c->halo) == 1) ? c->halo_reserve : 0;
+  c->reserve_sms = (halo_mode(c->halo) >= 1) ? c->halo_reserve : 0;
   int rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, mid, c->stream);
   if (rc == FUS_OK && fwd_pending)
     rc = halo_forward_end(c->halo, const_cast<double*>(u), const_cast<double*>(v), c->stream);

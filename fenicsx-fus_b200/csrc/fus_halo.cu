@@ -10,6 +10,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -88,6 +90,57 @@ int load_nccl() {
   } while (0)
 
 inline int blocks_for(long long n) { return (int)std::max<long long>(1, (n + 255) / 256); }
+
+// FUS_HALO_PROF=1: device time of every exchange phase, printed per rank when the halo is destroyed
+struct PhaseProf {
+  const char* name;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+};
+bool g_prof = std::getenv("FUS_HALO_PROF") != nullptr;
+// FUS_HALO_SKIP=1: timing experiment only -- issue no exchange at all (results are wrong)
+bool g_skip = std::getenv("FUS_HALO_SKIP") != nullptr;
+// FUS_HALO_LIGHTFENCE=1: one system fence per block (thread 0, after the block barrier)
+bool g_lightfence = std::getenv("FUS_HALO_LIGHTFENCE") != nullptr;
+PhaseProf g_phase[6] = {{"put_fwd", {}}, {"wait_fwd", {}}, {"put_rev", {}},
+                        {"wait_rev", {}}, {"nccl_fwd", {}}, {"nccl_rev", {}}};
+struct PhaseScope {
+  cudaEvent_t stop = nullptr;
+  cudaStream_t st;
+  PhaseScope(int phase, cudaStream_t s) : st(s) {
+    if (!g_prof || g_phase[phase].ev.size() > 4000)
+      return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    g_phase[phase].ev.push_back({a, b});
+    stop = b;
+  }
+  ~PhaseScope() {
+    if (stop)
+      cudaEventRecord(stop, st);
+  }
+};
+void phase_report(int rank) {
+  if (!g_prof)
+    return;
+  cudaDeviceSynchronize();
+  for (auto& ph : g_phase) {
+    if (ph.ev.empty())
+      continue;
+    std::vector<float> v;
+    for (auto& e : ph.ev) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e.first, e.second);
+      v.push_back(ms);
+    }
+    std::sort(v.begin(), v.end());
+    std::fprintf(stderr, "[fus halo rank %d] %-9s n=%zu median=%.1f us p90=%.1f us max=%.1f us\n",
+                 rank, ph.name, v.size(), 1e3 * v[v.size() / 2], 1e3 * v[(v.size() * 9) / 10],
+                 1e3 * v.back());
+    ph.ev.clear();
+  }
+}
 } // namespace
 
 struct Halo {
@@ -197,6 +250,7 @@ void halo_destroy(Halo* h) {
   if (!h)
     return;
   cudaSetDevice(h->device);
+  phase_report(h->rank);
   if (h->comm_stream)
     cudaStreamSynchronize(h->comm_stream);
   if (h->comm && g_nccl.CommDestroy)
@@ -235,6 +289,7 @@ long long halo_interface_cells(const Halo* h) {
 // One grouped exchange.  `fwd`: owners send send_idx entries, ghosts receive; otherwise reversed.
 // nv vectors are concatenated per neighbour: [neighbour k][vector][entry].
 static int exchange(Halo* h, bool fwd, int nv, cudaStream_t st) {
+  PhaseScope ps(fwd ? 4 : 5, st);
   const std::vector<int64_t>& soff = fwd ? h->send_off : h->recv_off;
   const std::vector<int64_t>& roff = fwd ? h->recv_off : h->send_off;
   FUS_NCCL(g_nccl.GroupStart());
@@ -315,7 +370,7 @@ OffTables& tables(Halo* h) {
 } // namespace
 
 int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty())
+  if (h->neigh.empty() || g_skip)
     return FUS_OK;
   const int nv = b ? 2 : 1, nn = (int)h->neigh.size();
   OffTables& T = tables(h);
@@ -357,7 +412,7 @@ __global__ void __launch_bounds__(256)
     peer_put_kernel(const double* __restrict__ a, const double* __restrict__ b,
                     const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
                     long long n, int nv, const PeerTable* __restrict__ tab, int forward,
-                    unsigned int* counter, unsigned long long epoch) {
+                    unsigned int* counter, unsigned long long epoch, int lightfence) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     int k = 0;
@@ -370,9 +425,12 @@ __global__ void __launch_bounds__(256)
     if (nv == 2)
       dst[len + j] = b[d];
   }
-  __threadfence_system();
+  if (!lightfence)
+    __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (lightfence)
+      __threadfence_system(); // cumulative over the block's stores ordered by the barrier
     const unsigned int prev = atomicAdd(counter, 1u);
     if (prev == gridDim.x - 1) { // every block's stores are fenced before its increment
       *counter = 0;
@@ -431,9 +489,11 @@ static int peer_put(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
   ++epoch;
   if (n == 0)
     return FUS_OK;
+  PhaseScope ps(fwd ? 0 : 2, st);
   peer_put_kernel<<<blocks_for(n), 256, 0, st>>>(a, b, fwd ? h->d_send_idx : h->d_recv_idx,
                                                  fwd ? T.d_soff : T.d_roff, nn, n, nv, h->d_tab,
-                                                 fwd ? 1 : 0, h->d_counter + (fwd ? 0 : 1), epoch);
+                                                 fwd ? 1 : 0, h->d_counter + (fwd ? 0 : 1), epoch,
+                                                 g_lightfence ? 1 : 0);
   FUS_CUDA_H(cudaGetLastError());
   return FUS_OK;
 }
@@ -448,6 +508,7 @@ static int peer_wait(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
   const double* data = (const double*)(h->d_mbox + (fwd ? 0 : h->off_rev));
   const unsigned long long* flags
       = (const unsigned long long*)(h->d_mbox + (fwd ? h->off_fflag : h->off_rflag));
+  PhaseScope ps(fwd ? 1 : 3, st);
   if (fwd)
     peer_wait_kernel<false><<<blocks_for(n), 256, 0, st>>>(a, b, h->d_recv_idx, T.d_roff, nn, n,
                                                            nv, data, flags, epoch, h->d_error);
@@ -536,10 +597,17 @@ int halo_peer_error(Halo* h) {
 }
 
 int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty())
+  if (h->neigh.empty() || g_skip)
     return FUS_OK;
-  if (h->peer)
-    return peer_put(h, true, a, b, st);
+  if (h->peer) { // one-sided put on the side stream, concurrent with the next cells on `st`
+    FUS_CUDA_H(cudaEventRecord(h->ev_fwd_ready, st));
+    FUS_CUDA_H(cudaStreamWaitEvent(h->comm_stream, h->ev_fwd_ready, 0));
+    int r = peer_put(h, true, a, b, h->comm_stream);
+    if (r != FUS_OK)
+      return r;
+    FUS_CUDA_H(cudaEventRecord(h->ev_fwd_done, h->comm_stream));
+    return FUS_OK;
+  }
   if (!h->overlap)
     return halo_forward(h, a, b, st);
   FUS_CUDA_H(cudaEventRecord(h->ev_fwd_ready, st));
@@ -552,10 +620,13 @@ int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
 }
 
 int halo_forward_end(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty())
+  if (h->neigh.empty() || g_skip)
     return FUS_OK;
-  if (h->peer)
+  if (h->peer) {
+    // our own put has read a/b before anything later on `st` may overwrite them
+    FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_fwd_done, 0));
     return peer_wait(h, true, a, b, st);
+  }
   if (!h->overlap)
     return FUS_OK;
   FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_fwd_done, 0));
@@ -579,16 +650,23 @@ static int reverse_on(Halo* h, double* a, double* b, cudaStream_t st) {
 }
 
 int halo_reverse(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty())
+  if (h->neigh.empty() || g_skip)
     return FUS_OK;
   return reverse_on(h, a, b, st);
 }
 
 int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
-  if (h->neigh.empty())
+  if (h->neigh.empty() || g_skip)
     return FUS_OK;
-  if (h->peer)
-    return peer_put(h, false, a, nullptr, st);
+  if (h->peer) {
+    FUS_CUDA_H(cudaEventRecord(h->ev_ready, st));
+    FUS_CUDA_H(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+    int r = peer_put(h, false, a, nullptr, h->comm_stream);
+    if (r != FUS_OK)
+      return r;
+    FUS_CUDA_H(cudaEventRecord(h->ev_done, h->comm_stream));
+    return FUS_OK;
+  }
   if (!h->overlap)
     return FUS_OK; // whole exchange happens in _end, after all cells
   FUS_CUDA_H(cudaEventRecord(h->ev_ready, st));
@@ -601,10 +679,12 @@ int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
 }
 
 int halo_reverse_end(Halo* h, double* a, cudaStream_t st) {
-  if (h->neigh.empty())
+  if (h->neigh.empty() || g_skip)
     return FUS_OK;
-  if (h->peer)
+  if (h->peer) {
+    FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_done, 0)); // ghost partial sums have been read
     return peer_wait(h, false, a, nullptr, st);
+  }
   if (!h->overlap)
     return reverse_on(h, a, nullptr, st);
   FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_done, 0));

@@ -1,9 +1,8 @@
 #!/bin/bash
-# halo experiments on N GPUs: bash scripts/gpu_halo_exp.sh N
-N=${1:-4}
+N=${1:-2}
 run() {
   tag=$1; shift
-  env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) bench.py --gpus $N --steps 20 --warmup 3 2>gpurun_out/halo_exp_$tag.err | grep "^{" > gpurun_out/halo_exp_$tag.json
+  env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) bench.py --gpus $N --steps 40 --warmup 5 2>gpurun_out/halo_exp_$tag.err | grep "^{" > gpurun_out/halo_exp_$tag.json
   python - <<PY
 import json
 try:
@@ -13,8 +12,11 @@ except Exception as e:
     print("$tag failed", e)
 PY
 }
-run default FUS_DUMMY=1
-run no_overlap FUS_HALO_OVERLAP=0
-run reserve16 FUS_HALO_RESERVE=16
-run p2pch2 NCCL_MAX_P2P_NCHANNELS=2 NCCL_MIN_P2P_NCHANNELS=1
-run p2pch2_res8 NCCL_MAX_P2P_NCHANNELS=2 NCCL_MIN_P2P_NCHANNELS=1 FUS_HALO_RESERVE=8
+run nccl_seq FUS_HALO_TRANSPORT=nccl
+run peer_r4 FUS_HALO_TRANSPORT=peer
+run peer_r0 FUS_HALO_TRANSPORT=peer FUS_HALO_RESERVE=0
+run peer_r8 FUS_HALO_TRANSPORT=peer FUS_HALO_RESERVE=8
+run peer_r4b FUS_HALO_TRANSPORT=peer
+run nccl_seq_b FUS_HALO_TRANSPORT=nccl
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tests/mp_model_check.py 2>&1 | grep "^{" | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print(d['status'], {k:v for k,v in d.items() if 'peer' in k})"
