@@ -154,6 +154,11 @@ class Context:
     def set_option(self, name, value):
         check(self.lib.fus_ctx_set_option(self.h, name.encode(), int(value)), "fus_ctx_set_option")
 
+    def get_option(self, name):
+        v = C.c_int(0)
+        check(self.lib.fus_ctx_get_option(self.h, name.encode(), C.byref(v)), "fus_ctx_get_option")
+        return v.value
+
     def sync(self):
         check(self.lib.fus_ctx_sync(self.h), "fus_ctx_sync")
 

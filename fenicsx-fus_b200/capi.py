@@ -42,6 +42,7 @@ SIGNATURES = {
     "fus_ctx_destroy": (_int, [_p]),
     "fus_ctx_set_stream": (_int, [_p, _p]),
     "fus_ctx_set_option": (_int, [_p, C.c_char_p, _int]),
+    "fus_ctx_get_option": (_int, [_p, C.c_char_p, C.POINTER(_int)]),
     "fus_ctx_sync": (_int, [_p]),
     "fus_ctx_get_geometry": (_int, [_p, _p, _p]),
     "fus_stiffness_apply_dev": (_int, [_p, _p, _p, _p]),

@@ -77,12 +77,17 @@ struct fus_ctx {
   double2* d_G2 = nullptr;
   double* d_detJ = nullptr;
   double dphi[64];
+  double wts[8];            // 1-D GLL weights
+  // optional affine compression of the geometric factors (option "geometry_mode" = 1)
+  double2* d_Ghat = nullptr;
+  bool affine_active = false;
   // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
   // profiles/), 0 column kernel, 1 point kernel, 2 line kernel
   int variant = -1;
   int col_blocks_per_sm = 0;
   int reserve_sms = 0;      // SMs left free for the halo kernels while cells overlap with them
-  int halo_reserve = 4;     // value of reserve_sms used inside a partitioned stage
+  int halo_reserve = 4;     // reserve_sms inside a partitioned stage, NCCL side-stream mode
+  int peer_reserve = 0;     // same, peer-direct mode
   int l2_persist = 0;       // keep the rhs accumulator b resident in L2 during rk4 (option)
   Halo* halo = nullptr;
   // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
@@ -153,6 +158,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     return FUS_OK;
   DMat<N> D;
   std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
+  std::memcpy(D.w, c->wts, sizeof(double) * N);
   const bool fuse = (x2 != nullptr);
   const int variant = (c->variant >= 0) ? c->variant : (N >= 5 ? 2 : 0);
   if (variant == 1) {
@@ -168,6 +174,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     return FUS_OK;
   }
   // variant 0: column kernel, variant 2: line kernel (same launch geometry rules)
+  const double2* Gptr = c->d_G2;
   auto launch = [&](auto kern_plain, auto kern_fuse, int threads, int smem_bytes, int cpb,
                     bool& configured, int& bps_plain, int& bps_fuse) -> int {
     if (!configured) {
@@ -193,14 +200,22 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     const int sms = std::max(1, c->num_sms - c->reserve_sms);
     const int blocks = (int)std::min<long long>(want, (long long)sms * bps);
     if (fuse)
-      kern_fuse<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, c->d_G2, coeff,
-                                                     coeff2, cb, ce, D);
+      kern_fuse<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, Gptr, coeff, coeff2,
+                                                     cb, ce, D);
     else
-      kern_plain<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, c->d_G2, coeff,
-                                                      coeff2, cb, ce, D);
+      kern_plain<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, Gptr, coeff, coeff2,
+                                                      cb, ce, D);
     FUS_LAUNCHED();
     return FUS_OK;
   };
+  if (c->affine_active) { // all cells are parallelepipeds: Ghat per cell instead of G per point
+    using L = LineCfg<N>;
+    static bool configured = false;
+    static int bp = 1, bf = 1;
+    Gptr = c->d_Ghat;
+    return launch(stiffness_line_kernel<N, false, true>, stiffness_line_kernel<N, true, true>,
+                  L::THREADS, L::SMEM_BYTES, L::CPB, configured, bp, bf);
+  }
   if (variant == 2) {
     using L = LineCfg<N>;
     static bool configured = false;
@@ -299,6 +314,26 @@ int g_download_n(fus_ctx* c, double* G) {
   return FUS_OK;
 }
 
+template <int N>
+int affine_detect_n(fus_ctx* c, int* all_affine) {
+  DMat<N> D;
+  std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
+  std::memcpy(D.w, c->wts, sizeof(double) * N);
+  int* d_flag = nullptr;
+  FUS_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+  const int one = 1;
+  FUS_CUDA(cudaMemcpyAsync(d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (!c->d_Ghat)
+    FUS_CUDA(cudaMalloc(&c->d_Ghat, sizeof(double2) * 3 * c->ncells));
+  affine_detect_kernel<N><<<grid_for(c->ncells, 128, 1 << 30), 128, 0, c->stream>>>(
+      c->d_G2, c->ncells, 1e-13, c->d_Ghat, d_flag, D);
+  FUS_LAUNCHED();
+  FUS_CUDA(cudaMemcpyAsync(all_affine, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  FUS_CUDA(cudaFree(d_flag));
+  return FUS_OK;
+}
+
 #define FUS_DISPATCH_N(c, fn, ...)                                                                 \
   [&]() -> int {                                                                                   \
     switch ((c)->N) {                                                                              \
@@ -349,6 +384,10 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   c->nowned = nowned;
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  {
+    double pts[8];
+    gll(P, pts, c->wts);
+  }
   if (const char* e = std::getenv("FUS_STIFFNESS_VARIANT")) { // A/B runs of bench.py
     const int v = std::atoi(e);
     if (v >= -1 && v <= 2)
@@ -502,6 +541,7 @@ int fus_ctx_destroy(fus_ctx* c) {
       cudaEventDestroy(pr.second);
     }
   cudaFree(c->d_dofmap);
+  cudaFree(c->d_Ghat);
   cudaFree(c->d_G2);
   cudaFree(c->d_detJ);
   if (c->own_stream && c->stream)
@@ -542,6 +582,21 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
     c->col_blocks_per_sm = value;
     return FUS_OK;
   }
+  if (!std::strcmp(name, "geometry_mode")) {
+    // 0: stream G per point (default).  1: if EVERY cell is affine, keep one Ghat per cell and
+    // rebuild G = w_q * Ghat in the kernel; otherwise stay on the streamed path.
+    if (value == 0) {
+      c->affine_active = false;
+      return FUS_OK;
+    }
+    if (!c->d_G2)
+      return FUS_ERR_STATE;
+    FUS_TRY(select_device(c));
+    int all_affine = 0;
+    FUS_TRY(FUS_DISPATCH_N(c, affine_detect_n, c, &all_affine));
+    c->affine_active = all_affine != 0;
+    return FUS_OK;
+  }
   if (!std::strcmp(name, "l2_persist")) {
     c->l2_persist = value != 0;
     return FUS_OK;
@@ -564,6 +619,22 @@ static int check_peer_error(fus_ctx* c) {
   if (c->halo && halo_peer_error(c->halo)) {
     set_error("halo exchange timed out waiting for a neighbour (peer transport)");
     return FUS_ERR_COMM;
+  }
+  return FUS_OK;
+}
+
+int fus_ctx_get_option(fus_ctx* c, const char* name, int* value) {
+  if (!c || !name || !value)
+    return FUS_ERR_ARG;
+  if (!std::strcmp(name, "geometry_compressed"))
+    *value = c->affine_active ? 1 : 0;
+  else if (!std::strcmp(name, "stiffness_variant"))
+    *value = c->variant;
+  else if (!std::strcmp(name, "halo_mode"))
+    *value = c->halo ? halo_mode(c->halo) : -1;
+  else {
+    set_error("unknown option %s", name);
+    return FUS_ERR_ARG;
   }
   return FUS_OK;
 }
@@ -936,7 +1007,9 @@ static int assemble_rhs(fus_model* m, double t, const double* u, const double* v
   const bool ov = halo_overlap(c->halo) != 0;
   const long long ni = halo_interface_cells(c->halo);
   const long long mid = ov ? ni + (c->ncells - ni) / 2 : c->ncells;
-  c->reserve_sms = (halo_mode(c->halo) >= 1) ? c->halo_reserve : 0;
+  // SMs kept free for the exchange kernels: only the NCCL side-stream mode needs them (NCCL's
+  // kernels are wide); the peer-direct puts are small and measured best with none reserved.
+  c->reserve_sms = (halo_mode(c->halo) == 1) ? c->halo_reserve : c->peer_reserve;
   int rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, mid, c->stream);
   if (rc == FUS_OK && fwd_pending)
     rc = halo_forward_end(c->halo, const_cast<double*>(u), const_cast<double*>(v), c->stream);
@@ -1106,7 +1179,7 @@ int fus_halo_setup(fus_ctx* c, int rank, int nranks, const void* uid, int nneigh
     if (const char* e = std::getenv("FUS_HALO_OVERLAP"))
       halo_set_overlap(c->halo, std::atoi(e));
     if (const char* e = std::getenv("FUS_HALO_RESERVE"))
-      c->halo_reserve = std::max(0, std::min(c->num_sms - 1, std::atoi(e)));
+      c->halo_reserve = c->peer_reserve = std::max(0, std::min(c->num_sms - 1, std::atoi(e)));
   }
   return rc;
 }

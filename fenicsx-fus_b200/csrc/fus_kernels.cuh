@@ -17,6 +17,7 @@ namespace fus {
 template <int N>
 struct DMat {
   double d[N * N]; // d[q*N+k] = phi_k'(xi_q)
+  double w[N];     // 1-D GLL weights (only read by the affine-compressed kernel)
 };
 
 template <int N>
@@ -303,7 +304,10 @@ struct LineCfg {
   static constexpr int GPF = (N <= 7) ? N : N / 2;
 };
 
-template <int N, bool FUSE2>
+// AFFINE: every cell is a parallelepiped, so G[c][q] = w_q * Ghat[c] exactly (J is constant in a
+// cell).  G2 then points to Ghat (3 double2 per CELL) and the 48 B/point stream disappears; the
+// quadrature weight is rebuilt from the 1-D weights.  Opt-in (option "geometry_mode"), see DESIGN.
+template <int N, bool FUSE2, bool AFFINE = false>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     stiffness_line_kernel(const double* __restrict__ x, const double* __restrict__ x2,
                           double* __restrict__ y, const int32_t* __restrict__ dofmap,
@@ -348,8 +352,13 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 
   int idx[N], idxn[N];
   double xv[N];
-  double2 g[GPF][3];
+  double2 g[AFFINE ? 1 : GPF][3];
+  double2 gh[3], ghn[3]; // AFFINE: Ghat of the current and of the next cell
+  const double wab = AFFINE ? D.w[a] * D.w[b] : 0.0;
   double cf = 0.0;
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+    gh[p] = ghn[p] = make_double2(0.0, 0.0);
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     idx[k] = 0;
@@ -357,7 +366,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     xv[k] = 0.0;
   }
 #pragma unroll
-  for (int k = 0; k < GPF; ++k)
+  for (int k = 0; k < (AFFINE ? 1 : GPF); ++k)
 #pragma unroll
     for (int p = 0; p < 3; ++p)
       g[k][p] = make_double2(0.0, 0.0);
@@ -380,12 +389,18 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
         xv[k] = __ldg(x + idx[k]);
       cf = __ldg(coeff + c);
     }
-    const double2* gp = G2 + c * (3 * N * NN) + t;
-#pragma unroll
-    for (int k = 0; k < GPF; ++k)
+    if constexpr (AFFINE) {
 #pragma unroll
       for (int p = 0; p < 3; ++p)
-        g[k][p] = ld_stream(gp + (k * 3 + p) * NN);
+        gh[p] = __ldg(G2 + c * 3 + p);
+    } else {
+      const double2* gp = G2 + c * (3 * N * NN) + t;
+#pragma unroll
+      for (int k = 0; k < GPF; ++k)
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          g[k][p] = ld_stream(gp + (k * 3 + p) * NN);
+    }
   }
   long long cn = c + stride;
   bool validn = lane_ok && (cn < cell_end);
@@ -394,6 +409,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 #pragma unroll
     for (int k = 0; k < N; ++k)
       idxn[k] = __ldg(dm + k * NN);
+    if constexpr (AFFINE) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        ghn[p] = __ldg(G2 + cn * 3 + p);
+    }
   }
 
   for (int it = 0; it < niter; ++it) {
@@ -472,12 +492,21 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
         f1 = S1A[i0 * C::B1_S0];
         f2 = S2A[i0 * C::B2_S0];
       }
-      const double2 ga = g[i0 % GPF][0], gb = g[i0 % GPF][1], gc = g[i0 % GPF][2];
-      const double t0 = cfc * (ga.x * f0[i0] + ga.y * f1 + gb.x * f2);
-      const double t1 = cfc * (ga.y * f0[i0] + gb.y * f1 + gc.x * f2);
-      const double t2 = cfc * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
+      double2 ga, gb, gc;
+      double scale;
+      if constexpr (AFFINE) {
+        ga = gh[0], gb = gh[1], gc = gh[2];
+        scale = cfc * (D.w[i0] * wab);
+      } else {
+        ga = g[i0 % GPF][0], gb = g[i0 % GPF][1], gc = g[i0 % GPF][2];
+        scale = cfc;
+      }
+      const double t0 = scale * (ga.x * f0[i0] + ga.y * f1 + gb.x * f2);
+      const double t1 = scale * (ga.y * f0[i0] + gb.y * f1 + gc.x * f2);
+      const double t2 = scale * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
       // refill the ring slot: level i0+GPF of this cell, or of the next cell once past the top
-      if (i0 + GPF < N) {
+      if constexpr (AFFINE) {
+      } else if (i0 + GPF < N) {
         if (valid) {
 #pragma unroll
           for (int p = 0; p < 3; ++p)
@@ -542,11 +571,21 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     c = cn;
     cn += stride;
     validn = lane_ok && (cn < cell_end);
+    if constexpr (AFFINE) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        gh[p] = ghn[p];
+    }
     if (validn) {
       const int32_t* dm = dofmap + cn * (N * NN) + t;
 #pragma unroll
       for (int k = 0; k < N; ++k)
         idxn[k] = __ldg(dm + k * NN);
+      if constexpr (AFFINE) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+          ghn[p] = __ldg(G2 + cn * 3 + p);
+      }
     }
   }
 }
@@ -686,6 +725,43 @@ __global__ void __launch_bounds__(128)
       o[2 * NN] = make_double2(dj * Gm[1][2], dj * Gm[2][2]);
     }
   }
+}
+
+// Affine-cell detection and compression: a cell is affine iff G[c][q]/w_q does not depend on q.
+// One thread per cell; writes Ghat (from the first point) and clears *all_affine otherwise.
+template <int N>
+__global__ void __launch_bounds__(128)
+    affine_detect_kernel(const double2* __restrict__ G2, long long ncells, double tol,
+                         double2* __restrict__ Ghat, int* all_affine,
+                         const __grid_constant__ DMat<N> D) {
+  constexpr int NN = N * N;
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells)
+    return;
+  const double2* gc = G2 + c * (3 * N * NN);
+  const double w000 = D.w[0] * D.w[0] * D.w[0];
+  double ref[6], mx = 0.0;
+  for (int p = 0; p < 3; ++p) {
+    const double2 v = gc[p * NN];
+    ref[2 * p] = v.x / w000;
+    ref[2 * p + 1] = v.y / w000;
+  }
+  for (int k = 0; k < 6; ++k)
+    mx = fmax(mx, fabs(ref[k]));
+  bool ok = true;
+  for (int i0 = 0; i0 < N && ok; ++i0)
+    for (int t = 0; t < NN && ok; ++t) {
+      const double w = D.w[i0] * D.w[t / N] * D.w[t % N];
+      for (int p = 0; p < 3; ++p) {
+        const double2 v = gc[(i0 * 3 + p) * NN + t];
+        if (fabs(v.x - w * ref[2 * p]) > tol * w * mx || fabs(v.y - w * ref[2 * p + 1]) > tol * w * mx)
+          ok = false;
+      }
+    }
+  for (int p = 0; p < 3; ++p)
+    Ghat[c * 3 + p] = make_double2(ref[2 * p], ref[2 * p + 1]);
+  if (!ok)
+    atomicExch(all_affine, 0);
 }
 
 // Reference layout G[c][q][6] (a chunk of cells already on the device) -> G2, and back.

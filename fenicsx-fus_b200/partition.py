@@ -70,12 +70,9 @@ class BoxPartition:
         nraw = int(lib.fus_box_num_dofs(P_, nl))
         # local grid coordinates of every raw dof
         pos = np.array([0, P_] + list(range(1, P_)), dtype=np.int64)   # Basix node -> offset
-        cz, cy, cx = np.meshgrid(np.arange(nl[2]), np.arange(nl[1]), np.arange(nl[0]),
-                                 indexing="ij")
-        # cell index c = (cx*ny + cy)*nz + cz  -> arrays in that order
+        # cell index c = (cx*ny + cy)*nz + cz
         cxs, cys, czs = (np.arange(ncl) // (nl[1] * nl[2]), (np.arange(ncl) // nl[2]) % nl[1],
                          np.arange(ncl) % nl[2])
-        del cz, cy, cx
         i0, i1, i2 = np.meshgrid(pos, pos, pos, indexing="ij")
         g = [np.zeros(nraw, dtype=np.int64) for _ in range(3)]
         for d, (cc, ii) in enumerate(((cxs, i0), (cys, i1), (czs, i2))):

@@ -112,6 +112,11 @@ int fus_ctx_destroy(fus_ctx* ctx);
 int fus_ctx_set_stream(fus_ctx* ctx, void* cuda_stream);
 /* Tuning/diagnostic knobs: "stiffness_variant" (0 = column kernel, 1 = per-point kernel). */
 int fus_ctx_set_option(fus_ctx* ctx, const char* name, int value);
+/* "geometry_mode" 1 asks for affine compression: if every cell is a parallelepiped the operator
+   keeps 6 numbers per CELL and rebuilds G = w_q * Ghat instead of streaming 48 B per point
+   (off by default; falls back to streaming when any cell is not affine).
+   fus_ctx_get_option reads back "geometry_compressed", "stiffness_variant", "halo_mode". */
+int fus_ctx_get_option(fus_ctx* ctx, const char* name, int* value);
 int fus_ctx_sync(fus_ctx* ctx);
 
 /* Read the device cell data back in the reference layouts (tests; G or detJ may be NULL). */

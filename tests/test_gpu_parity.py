@@ -288,3 +288,38 @@ def test_cpp_dropin_driver(fus, gpu):
     x = np.sin(0.001 * np.arange(V.ndofs))
     y = fus.StiffnessSpectral3D(V)(x, np.full(m.ncells, -1e-3), np.zeros(V.ndofs))
     assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
+
+
+@pytest.mark.parametrize("P", [2, 3, 4, 5, 6, 7])
+def test_affine_geometry_compression(fus, orc, gpu, P):
+    """Option geometry_mode=1: parallelepiped cells (here a sheared, anisotropic box) are detected
+    and the operator rebuilds G = w_q * Ghat from 6 numbers per cell; results stay within the
+    operator tolerance.  A warped mesh must be detected as non-affine and stay on the streamed path."""
+    A = np.array([[1.0, 0.3, 0.1], [0.0, 0.8, 0.25], [0.05, 0.0, 1.2]])
+    m = fus.BoxMesh((4, 3, 2), (0, 0, 0), (1.0, 0.6, 0.5), warp=lambda x: x @ A.T)
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context()
+    ctx.set_option("geometry_mode", 1)
+    assert ctx.get_option("geometry_compressed") == 1
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    assert np.abs(G[:, :, [1, 2, 4]]).max() > 1e-3 * np.abs(G).max()      # genuinely non-diagonal
+    rng = np.random.default_rng(P)
+    x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)
+    y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(V.ndofs))
+    e = rel_l2(y, yo)
+    note(f"affine_stiffness_P{P}", e)
+    assert e < TOL_APPLY
+    # fused two-vector gather (lossy) through the compressed kernel as well
+    mdl = fus.LossySpectral3D(V, 1500.0, 1000.0, 3e-3, 0.5e6, 1e5, 1500.0)
+    u, v = rng.uniform(-1, 1, V.ndofs), 1e6 * rng.uniform(-1, 1, V.ndofs)
+    k1 = mdl.f1(1e-6, u, v)
+    ctx.set_option("geometry_mode", 0)
+    assert ctx.get_option("geometry_compressed") == 0
+    k0 = mdl.f1(1e-6, u, v)
+    assert rel_l2(k1, k0) < TOL_APPLY
+    # non-affine cells: detection refuses, results unchanged
+    mw, Vw, Gw, _ = make_case(fus, orc, P, (3, 2, 2), 1)
+    cw = Vw.context()
+    cw.set_option("geometry_mode", 1)
+    assert cw.get_option("geometry_compressed") == 0
