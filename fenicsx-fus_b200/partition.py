@@ -69,25 +69,30 @@ class BoxPartition:
         capi.check(lib.fus_box_dofmap(P_, nl, numbering, raw), "fus_box_dofmap")
         nraw = int(lib.fus_box_num_dofs(P_, nl))
         # local grid coordinates of every raw dof
-        pos = np.array([0, P_] + list(range(1, P_)), dtype=np.int64)   # Basix node -> offset
+        pos = np.array([0, P_] + list(range(1, P_)), dtype=np.int32)   # Basix node -> offset
         # cell index c = (cx*ny + cy)*nz + cz
-        cxs, cys, czs = (np.arange(ncl) // (nl[1] * nl[2]), (np.arange(ncl) // nl[2]) % nl[1],
-                         np.arange(ncl) % nl[2])
+        cid = np.arange(ncl, dtype=np.int32)
+        cxs, cys, czs = cid // (nl[1] * nl[2]), (cid // nl[2]) % nl[1], cid % nl[2]
+        del cid
         i0, i1, i2 = np.meshgrid(pos, pos, pos, indexing="ij")
-        g = [np.zeros(nraw, dtype=np.int64) for _ in range(3)]
+        g = [np.zeros(nraw, dtype=np.int32) for _ in range(3)]   # int32 throughout: 1e9-dof runs
         for d, (cc, ii) in enumerate(((cxs, i0), (cys, i1), (czs, i2))):
-            gd = (cc[:, None] * P_ + ii.reshape(1, -1)).reshape(-1)
+            gd = (cc[:, None] * np.int32(P_) + ii.reshape(1, -1).astype(np.int32)).reshape(-1)
             g[d][raw.reshape(-1)] = gd
+            del gd
         top = [int(nl[d]) * P_ for d in range(3)]
         ghost = np.zeros(nraw, dtype=bool)
-        owner = np.zeros((nraw, 3), dtype=np.int64)
+        owner_rank = np.zeros(nraw, dtype=np.int32)
+        mult = (Py * Pz, Pz, 1)
         for d in range(3):
             on_low = (g[d] == 0) & self.has_lower[d]
             ghost |= on_low
-            owner[:, d] = self.rcoord[d] - on_low.astype(np.int64)
-        owner_rank = (owner[:, 0] * Py + owner[:, 1]) * Pz + owner[:, 2]
-        key = ((g[0] + self.cell_lo[0] * P_) * M[1] + (g[1] + self.cell_lo[1] * P_)) * M[2] \
-            + (g[2] + self.cell_lo[2] * P_)                          # global node id
+            owner_rank += np.int32(mult[d]) * (np.int32(self.rcoord[d]) - on_low.astype(np.int32))
+            del on_low
+        key = (g[0].astype(np.int64) + self.cell_lo[0] * P_) * M[1]
+        key += g[1] + self.cell_lo[1] * P_
+        key *= M[2]
+        key += g[2] + self.cell_lo[2] * P_                           # global node id
 
         # ---- local numbering: owned (raw order), then ghosts grouped by owner, by global key --
         owned_raw = np.flatnonzero(~ghost)
@@ -113,9 +118,10 @@ class BoxPartition:
         # send: for every upper neighbour r+delta, my owned nodes on the top planes of delta
         owned_mask_new = np.zeros(nraw, dtype=bool)
         owned_mask_new[:self.nowned] = True
-        gn = [np.empty(nraw, dtype=np.int64) for _ in range(3)]
+        gn = [np.empty(nraw, dtype=np.int32) for _ in range(3)]
         for d in range(3):
             gn[d][new_of_raw] = g[d]
+        del g, key
         for delta in itertools.product((0, 1), repeat=3):
             if not any(delta):
                 continue
