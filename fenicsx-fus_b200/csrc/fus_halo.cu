@@ -150,6 +150,7 @@ struct Halo {
   std::vector<int64_t> send_off, recv_off; // per neighbour, in entries
   int64_t nsend = 0, nrecv = 0;
   int32_t *d_send_idx = nullptr, *d_recv_idx = nullptr;
+  int64_t *d_soff = nullptr, *d_roff = nullptr; // device copies of send_off / recv_off
   double *d_sbuf = nullptr, *d_rbuf = nullptr; // 2 vectors deep
   int64_t nowned = 0, ndofs = 0, ninterface = 0;
   int overlap = 0; // NCCL on a side stream: measured slower than in-order beyond 2 ranks (profiles/)
@@ -207,8 +208,13 @@ int halo_create(Halo** out, int device, int rank, int nranks, const void* uid, i
   h->ndofs = ndofs;
   h->ninterface = ninterface_cells;
   h->neigh.assign(neigh, neigh + nneigh);
-  h->send_off.assign(send_off, send_off + nneigh + 1);
-  h->recv_off.assign(recv_off, recv_off + nneigh + 1);
+  if (nneigh > 0) {
+    h->send_off.assign(send_off, send_off + nneigh + 1);
+    h->recv_off.assign(recv_off, recv_off + nneigh + 1);
+  } else {
+    h->send_off.assign(1, 0);
+    h->recv_off.assign(1, 0);
+  }
   h->nsend = nneigh ? send_off[nneigh] : 0;
   h->nrecv = nneigh ? recv_off[nneigh] : 0;
   for (int64_t i = 0; i < h->nsend; ++i)
@@ -235,6 +241,13 @@ int halo_create(Halo** out, int device, int rank, int nranks, const void* uid, i
                           cudaMemcpyHostToDevice));
   int prio_lo = 0, prio_hi = 0;
   FUS_CUDA_H(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  {
+    const size_t ob = sizeof(int64_t) * (size_t)(nneigh + 1);
+    FUS_CUDA_H(cudaMalloc(&h->d_soff, ob));
+    FUS_CUDA_H(cudaMalloc(&h->d_roff, ob));
+    FUS_CUDA_H(cudaMemcpy(h->d_soff, h->send_off.data(), ob, cudaMemcpyHostToDevice));
+    FUS_CUDA_H(cudaMemcpy(h->d_roff, h->recv_off.data(), ob, cudaMemcpyHostToDevice));
+  }
   FUS_CUDA_H(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio_hi));
   FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
   FUS_CUDA_H(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
@@ -262,6 +275,8 @@ void halo_destroy(Halo* h) {
   cudaFree(h->d_tab);
   cudaFree(h->d_counter);
   cudaFree(h->d_error);
+  cudaFree(h->d_soff);
+  cudaFree(h->d_roff);
   cudaFree(h->d_send_idx);
   cudaFree(h->d_recv_idx);
   cudaFree(h->d_sbuf);
@@ -349,31 +364,18 @@ __global__ void __launch_bounds__(256)
 }
 
 namespace {
-// device copies of the offset tables, created lazily
+// device copies of the per-neighbour offset tables (owned by the Halo, made in halo_create)
 struct OffTables {
-  int64_t *d_soff = nullptr, *d_roff = nullptr;
+  int64_t *d_soff, *d_roff;
 };
-OffTables& tables(Halo* h) {
-  static std::vector<std::pair<Halo*, OffTables>> all;
-  for (auto& p : all)
-    if (p.first == h)
-      return p.second;
-  OffTables t;
-  const size_t nb = sizeof(int64_t) * h->send_off.size();
-  cudaMalloc(&t.d_soff, nb);
-  cudaMalloc(&t.d_roff, nb);
-  cudaMemcpy(t.d_soff, h->send_off.data(), nb, cudaMemcpyHostToDevice);
-  cudaMemcpy(t.d_roff, h->recv_off.data(), nb, cudaMemcpyHostToDevice);
-  all.push_back({h, t});
-  return all.back().second;
-}
+inline OffTables tables(Halo* h) { return OffTables{h->d_soff, h->d_roff}; }
 } // namespace
 
 int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
   if (h->neigh.empty() || g_skip)
     return FUS_OK;
   const int nv = b ? 2 : 1, nn = (int)h->neigh.size();
-  OffTables& T = tables(h);
+  const OffTables T = tables(h);
   if (h->nsend)
     halo_pack_kernel<<<blocks_for(h->nsend), 256, 0, st>>>(a, b, h->d_send_idx, T.d_soff, nn,
                                                           h->d_sbuf, h->nsend, nv);
@@ -483,7 +485,7 @@ static int peer_put(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
     return FUS_ERR_ARG;
   }
   const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
-  OffTables& T = tables(h);
+  const OffTables T = tables(h);
   const long long n = fwd ? h->nsend : h->nrecv;
   unsigned long long& epoch = fwd ? h->epoch_fwd : h->epoch_rev;
   ++epoch;
@@ -500,7 +502,7 @@ static int peer_put(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
 
 static int peer_wait(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
   const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
-  OffTables& T = tables(h);
+  const OffTables T = tables(h);
   const long long n = fwd ? h->nrecv : h->nsend;
   const unsigned long long epoch = fwd ? h->epoch_fwd : h->epoch_rev;
   if (n == 0)
@@ -635,7 +637,7 @@ int halo_forward_end(Halo* h, double* a, double* b, cudaStream_t st) {
 
 static int reverse_on(Halo* h, double* a, double* b, cudaStream_t st) {
   const int nv = b ? 2 : 1, nn = (int)h->neigh.size();
-  OffTables& T = tables(h);
+  const OffTables T = tables(h);
   if (h->nrecv)
     halo_pack_kernel<<<blocks_for(h->nrecv), 256, 0, st>>>(a, b, h->d_recv_idx, T.d_roff, nn,
                                                           h->d_sbuf, h->nrecv, nv);
