@@ -14,9 +14,17 @@ import numpy as np
 from . import capi
 from .capi import KINDS, FusError, check  # noqa: F401
 
-__all__ = ["BoxMesh", "FunctionSpace", "StiffnessSpectral3D", "MassSpectral3D",
+__all__ = ["BoxMesh", "FunctionSpace", "HexMesh", "HexFunctionSpace", "StiffnessSpectral3D", "MassSpectral3D",
            "LinearSpectral3D", "LossySpectral3D", "WesterveltSpectral3D", "gll",
            "tabulate_dphi", "compute_diffusivity_of_sound", "launch_count", "device_count"]
+
+
+def __getattr__(name):
+    # unstructured-mesh ingestion lives in its own module (needs numpy only); import lazily
+    if name in ("HexMesh", "HexFunctionSpace"):
+        from . import unstructured
+        return getattr(unstructured, name)
+    raise AttributeError(name)
 
 
 def gll(P):
