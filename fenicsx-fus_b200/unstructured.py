@@ -26,12 +26,35 @@ def _vertex(bits):
     return bits[0] + 2 * bits[1] + 4 * bits[2]
 
 
+def morton_order(centroids, bits=10):
+    """Permutation that sorts points along a Z-order curve: neighbouring cells end up close in
+    memory, which is what the gather/scatter of the operator wants from a mesh in arbitrary order
+    (measured: 0.272 ms -> see profiles/ for a randomly ordered 54^3 box at P=4)."""
+    c = np.asarray(centroids, dtype=np.float64)
+    lo, hi = c.min(axis=0), c.max(axis=0)
+    q = ((c - lo) / np.where(hi > lo, hi - lo, 1.0) * ((1 << bits) - 1)).astype(np.uint64)
+    key = np.zeros(c.shape[0], dtype=np.uint64)
+    for b in range(bits):
+        for d in range(3):
+            key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + (2 - d))
+    return np.argsort(key, kind="stable")
+
+
 class HexMesh:
     """x: (nverts,3); xdofmap: (ncells,8) in DOLFINx tensor vertex order;
     facets: (nfacets,3) exterior facets {cell, local facet, tag} (tag 0 when untagged)."""
 
-    def __init__(self, x, cells_tensor, facet_quads=None, facet_values=None):
+    def __init__(self, x, cells_tensor, facet_quads=None, facet_values=None, reorder=None):
         self.x = np.ascontiguousarray(x, dtype=np.float64)
+        cells_tensor = np.asarray(cells_tensor)
+        # cell_perm[k] = index in the input of the cell stored at position k (per-cell data given
+        # in input order must be permuted with it)
+        self.cell_perm = np.arange(cells_tensor.shape[0])
+        if reorder == "morton":
+            self.cell_perm = morton_order(self.x[cells_tensor].mean(axis=1))
+            cells_tensor = cells_tensor[self.cell_perm]
+        elif reorder is not None:
+            raise ValueError("reorder must be None or 'morton'")
         self.xdofmap = np.ascontiguousarray(cells_tensor, dtype=np.int32)
         self.ncells = self.xdofmap.shape[0]
         self.n = None
@@ -46,7 +69,7 @@ class HexMesh:
             np.stack([self.ext_cell, self.ext_lf, tags], axis=1), dtype=np.int32)
 
     @classmethod
-    def from_xdmf_h5(cls, h5_path, name="hex"):
+    def from_xdmf_h5(cls, h5_path, name="hex", reorder="morton"):
         f = hdf5min.File(h5_path)
         topo = f.read(f"/Mesh/{name}/topology")
         geom = f.read(f"/Mesh/{name}/geometry")
@@ -56,7 +79,7 @@ class HexMesh:
             vals = f.read(f"/MeshTags/{name}_facets/Values")
         except KeyError:
             pass
-        return cls(geom, topo[:, _VTK_TO_TENSOR], quads, vals)
+        return cls(geom, topo[:, _VTK_TO_TENSOR], quads, vals, reorder=reorder)
 
     def _build_faces(self):
         """Global face ids of the 6 faces of every cell and the exterior ones."""

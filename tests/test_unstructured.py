@@ -191,7 +191,8 @@ def test_gpu_models_on_reference_mesh(fus, orc, gpu, ref_mesh, kind):
     c0 = np.where(cx < 0.5, 1500.0, 2300.0)
     rho0 = np.where(cx < 0.5, 1000.0, 1700.0)
     f, p0, s0 = 2.0e3, 1.0e5, 1500.0                  # unit cube: wavelength 0.75 m
-    delta0 = np.full(nc, fus.compute_diffusivity_of_sound(2 * np.pi * f, 1500.0, 0.5))
+    # small attenuation: delta k_max^2 dt must stay inside RK4's stability interval
+    delta0 = np.full(nc, fus.compute_diffusivity_of_sound(2 * np.pi * f, 1500.0, 0.01))
     beta0 = np.full(nc, 3.5)
     dt = 0.15 * m.h_min() / (2300.0 * P * P)
     G, dJ = orc.geometry(P, m.x, m.xdofmap)
@@ -210,5 +211,5 @@ def test_gpu_models_on_reference_mesh(fus, orc, gpu, ref_mesh, kind):
     steps = mdl.rk4(t0, tf, dt)
     u, v = np.zeros(nd), np.zeros(nd)
     assert om.rk4(t0, tf, dt, u, v) == steps
-    assert np.isfinite(u).all() and np.linalg.norm(u) > 0
+    assert np.isfinite(u).all() and 0 < np.abs(u).max() < 1e3 * p0     # a stable run
     assert rel_l2(mdl.u_sol(), u) < 1e-10 and rel_l2(mdl.v_sol(), v) < 1e-10
