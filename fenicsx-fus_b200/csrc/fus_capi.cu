@@ -89,6 +89,7 @@ struct fus_ctx {
   int halo_reserve = 4;     // reserve_sms inside a partitioned stage, NCCL side-stream mode
   int peer_reserve = 0;     // same, peer-direct mode
   int l2_persist = 0;       // keep the rhs accumulator b resident in L2 during rk4 (option)
+  int use_graph = 1;        // replay RK4 steps from a captured CUDA graph (option "use_graph")
   Halo* halo = nullptr;
   // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
   bool profile = false;
@@ -139,6 +140,17 @@ struct fus_model {
   // state (u0,v0 double as u_n,v_n) and work vectors
   double *d_u0 = nullptr, *d_v0 = nullptr, *d_ua = nullptr, *d_va = nullptr, *d_un = nullptr,
          *d_vn = nullptr, *d_b = nullptr;
+  // rk4: per-(step,stage) source scalars computed on the host, step counter on the device
+  double* d_src = nullptr;
+  size_t src_cap = 0;
+  int* d_stepctr = nullptr;
+  // one RK4 step captured as a CUDA graph (replayed while dt, stream and halo mode stay the same)
+  cudaGraphExec_t step_graph = nullptr;
+  double graph_dt = 0.0;
+  cudaStream_t graph_stream = nullptr;
+  int graph_halo_mode = -2;
+  long long graph_launches = 0;
+  bool use_graph = true;
 };
 
 namespace {
@@ -395,6 +407,8 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   }
   if (const char* e = std::getenv("FUS_L2_PERSIST"))
     c->l2_persist = std::atoi(e) != 0;
+  if (const char* e = std::getenv("FUS_USE_GRAPH"))
+    c->use_graph = std::atoi(e) != 0;
   *out = c;
   FUS_CUDA(cudaSetDevice(device));
   FUS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -599,6 +613,10 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   }
   if (!std::strcmp(name, "l2_persist")) {
     c->l2_persist = value != 0;
+    return FUS_OK;
+  }
+  if (!std::strcmp(name, "use_graph")) {
+    c->use_graph = value != 0;
     return FUS_OK;
   }
   if (!std::strcmp(name, "halo_reserve_sms")) {
@@ -893,6 +911,10 @@ int fus_model_destroy(fus_model* m) {
     return FUS_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  if (m->step_graph)
+    cudaGraphExecDestroy(m->step_graph);
+  cudaFree(m->d_src);
+  cudaFree(m->d_stepctr);
   for (void* p : {(void*)m->d_lin, (void*)m->d_att, (void*)m->d_m, (void*)m->d_dnl,
                   (void*)m->d_bidx, (void*)m->d_bsrc, (void*)m->d_bdsrc, (void*)m->d_babs,
                   (void*)m->d_u0, (void*)m->d_v0, (void*)m->d_ua, (void*)m->d_va, (void*)m->d_un,
@@ -979,17 +1001,20 @@ static void source_scalars(const fus_model* m, double t, double* g, double* dg) 
 // the right-hand side assembly of f1 (Linear.hpp:203-206, Lossy.hpp:229-234, Westervelt.hpp:260-265).
 // u, v must have fresh ghosts on entry.
 static int assemble_rhs(fus_model* m, double t, const double* u, const double* v,
-                        bool fwd_pending) {
+                        bool fwd_pending, int table_stage = -1) {
   fus_ctx* c = m->ctx;
-  double g, dg;
-  source_scalars(m, t, &g, &dg);
+  double g = 0.0, dg = 0.0;
+  if (table_stage < 0)
+    source_scalars(m, t, &g, &dg);
+  const double* table = (table_stage >= 0) ? m->d_src : nullptr;
   const double* x2 = (m->kind >= FUS_LOSSY) ? v : nullptr;
   const double* c2 = (m->kind >= FUS_LOSSY) ? m->d_att : nullptr;
   auto boundary = [&]() -> int {
     if (m->nb) {
       ProfScope prof(c, 2, c->stream);
       boundary_kernel<<<grid_for(m->nb, 256, 1 << 30), 256, 0, c->stream>>>(
-          m->d_b, v, m->d_bidx, m->d_bsrc, m->d_bdsrc, m->d_babs, m->nb, g, dg);
+          m->d_b, v, m->d_bidx, m->d_bsrc, m->d_bdsrc, m->d_babs, m->nb, g, dg, table,
+          m->d_stepctr, table_stage < 0 ? 0 : table_stage);
       FUS_LAUNCHED();
     }
     return FUS_OK;
@@ -1069,6 +1094,32 @@ static int launch_stage(fus_model* m, const StageArgs& A) {
   return FUS_OK;
 }
 
+// One RK4 step = 4 x (operator + boundary terms + fused epilogue), plus the halo traffic when
+// partitioned.  Issued eagerly or captured into a CUDA graph by fus_model_rk4.
+static int issue_step(fus_model* m, StageArgs& A, double dt) {
+  fus_ctx* c = m->ctx;
+  const double a_runge[4] = {0.0, 0.5, 0.5, 1.0};
+  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  if (c->halo) // scatter_fwd of the step's first stage input (Linear.hpp:196-199)
+    FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
+  for (int i = 0; i < 4; ++i) {
+    const double* u_in = (i == 0) ? m->d_u0 : m->d_un;
+    const double* v_in = (i == 0) ? m->d_v0 : m->d_vn;
+    FUS_TRY(assemble_rhs(m, 0.0, u_in, v_in, true, i));
+    A.bw_dt = dt * b_runge[i];
+    A.a_next_dt = (i < 3) ? dt * a_runge[i + 1] : 0.0;
+    switch (i) {
+    case 0: FUS_TRY(launch_stage<0>(m, A)); break;
+    case 1: FUS_TRY(launch_stage<1>(m, A)); break;
+    case 2: FUS_TRY(launch_stage<2>(m, A)); break;
+    case 3: FUS_TRY(launch_stage<3>(m, A)); break;
+    }
+    if (c->halo && i < 3) // next stage input; joined inside the next assemble_rhs
+      FUS_TRY(halo_forward_begin(c->halo, m->d_un, m->d_vn, c->stream));
+  }
+  return FUS_OK;
+}
+
 extern "C" {
 
 int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeStep,
@@ -1079,12 +1130,52 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   }
   fus_ctx* c = m->ctx;
   FUS_TRY(select_device(c));
-  // Same host-side time arithmetic as the reference loop (Linear.hpp:231-298).
-  double t = startTime, tf = finalTime, dt = timeStep;
-  int step = 0;
-  const double a_runge[4] = {0.0, 0.5, 0.5, 1.0};
-  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  // Same host-side time arithmetic as the reference loop (Linear.hpp:231-298), run ahead of the
+  // device: the step sizes and the source scalars of every (step, stage) are tabulated first.
   const double c_runge[4] = {0.0, 0.5, 0.5, 1.0};
+  std::vector<double> dts, table;
+  {
+    double t = startTime, tf = finalTime, dt = timeStep;
+    while (t < tf) {
+      dt = std::min(dt, tf - t);
+      for (int i = 0; i < 4; ++i) {
+        double g, dg;
+        source_scalars(m, t + c_runge[i] * dt, &g, &dg);
+        table.push_back(g);
+        table.push_back(dg);
+      }
+      dts.push_back(dt);
+      t += dt;
+      if (dts.size() > (size_t)100000000) {
+        set_error("fus_model_rk4: more than 1e8 steps requested");
+        return FUS_ERR_ARG;
+      }
+    }
+  }
+  const int step_total = (int)dts.size();
+  if (nsteps)
+    *nsteps = step_total;
+  if (step_total == 0)
+    return FUS_OK;
+  if (table.size() > m->src_cap) {
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(m->d_src);
+    m->d_src = nullptr;
+    m->src_cap = std::max<size_t>(table.size(), 4096);
+    FUS_CUDA(cudaMalloc(&m->d_src, sizeof(double) * m->src_cap));
+    if (m->step_graph) { // the graph holds the old table pointer
+      cudaGraphExecDestroy(m->step_graph);
+      m->step_graph = nullptr;
+    }
+  }
+  if (!m->d_stepctr)
+    FUS_CUDA(cudaMalloc(&m->d_stepctr, sizeof(int)));
+  // the previous call may still be reading the table: the copy is stream-ordered after it
+  FUS_CUDA(cudaMemcpyAsync(m->d_src, table.data(), sizeof(double) * table.size(),
+                           cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream)); // `table` is pageable and goes out of scope
+  FUS_CUDA(cudaMemsetAsync(m->d_stepctr, 0, sizeof(int), c->stream));
+
   StageArgs A;
   A.b = m->d_b;
   A.m = m->d_m;
@@ -1097,9 +1188,9 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   A.vn = m->d_vn;
   A.nowned = c->nowned;
   A.ntotal = c->ndofs;
+  A.step_ctr = m->d_stepctr;
   FUS_CUDA(cudaMemsetAsync(m->d_b, 0, sizeof(double) * c->ndofs, c->stream));
-  // Optional: pin b in the persisting part of the 126 MB L2.  b is RED-accumulated by the operator,
-  // read and zeroed by the epilogue, 4x per step; resident, it never crosses HBM.
+  // Optional: pin b in the persisting part of the 126 MB L2 (measured slower overall, off).
   bool l2_window = false;
   if (c->l2_persist) {
     cudaDeviceProp prop;
@@ -1120,40 +1211,74 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
       l2_window = true;
     }
   }
-  if (c->halo)
-    FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
-  while (t < tf) {
-    dt = std::min(dt, tf - t);
-    for (int i = 0; i < 4; ++i) {
-      const double tn = t + c_runge[i] * dt;
-      const double* u_in = (i == 0) ? m->d_u0 : m->d_un;
-      const double* v_in = (i == 0) ? m->d_v0 : m->d_vn;
-      FUS_TRY(assemble_rhs(m, tn, u_in, v_in, true));
-      A.bw_dt = dt * b_runge[i];
-      A.a_next_dt = (i < 3) ? dt * a_runge[i + 1] : 0.0;
-      switch (i) {
-      case 0: FUS_TRY(launch_stage<0>(m, A)); break;
-      case 1: FUS_TRY(launch_stage<1>(m, A)); break;
-      case 2: FUS_TRY(launch_stage<2>(m, A)); break;
-      case 3: FUS_TRY(launch_stage<3>(m, A)); break;
-      }
-      if (c->halo) // scatter_fwd of the next stage input (Linear.hpp:196-199), joined inside it
-        FUS_TRY(halo_forward_begin(c->halo, (i < 3) ? m->d_un : m->d_u0,
-                                   (i < 3) ? m->d_vn : m->d_v0, c->stream));
-    }
-    t += dt;
-    step += 1;
+
+  // CUDA graph: steps are identical launches once the scalars come from the table, so one step
+  // is captured (both streams of the peer-direct halo included) and replayed.  Not used while
+  // per-kernel profiling is on (event pairs), with the NCCL transport, or for the odd last step.
+  const int hmode = c->halo ? halo_mode(c->halo) : -1;
+  const bool graph_ok = m->use_graph && c->use_graph && !c->profile && !l2_window
+                        && (hmode == -1 || hmode == 2);
+  if (m->step_graph
+      && (m->graph_dt != dts[0] || m->graph_stream != c->stream || m->graph_halo_mode != hmode)) {
+    cudaGraphExecDestroy(m->step_graph);
+    m->step_graph = nullptr;
   }
-  if (c->halo) // u_n, v_n leave with fresh ghosts (Linear.hpp:312-313)
+  int rc = FUS_OK;
+  for (int s = 0; s < step_total && rc == FUS_OK; ++s) {
+    const bool full = dts[s] == dts[0];
+    if (graph_ok && full && m->step_graph) {
+      FUS_CUDA(cudaGraphLaunch(m->step_graph, c->stream));
+      g_launches.fetch_add(m->graph_launches, std::memory_order_relaxed);
+      continue;
+    }
+    // capture once everything lazy (function attributes, occupancy) has run eagerly: step >= 1
+    const bool capture = graph_ok && full && s >= 1 && step_total - s >= 2;
+    if (capture) {
+      cudaGraph_t graph = nullptr;
+      const long long before = g_launches.load();
+      FUS_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      rc = issue_step(m, A, dts[s]);
+      cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+      m->graph_launches = g_launches.load() - before; // kernels per replay (captured, not run)
+      g_launches.store(before);
+      if (rc == FUS_OK && ce == cudaSuccess && graph) {
+        ce = cudaGraphInstantiate(&m->step_graph, graph, 0);
+        if (ce == cudaSuccess) {
+          m->graph_dt = dts[0];
+          m->graph_stream = c->stream;
+          m->graph_halo_mode = hmode;
+        } else {
+          m->step_graph = nullptr;
+        }
+      }
+      if (graph)
+        cudaGraphDestroy(graph);
+      if (rc != FUS_OK)
+        break;
+      if (!m->step_graph) { // capture unavailable here: fall back to eager issue for good
+        cudaGetLastError();
+        m->use_graph = false;
+        rc = issue_step(m, A, dts[s]);
+      } else {
+        FUS_CUDA(cudaGraphLaunch(m->step_graph, c->stream));
+        g_launches.fetch_add(m->graph_launches, std::memory_order_relaxed);
+      }
+      continue;
+    }
+    rc = issue_step(m, A, dts[s]);
+  }
+  if (rc != FUS_OK)
+    return rc;
+  if (c->halo) { // u_n, v_n leave with fresh ghosts (Linear.hpp:312-313)
+    FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
     FUS_TRY(halo_forward_end(c->halo, m->d_u0, m->d_v0, c->stream));
+  }
   if (l2_window) {
     cudaStreamAttrValue av;
     std::memset(&av, 0, sizeof(av));
     FUS_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av));
     FUS_CUDA(cudaCtxResetPersistingL2Cache());
   }
-  if (nsteps)
-    *nsteps = step;
   return FUS_OK;
 }
 

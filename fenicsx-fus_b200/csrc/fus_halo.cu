@@ -165,7 +165,8 @@ struct Halo {
   struct PeerTable* d_tab = nullptr;         // device copy of the per-neighbour destination table
   unsigned int* d_counter = nullptr;         // block-completion counters (fwd, rev)
   int* d_error = nullptr;
-  unsigned long long epoch_fwd = 0, epoch_rev = 0;
+  unsigned long long* d_epoch = nullptr;     // [fwd, rev] exchange counters, advanced on the device
+                                             // so that a captured CUDA graph can replay the step
 };
 
 constexpr int kMaxNeigh = 26;
@@ -274,6 +275,7 @@ void halo_destroy(Halo* h) {
   cudaFree(h->d_mbox);
   cudaFree(h->d_tab);
   cudaFree(h->d_counter);
+  cudaFree(h->d_epoch);
   cudaFree(h->d_error);
   cudaFree(h->d_soff);
   cudaFree(h->d_roff);
@@ -414,7 +416,10 @@ __global__ void __launch_bounds__(256)
     peer_put_kernel(const double* __restrict__ a, const double* __restrict__ b,
                     const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
                     long long n, int nv, const PeerTable* __restrict__ tab, int forward,
-                    unsigned int* counter, unsigned long long epoch, int lightfence) {
+                    unsigned int* counter, unsigned long long* epoch_ctr, int lightfence) {
+  // every block reads the counter before it can be advanced: the last block only advances it
+  // after all blocks have passed their atomicAdd below
+  const unsigned long long epoch = *(volatile unsigned long long*)epoch_ctr + 1ull;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     int k = 0;
@@ -436,6 +441,7 @@ __global__ void __launch_bounds__(256)
     const unsigned int prev = atomicAdd(counter, 1u);
     if (prev == gridDim.x - 1) { // every block's stores are fenced before its increment
       *counter = 0;
+      *epoch_ctr = epoch;
       __threadfence_system();
       for (int k = 0; k < nneigh; ++k)
         if (off[k + 1] > off[k])
@@ -449,7 +455,10 @@ __global__ void __launch_bounds__(256)
     peer_wait_kernel(double* __restrict__ a, double* __restrict__ b,
                      const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
                      long long n, int nv, const double* mbox_data,
-                     const unsigned long long* flags, unsigned long long epoch, int* error) {
+                     const unsigned long long* flags, const unsigned long long* epoch_ctr,
+                     int* error) {
+  // the local put of this exchange is ordered before this kernel and has advanced the counter
+  const unsigned long long epoch = *(volatile const unsigned long long*)epoch_ctr;
   if (threadIdx.x < nneigh && off[threadIdx.x + 1] > off[threadIdx.x]) {
     const long long t0 = clock64();
     while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
@@ -487,15 +496,12 @@ static int peer_put(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
   const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
   const OffTables T = tables(h);
   const long long n = fwd ? h->nsend : h->nrecv;
-  unsigned long long& epoch = fwd ? h->epoch_fwd : h->epoch_rev;
-  ++epoch;
-  if (n == 0)
-    return FUS_OK;
+  // launched even with nothing to send: the kernel also advances the exchange counter
   PhaseScope ps(fwd ? 0 : 2, st);
   peer_put_kernel<<<blocks_for(n), 256, 0, st>>>(a, b, fwd ? h->d_send_idx : h->d_recv_idx,
                                                  fwd ? T.d_soff : T.d_roff, nn, n, nv, h->d_tab,
-                                                 fwd ? 1 : 0, h->d_counter + (fwd ? 0 : 1), epoch,
-                                                 g_lightfence ? 1 : 0);
+                                                 fwd ? 1 : 0, h->d_counter + (fwd ? 0 : 1),
+                                                 h->d_epoch + (fwd ? 0 : 1), g_lightfence ? 1 : 0);
   FUS_CUDA_H(cudaGetLastError());
   return FUS_OK;
 }
@@ -504,7 +510,7 @@ static int peer_wait(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
   const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
   const OffTables T = tables(h);
   const long long n = fwd ? h->nrecv : h->nsend;
-  const unsigned long long epoch = fwd ? h->epoch_fwd : h->epoch_rev;
+  const unsigned long long* epoch = h->d_epoch + (fwd ? 0 : 1);
   if (n == 0)
     return FUS_OK;
   const double* data = (const double*)(h->d_mbox + (fwd ? 0 : h->off_rev));
@@ -540,6 +546,8 @@ int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3) {
     FUS_CUDA_H(cudaMemset(h->d_mbox, 0, h->mbox_bytes));
     FUS_CUDA_H(cudaMalloc(&h->d_counter, 2 * sizeof(unsigned int)));
     FUS_CUDA_H(cudaMemset(h->d_counter, 0, 2 * sizeof(unsigned int)));
+    FUS_CUDA_H(cudaMalloc(&h->d_epoch, 2 * sizeof(unsigned long long)));
+    FUS_CUDA_H(cudaMemset(h->d_epoch, 0, 2 * sizeof(unsigned long long)));
     FUS_CUDA_H(cudaMalloc(&h->d_error, sizeof(int)));
     FUS_CUDA_H(cudaMemset(h->d_error, 0, sizeof(int)));
     FUS_CUDA_H(cudaDeviceSynchronize());

@@ -818,7 +818,16 @@ static __global__ void __launch_bounds__(256)
     boundary_kernel(double* __restrict__ b, const double* __restrict__ v,
                     const int32_t* __restrict__ bidx, const double* __restrict__ bsrc,
                     const double* __restrict__ bdsrc, const double* __restrict__ babs,
-                    long long nb, double g, double dg) {
+                    long long nb, double g, double dg, const double* __restrict__ src_table,
+                    const int* __restrict__ step_ctr, int stage) {
+  // Inside fus_model_rk4 the source scalars come from a table computed on the host for every
+  // (step, stage) with the reference's own time arithmetic, indexed by a device step counter, so
+  // that one captured CUDA graph can replay any step.
+  if (src_table) {
+    const int s = *step_ctr;
+    g = src_table[(s * 4 + stage) * 2];
+    dg = src_table[(s * 4 + stage) * 2 + 1];
+  }
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nb) {
     const int d = bidx[k];
@@ -854,6 +863,7 @@ struct StageArgs {
   long long ntotal;
   double a_next_dt; // a_{i+1} * dt
   double bw_dt;     // b_i * dt
+  int* step_ctr;    // advanced by the stage-3 epilogue (index into the source-scalar table)
 };
 
 template <int STAGE, bool WESTERVELT>
@@ -894,6 +904,8 @@ __global__ void __launch_bounds__(256) rk4_stage_kernel(const StageArgs A) {
   }
   for (long long i = A.nowned + i0; i < A.ntotal; i += stride)
     A.b[i] = 0.0; // ghost partial sums have been sent to their owners
+  if (STAGE == 3 && A.step_ctr && i0 == 0)
+    *A.step_ctr += 1; // nothing else in this kernel reads it
 }
 
 // out = b / m (Westervelt: with the solution-dependent terms) -- single f1 evaluation for tests
