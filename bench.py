@@ -222,7 +222,8 @@ def run_gpu_arm(args):
                                   hi=tuple(h * n for n in n_global))
     V = part.function_space(device=local_rank)
     ctx = V.context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()         # not the legacy default stream: it cannot be captured
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     transport = "none"
     if world > 1:

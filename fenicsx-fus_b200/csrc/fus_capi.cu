@@ -1232,11 +1232,17 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
       continue;
     }
     // capture once everything lazy (function attributes, occupancy) has run eagerly: step >= 1
-    const bool capture = graph_ok && full && s >= 1 && step_total - s >= 2;
+    const bool capture = graph_ok && m->use_graph && full && s >= 1 && step_total - s >= 2;
     if (capture) {
       cudaGraph_t graph = nullptr;
       const long long before = g_launches.load();
-      FUS_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        // e.g. the legacy default stream cannot be captured: stay on eager issue
+        cudaGetLastError();
+        m->use_graph = false;
+        rc = issue_step(m, A, dts[s]);
+        continue;
+      }
       rc = issue_step(m, A, dts[s]);
       cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
       m->graph_launches = g_launches.load() - before; // kernels per replay (captured, not run)
