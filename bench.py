@@ -167,10 +167,13 @@ def run_reference_arm(args):
         return 0
     # full workload if it fits a few minutes, else a bounded sample of it
     n_cells = N_BENCH
-    probe, cores, _, _, kind, _ = cpu_linear_rk4(18, 2, 1)
-    est = (N_BENCH * P_BENCH + 1) ** 3 * (args.steps + args.warmup) / probe
-    if est > 150.0:
-        n_cells = 27
+    if os.environ.get("FUS_REF_CELLS"):            # tests: force a small sample
+        n_cells = int(os.environ["FUS_REF_CELLS"])
+    else:
+        probe, cores, _, _, kind, _ = cpu_linear_rk4(18, 2, 1)
+        est = (N_BENCH * P_BENCH + 1) ** 3 * (args.steps + args.warmup) / probe
+        if est > 150.0:
+            n_cells = 27
     val, cores, done, nd, kind, el = cpu_linear_rk4(n_cells, args.steps, args.warmup)
     sample = (f"LinearSpectral3D RK4, P={P_BENCH}, box {n_cells}^3 cells ({nd} dofs), {done} steps, "
               f"{cores} OpenMP threads as ranks, cell loops on the reference's sum_factorisation.hpp")

@@ -125,6 +125,18 @@ struct ProfScope {
 };
 } // namespace
 
+namespace {
+// device scratch that is released on every exit path
+template <typename T>
+struct DevPtr {
+  T* p = nullptr;
+  DevPtr() = default;
+  DevPtr(const DevPtr&) = delete;
+  DevPtr& operator=(const DevPtr&) = delete;
+  ~DevPtr() { cudaFree(p); }
+};
+} // namespace
+
 struct fus_model {
   fus_ctx* ctx = nullptr;
   int kind = 0;
@@ -293,36 +305,35 @@ template <int N>
 int g_upload_n(fus_ctx* c, const double* G) {
   // stream the reference-layout G through a bounded staging buffer
   const long long chunk_cells = std::max<long long>(1, (64ll << 20) / (c->Nd * 48));
-  double* d_stage = nullptr;
-  FUS_CUDA(cudaMalloc(&d_stage, (size_t)chunk_cells * c->Nd * 48));
+  DevPtr<double> stage;
+  FUS_CUDA(cudaMalloc(&stage.p, (size_t)chunk_cells * c->Nd * 48));
   for (long long c0 = 0; c0 < c->ncells; c0 += chunk_cells) {
     const long long nc = std::min<long long>(chunk_cells, c->ncells - c0);
-    FUS_CUDA(cudaMemcpyAsync(d_stage, G + c0 * c->Nd * 6, (size_t)nc * c->Nd * 48,
+    FUS_CUDA(cudaMemcpyAsync(stage.p, G + c0 * c->Nd * 6, (size_t)nc * c->Nd * 48,
                              cudaMemcpyHostToDevice, c->stream));
     g_to_device_layout_kernel<N><<<grid_for(nc * c->Nd, 256, c->num_sms * 8), 256, 0,
-                                   c->stream>>>(d_stage, nc, c->d_G2 + c0 * (3 * c->Nd));
+                                   c->stream>>>(stage.p, nc, c->d_G2 + c0 * (3 * c->Nd));
     FUS_LAUNCHED();
+    // the staging buffer is reused by the next chunk
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
   }
-  FUS_CUDA(cudaStreamSynchronize(c->stream));
-  FUS_CUDA(cudaFree(d_stage));
   return FUS_OK;
 }
 
 template <int N>
 int g_download_n(fus_ctx* c, double* G) {
   const long long chunk_cells = std::max<long long>(1, (64ll << 20) / (c->Nd * 48));
-  double* d_stage = nullptr;
-  FUS_CUDA(cudaMalloc(&d_stage, (size_t)chunk_cells * c->Nd * 48));
+  DevPtr<double> stage;
+  FUS_CUDA(cudaMalloc(&stage.p, (size_t)chunk_cells * c->Nd * 48));
   for (long long c0 = 0; c0 < c->ncells; c0 += chunk_cells) {
     const long long nc = std::min<long long>(chunk_cells, c->ncells - c0);
     g_from_device_layout_kernel<N><<<grid_for(nc * c->Nd, 256, c->num_sms * 8), 256, 0,
-                                     c->stream>>>(c->d_G2 + c0 * (3 * c->Nd), nc, d_stage);
+                                     c->stream>>>(c->d_G2 + c0 * (3 * c->Nd), nc, stage.p);
     FUS_LAUNCHED();
-    FUS_CUDA(cudaMemcpyAsync(G + c0 * c->Nd * 6, d_stage, (size_t)nc * c->Nd * 48,
+    FUS_CUDA(cudaMemcpyAsync(G + c0 * c->Nd * 6, stage.p, (size_t)nc * c->Nd * 48,
                              cudaMemcpyDeviceToHost, c->stream));
     FUS_CUDA(cudaStreamSynchronize(c->stream));
   }
-  FUS_CUDA(cudaFree(d_stage));
   return FUS_OK;
 }
 
@@ -526,18 +537,16 @@ int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowne
   }
   fus_ctx* c = *out;
   FUS_TRY(tabulate_dphi(P, c->dphi));
-  double* d_xg = nullptr;
-  int32_t* d_xd = nullptr;
-  FUS_CUDA(cudaMalloc(&d_xg, sizeof(double) * 3 * nverts));
-  FUS_CUDA(cudaMalloc(&d_xd, sizeof(int32_t) * 8 * ncells));
-  FUS_CUDA(cudaMemcpyAsync(d_xg, xg, sizeof(double) * 3 * nverts, cudaMemcpyHostToDevice,
+  DevPtr<double> d_xg;
+  DevPtr<int32_t> d_xd;
+  FUS_CUDA(cudaMalloc(&d_xg.p, sizeof(double) * 3 * nverts));
+  FUS_CUDA(cudaMalloc(&d_xd.p, sizeof(int32_t) * 8 * ncells));
+  FUS_CUDA(cudaMemcpyAsync(d_xg.p, xg, sizeof(double) * 3 * nverts, cudaMemcpyHostToDevice,
                            c->stream));
-  FUS_CUDA(cudaMemcpyAsync(d_xd, xdofmap, sizeof(int32_t) * 8 * ncells, cudaMemcpyHostToDevice,
+  FUS_CUDA(cudaMemcpyAsync(d_xd.p, xdofmap, sizeof(int32_t) * 8 * ncells, cudaMemcpyHostToDevice,
                            c->stream));
-  FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_n, c, d_xg, d_xd, true, true));
+  FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_n, c, d_xg.p, d_xd.p, true, true));
   FUS_CUDA(cudaStreamSynchronize(c->stream));
-  FUS_CUDA(cudaFree(d_xg));
-  FUS_CUDA(cudaFree(d_xd));
   return FUS_OK;
 }
 
@@ -730,24 +739,19 @@ static int apply_host(fus_ctx* c, const double* x, const double* coeffs, double*
   if (!c || !x || !coeffs || !y)
     return FUS_ERR_ARG;
   FUS_TRY(select_device(c));
-  double *dx = nullptr, *dy = nullptr, *dc = nullptr;
+  DevPtr<double> dx, dy, dc;
   const size_t vb = sizeof(double) * c->ndofs, cbytes = sizeof(double) * c->ncells;
-  FUS_CUDA(cudaMalloc(&dx, vb));
-  FUS_CUDA(cudaMalloc(&dy, vb));
-  FUS_CUDA(cudaMalloc(&dc, cbytes));
-  FUS_CUDA(cudaMemcpyAsync(dx, x, vb, cudaMemcpyHostToDevice, c->stream));
-  FUS_CUDA(cudaMemcpyAsync(dy, y, vb, cudaMemcpyHostToDevice, c->stream));
-  FUS_CUDA(cudaMemcpyAsync(dc, coeffs, cbytes, cudaMemcpyHostToDevice, c->stream));
-  int r = stiff ? launch_stiffness(c, dx, nullptr, dc, nullptr, dy, 0, c->ncells, c->stream)
-                : launch_mass(c, dx, dc, dy, 0, c->ncells, c->stream);
-  if (r == FUS_OK) {
-    FUS_CUDA(cudaMemcpyAsync(y, dy, vb, cudaMemcpyDeviceToHost, c->stream));
-    FUS_CUDA(cudaStreamSynchronize(c->stream));
-  }
-  cudaFree(dx);
-  cudaFree(dy);
-  cudaFree(dc);
-  return r;
+  FUS_CUDA(cudaMalloc(&dx.p, vb));
+  FUS_CUDA(cudaMalloc(&dy.p, vb));
+  FUS_CUDA(cudaMalloc(&dc.p, cbytes));
+  FUS_CUDA(cudaMemcpyAsync(dx.p, x, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(dy.p, y, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(dc.p, coeffs, cbytes, cudaMemcpyHostToDevice, c->stream));
+  FUS_TRY(stiff ? launch_stiffness(c, dx.p, nullptr, dc.p, nullptr, dy.p, 0, c->ncells, c->stream)
+                : launch_mass(c, dx.p, dc.p, dy.p, 0, c->ncells, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(y, dy.p, vb, cudaMemcpyDeviceToHost, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
 }
 
 int fus_stiffness_apply_host(fus_ctx* c, const double* x, const double* coeffs, double* y) {

@@ -110,7 +110,16 @@ int fus_ctx_destroy(fus_ctx* ctx);
 
 /* Launch all work of this context on the given cudaStream_t (default: a private stream). */
 int fus_ctx_set_stream(fus_ctx* ctx, void* cuda_stream);
-/* Tuning/diagnostic knobs: "stiffness_variant" (0 = column kernel, 1 = per-point kernel). */
+/* Tuning/diagnostic knobs (all optional; defaults in brackets):
+     "stiffness_variant"  [-1] -1 auto (column kernel for P <= 3, line kernel for P >= 4),
+                               0 column, 1 per-point (cross-check), 2 line kernel
+     "geometry_mode"      [0]  see below
+     "use_graph"          [1]  replay RK4 steps from a captured CUDA graph when possible
+     "profile_kernels"    [0]  CUDA event pair around every launch (disables graph replay)
+     "l2_persist"         [0]  L2 persistence window on the rhs accumulator (measured slower)
+     "halo_overlap"       [0]  NCCL transport: run the exchanges on a side stream
+     "halo_reserve_sms"   [4]  SMs left free for NCCL kernels in that mode
+     "col_blocks_per_sm"  [0]  cap on resident blocks of the stiffness kernels (0 = occupancy) */
 int fus_ctx_set_option(fus_ctx* ctx, const char* name, int value);
 /* "geometry_mode" 1 asks for affine compression: if every cell is a parallelepiped the operator
    keeps 6 numbers per CELL and rebuilds G = w_q * Ghat instead of streaming 48 B per point
