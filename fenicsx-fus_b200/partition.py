@@ -27,7 +27,129 @@ def _split(n, parts, r):
     return start, start + base + (1 if r < rem else 0)
 
 
-class BoxPartition:
+class _PartitionBase:
+    """What the operator / model / halo layers need from a partition of any mesh:
+    x, xdofmap, dofmap (local numbering, owned first), ndofs, nowned, ncells, facets, P, N, rank,
+    nranks, neigh, send_lists, recv_lists, ninterface_cells, n_local (box only)."""
+    n_local = None
+
+    # -------------------------------------------------------------------------------------------
+    def function_space(self, device=0):
+        """FunctionSpace-like object over the local block for the operator/model classes."""
+        import types
+
+        from . import Context
+        mesh = types.SimpleNamespace(x=self.x, xdofmap=self.xdofmap, facets=self.facets,
+                                     ncells=self.ncells, n=self.n_local)
+        V = types.SimpleNamespace(mesh=mesh, P=self.P, N=self.N, ndofs=self.ndofs,
+                                  nowned=self.nowned, dofmap=self.dofmap, _ctx=None)
+
+        def context(dev=device):
+            if V._ctx is None:
+                V._ctx = Context.from_mesh(V, dev, nowned=self.nowned)
+            return V._ctx
+        V.context = context
+        return V
+
+    def halo_arrays(self):
+        nn = len(self.neigh)
+        neigh = np.array(self.neigh, dtype=np.int32)
+        soff = np.zeros(nn + 1, dtype=np.int64)
+        roff = np.zeros(nn + 1, dtype=np.int64)
+        for k in range(nn):
+            soff[k + 1] = soff[k] + self.send_lists[k].size
+            roff[k + 1] = roff[k] + self.recv_lists[k].size
+        sidx = np.concatenate(self.send_lists) if nn else np.zeros(0, np.int32)
+        ridx = np.concatenate(self.recv_lists) if nn else np.zeros(0, np.int32)
+        return (neigh, soff, np.ascontiguousarray(sidx, dtype=np.int32), roff,
+                np.ascontiguousarray(ridx, dtype=np.int32))
+
+    def setup_halo(self, ctx, dist):
+        """Create the NCCL communicator of the context: rank 0 makes the unique id, it is
+        broadcast with torch.distributed, every rank calls fus_halo_setup."""
+        import torch
+        lib = capi.load()
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            capi.check(lib.fus_comm_unique_id(uid.ctypes.data_as(C.c_void_p)), "fus_comm_unique_id")
+        t = torch.from_numpy(uid).cuda() if dist.get_backend() == "nccl" else torch.from_numpy(uid)
+        dist.broadcast(t, src=0)
+        uid = t.cpu().numpy().copy()
+        neigh, soff, sidx, roff, ridx = self.halo_arrays()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        capi.check(lib.fus_halo_setup(ctx.h, self.rank, self.nranks, p(uid), len(self.neigh),
+                                      p(neigh), p(soff), p(sidx), p(roff), p(ridx),
+                                      self.ninterface_cells), "fus_halo_setup")
+
+    def connect_peers(self, ctx, dist):
+        """Switch the context's in-loop exchanges to the peer-direct transport: every rank exports
+        its mailbox (CUDA IPC handle + layout), all ranks gather them, each rank opens its
+        neighbours' mailboxes.  Returns False (and leaves NCCL in place) if IPC is unavailable."""
+        lib = capi.load()
+        handle = np.zeros(64, dtype=np.uint8)
+        layout = np.zeros(3, dtype=np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = lib.fus_halo_peer_export(ctx.h, p(handle), p(layout))
+        neigh, soff, _, roff, _ = self.halo_arrays()
+        mine = dict(ok=(rc == 0), handle=handle.tobytes(), layout=layout.tolist(),
+                    neigh=[int(q) for q in neigh], soff=soff.tolist(), roff=roff.tolist())
+        allinfo = [None] * self.nranks
+        dist.all_gather_object(allinfo, mine)
+        if not all(i["ok"] for i in allinfo):
+            return False
+        nn = len(self.neigh)
+        handles = np.zeros((max(nn, 1), 64), dtype=np.uint8)
+        boff = np.zeros((max(nn, 1), 4), dtype=np.int64)
+        for k, q in enumerate(self.neigh):
+            info = allinfo[q]
+            j = info["neigh"].index(self.rank)
+            off_rev, off_fflag, off_rflag = info["layout"]
+            handles[k] = np.frombuffer(info["handle"], dtype=np.uint8)
+            boff[k] = (8 * 2 * info["roff"][j], off_fflag + 8 * j,
+                       off_rev + 8 * info["soff"][j], off_rflag + 8 * j)
+        rc = lib.fus_halo_peer_connect(ctx.h, p(handles), p(boff))
+        flags = [None] * self.nranks
+        dist.all_gather_object(flags, rc == 0)
+        if not all(flags):
+            raise capi.FusError("peer transport connected on some ranks only: "
+                                + lib.fus_last_error().decode(errors="replace"))
+        return True
+
+    # ---- host-side halo (CPU tests over gloo; the device path is fus_halo.cu) -----------------
+    def scatter_fwd_host(self, dist, x):
+        import torch
+        ops, bufs = [], []
+        for q, s, r in zip(self.neigh, self.send_lists, self.recv_lists):
+            if s.size:
+                ops.append(dist.P2POp(dist.isend, torch.from_numpy(x[s].copy()), q))
+            if r.size:
+                b = torch.zeros(r.size, dtype=torch.float64)
+                bufs.append((r, b))
+                ops.append(dist.P2POp(dist.irecv, b, q))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for r, b in bufs:
+            x[r] = b.numpy()
+
+    def scatter_rev_host(self, dist, x):
+        import torch
+        ops, bufs = [], []
+        for q, s, r in zip(self.neigh, self.send_lists, self.recv_lists):
+            if r.size:
+                ops.append(dist.P2POp(dist.isend, torch.from_numpy(x[r].copy()), q))
+            if s.size:
+                b = torch.zeros(s.size, dtype=torch.float64)
+                bufs.append((s, b))
+                ops.append(dist.P2POp(dist.irecv, b, q))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for s, b in bufs:
+            np.add.at(x, s, b.numpy())
+
+
+class BoxPartition(_PartitionBase):
     def __init__(self, P, n_global, pgrid, rank, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0),
                  numbering=1):
         lib = capi.load()
@@ -171,117 +293,86 @@ class BoxPartition:
         f[:, 0] = inv[f[:, 0]]
         self.facets = np.ascontiguousarray(f)
 
-    # -------------------------------------------------------------------------------------------
-    def function_space(self, device=0):
-        """FunctionSpace-like object over the local block for the operator/model classes."""
-        import types
 
-        from . import Context
-        mesh = types.SimpleNamespace(x=self.x, xdofmap=self.xdofmap, facets=self.facets,
-                                     ncells=self.ncells, n=self.n_local)
-        V = types.SimpleNamespace(mesh=mesh, P=self.P, N=self.N, ndofs=self.ndofs,
-                                  nowned=self.nowned, dofmap=self.dofmap, _ctx=None)
+class HexPartition(_PartitionBase):
+    """Partition of an unstructured HexMesh over `nranks` GPUs.
 
-        def context(dev=device):
-            if V._ctx is None:
-                V._ctx = Context.from_mesh(V, dev, nowned=self.nowned)
-            return V._ctx
-        V.context = context
-        return V
+    Cells are dealt out as contiguous chunks of the (Morton-ordered) cell list; a dof shared by
+    several ranks is owned by the lowest of them.  Every rank builds the global numbering
+    (fine for meshes that fit one host) and keeps its own part: owned dofs first in order of first
+    appearance, then ghosts grouped by owner and sorted by global id; interface cells first."""
 
-    def halo_arrays(self):
-        nn = len(self.neigh)
-        neigh = np.array(self.neigh, dtype=np.int32)
-        soff = np.zeros(nn + 1, dtype=np.int64)
-        roff = np.zeros(nn + 1, dtype=np.int64)
-        for k in range(nn):
-            soff[k + 1] = soff[k] + self.send_lists[k].size
-            roff[k + 1] = roff[k] + self.recv_lists[k].size
-        sidx = np.concatenate(self.send_lists) if nn else np.zeros(0, np.int32)
-        ridx = np.concatenate(self.recv_lists) if nn else np.zeros(0, np.int32)
-        return (neigh, soff, np.ascontiguousarray(sidx, dtype=np.int32), roff,
-                np.ascontiguousarray(ridx, dtype=np.int32))
-
-    def setup_halo(self, ctx, dist):
-        """Create the NCCL communicator of the context: rank 0 makes the unique id, it is
-        broadcast with torch.distributed, every rank calls fus_halo_setup."""
-        import torch
-        lib = capi.load()
-        uid = np.zeros(128, dtype=np.uint8)
-        if self.rank == 0:
-            capi.check(lib.fus_comm_unique_id(uid.ctypes.data_as(C.c_void_p)), "fus_comm_unique_id")
-        t = torch.from_numpy(uid).cuda() if dist.get_backend() == "nccl" else torch.from_numpy(uid)
-        dist.broadcast(t, src=0)
-        uid = t.cpu().numpy().copy()
-        neigh, soff, sidx, roff, ridx = self.halo_arrays()
-        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        capi.check(lib.fus_halo_setup(ctx.h, self.rank, self.nranks, p(uid), len(self.neigh),
-                                      p(neigh), p(soff), p(sidx), p(roff), p(ridx),
-                                      self.ninterface_cells), "fus_halo_setup")
-
-    def connect_peers(self, ctx, dist):
-        """Switch the context's in-loop exchanges to the peer-direct transport: every rank exports
-        its mailbox (CUDA IPC handle + layout), all ranks gather them, each rank opens its
-        neighbours' mailboxes.  Returns False (and leaves NCCL in place) if IPC is unavailable."""
-        lib = capi.load()
-        handle = np.zeros(64, dtype=np.uint8)
-        layout = np.zeros(3, dtype=np.int64)
-        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        rc = lib.fus_halo_peer_export(ctx.h, p(handle), p(layout))
-        neigh, soff, _, roff, _ = self.halo_arrays()
-        mine = dict(ok=(rc == 0), handle=handle.tobytes(), layout=layout.tolist(),
-                    neigh=[int(q) for q in neigh], soff=soff.tolist(), roff=roff.tolist())
-        allinfo = [None] * self.nranks
-        dist.all_gather_object(allinfo, mine)
-        if not all(i["ok"] for i in allinfo):
-            return False
-        nn = len(self.neigh)
-        handles = np.zeros((max(nn, 1), 64), dtype=np.uint8)
-        boff = np.zeros((max(nn, 1), 4), dtype=np.int64)
-        for k, q in enumerate(self.neigh):
-            info = allinfo[q]
-            j = info["neigh"].index(self.rank)
-            off_rev, off_fflag, off_rflag = info["layout"]
-            handles[k] = np.frombuffer(info["handle"], dtype=np.uint8)
-            boff[k] = (8 * 2 * info["roff"][j], off_fflag + 8 * j,
-                       off_rev + 8 * info["soff"][j], off_rflag + 8 * j)
-        rc = lib.fus_halo_peer_connect(ctx.h, p(handles), p(boff))
-        flags = [None] * self.nranks
-        dist.all_gather_object(flags, rc == 0)
-        if not all(flags):
-            raise capi.FusError("peer transport connected on some ranks only: "
-                                + lib.fus_last_error().decode(errors="replace"))
-        return True
-
-    # ---- host-side halo (CPU tests over gloo; the device path is fus_halo.cu) -----------------
-    def scatter_fwd_host(self, dist, x):
-        import torch
-        ops, bufs = [], []
-        for q, s, r in zip(self.neigh, self.send_lists, self.recv_lists):
-            if s.size:
-                ops.append(dist.P2POp(dist.isend, torch.from_numpy(x[s].copy()), q))
-            if r.size:
-                b = torch.zeros(r.size, dtype=torch.float64)
-                bufs.append((r, b))
-                ops.append(dist.P2POp(dist.irecv, b, q))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for r, b in bufs:
-            x[r] = b.numpy()
-
-    def scatter_rev_host(self, dist, x):
-        import torch
-        ops, bufs = [], []
-        for q, s, r in zip(self.neigh, self.send_lists, self.recv_lists):
-            if r.size:
-                ops.append(dist.P2POp(dist.isend, torch.from_numpy(x[r].copy()), q))
-            if s.size:
-                b = torch.zeros(s.size, dtype=torch.float64)
-                bufs.append((s, b))
-                ops.append(dist.P2POp(dist.irecv, b, q))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for s, b in bufs:
-            np.add.at(x, s, b.numpy())
+    def __init__(self, mesh, P, nranks, rank, space=None):
+        from .unstructured import HexFunctionSpace
+        self.P, self.N = int(P), int(P) + 1
+        self.rank, self.nranks = int(rank), int(nranks)
+        V = space if space is not None else HexFunctionSpace(mesh, P)
+        nc = mesh.ncells
+        cell_rank = (np.arange(nc, dtype=np.int64) * self.nranks // nc).astype(np.int32)
+        mine = np.flatnonzero(cell_rank == self.rank)
+        if mine.size == 0:
+            raise ValueError("a rank has no cells")
+        gdm = V.dofmap                                               # global ids (nc, Nd)
+        Nd = gdm.shape[1]
+        # which ranks touch which dof
+        pairs = np.unique(np.stack([gdm.reshape(-1).astype(np.int64),
+                                    np.repeat(cell_rank, Nd).astype(np.int64)], axis=1), axis=0)
+        owner = np.full(V.ndofs, self.nranks, dtype=np.int32)
+        np.minimum.at(owner, pairs[:, 0], pairs[:, 1].astype(np.int32))
+        touched_by_me = pairs[pairs[:, 1] == self.rank, 0]
+        # local numbering
+        loc = gdm[mine]
+        flat = loc.reshape(-1)
+        uniq, first = np.unique(flat, return_index=True)
+        uniq = uniq[np.argsort(first, kind="stable")]                 # first appearance order
+        is_owned = owner[uniq] == self.rank
+        owned = uniq[is_owned]
+        ghosts = uniq[~is_owned]
+        ghosts = ghosts[np.lexsort((ghosts, owner[ghosts]))]
+        self.nowned, self.ndofs = int(owned.size), int(uniq.size)
+        self.ndofs_global = int(V.ndofs)
+        self.global_key = np.concatenate([owned, ghosts]).astype(np.int64)
+        g2l = np.full(V.ndofs, -1, dtype=np.int64)
+        g2l[self.global_key] = np.arange(self.ndofs)
+        dofmap = g2l[loc]
+        # halo lists
+        neigh = {}
+        for q in np.unique(owner[ghosts]):
+            sel = ghosts[owner[ghosts] == q]                         # sorted by global id
+            neigh.setdefault(int(q), {})["recv"] = g2l[sel].astype(np.int32)
+        owned_mask = np.zeros(V.ndofs, dtype=bool)
+        owned_mask[owned] = True
+        for q in range(self.nranks):
+            if q == self.rank:
+                continue
+            tq = pairs[pairs[:, 1] == q, 0]
+            sel = np.sort(tq[owned_mask[tq]])
+            if sel.size:
+                neigh.setdefault(int(q), {})["send"] = g2l[sel].astype(np.int32)
+        self.neigh = sorted(neigh)
+        e = np.zeros(0, dtype=np.int32)
+        self.send_lists = [neigh[q].get("send", e) for q in self.neigh]
+        self.recv_lists = [neigh[q].get("recv", e) for q in self.neigh]
+        # interface cells first
+        shared = np.zeros(self.ndofs, dtype=bool)
+        shared[self.nowned:] = True
+        for s_ in self.send_lists:
+            shared[s_] = True
+        is_iface = shared[dofmap].any(axis=1)
+        perm = np.concatenate([np.flatnonzero(is_iface), np.flatnonzero(~is_iface)])
+        self.ninterface_cells = int(is_iface.sum())
+        self.dofmap = np.ascontiguousarray(dofmap[perm], dtype=np.int32)
+        self.cell_global = mine[perm]
+        self.ncells = int(mine.size)
+        # geometry: keep only the vertices the local cells use
+        xd = mesh.xdofmap[self.cell_global]
+        vu, vinv = np.unique(xd.reshape(-1), return_inverse=True)
+        self.x = np.ascontiguousarray(mesh.x[vu])
+        self.xdofmap = np.ascontiguousarray(vinv.reshape(xd.shape), dtype=np.int32)
+        # exterior facets of local cells
+        inv = np.full(nc, -1, dtype=np.int64)
+        inv[self.cell_global] = np.arange(self.ncells)
+        f = mesh.facets[cell_rank[mesh.facets[:, 0]] == self.rank].copy()
+        f[:, 0] = inv[f[:, 0]]
+        self.facets = np.ascontiguousarray(f, dtype=np.int32)
+        del touched_by_me

@@ -100,6 +100,33 @@ def main():
                                         mdl.v_sol()[:part.nowned].copy(),
                                         mdl.mass()[:part.nowned].copy())
             mdl.destroy()
+    # ---- unstructured mesh (the reference's own test mesh), partitioned with HexPartition -------
+    from fenicsx_fus_b200.partition import HexPartition
+    from fenicsx_fus_b200.unstructured import HexFunctionSpace, HexMesh
+    gm = np.load(os.path.join(ROOT, "tests", "golden", "ref_mesh_hex6312.npz"))
+    umesh = HexMesh(gm["geometry"], gm["topology_vtk"][:, (0, 1, 3, 2, 4, 5, 7, 6)],
+                    gm["facet_quads"], gm["facet_values"], reorder="morton")
+    UP = 2
+    UV = HexFunctionSpace(umesh, UP)
+    hp = HexPartition(umesh, UP, world, rank, space=UV)
+    hV = hp.function_space(device=local)
+    hctx = hV.context(local)
+    hp.setup_halo(hctx, dist)
+    report["unstructured_peer_connected"] = bool(hp.connect_peers(hctx, dist))
+    ucent = umesh.x[umesh.xdofmap].mean(axis=1)[:, 0]
+    uc0g = np.where(ucent < 0.5, 1500.0, 2300.0)
+    urho0g = np.where(ucent < 0.5, 1000.0, 1700.0)
+    uf, up0 = 2.0e3, 1.0e5
+    udt = 0.15 * umesh.h_min() / (2300.0 * UP * UP)
+    umdl = fus.LinearSpectral3D(hV, uc0g[hp.cell_global], urho0g[hp.cell_global], uf, up0, 1500.0,
+                                facets=hp.facets, device=local)
+    ukey = hp.global_key.astype(np.float64)
+    umdl.init(1e2 * np.sin(0.013 * ukey), 1e6 * np.cos(0.007 * ukey))
+    usteps = umdl.rk4(1e-4, 1e-4 + 8 * udt, udt)
+    results[("unstructured_linear", "peer")] = (usteps, umdl.u_sol()[:hp.nowned].copy(),
+                                                hp.global_key[:hp.nowned].copy())
+    umdl.destroy()
+
     gathered = [None] * world
     dist.gather_object((part.global_key[:part.nowned], results, report), gathered if rank == 0 else None,
                        dst=0)
@@ -138,6 +165,23 @@ def main():
                 out[f"{kind}_overlap{overlap}"] = {"u": eu, "v": ev, "mass": em}
                 if not (eu < 1e-10 and ev < 1e-10 and em < 1e-12):
                     status = 1
+        # unstructured: single-domain oracle on the global numbering
+        Gu, dJu = orc.geometry(UP, umesh.x, umesh.xdofmap)
+        fnu, fsu = orc.facet_data(UP, umesh.x, umesh.xdofmap, umesh.facets)
+        omu = orc.model("linear", UP, UV.ndofs, UV.dofmap, Gu, dJu, orc.dphi(UP), uc0g, urho0g, None,
+                        None, umesh.facets, fnu, fsu, uf, up0, 1500.0)
+        kg = np.arange(UV.ndofs, dtype=np.float64)
+        uu, vv = 1e2 * np.sin(0.013 * kg), 1e6 * np.cos(0.007 * kg)
+        ust = omu.rk4(1e-4, 1e-4 + 8 * udt, udt, uu, vv)
+        gu = np.zeros(UV.ndofs)
+        for _, res, _ in gathered:
+            st, ul, keys = res[("unstructured_linear", "peer")]
+            assert st == ust
+            gu[keys] = ul
+        eu = np.linalg.norm(gu - uu) / np.linalg.norm(uu)
+        out["unstructured_linear_peer"] = {"u": eu}
+        if not eu < 1e-10:
+            status = 1
         if not all(s["scatter_fwd_exact"] and s["scatter_rev_exact"] for s in out["scatter"]):
             status = 1
         if not all(s.get("peer_connected") for s in out["scatter"]):

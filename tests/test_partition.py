@@ -128,3 +128,90 @@ def test_distributed_operator_gloo_world2(fus, orc, tmp_path, P, n, pg):
         got_y[d["key"]] = d["y"]
         got_m[d["key"]] = d["m"]
     assert rel_l2(got_y, y) < 1e-14 and rel_l2(got_m, m) < 1e-14
+
+
+# ---- unstructured meshes ----------------------------------------------------------------------
+def _ref_mesh():
+    from fenicsx_fus_b200.unstructured import HexMesh
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_mesh_hex6312.npz"))
+    return HexMesh(g["geometry"], g["topology_vtk"][:, (0, 1, 3, 2, 4, 5, 7, 6)], g["facet_quads"],
+                   g["facet_values"], reorder="morton")
+
+
+@pytest.mark.parametrize("P,nranks", [(1, 3), (2, 4)])
+def test_hex_partition_invariants(fus, P, nranks):
+    from fenicsx_fus_b200.partition import HexPartition
+    from fenicsx_fus_b200.unstructured import HexFunctionSpace
+    m = _ref_mesh()
+    V = HexFunctionSpace(m, P)
+    parts = [HexPartition(m, P, nranks, r, space=V) for r in range(nranks)]
+    owned = np.concatenate([p.global_key[:p.nowned] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(V.ndofs))          # every dof owned exactly once
+    assert np.array_equal(np.sort(np.concatenate([p.cell_global for p in parts])), np.arange(m.ncells))
+    assert sum(p.facets.shape[0] for p in parts) == m.facets.shape[0]
+    for p in parts:
+        assert sorted(np.unique(p.dofmap)) == list(range(p.ndofs))
+        for q, s, r in zip(p.neigh, p.send_lists, p.recv_lists):
+            o = parts[q]
+            k = o.neigh.index(p.rank)
+            assert np.array_equal(p.global_key[s], o.global_key[o.recv_lists[k]])
+            assert np.array_equal(p.global_key[r], o.global_key[o.send_lists[k]])
+            assert np.all(s < p.nowned) and np.all(r >= p.nowned)
+        rec = np.concatenate(p.recv_lists) if p.neigh else np.zeros(0, int)
+        assert np.array_equal(np.sort(rec), np.arange(p.nowned, p.ndofs))
+        shared = np.zeros(p.ndofs, bool)
+        shared[p.nowned:] = True
+        for s in p.send_lists:
+            shared[s] = True
+        touch = shared[p.dofmap].any(1)
+        assert touch[:p.ninterface_cells].all() and not touch[p.ninterface_cells:].any()
+        # local geometry is the global one restricted to the local cells
+        assert np.array_equal(p.x[p.xdofmap], m.x[m.xdofmap[p.cell_global]])
+
+
+def _worker_hex(rank, world, port, P, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fenicsx_fus_b200.partition import HexPartition
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    m = _ref_mesh()
+    p = HexPartition(m, P, world, rank)
+    G, dJ = orc.geometry(P, p.x, p.xdofmap)
+    x = np.zeros(p.ndofs)
+    x[:p.nowned] = np.sin(0.37 * p.global_key[:p.nowned]) + 0.1
+    p.scatter_fwd_host(dist, x)
+    assert np.array_equal(x, np.sin(0.37 * p.global_key) + 0.1)
+    coeffs = 1.0 + 0.01 * (p.cell_global % 7)
+    y = np.zeros(p.ndofs)
+    ni = p.ninterface_cells
+    orc.stiffness_apply(P, p.dofmap[:ni], G[:ni], orc.dphi(P), coeffs[:ni], x, y)
+    orc.stiffness_apply(P, p.dofmap[ni:], G[ni:], orc.dphi(P), coeffs[ni:], x, y)
+    p.scatter_rev_host(dist, y)
+    np.savez(os.path.join(out_dir, f"hrank{rank}.npz"), key=p.global_key[:p.nowned], y=y[:p.nowned])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_operator_gloo_world2_unstructured(fus, orc, tmp_path):
+    """The partitioned algorithm on the reference's unstructured test mesh, two gloo ranks."""
+    import torch.multiprocessing as mp
+    from fenicsx_fus_b200.unstructured import HexFunctionSpace
+    P = 2
+    mp.spawn(_worker_hex, args=(2, _free_port(), P, str(tmp_path)), nprocs=2, join=True)
+    m = _ref_mesh()
+    V = HexFunctionSpace(m, P)
+    G, _ = orc.geometry(P, m.x, m.xdofmap)
+    x = np.sin(0.37 * np.arange(V.ndofs)) + 0.1
+    coeffs = 1.0 + 0.01 * (np.arange(m.ncells) % 7)
+    y = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(V.ndofs))
+    got = np.full(V.ndofs, np.nan)
+    for r in range(2):
+        d = np.load(os.path.join(str(tmp_path), f"hrank{r}.npz"))
+        got[d["key"]] = d["y"]
+    assert rel_l2(got, y) < 1e-14
