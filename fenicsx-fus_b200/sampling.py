@@ -1,0 +1,121 @@
+"""Point evaluation of a GLL field after the time loop.
+
+Host-side post-processing, the step the reference's examples run right after `rk4`
+(`cpp/mwe/parallel_eval_line/main.cpp:47-106`, `python/src/fenicsxfus/utils.py:10-47`):
+find the cell containing each point, then evaluate the tensor-product Lagrange expansion there.
+
+`compute_eval_params(mesh, points)` mirrors the reference helper of the same name: it returns the
+points that fall inside the (local) mesh and one containing cell for each; `eval_function`
+mirrors `fem::Function::eval`.  Works for any mesh object with `x` (nverts,3) and `xdofmap`
+(ncells,8 in tensor vertex order): BoxMesh, HexMesh or a partition's local mesh.
+"""
+import numpy as np
+
+from . import capi
+
+
+def _trilinear(X, xi):
+    """x(xi) and Jacobian for cells X (n,8,3) at reference points xi (n,3)."""
+    n = X.shape[0]
+    x = np.zeros((n, 3))
+    J = np.zeros((n, 3, 3))
+    for v in range(8):
+        b = (v & 1, (v >> 1) & 1, (v >> 2) & 1)
+        l = [xi[:, d] if b[d] else 1.0 - xi[:, d] for d in range(3)]
+        dl = [1.0 if b[d] else -1.0 for d in range(3)]
+        w = l[0] * l[1] * l[2]
+        x += w[:, None] * X[:, v]
+        g = np.stack([dl[0] * l[1] * l[2], l[0] * dl[1] * l[2], l[0] * l[1] * dl[2]], axis=1)
+        J += X[:, v, :, None] * g[:, None, :]
+    return x, J
+
+
+def pull_back(X, pts, iters=30, tol=1e-14):
+    """Reference coordinates of physical points pts (n,3) in cells X (n,8,3) by Newton."""
+    xi = np.full((X.shape[0], 3), 0.5)
+    for _ in range(iters):
+        x, J = _trilinear(X, xi)
+        r = pts - x
+        dxi = np.linalg.solve(J, r[:, :, None])[:, :, 0]
+        xi += dxi
+        if np.abs(dxi).max() < tol:
+            break
+    return xi
+
+
+def compute_eval_params(mesh, points, padding=1e-12):
+    """points: (3, n) like the reference helper (or (n, 3)).  Returns (points_on_proc (m,3),
+    cells (m,), reference coordinates (m,3), indices of the kept points (m,))."""
+    pts = np.asarray(points, dtype=np.float64)
+    if pts.ndim != 2 or 3 not in pts.shape:
+        raise ValueError("points must be (3, n) or (n, 3)")
+    if pts.shape[0] == 3 and pts.shape[1] != 3:
+        pts = pts.T
+    pts = np.ascontiguousarray(pts)
+    X = mesh.x[mesh.xdofmap]                                   # (nc, 8, 3)
+    lo, hi = X.min(axis=1) - padding, X.max(axis=1) + padding
+    # uniform background grid over the mesh bounding box: cells registered in every bin they touch
+    glo, ghi = lo.min(axis=0), hi.max(axis=0)
+    nc = X.shape[0]
+    nb = max(1, int(round(nc ** (1.0 / 3.0))))
+    h = np.where(ghi > glo, (ghi - glo) / nb, 1.0)
+    b0 = np.clip(((lo - glo) / h).astype(np.int64), 0, nb - 1)
+    b1 = np.clip(((hi - glo) / h).astype(np.int64), 0, nb - 1)
+    bins = {}
+    for c in range(nc):
+        for i in range(b0[c, 0], b1[c, 0] + 1):
+            for j in range(b0[c, 1], b1[c, 1] + 1):
+                for k in range(b0[c, 2], b1[c, 2] + 1):
+                    bins.setdefault((i, j, k), []).append(c)
+    keep, cells, xis = [], [], []
+    pb = np.clip(((pts - glo) / h).astype(np.int64), 0, nb - 1)
+    inside_box = np.all((pts >= glo) & (pts <= ghi), axis=1)
+    for n in range(pts.shape[0]):
+        if not inside_box[n]:
+            continue
+        cand = [c for c in bins.get(tuple(pb[n]), ())
+                if np.all(pts[n] >= lo[c]) and np.all(pts[n] <= hi[c])]
+        if not cand:
+            continue
+        cand = np.array(cand)
+        xi = pull_back(X[cand], np.repeat(pts[n][None, :], cand.size, axis=0))
+        ok = np.all((xi > -1e-10) & (xi < 1 + 1e-10), axis=1)
+        if ok.any():
+            k = int(np.flatnonzero(ok)[0])
+            keep.append(n)
+            cells.append(int(cand[k]))
+            xis.append(np.clip(xi[k], 0.0, 1.0))
+    keep = np.array(keep, dtype=np.int64)
+    return (pts[keep], np.array(cells, dtype=np.int32),
+            np.array(xis).reshape(-1, 3), keep)
+
+
+def lagrange_1d(P, s):
+    """Values phi_i(s) of the degree-P Lagrange basis on the GLL nodes (Basix order) at s (n,)."""
+    pts, wts = np.zeros(P + 1), np.zeros(P + 1)
+    capi.check(capi.load().fus_gll(P, pts, wts), "fus_gll")
+    s = np.asarray(s, dtype=np.float64)
+    out = np.ones((s.size, P + 1))
+    for i in range(P + 1):
+        for j in range(P + 1):
+            if j != i:
+                out[:, i] *= (s - pts[j]) / (pts[i] - pts[j])
+    return out
+
+
+def eval_function(V, u, cells, xi):
+    """u at reference points xi (m,3) of the given cells: sum_i u[dofmap[c,i]] phi_i0 phi_i1 phi_i2
+    (fem::Function::eval)."""
+    P, N = V.P, V.P + 1
+    l0, l1, l2 = (lagrange_1d(P, xi[:, d]) for d in range(3))
+    coeff = np.asarray(u)[V.dofmap[cells]].reshape(-1, N, N, N)
+    return np.einsum("mabc,ma,mb,mc->m", coeff, l0, l1, l2)
+
+
+def eval_line(V, u, start, end, num_points=100):
+    """Sample u on a straight line (the reference's parallel_eval_line example).  Returns
+    (points kept, values)."""
+    tt = np.linspace(0.0, 1.0, num_points)[:, None]
+    pts = (1 - tt) * np.asarray(start, float)[None, :] + tt * np.asarray(end, float)[None, :]
+    pk, cells, xi, _ = compute_eval_params(V.mesh, pts)
+    return pk, eval_function(V, u, cells, xi)
