@@ -90,6 +90,7 @@ struct fus_ctx {
   int peer_reserve = 0;     // same, peer-direct mode
   int l2_persist = 0;       // keep the rhs accumulator b resident in L2 during rk4 (option)
   int use_graph = 1;        // replay RK4 steps from a captured CUDA graph (option "use_graph")
+  long long config_epoch = 0; // bumped by anything that changes what a step launches
   Halo* halo = nullptr;
   // optional per-kernel event timing (bench.py roofline): family 0 stiffness, 1 stage, 2 boundary
   bool profile = false;
@@ -161,6 +162,7 @@ struct fus_model {
   double graph_dt = 0.0;
   cudaStream_t graph_stream = nullptr;
   int graph_halo_mode = -2;
+  long long graph_epoch = -1;
   long long graph_launches = 0;
   bool use_graph = true;
 };
@@ -582,12 +584,17 @@ int fus_ctx_set_stream(fus_ctx* c, void* s) {
     FUS_CUDA(cudaStreamDestroy(c->stream));
   c->stream = (cudaStream_t)s;
   c->own_stream = false;
+  ++c->config_epoch;
   return FUS_OK;
 }
 
 int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   if (!c || !name)
     return FUS_ERR_ARG;
+  for (const char* k : {"stiffness_variant", "geometry_mode", "col_blocks_per_sm", "halo_overlap",
+                        "halo_reserve_sms"})
+    if (!std::strcmp(name, k))
+      ++c->config_epoch; // a captured step graph would replay the previous choice
   if (!std::strcmp(name, "stiffness_variant")) {
     if (value < -1 || value > 2)
       return FUS_ERR_ARG;
@@ -1223,7 +1230,8 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   const bool graph_ok = m->use_graph && c->use_graph && !c->profile && !l2_window
                         && (hmode == -1 || hmode == 2);
   if (m->step_graph
-      && (m->graph_dt != dts[0] || m->graph_stream != c->stream || m->graph_halo_mode != hmode)) {
+      && (m->graph_dt != dts[0] || m->graph_stream != c->stream || m->graph_halo_mode != hmode
+          || m->graph_epoch != c->config_epoch)) {
     cudaGraphExecDestroy(m->step_graph);
     m->step_graph = nullptr;
   }
@@ -1257,6 +1265,7 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
           m->graph_dt = dts[0];
           m->graph_stream = c->stream;
           m->graph_halo_mode = hmode;
+          m->graph_epoch = c->config_epoch;
         } else {
           m->step_graph = nullptr;
         }
@@ -1304,6 +1313,7 @@ int fus_halo_setup(fus_ctx* c, int rank, int nranks, const void* uid, int nneigh
     return FUS_ERR_ARG;
   }
   FUS_TRY(select_device(c));
+  ++c->config_epoch;
   if (c->halo) {
     halo_destroy(c->halo);
     c->halo = nullptr;
@@ -1332,6 +1342,7 @@ int fus_halo_peer_connect(fus_ctx* c, const void* handles, const int64_t* byte_o
   if (!c || !c->halo)
     return FUS_ERR_STATE;
   FUS_TRY(select_device(c));
+  ++c->config_epoch;
   return halo_peer_connect(c->halo, handles, byte_off);
 }
 

@@ -323,3 +323,42 @@ def test_affine_geometry_compression(fus, orc, gpu, P):
     cw = Vw.context()
     cw.set_option("geometry_mode", 1)
     assert cw.get_option("geometry_compressed") == 0
+
+
+def test_step_graph_follows_configuration_changes(fus, orc, gpu):
+    """fus_model_rk4 replays a captured CUDA graph; switching the kernel variant or the geometry
+    mode afterwards must not replay the stale launches.  Same steps, four configurations, and a
+    different dt: all agree with the oracle."""
+    P, n, h = 4, (4, 3, 3), 0.002
+    m = fus.BoxMesh(n, (0, 0, 0), tuple(h * k for k in n))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context()
+    mdl = fus.LinearSpectral3D(V, 1500.0, 1000.0, 0.5e6, 6.0e4, 1500.0)
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    nc = m.ncells
+    om = orc.model("linear", P, V.ndofs, V.dofmap, G, dJ, orc.dphi(P), np.full(nc, 1500.0),
+                   np.full(nc, 1000.0), None, None, m.facets, fn, fs, 0.5e6, 6.0e4, 1500.0)
+    dt = 0.65 * np.sqrt(3) * h / (1500.0 * P * P)
+    rng = np.random.default_rng(0)
+    u0, v0 = 1e3 * rng.uniform(-1, 1, V.ndofs), 1e9 * rng.uniform(-1, 1, V.ndofs)
+
+    def run(step, nsteps=8):
+        mdl.init(u0.copy(), v0.copy())
+        assert mdl.rk4(0.0, (nsteps - 0.5) * step, step) == nsteps
+        return mdl.u_sol()
+
+    u, v = u0.copy(), v0.copy()
+    om.rk4(0.0, 7.5 * dt, dt, u, v)
+    ref = run(dt)                                   # captures the graph (line kernel, streamed G)
+    assert rel_l2(ref, u) < TOL_STEPS
+    for name, val in (("stiffness_variant", 0), ("geometry_mode", 1), ("use_graph", 0),
+                      ("stiffness_variant", 2)):
+        ctx.set_option(name, val)
+        assert rel_l2(run(dt), u) < TOL_STEPS, (name, val)
+    assert ctx.get_option("geometry_compressed") == 1
+    ctx.set_option("use_graph", 1)
+    u2, v2 = u0.copy(), v0.copy()
+    om.rk4(0.0, 7.5 * (0.5 * dt), 0.5 * dt, u2, v2)
+    assert rel_l2(run(0.5 * dt), u2) < TOL_STEPS     # other dt: graph re-captured
+    assert rel_l2(run(dt), u) < TOL_STEPS
