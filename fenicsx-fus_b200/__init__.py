@@ -79,6 +79,21 @@ class BoxMesh:
         lib.fus_box_facets(self.n, self.facets.ctypes.data_as(C.c_void_p))
         self.ncells = nx * ny * nz
 
+    def tag_source_disc(self, centre_yz, radius):
+        """Re-tag the x = lo face: only facets whose centroid lies within `radius` of
+        (y, z) = centre_yz keep tag 1 (source), the rest of that face becomes 0.  Stands in for the
+        transducer surface of the reference's bowl meshes, which are not available
+        (SURVEY.md section 8d config 4)."""
+        corners = {2: (0, 2, 4, 6)}                       # local facet 2 is x = 0
+        f = self.facets
+        on = f[:, 1] == 2
+        cen = self.x[self.xdofmap[f[on, 0]][:, corners[2]]].mean(axis=1)
+        d = np.hypot(cen[:, 1] - centre_yz[0], cen[:, 2] - centre_yz[1])
+        tags = f[:, 2].copy()
+        tags[np.flatnonzero(on)] = np.where(d <= radius, 1, 0)
+        self.facets = np.ascontiguousarray(np.stack([f[:, 0], f[:, 1], tags], axis=1), dtype=np.int32)
+        return int((tags == 1).sum())
+
     def h_min(self):
         """Cell diameter as dolfinx::mesh::h reports it for an undeformed box (sqrt(3) h)."""
         h = (self.hi - self.lo) / self.n

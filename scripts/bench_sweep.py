@@ -110,6 +110,7 @@ def main():
                 c0, rho0 = np.full(nc, 1480.0), np.full(nc, 1000.0)
                 alpha = 0.2 / 20 * np.log(10)   # 0.2 dB/m in Np/m
                 delta = np.full(nc, fus.compute_diffusivity_of_sound(2 * np.pi * f0, 1480.0, alpha))
+                m.tag_source_disc((L / 2, L / 2), 0.032)   # H131 aperture radius 32 mm
                 mdl = fus.WesterveltSpectral3D(V, c0, rho0, delta, np.full(nc, 3.5), f0,
                                                1000.0 * 1480.0 * 0.2726428, 1480.0)
                 cmax, cfl = 1480.0, 0.2

@@ -122,3 +122,32 @@ def test_bad_arguments_are_errors_not_crashes(fus):
     rc = lib.fus_ctx_create(9, 1, 1000, 1000, np.zeros(1000, dtype=np.int32), None, None,
                             np.zeros(100), 0, C.byref(h))
     assert rc < 0 and lib.fus_last_error()
+
+
+def test_source_disc_tags(fus, orc):
+    """Config 4 stand-in for the bowl transducer: a disc of source facets on x = 0; the lumped
+    source vector then integrates to (1/rho) * tagged area and matches the oracle's facet assembly."""
+    from fenicsx_fus_b200 import capi
+    P, n, L = 2, (4, 8, 8), 0.08
+    m = fus.BoxMesh(n, (0, 0, 0), (0.04, L, L))
+    ntag = m.tag_source_disc((L / 2, L / 2), 0.025)
+    h = L / 8
+    cen = (np.arange(8) + 0.5) * h
+    expect = sum(np.hypot(y - L / 2, z - L / 2) <= 0.025 for y in cen for z in cen)
+    assert ntag == expect and 0 < ntag < 64
+    assert (m.facets[:, 2] == 2).sum() == 64              # the absorbing face is untouched
+    V = fus.FunctionSpace(m, P)
+    nc, nd = m.ncells, V.ndofs
+    c0, rho0 = np.full(nc, 1480.0), np.full(nc, 1000.0)
+    src, dsrc, absb, bmass = (np.zeros(nd) for _ in range(4))
+    rc = capi.load().fus_boundary_vectors(capi.KINDS["linear"], P, nc, nd, m.x, m.xdofmap, V.dofmap,
+                                          m.facets.shape[0], m.facets, c0, rho0, None,
+                                          capi.optional(src), capi.optional(dsrc),
+                                          capi.optional(absb), capi.optional(bmass))
+    assert rc == 0
+    assert abs(src.sum() - ntag * h * h / 1000.0) < 1e-15
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    ref = np.zeros(nd)
+    for k in np.flatnonzero(m.facets[:, 2] == 1):
+        np.add.at(ref, V.dofmap[m.facets[k, 0], fn[k]], fs[k] / 1000.0)
+    assert np.allclose(src, ref, rtol=1e-13, atol=1e-20)
