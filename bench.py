@@ -192,6 +192,48 @@ def run_reference_arm(args):
     return 0
 
 
+def child_extras(timeout_s=170.0):
+    """Secondary measurements in a CHILD process (scripts/bench_sweep.py), after the headline
+    numbers are in hand: the degree sweep of BASELINE config 2 (single operator application, P=2..7,
+    ~10 M dofs) with the geometric factors streamed and rebuilt on the fly, and the headline RK4
+    workload per geometry mode.  A child so that nothing it does -- a fault in a newer kernel, a
+    time-out -- can cost the headline line."""
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_sweep.py"), "--degrees",
+           "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,2", "--rk4-geometry-modes",
+           "0,2", "--models", "", "--repeats", "20"]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    t0 = time.perf_counter()
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+        out, rc, err = res.stdout, res.returncode, res.stderr[-400:]
+    except subprocess.TimeoutExpired as ex:
+        out = ex.stdout.decode() if isinstance(ex.stdout, bytes) else (ex.stdout or "")
+        rc, err = -9, f"timed out after {timeout_s:.0f} s"
+    rows = []
+    for ln in out.splitlines():
+        if ln.startswith("{"):
+            try:
+                rows.append(json.loads(ln))
+            except ValueError:
+                pass
+    keep = ("P", "dofs", "geometry_mode", "ms_min", "ms_median", "gdof_per_s",
+            "frac_of_measured_peak", "ms_per_step", "dof_updates_per_s", "operator_ms",
+            "rel_l2_vs_first_mode")
+    res = {"wall_s": time.perf_counter() - t0, "exit": rc,
+           "degree_sweep_operator_apply": [{k: r[k] for k in keep if k in r} for r in rows
+                                           if r.get("config") == "degree_sweep"],
+           "headline_rk4_by_geometry_mode": [{k: r[k] for k in keep if k in r} for r in rows
+                                             if r.get("config") == "headline_rk4_by_geometry_mode"],
+           "note": ("geometry_mode 0 streams the reference's G (48 B/point; the roofline's bytes), "
+                    "2 rebuilds it per point from the trilinear cell map (192 B/cell); "
+                    "frac_of_measured_peak always uses the streamed algorithmic bytes")}
+    if rc != 0:
+        res["stderr_tail"] = err
+    return res
+
+
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
@@ -388,6 +430,16 @@ def run_gpu_arm(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable",
                    "sample": repr(ex)[:200]}
 
+    if world == 1 and not args.no_extras and (P, N_BENCH) == (4, 54):
+        # release this process's device memory first; the child builds its own contexts
+        mdl.destroy()
+        ctx.destroy()
+        torch.cuda.empty_cache()
+        try:
+            extras["child_process_sweep"] = child_extras()
+        except Exception as ex:  # never at the expense of the headline line
+            extras["child_process_sweep"] = {"error": repr(ex)[:300]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
@@ -434,6 +486,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the child-process sweep (profiler passes)")
     # non-headline workloads for our own scaling studies (the driver never passes these)
     ap.add_argument("--degree", type=int, default=P_BENCH)
     ap.add_argument("--cells", type=int, default=N_BENCH, help="cells per direction per GPU")

@@ -36,6 +36,8 @@ SIGNATURES = {
     "fus_box_facets": (_ll, [_i32, _p]),
     "fus_boundary_vectors": (_int, [_int, _int, _ll, _ll, _f64, _i32, _i32, _ll, _i32, _f64, _f64,
                                     _p, _p, _p, _p, _p]),
+    "fus_trilinear_coeffs": (_int, [_ll, _f64, _i32, _f64]),
+    "fus_trilinear_geometry": (_int, [_int, _ll, _f64, _p, _p]),
     "fus_ctx_create": (_int, [_int, _ll, _ll, _ll, _i32, _p, _p, _f64, _int, C.POINTER(_p)]),
     "fus_ctx_create_from_mesh": (_int, [_int, _ll, _ll, _ll, _i32, _ll, _f64, _i32, _int,
                                         C.POINTER(_p)]),

@@ -77,10 +77,12 @@ struct fus_ctx {
   double2* d_G2 = nullptr;
   double* d_detJ = nullptr;
   double dphi[64];
-  double wts[8];            // 1-D GLL weights
-  // optional affine compression of the geometric factors (option "geometry_mode" = 1)
+  double pts[8], wts[8];    // 1-D GLL points and weights
+  // optional compressed geometry (option "geometry_mode"): 1 = one Ghat per affine cell,
+  // 2 = trilinear map coefficients per cell, G rebuilt in the kernel (fus_trilinear.hpp)
   double2* d_Ghat = nullptr;
-  bool affine_active = false;
+  double* d_tri = nullptr;
+  int geom_active = 0;      // what the stiffness operator currently uses: 0 streamed G, 1, 2
   // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
   // profiles/), 0 column kernel, 1 point kernel, 2 line kernel
   int variant = -1;
@@ -185,6 +187,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   DMat<N> D;
   std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
   std::memcpy(D.w, c->wts, sizeof(double) * N);
+  std::memcpy(D.x, c->pts, sizeof(double) * N);
   const bool fuse = (x2 != nullptr);
   const int variant = (c->variant >= 0) ? c->variant : (N >= 5 ? 2 : 0);
   if (variant == 1) {
@@ -234,12 +237,20 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     FUS_LAUNCHED();
     return FUS_OK;
   };
-  if (c->affine_active) { // all cells are parallelepipeds: Ghat per cell instead of G per point
+  if (c->geom_active == 1) { // all cells are parallelepipeds: Ghat per cell instead of G per point
     using L = LineCfg<N>;
     static bool configured = false;
     static int bp = 1, bf = 1;
     Gptr = c->d_Ghat;
-    return launch(stiffness_line_kernel<N, false, true>, stiffness_line_kernel<N, true, true>,
+    return launch(stiffness_line_kernel<N, false, 1>, stiffness_line_kernel<N, true, 1>,
+                  L::THREADS, L::SMEM_BYTES, L::CPB, configured, bp, bf);
+  }
+  if (c->geom_active == 2) { // trilinear cells: G rebuilt per point from 192 B per cell
+    using L = LineCfg<N>;
+    static bool configured = false;
+    static int bp = 1, bf = 1;
+    Gptr = reinterpret_cast<const double2*>(c->d_tri);
+    return launch(stiffness_line_kernel<N, false, 2>, stiffness_line_kernel<N, true, 2>,
                   L::THREADS, L::SMEM_BYTES, L::CPB, configured, bp, bf);
   }
   if (variant == 2) {
@@ -344,6 +355,7 @@ int affine_detect_n(fus_ctx* c, int* all_affine) {
   DMat<N> D;
   std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
   std::memcpy(D.w, c->wts, sizeof(double) * N);
+  std::memcpy(D.x, c->pts, sizeof(double) * N);
   int* d_flag = nullptr;
   FUS_CUDA(cudaMalloc(&d_flag, sizeof(int)));
   const int one = 1;
@@ -409,10 +421,7 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   c->nowned = nowned;
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  {
-    double pts[8];
-    gll(P, pts, c->wts);
-  }
+  gll(P, c->pts, c->wts);
   if (const char* e = std::getenv("FUS_STIFFNESS_VARIANT")) { // A/B runs of bench.py
     const int v = std::atoi(e);
     if (v >= -1 && v <= 2)
@@ -487,38 +496,56 @@ int fus_boundary_vectors(int kind, int P, int64_t ncells, int64_t ndofs, const d
   return boundary_vectors(kind, P, ncells, ndofs, xg, xdofmap, tensor_dofmap, nfacets, facets, c0,
                           rho0, delta0, src, dsrc, absb, bmass);
 }
+int fus_trilinear_coeffs(int64_t ncells, const double* xg, const int32_t* xdofmap,
+                         double* coeffs) {
+  return trilinear_coeffs(ncells, xg, xdofmap, coeffs);
+}
+int fus_trilinear_geometry(int P, int64_t ncells, const double* coeffs, double* G, double* detJ) {
+  return trilinear_geometry(P, ncells, coeffs, G, detJ);
+}
 
 // ---- context ----------------------------------------------------------------------------------
+// a context that failed half-way through its construction is released, never handed back
+static int ctx_fail(fus_ctx** out, int rc) {
+  if (rc != FUS_OK && out && *out) {
+    fus_ctx_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
 int fus_ctx_create(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
                    const int32_t* tensor_dofmap, const double* G, const double* detJ,
                    const double* dphi, int device, fus_ctx** out) {
+  if (out)
+    *out = nullptr;
   if (!dphi || (!G && !detJ)) {
     set_error("fus_ctx_create: dphi and at least one of G, detJ are required");
     return FUS_ERR_ARG;
   }
   int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, G != nullptr,
                      detJ != nullptr, out);
-  if (r != FUS_OK) {
-    if (out && *out) {
-      fus_ctx_destroy(*out);
-      *out = nullptr;
-    }
-    return r;
-  }
+  if (r != FUS_OK)
+    return ctx_fail(out, r);
   fus_ctx* c = *out;
   std::memcpy(c->dphi, dphi, sizeof(double) * c->N * c->N);
-  if (detJ)
-    FUS_CUDA(cudaMemcpyAsync(c->d_detJ, detJ, sizeof(double) * ncells * c->Nd,
-                             cudaMemcpyHostToDevice, c->stream));
-  if (G)
-    FUS_TRY(FUS_DISPATCH_N(c, g_upload_n, c, G));
-  FUS_CUDA(cudaStreamSynchronize(c->stream));
-  return FUS_OK;
+  auto fill = [&]() -> int {
+    if (detJ)
+      FUS_CUDA(cudaMemcpyAsync(c->d_detJ, detJ, sizeof(double) * ncells * c->Nd,
+                               cudaMemcpyHostToDevice, c->stream));
+    if (G)
+      FUS_TRY(FUS_DISPATCH_N(c, g_upload_n, c, G));
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    return FUS_OK;
+  };
+  return ctx_fail(out, fill());
 }
 
 int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
                              const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
                              const int32_t* xdofmap, int device, fus_ctx** out) {
+  if (out)
+    *out = nullptr;
   if (!xg || !xdofmap || nverts < 8) {
     set_error("fus_ctx_create_from_mesh: mesh geometry required");
     return FUS_ERR_ARG;
@@ -530,26 +557,29 @@ int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowne
       return FUS_ERR_ARG;
     }
   int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, true, true, out);
-  if (r != FUS_OK) {
-    if (out && *out) {
-      fus_ctx_destroy(*out);
-      *out = nullptr;
-    }
-    return r;
-  }
+  if (r != FUS_OK)
+    return ctx_fail(out, r);
   fus_ctx* c = *out;
-  FUS_TRY(tabulate_dphi(P, c->dphi));
-  DevPtr<double> d_xg;
-  DevPtr<int32_t> d_xd;
-  FUS_CUDA(cudaMalloc(&d_xg.p, sizeof(double) * 3 * nverts));
-  FUS_CUDA(cudaMalloc(&d_xd.p, sizeof(int32_t) * 8 * ncells));
-  FUS_CUDA(cudaMemcpyAsync(d_xg.p, xg, sizeof(double) * 3 * nverts, cudaMemcpyHostToDevice,
-                           c->stream));
-  FUS_CUDA(cudaMemcpyAsync(d_xd.p, xdofmap, sizeof(int32_t) * 8 * ncells, cudaMemcpyHostToDevice,
-                           c->stream));
-  FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_n, c, d_xg.p, d_xd.p, true, true));
-  FUS_CUDA(cudaStreamSynchronize(c->stream));
-  return FUS_OK;
+  auto fill = [&]() -> int {
+    FUS_TRY(tabulate_dphi(P, c->dphi));
+    DevPtr<double> d_xg;
+    DevPtr<int32_t> d_xd;
+    FUS_CUDA(cudaMalloc(&d_xg.p, sizeof(double) * 3 * nverts));
+    FUS_CUDA(cudaMalloc(&d_xd.p, sizeof(int32_t) * 8 * ncells));
+    FUS_CUDA(cudaMemcpyAsync(d_xg.p, xg, sizeof(double) * 3 * nverts, cudaMemcpyHostToDevice,
+                             c->stream));
+    FUS_CUDA(cudaMemcpyAsync(d_xd.p, xdofmap, sizeof(int32_t) * 8 * ncells,
+                             cudaMemcpyHostToDevice, c->stream));
+    FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_n, c, d_xg.p, d_xd.p, true, true));
+    // the trilinear map itself, 192 B per cell: what option geometry_mode = 2 reads instead of G
+    FUS_CUDA(cudaMalloc(&c->d_tri, sizeof(double) * FUS_TRI_STRIDE * ncells));
+    tri_coeff_kernel<<<grid_for(ncells, 128, 1 << 30), 128, 0, c->stream>>>(d_xg.p, d_xd.p, ncells,
+                                                                          c->d_tri);
+    FUS_LAUNCHED();
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    return FUS_OK;
+  };
+  return ctx_fail(out, fill());
 }
 
 int fus_ctx_destroy(fus_ctx* c) {
@@ -567,6 +597,7 @@ int fus_ctx_destroy(fus_ctx* c) {
     }
   cudaFree(c->d_dofmap);
   cudaFree(c->d_Ghat);
+  cudaFree(c->d_tri);
   cudaFree(c->d_G2);
   cudaFree(c->d_detJ);
   if (c->own_stream && c->stream)
@@ -614,17 +645,31 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   }
   if (!std::strcmp(name, "geometry_mode")) {
     // 0: stream G per point (default).  1: if EVERY cell is affine, keep one Ghat per cell and
-    // rebuild G = w_q * Ghat in the kernel; otherwise stay on the streamed path.
+    // rebuild G = w_q * Ghat in the kernel; otherwise stay on the streamed path.  2: rebuild G per
+    // point from the trilinear cell map (any mesh; needs a context created from the mesh).
     if (value == 0) {
-      c->affine_active = false;
+      c->geom_active = 0;
       return FUS_OK;
+    }
+    if (value == 2) {
+      if (!c->d_tri) {
+        set_error("geometry_mode 2 needs the cell vertices: create the context with "
+                  "fus_ctx_create_from_mesh");
+        return FUS_ERR_STATE;
+      }
+      c->geom_active = 2;
+      return FUS_OK;
+    }
+    if (value != 1) {
+      set_error("geometry_mode must be 0, 1 or 2");
+      return FUS_ERR_ARG;
     }
     if (!c->d_G2)
       return FUS_ERR_STATE;
     FUS_TRY(select_device(c));
     int all_affine = 0;
     FUS_TRY(FUS_DISPATCH_N(c, affine_detect_n, c, &all_affine));
-    c->affine_active = all_affine != 0;
+    c->geom_active = all_affine ? 1 : 0;
     return FUS_OK;
   }
   if (!std::strcmp(name, "l2_persist")) {
@@ -661,7 +706,7 @@ int fus_ctx_get_option(fus_ctx* c, const char* name, int* value) {
   if (!c || !name || !value)
     return FUS_ERR_ARG;
   if (!std::strcmp(name, "geometry_compressed"))
-    *value = c->affine_active ? 1 : 0;
+    *value = c->geom_active;
   else if (!std::strcmp(name, "stiffness_variant"))
     *value = c->variant;
   else if (!std::strcmp(name, "halo_mode"))
@@ -819,6 +864,8 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
                      const double* delta0, const double* beta0, const double* src,
                      const double* dsrc, const double* absb, const double* bmass, double freq,
                      double p0, double s0, fus_model** out) {
+  if (out)
+    *out = nullptr;
   if (!c || !out || !c0 || !rho0 || kind < 0 || kind > 2) {
     set_error("fus_model_create: bad argument");
     return FUS_ERR_ARG;
@@ -833,7 +880,6 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
   }
   FUS_TRY(select_device(c));
   fus_model* m = new fus_model();
-  *out = m;
   m->ctx = c;
   m->kind = kind;
   m->freq = freq;
@@ -854,66 +900,75 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
     mco[i] = 1.0 / rho0[i] / c0[i] / c0[i];
   }
   const size_t cb = sizeof(double) * nc;
-  double *d_mco = nullptr, *d_nl2 = nullptr;
-  FUS_CUDA(cudaMalloc(&m->d_lin, cb));
-  FUS_CUDA(cudaMalloc(&m->d_att, cb));
-  FUS_CUDA(cudaMalloc(&d_mco, cb));
-  FUS_CUDA(cudaMemcpyAsync(m->d_lin, lin.data(), cb, cudaMemcpyHostToDevice, c->stream));
-  FUS_CUDA(cudaMemcpyAsync(m->d_att, att.data(), cb, cudaMemcpyHostToDevice, c->stream));
-  FUS_CUDA(cudaMemcpyAsync(d_mco, mco.data(), cb, cudaMemcpyHostToDevice, c->stream));
-  for (double** v : {&m->d_m, &m->d_u0, &m->d_v0, &m->d_ua, &m->d_va, &m->d_un, &m->d_vn, &m->d_b})
-    FUS_TRY(model_alloc_vec(c, v));
-  // lumped mass: the form `a` assembled with u == 1 (Linear.hpp:127-134), + facet mass term
-  std::vector<double> ones(nd, 1.0);
-  FUS_CUDA(cudaMemcpyAsync(m->d_un, ones.data(), sizeof(double) * nd, cudaMemcpyHostToDevice,
-                           c->stream));
-  FUS_TRY(launch_mass(c, m->d_un, d_mco, m->d_m, 0, nc, c->stream));
-  if (bmass) {
-    FUS_CUDA(cudaMemcpyAsync(m->d_vn, bmass, sizeof(double) * nd, cudaMemcpyHostToDevice,
+  auto build = [&]() -> int {
+    DevPtr<double> mco_dev, nl2_dev; // set-up scratch, released on every exit path
+    FUS_CUDA(cudaMalloc(&m->d_lin, cb));
+    FUS_CUDA(cudaMalloc(&m->d_att, cb));
+    FUS_CUDA(cudaMalloc(&mco_dev.p, cb));
+    double*& d_mco = mco_dev.p;
+    double*& d_nl2 = nl2_dev.p;
+    FUS_CUDA(cudaMemcpyAsync(m->d_lin, lin.data(), cb, cudaMemcpyHostToDevice, c->stream));
+    FUS_CUDA(cudaMemcpyAsync(m->d_att, att.data(), cb, cudaMemcpyHostToDevice, c->stream));
+    FUS_CUDA(cudaMemcpyAsync(d_mco, mco.data(), cb, cudaMemcpyHostToDevice, c->stream));
+    for (double** v : {&m->d_m, &m->d_u0, &m->d_v0, &m->d_ua, &m->d_va, &m->d_un, &m->d_vn, &m->d_b})
+      FUS_TRY(model_alloc_vec(c, v));
+    // lumped mass: the form `a` assembled with u == 1 (Linear.hpp:127-134), + facet mass term
+    std::vector<double> ones(nd, 1.0);
+    FUS_CUDA(cudaMemcpyAsync(m->d_un, ones.data(), sizeof(double) * nd, cudaMemcpyHostToDevice,
                              c->stream));
-    add_kernel<<<grid_for(nd, 256, 1 << 30), 256, 0, c->stream>>>(m->d_m, m->d_vn, nd);
-    FUS_LAUNCHED();
-  }
-  if (kind == FUS_WESTERVELT) {
-    FUS_CUDA(cudaMalloc(&d_nl2, cb));
-    FUS_CUDA(cudaMemcpyAsync(d_nl2, nl2.data(), cb, cudaMemcpyHostToDevice, c->stream));
-    FUS_TRY(model_alloc_vec(c, &m->d_dnl));
-    FUS_TRY(launch_mass(c, m->d_un, d_nl2, m->d_dnl, 0, nc, c->stream));
-  }
-  if (c->halo) { // sum the per-rank partial sums on the owners, once (Linear.hpp:134)
-    FUS_TRY(halo_reverse(c->halo, m->d_m, nullptr, c->stream));
-    if (m->d_dnl)
-      FUS_TRY(halo_reverse(c->halo, m->d_dnl, nullptr, c->stream));
-  }
-  FUS_CUDA(cudaStreamSynchronize(c->stream));
-  FUS_CUDA(cudaMemsetAsync(m->d_un, 0, sizeof(double) * nd, c->stream));
-  FUS_CUDA(cudaMemsetAsync(m->d_vn, 0, sizeof(double) * nd, c->stream));
-  cudaFree(d_mco);
-  cudaFree(d_nl2);
-  // compact the boundary vectors
-  std::vector<int32_t> bidx;
-  std::vector<double> bs, bd, ba;
-  for (int64_t i = 0; i < nd; ++i) {
-    const double a = src ? src[i] : 0.0, b = dsrc ? dsrc[i] : 0.0, e = absb ? absb[i] : 0.0;
-    if (a != 0.0 || b != 0.0 || e != 0.0) {
-      bidx.push_back((int32_t)i);
-      bs.push_back(a);
-      bd.push_back(b);
-      ba.push_back(e);
+    FUS_TRY(launch_mass(c, m->d_un, d_mco, m->d_m, 0, nc, c->stream));
+    if (bmass) {
+      FUS_CUDA(cudaMemcpyAsync(m->d_vn, bmass, sizeof(double) * nd, cudaMemcpyHostToDevice,
+                               c->stream));
+      add_kernel<<<grid_for(nd, 256, 1 << 30), 256, 0, c->stream>>>(m->d_m, m->d_vn, nd);
+      FUS_LAUNCHED();
     }
+    if (kind == FUS_WESTERVELT) {
+      FUS_CUDA(cudaMalloc(&d_nl2, cb));
+      FUS_CUDA(cudaMemcpyAsync(d_nl2, nl2.data(), cb, cudaMemcpyHostToDevice, c->stream));
+      FUS_TRY(model_alloc_vec(c, &m->d_dnl));
+      FUS_TRY(launch_mass(c, m->d_un, d_nl2, m->d_dnl, 0, nc, c->stream));
+    }
+    if (c->halo) { // sum the per-rank partial sums on the owners, once (Linear.hpp:134)
+      FUS_TRY(halo_reverse(c->halo, m->d_m, nullptr, c->stream));
+      if (m->d_dnl)
+        FUS_TRY(halo_reverse(c->halo, m->d_dnl, nullptr, c->stream));
+    }
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    FUS_CUDA(cudaMemsetAsync(m->d_un, 0, sizeof(double) * nd, c->stream));
+    FUS_CUDA(cudaMemsetAsync(m->d_vn, 0, sizeof(double) * nd, c->stream));
+    // compact the boundary vectors
+    std::vector<int32_t> bidx;
+    std::vector<double> bs, bd, ba;
+    for (int64_t i = 0; i < nd; ++i) {
+      const double a = src ? src[i] : 0.0, b = dsrc ? dsrc[i] : 0.0, e = absb ? absb[i] : 0.0;
+      if (a != 0.0 || b != 0.0 || e != 0.0) {
+        bidx.push_back((int32_t)i);
+        bs.push_back(a);
+        bd.push_back(b);
+        ba.push_back(e);
+      }
+    }
+    m->nb = (int64_t)bidx.size();
+    if (m->nb) {
+      FUS_CUDA(cudaMalloc(&m->d_bidx, sizeof(int32_t) * m->nb));
+      FUS_CUDA(cudaMalloc(&m->d_bsrc, sizeof(double) * m->nb));
+      FUS_CUDA(cudaMalloc(&m->d_bdsrc, sizeof(double) * m->nb));
+      FUS_CUDA(cudaMalloc(&m->d_babs, sizeof(double) * m->nb));
+      FUS_CUDA(cudaMemcpy(m->d_bidx, bidx.data(), sizeof(int32_t) * m->nb, cudaMemcpyHostToDevice));
+      FUS_CUDA(cudaMemcpy(m->d_bsrc, bs.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
+      FUS_CUDA(cudaMemcpy(m->d_bdsrc, bd.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
+      FUS_CUDA(cudaMemcpy(m->d_babs, ba.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
+    }
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    return FUS_OK;
+  };
+  const int rc = build();
+  if (rc != FUS_OK) { // nothing half-built is handed back
+    fus_model_destroy(m);
+    return rc;
   }
-  m->nb = (int64_t)bidx.size();
-  if (m->nb) {
-    FUS_CUDA(cudaMalloc(&m->d_bidx, sizeof(int32_t) * m->nb));
-    FUS_CUDA(cudaMalloc(&m->d_bsrc, sizeof(double) * m->nb));
-    FUS_CUDA(cudaMalloc(&m->d_bdsrc, sizeof(double) * m->nb));
-    FUS_CUDA(cudaMalloc(&m->d_babs, sizeof(double) * m->nb));
-    FUS_CUDA(cudaMemcpy(m->d_bidx, bidx.data(), sizeof(int32_t) * m->nb, cudaMemcpyHostToDevice));
-    FUS_CUDA(cudaMemcpy(m->d_bsrc, bs.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
-    FUS_CUDA(cudaMemcpy(m->d_bdsrc, bd.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
-    FUS_CUDA(cudaMemcpy(m->d_babs, ba.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
-  }
-  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  *out = m;
   return FUS_OK;
 }
 

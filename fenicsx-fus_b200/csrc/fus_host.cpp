@@ -8,6 +8,7 @@
 //   boundary vectors    FFCx `ds` kernels of forms.py + fem::assemble_vector (Linear.hpp:133,205)
 // (paths relative to cpp/fenicsx-sf/common/ of the reference)
 #include "fus_internal.hpp"
+#include "fus_trilinear.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -295,6 +296,54 @@ int boundary_vectors(int kind, int P, int64_t ncells, int64_t ndofs, const doubl
         }
       }
   }
+  return FUS_OK;
+}
+
+// ---- trilinear cell map (option geometry_mode = 2) ----------------------------------------------
+
+int trilinear_coeffs(int64_t ncells, const double* xg, const int32_t* xdofmap, double* coeffs) {
+  if (ncells < 0 || !xg || !xdofmap || !coeffs)
+    return FUS_ERR_ARG;
+  for (int64_t c = 0; c < ncells; ++c) {
+    double X[8][3];
+    for (int v = 0; v < 8; ++v)
+      for (int r = 0; r < 3; ++r)
+        X[v][r] = xg[3 * (int64_t)xdofmap[8 * c + v] + r];
+    tri_cell_coeffs(X, coeffs + c * FUS_TRI_STRIDE);
+  }
+  return FUS_OK;
+}
+
+// G and detJ of the reference (precompute.hpp:33-213) for a batch of cells, rebuilt point by point
+// with exactly the helpers the trilinear stiffness kernel runs: column b of the scaled K K^T is
+// the transform of the unit vector e_b.
+int trilinear_geometry(int P, int64_t ncells, const double* coeffs, double* G, double* detJ) {
+  if (P < 1 || P > 15 || ncells < 0 || !coeffs)
+    return FUS_ERR_ARG;
+  const int N = P + 1;
+  std::vector<double> pts(N), wts(N);
+  gll(P, pts.data(), wts.data());
+  for (int64_t c = 0; c < ncells; ++c)
+    for (int a = 0; a < N; ++a)
+      for (int b = 0; b < N; ++b) {
+        TriLine L;
+        tri_line_setup(coeffs + c * FUS_TRI_STRIDE, pts[a], pts[b], L);
+        for (int i0 = 0; i0 < N; ++i0) {
+          const int64_t q = (c * N + i0) * N * N + a * N + b;
+          const double w = wts[i0] * (wts[a] * wts[b]);
+          double col[3][3], adet = 0.0;
+          for (int e = 0; e < 3; ++e)
+            adet = tri_transform(L, pts[i0], w, e == 0, e == 1, e == 2, col[e][0], col[e][1],
+                                 col[e][2]);
+          if (detJ)
+            detJ[q] = adet * w;
+          if (G) {
+            double* g = G + 6 * q;
+            g[0] = col[0][0], g[1] = col[1][0], g[2] = col[2][0];
+            g[3] = col[1][1], g[4] = col[2][1], g[5] = col[2][2];
+          }
+        }
+      }
   return FUS_OK;
 }
 

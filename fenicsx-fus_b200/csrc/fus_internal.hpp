@@ -17,6 +17,8 @@ int boundary_vectors(int kind, int P, int64_t ncells, int64_t ndofs, const doubl
                      const int32_t* xdofmap, const int32_t* dm, int64_t nfacets,
                      const int32_t* facets, const double* c0, const double* rho0,
                      const double* delta0, double* src, double* dsrc, double* absb, double* bmass);
+int trilinear_coeffs(int64_t ncells, const double* xg, const int32_t* xdofmap, double* coeffs);
+int trilinear_geometry(int P, int64_t ncells, const double* coeffs, double* G, double* detJ);
 
 void set_error(const char* fmt, ...);
 

@@ -8,6 +8,8 @@
 //   t = i1*N + i2, i.e. for one cell and one i0-level the N*N points of a component pair are
 //   contiguous: a thread column (i1,i2) streams its 3*N double2 with 16-byte coalesced loads.
 #pragma once
+#include "fus_trilinear.hpp"
+
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -17,7 +19,8 @@ namespace fus {
 template <int N>
 struct DMat {
   double d[N * N]; // d[q*N+k] = phi_k'(xi_q)
-  double w[N];     // 1-D GLL weights (only read by the affine-compressed kernel)
+  double w[N];     // 1-D GLL weights (only read by the compressed-geometry kernels)
+  double x[N];     // 1-D GLL points  (only read by the trilinear-geometry kernel)
 };
 
 template <int N>
@@ -304,11 +307,17 @@ struct LineCfg {
   static constexpr int GPF = (N <= 7) ? N : N / 2;
 };
 
-// AFFINE: every cell is a parallelepiped, so G[c][q] = w_q * Ghat[c] exactly (J is constant in a
-// cell).  G2 then points to Ghat (3 double2 per CELL) and the 48 B/point stream disappears; the
-// quadrature weight is rebuilt from the 1-D weights.  Opt-in (option "geometry_mode"), see DESIGN.
-template <int N, bool FUSE2, bool AFFINE = false>
-__global__ void __launch_bounds__(LineCfg<N>::THREADS)
+// GEOM selects where the geometric factors come from (option "geometry_mode", see DESIGN):
+//   0  streamed: G2[cell][i0][p][t], 48 B per point (the reference's data, the headline path)
+//   1  affine:   every cell is a parallelepiped, so G[c][q] = w_q * Ghat[c] exactly (J is constant
+//                in a cell).  G2 points to Ghat (3 double2 per CELL); the quadrature weight is
+//                rebuilt from the 1-D weights.
+//   2  trilinear: G2 points to the monomial coefficients of the cell map (FUS_TRI_STRIDE doubles
+//                per CELL, fus_trilinear.hpp) and |det J| w K K^T f is evaluated per point from
+//                them: exact for every mesh with a degree-1 coordinate element, 192 B per cell
+//                instead of 48 B per point, ~45 more FP64 operations per point.
+template <int N, bool FUSE2, int GEOM = 0>
+__global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3 : 0)
     stiffness_line_kernel(const double* __restrict__ x, const double* __restrict__ x2,
                           double* __restrict__ y, const int32_t* __restrict__ dofmap,
                           const double2* __restrict__ G2, const double* __restrict__ coeff,
@@ -316,7 +325,10 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
                           long long cell_end, const __grid_constant__ DMat<N> D) {
   using C = LineCfg<N>;
   constexpr int NN = C::NN, GPF = C::GPF;
+  constexpr bool AFFINE = (GEOM == 1), TRI = (GEOM == 2);
+  constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
+  static_assert(GEOM >= 0 && GEOM <= 2, "unknown geometry mode");
   extern __shared__ double smem[];
 
   const int tid = threadIdx.x;
@@ -352,10 +364,38 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 
   int idx[N], idxn[N];
   double xv[N];
-  double2 g[AFFINE ? 1 : GPF][3];
+  double2 g[GEOM != 0 ? 1 : GPF][3];
   double2 gh[3], ghn[3]; // AFFINE: Ghat of the current and of the next cell
-  const double wab = AFFINE ? D.w[a] * D.w[b] : 0.0;
+  // TRI: the pieces of J on this thread's line (xi1,xi2) = (x[a],x[b]) for the current cell.  The
+  // 192 B of a cell are read by all its threads at the same addresses, so there is nothing to keep
+  // in flight: the next cell's two lines are prefetched into L2 and loaded when it becomes current.
+  TriLine tl;
+  const double wab = (GEOM != 0) ? D.w[a] * D.w[b] : 0.0;
+  const double xia = TRI ? D.x[a] : 0.0, xib = TRI ? D.x[b] : 0.0;
   double cf = 0.0;
+  if constexpr (TRI) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { // identity map: padding lanes stay finite
+      tl.j0[i] = (i == 0), tl.a0[i] = (i == 1), tl.b0[i] = (i == 2);
+      tl.da[i] = tl.db[i] = 0.0;
+    }
+  }
+  // coefficients of cell `cell` -> line pieces
+  auto tri_setup = [&](long long cell) {
+    double cq[FUS_TRI_STRIDE];
+#pragma unroll
+    for (int k = 0; k < TQ; ++k) {
+      const double2 v = __ldg(G2 + cell * TQ + k);
+      cq[2 * k] = v.x;
+      cq[2 * k + 1] = v.y;
+    }
+    tri_line_setup(cq, xia, xib, tl);
+  };
+  auto tri_prefetch = [&](long long cell) {
+    const double2* q = G2 + cell * TQ;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + TQ - 1));
+  };
 #pragma unroll
   for (int p = 0; p < 3; ++p)
     gh[p] = ghn[p] = make_double2(0.0, 0.0);
@@ -366,7 +406,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
     xv[k] = 0.0;
   }
 #pragma unroll
-  for (int k = 0; k < (AFFINE ? 1 : GPF); ++k)
+  for (int k = 0; k < (GEOM != 0 ? 1 : GPF); ++k)
 #pragma unroll
     for (int p = 0; p < 3; ++p)
       g[k][p] = make_double2(0.0, 0.0);
@@ -393,6 +433,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
 #pragma unroll
       for (int p = 0; p < 3; ++p)
         gh[p] = __ldg(G2 + c * 3 + p);
+    } else if constexpr (TRI) {
+      tri_setup(c);
     } else {
       const double2* gp = G2 + c * (3 * N * NN) + t;
 #pragma unroll
@@ -414,6 +456,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
       for (int p = 0; p < 3; ++p)
         ghn[p] = __ldg(G2 + cn * 3 + p);
     }
+    if constexpr (TRI)
+      tri_prefetch(cn);
   }
 
   for (int it = 0; it < niter; ++it) {
@@ -492,20 +536,25 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
         f1 = S1A[i0 * C::B1_S0];
         f2 = S2A[i0 * C::B2_S0];
       }
-      double2 ga, gb, gc;
-      double scale;
-      if constexpr (AFFINE) {
-        ga = gh[0], gb = gh[1], gc = gh[2];
-        scale = cfc * (D.w[i0] * wab);
+      double t0, t1, t2;
+      if constexpr (TRI) {
+        tri_transform(tl, D.x[i0], cfc * (D.w[i0] * wab), f0[i0], f1, f2, t0, t1, t2);
       } else {
-        ga = g[i0 % GPF][0], gb = g[i0 % GPF][1], gc = g[i0 % GPF][2];
-        scale = cfc;
+        double2 ga, gb, gc;
+        double scale;
+        if constexpr (AFFINE) {
+          ga = gh[0], gb = gh[1], gc = gh[2];
+          scale = cfc * (D.w[i0] * wab);
+        } else {
+          ga = g[i0 % GPF][0], gb = g[i0 % GPF][1], gc = g[i0 % GPF][2];
+          scale = cfc;
+        }
+        t0 = scale * (ga.x * f0[i0] + ga.y * f1 + gb.x * f2);
+        t1 = scale * (ga.y * f0[i0] + gb.y * f1 + gc.x * f2);
+        t2 = scale * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
       }
-      const double t0 = scale * (ga.x * f0[i0] + ga.y * f1 + gb.x * f2);
-      const double t1 = scale * (ga.y * f0[i0] + gb.y * f1 + gc.x * f2);
-      const double t2 = scale * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
       // refill the ring slot: level i0+GPF of this cell, or of the next cell once past the top
-      if constexpr (AFFINE) {
+      if constexpr (GEOM != 0) {
       } else if (i0 + GPF < N) {
         if (valid) {
 #pragma unroll
@@ -576,6 +625,10 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
       for (int p = 0; p < 3; ++p)
         gh[p] = ghn[p];
     }
+    if constexpr (TRI) {
+      if (valid)
+        tri_setup(c);
+    }
     if (validn) {
       const int32_t* dm = dofmap + cn * (N * NN) + t;
 #pragma unroll
@@ -586,6 +639,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS)
         for (int p = 0; p < 3; ++p)
           ghn[p] = __ldg(G2 + cn * 3 + p);
       }
+      if constexpr (TRI)
+        tri_prefetch(cn);
     }
   }
 }
@@ -725,6 +780,29 @@ __global__ void __launch_bounds__(128)
       o[2 * NN] = make_double2(dj * Gm[1][2], dj * Gm[2][2]);
     }
   }
+}
+
+// Monomial coefficients of the trilinear cell map (fus_trilinear.hpp), one thread per cell:
+// what the trilinear-geometry operator reads instead of G.
+static __global__ void __launch_bounds__(128)
+    tri_coeff_kernel(const double* __restrict__ xg, const int32_t* __restrict__ xdofmap,
+                     long long ncells, double* __restrict__ coeffs) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells)
+    return;
+  double X[8][3];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    const double* p = xg + 3 * (long long)__ldg(xdofmap + 8 * c + v);
+    X[v][0] = p[0];
+    X[v][1] = p[1];
+    X[v][2] = p[2];
+  }
+  double out[FUS_TRI_STRIDE];
+  tri_cell_coeffs(X, out);
+#pragma unroll
+  for (int k = 0; k < FUS_TRI_STRIDE; ++k)
+    coeffs[c * FUS_TRI_STRIDE + k] = out[k];
 }
 
 // Affine-cell detection and compression: a cell is affine iff G[c][q]/w_q does not depend on q.

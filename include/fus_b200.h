@@ -87,6 +87,18 @@ int fus_boundary_vectors(int kind, int P, int64_t ncells, int64_t ndofs, const d
                          const double* delta0, double* src, double* dsrc, double* absb,
                          double* bmass);
 
+/* The trilinear cell map in monomial form: coeffs[ncells][FUS_TRI_STRIDE] doubles, 21 used
+   ({c100,c010,c001,c110,c101,c011,c111} x 3 coordinates).  This is what the operator reads per
+   CELL with option "geometry_mode" = 2 instead of the 6 doubles per POINT that
+   compute_scaled_geometrical_factor stores (precompute.hpp:101-213). */
+#define FUS_TRI_STRIDE 24
+int fus_trilinear_coeffs(int64_t ncells, const double* xg, const int32_t* xdofmap,
+                         double* coeffs);
+/* G[ncells][Nd][6] and detJ[ncells][Nd] in the reference layouts (either may be NULL) rebuilt
+   from those coefficients by the same arithmetic the trilinear stiffness kernel runs
+   (host evaluation; used to check that path against precompute.hpp without a GPU). */
+int fus_trilinear_geometry(int P, int64_t ncells, const double* coeffs, double* G, double* detJ);
+
 /* ------------------------------------------------------------------------------------------
  * Operator context (device).  Owns device copies of the cell data; host arrays are only
  * borrowed during the call.
@@ -113,7 +125,7 @@ int fus_ctx_set_stream(fus_ctx* ctx, void* cuda_stream);
 /* Tuning/diagnostic knobs (all optional; defaults in brackets):
      "stiffness_variant"  [-1] -1 auto (column kernel for P <= 3, line kernel for P >= 4),
                                0 column, 1 per-point (cross-check), 2 line kernel
-     "geometry_mode"      [0]  see below
+     "geometry_mode"      [0]  0 streamed G, 1 affine compression, 2 trilinear on the fly (below)
      "use_graph"          [1]  replay RK4 steps from a captured CUDA graph when possible
      "profile_kernels"    [0]  CUDA event pair around every launch (disables graph replay)
      "l2_persist"         [0]  L2 persistence window on the rhs accumulator (measured slower)
@@ -124,7 +136,11 @@ int fus_ctx_set_option(fus_ctx* ctx, const char* name, int value);
 /* "geometry_mode" 1 asks for affine compression: if every cell is a parallelepiped the operator
    keeps 6 numbers per CELL and rebuilds G = w_q * Ghat instead of streaming 48 B per point
    (off by default; falls back to streaming when any cell is not affine).
-   fus_ctx_get_option reads back "geometry_compressed", "stiffness_variant", "halo_mode". */
+   "geometry_mode" 2 rebuilds |det J| w K K^T at every point from the trilinear cell map (192 B per
+   cell, fus_trilinear_coeffs): valid for any mesh with a degree-1 coordinate element, needs a
+   context made by fus_ctx_create_from_mesh (FUS_ERR_STATE otherwise).
+   fus_ctx_get_option reads back "geometry_compressed" (the mode in use: 0, 1 or 2),
+   "stiffness_variant", "halo_mode". */
 int fus_ctx_get_option(fus_ctx* ctx, const char* name, int* value);
 int fus_ctx_sync(fus_ctx* ctx);
 

@@ -5,8 +5,12 @@
     (cpp/fenicsx-sf/experiments/measure_fraction_of_peak_performance/main.cpp:44-116):
     time = min over repeats, reported as Gdof/s and as fraction of the HBM roofline with the
     algorithmic bytes 52 r + 16 per dof (SURVEY.md section 8d);
-  * config 3/4: RK4 steps of the heterogeneous linear, lossy and Westervelt models at P=4.
-Writes one JSON object per line to stdout.
+  * config 3/4: RK4 steps of the heterogeneous linear, lossy and Westervelt models at P=4;
+  * --geometry-modes: the same sweep with the geometric factors streamed (0, the reference's data and
+    the roofline denominator) or rebuilt per point from the trilinear cell map (2, fus_trilinear.hpp);
+    --rk4-geometry-modes: RK4 throughput of the headline workload (linear, P=4, 54^3) per mode and the
+    relative L2 difference of the fields between modes.
+Writes one JSON object per line to stdout.  bench.py runs this in a child process for its `extras`.
 """
 import argparse
 import json
@@ -34,11 +38,15 @@ def main():
     ap.add_argument("--degrees", default="2,3,4,5,6,7")
     ap.add_argument("--repeats", type=int, default=20)
     ap.add_argument("--models", default="linear_het,lossy,westervelt")
-    ap.add_argument("--variants", default="0")
+    ap.add_argument("--variants", default="0", help="-1 = the library's own choice per degree")
+    ap.add_argument("--geometry-modes", default="0")
+    ap.add_argument("--rk4-geometry-modes", default="")
     ap.add_argument("--numbering", type=int, default=1)
     args = ap.parse_args()
     pk = peak()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()        # the legacy default stream cannot be graph-captured
+    torch.cuda.set_stream(stream)
+    gmodes = [int(s) for s in args.geometry_modes.split(",") if s]
     for P in [int(s) for s in args.degrees.split(",") if s]:
         n = SWEEP[P]
         m = fus.BoxMesh((n, n, n))
@@ -50,8 +58,12 @@ def main():
         y = torch.zeros_like(x)
         coeffs = torch.full((m.ncells,), -1.0 / 1000.0, dtype=torch.float64, device="cuda")
         K = fus.StiffnessSpectral3D(V)
-        for variant in [int(s) for s in args.variants.split(",")]:
+        for variant, gmode in [(int(s), g) for s in args.variants.split(",") for g in gmodes]:
             ctx.set_option("stiffness_variant", variant)
+            ctx.set_option("geometry_mode", gmode)
+            if ctx.get_option("geometry_compressed") != gmode:
+                continue
+            y.zero_()
             for _ in range(3):
                 K(x, coeffs, y)
             times = []
@@ -66,13 +78,16 @@ def main():
             npts = m.ncells * (P + 1) ** 3
             alg = 52.0 * npts + 16.0 * V.ndofs
             print(json.dumps({"config": "degree_sweep", "P": P, "n": n, "dofs": V.ndofs,
-                              "variant": variant, "numbering": args.numbering,
+                              "variant": variant, "geometry_mode": gmode,
+                              "numbering": args.numbering,
+                              "y_norm_after_repeats": float(torch.linalg.vector_norm(y).item()),
                               "ms_min": tmin, "ms_median": tmed,
                               "gdof_per_s": V.ndofs / (tmin * 1e-3) / 1e9,
                               "alg_gbs_min": alg / (tmin * 1e-3) / 1e9,
                               "alg_gbs_median": alg / (tmed * 1e-3) / 1e9,
                               "frac_of_measured_peak": alg / (tmed * 1e-3) / 1e9 / pk}), flush=True)
-        ctx.set_option("stiffness_variant", 0)
+        ctx.set_option("stiffness_variant", -1)
+        ctx.set_option("geometry_mode", 0)
         del K, x, y, coeffs
         V._ctx = None
         ctx.destroy()
@@ -82,6 +97,50 @@ def main():
     P, n, L = 4, 54, 0.12
     h = L / n
     models = [s for s in args.models.split(",") if s]
+    rk4_modes = [int(s) for s in args.rk4_geometry_modes.split(",") if s]
+    if rk4_modes:        # headline workload (bench.py) with the geometric factors from each source
+        m = fus.BoxMesh((n, n, n), (0, 0, 0), (L, L, L))
+        V = fus.FunctionSpace(m, P, numbering=args.numbering)
+        ctx = V.context()
+        ctx.set_stream(stream.cuda_stream)
+        mdl = fus.LinearSpectral3D(V, 1500.0, 1000.0, 0.5e6, 6e4, 1500.0)
+        dt0 = 0.65 * np.sqrt(3) * h / (1500.0 * P * P)
+        dt = 2e-6 / (int(2e-6 / dt0) + 1)
+        K, ref = 20, None
+        for gmode in rk4_modes:
+            ctx.set_option("geometry_mode", gmode)
+            if ctx.get_option("geometry_compressed") != gmode:
+                continue
+            mdl.init()
+            mdl.rk4(0.0, 2.5 * dt, dt)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            done = mdl.rk4(3 * dt, 3 * dt + (K - 0.5) * dt, dt)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            ctx.set_option("profile_kernels", 1)
+            mdl.rk4(0.0, (K - 0.5) * dt, dt)
+            torch.cuda.synchronize()
+            ctx.set_option("profile_kernels", 0)
+            n_st, ms_st = ctx.profile("stiffness")
+            mdl.init()
+            mdl.rk4(0.0, (K - 0.5) * dt, dt)
+            u = mdl.u_sol()
+            if ref is None:
+                ref = u
+            print(json.dumps({"config": "headline_rk4_by_geometry_mode", "geometry_mode": gmode,
+                              "P": P, "dofs": V.ndofs, "steps": done, "ms_per_step": ms / done,
+                              "dof_updates_per_s": V.ndofs * done / (ms * 1e-3),
+                              "operator_ms": ms_st / max(n_st, 1),
+                              "rel_l2_vs_first_mode": float(np.linalg.norm(u - ref)
+                                                            / max(np.linalg.norm(ref), 1e-300)),
+                              "u_norm": float(np.linalg.norm(u))}), flush=True)
+        ctx.set_option("geometry_mode", 0)
+        mdl.destroy()
+        V._ctx = None
+        ctx.destroy()
     if models:
         m = fus.BoxMesh((n, n, n), (0, 0, 0), (L, L, L))
         V = fus.FunctionSpace(m, P, numbering=args.numbering)

@@ -17,16 +17,16 @@ BRC=$?
 echo "bench exit $BRC"; tail -c 3000 $OUT/bench_${TAG}.json; tail -n 5 $OUT/bench_${TAG}.err
 if [ $BRC -eq 0 ] && [ "${SKIP_NCU:-0}" != "1" ]; then
   echo "== ncu launch list"
-  timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/plain_${TAG}.log 2>&1 &&
+  timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $OUT/plain_${TAG}.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-      --log-file $OUT/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_list_${TAG}.log 2>&1
+      --log-file $OUT/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $OUT/ncu_list_${TAG}.log 2>&1
   echo "ncu list exit $?"
   echo "== ncu full (stiffness kernel)"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:stiffness_line -s 4 -c 2 \
-      -f -o $OUT/prof_stiffness_${TAG} python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_${TAG}.log 2>&1
+      -f -o $OUT/prof_stiffness_${TAG} python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $OUT/ncu_full_${TAG}.log 2>&1
   echo "ncu full exit $?"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:rk4_stage -s 4 -c 2 \
-      -f -o $OUT/prof_stage_${TAG} python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_full2_${TAG}.log 2>&1
+      -f -o $OUT/prof_stage_${TAG} python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras > $OUT/ncu_full2_${TAG}.log 2>&1
   echo "ncu stage exit $?"
 fi
 ls -la $OUT | tail -n 20

@@ -43,3 +43,20 @@ def test_gpu_arm_has_no_cpu_fallback():
                           "--warmup", "0"], capture_output=True, text=True, timeout=300)
     assert res.returncode != 0
     assert "no B200 visible" in (res.stderr + res.stdout) or "CUDA" in (res.stderr + res.stdout)
+
+
+def test_child_extras_never_raise():
+    """The secondary sweep runs in a child process; whatever happens there (here: no GPU) comes
+    back as data, so the headline line is always printed."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import fenicsx_fus_b200 as fus
+    if fus.device_count() > 0:
+        return
+    res = bench.child_extras(timeout_s=240.0)
+    assert res["exit"] != 0 and res["degree_sweep_operator_apply"] == []
+    assert res["headline_rk4_by_geometry_mode"] == [] and "stderr_tail" in res
+    short = bench.child_extras(timeout_s=0.05)
+    assert short["exit"] == -9 and "timed out" in short["stderr_tail"]

@@ -325,6 +325,72 @@ def test_affine_geometry_compression(fus, orc, gpu, P):
     assert cw.get_option("geometry_compressed") == 0
 
 
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_trilinear_geometry_on_the_fly(fus, orc, gpu, P):
+    """Option geometry_mode=2: the operator reads the trilinear cell map (192 B per cell) and
+    rebuilds |det J| w K K^T at every point instead of streaming the reference's G
+    (precompute.hpp:101-213).  Warped cells (all six entries of G non-zero, J varies inside the
+    cell), a cell count that is not a multiple of any packing, box placed away from the origin."""
+    m = fus.BoxMesh((5, 3, 2), (0.4, -0.3, 1.0), (0.9, 0.0, 1.2),
+                    warp=lambda x: warp_vertices(x, 0.08, 3))
+    V = fus.FunctionSpace(m, P, numbering=P % 2)
+    ctx = V.context()
+    ctx.set_option("geometry_mode", 2)
+    assert ctx.get_option("geometry_compressed") == 2
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    rng = np.random.default_rng(100 + P)
+    x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)
+    y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(V.ndofs))
+    e = rel_l2(y, yo)
+    note(f"trilinear_stiffness_P{P}", e)
+    assert e < TOL_APPLY
+    # the fused two-vector gather (lossy model) and the whole stage through the same kernel
+    mdl = fus.LossySpectral3D(V, 1500.0, 1000.0, 3e-3, 0.5e6, 1e5, 1500.0)
+    u, v = rng.uniform(-1, 1, V.ndofs), 1e6 * rng.uniform(-1, 1, V.ndofs)
+    k2 = mdl.f1(1e-6, u, v)
+    ctx.set_option("geometry_mode", 0)
+    assert ctx.get_option("geometry_compressed") == 0
+    k0 = mdl.f1(1e-6, u, v)
+    assert rel_l2(k2, k0) < TOL_APPLY
+
+
+def test_trilinear_geometry_rk4_and_errors(fus, orc, gpu):
+    """geometry_mode=2 inside the captured RK4 loop (linear model, warped mesh) against the oracle;
+    a context made from precomputed arrays has no vertices and must refuse the mode."""
+    P, n, h = 4, (4, 3, 2), 0.002
+    m = fus.BoxMesh(n, (0, 0, 0), tuple(h * k for k in n), warp=lambda x: warp_vertices(x, 0.05, 5))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context()
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    nc = m.ncells
+    mdl = fus.LinearSpectral3D(V, 1500.0, 1000.0, 0.5e6, 6.0e4, 1500.0)
+    om = orc.model("linear", P, V.ndofs, V.dofmap, G, dJ, orc.dphi(P), np.full(nc, 1500.0),
+                   np.full(nc, 1000.0), None, None, m.facets, fn, fs, 0.5e6, 6.0e4, 1500.0)
+    dt = 0.5 * np.sqrt(3) * h / (1500.0 * P * P)
+    rng = np.random.default_rng(4)
+    u0, v0 = 1e3 * rng.uniform(-1, 1, V.ndofs), 1e9 * rng.uniform(-1, 1, V.ndofs)
+    u, v = u0.copy(), v0.copy()
+    om.rk4(0.0, 9.5 * dt, dt, u, v)
+    ctx.set_option("geometry_mode", 2)
+    mdl.init(u0.copy(), v0.copy())
+    assert mdl.rk4(0.0, 9.5 * dt, dt) == 10
+    e = rel_l2(mdl.u_sol(), u)
+    note("trilinear_linear_rk4_10steps", e)
+    assert e < TOL_STEPS
+    ctx.set_option("geometry_mode", 0)
+    mdl.init(u0.copy(), v0.copy())
+    assert mdl.rk4(0.0, 9.5 * dt, dt) == 10
+    assert rel_l2(mdl.u_sol(), u) < TOL_STEPS
+    ca = fus.Context.from_arrays(P, V.dofmap, V.ndofs, G, dJ, orc.dphi(P))
+    with pytest.raises(fus.FusError):
+        ca.set_option("geometry_mode", 2)
+    assert ca.get_option("geometry_compressed") == 0
+    with pytest.raises(fus.FusError):
+        ca.set_option("geometry_mode", 3)
+
+
 def test_step_graph_follows_configuration_changes(fus, orc, gpu):
     """fus_model_rk4 replays a captured CUDA graph; switching the kernel variant or the geometry
     mode afterwards must not replay the stale launches.  Same steps, four configurations, and a

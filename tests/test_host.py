@@ -151,3 +151,55 @@ def test_source_disc_tags(fus, orc):
     for k in np.flatnonzero(m.facets[:, 2] == 1):
         np.add.at(ref, V.dofmap[m.facets[k, 0], fn[k]], fs[k] / 1000.0)
     assert np.allclose(src, ref, rtol=1e-13, atol=1e-20)
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_trilinear_map_rebuilds_reference_geometry(fus, orc, P):
+    """The arithmetic of the geometry_mode=2 stiffness kernel (fus_trilinear.hpp, compiled for the
+    host behind fus_trilinear_geometry): |det J| w K K^T and |det J| w rebuilt from the 21 monomial
+    coefficients of the cell map equal compute_scaled_geometrical_factor /
+    compute_scaled_jacobian_determinant (precompute.hpp:33-213, the oracle) on warped cells placed
+    away from the origin.  Both sides lose eps*|x|/h to cancellation, hence 1e-12."""
+    from fenicsx_fus_b200 import capi
+    lib = capi.load()
+    m = fus.BoxMesh((3, 2, 2), (0.3, -0.2, 1.0), (0.33, -0.18, 1.02),
+                    warp=lambda x: warp_vertices(x, 0.12, 11))
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    assert np.abs(G[:, :, [1, 2, 4]]).max() > 1e-2 * np.abs(G).max()      # all six entries matter
+    co = np.zeros((m.ncells, 24))
+    assert lib.fus_trilinear_coeffs(m.ncells, m.x, m.xdofmap, co) == 0
+    assert (co[:, 21:] == 0).all()
+    G2, dJ2 = np.zeros_like(G), np.zeros_like(dJ)
+    assert lib.fus_trilinear_geometry(P, m.ncells, co, capi.optional(G2), capi.optional(dJ2)) == 0
+    assert np.abs(G2 - G).max() <= 1e-12 * np.abs(G).max()
+    assert np.abs(dJ2 - dJ).max() <= 1e-12 * np.abs(dJ).max()
+    # an affine cell has no mixed terms; G and detJ alone can be requested
+    mb = fus.BoxMesh((2, 1, 1), (0, 0, 0), (2.0, 0.5, 0.25))
+    cb = np.zeros((mb.ncells, 24))
+    assert lib.fus_trilinear_coeffs(mb.ncells, mb.x, mb.xdofmap, cb) == 0
+    assert np.allclose(cb[:, :9].reshape(-1, 3, 3), np.diag([1.0, 0.5, 0.25]), atol=1e-16)
+    assert (cb[:, 9:] == 0).all()
+    dJb = np.zeros((mb.ncells, (P + 1) ** 3))
+    assert lib.fus_trilinear_geometry(P, mb.ncells, cb, None, capi.optional(dJb)) == 0
+    assert abs(dJb.sum() - 2.0 * 0.5 * 0.25) < 1e-14
+    assert lib.fus_trilinear_geometry(0, 1, cb, None, None) < 0
+
+
+def test_trilinear_map_on_the_reference_mesh(fus, orc):
+    """Same check on the reference's own unstructured test mesh (6 312 general hexahedra,
+    cpp/fenicsx-sf/tests/test_operators3d/mesh.h5, committed fixture)."""
+    import os
+    from fenicsx_fus_b200 import capi
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_mesh_hex6312.npz"))
+    x = np.ascontiguousarray(d["geometry"], dtype=np.float64)
+    # VTK vertex order -> DOLFINx tensor order (SURVEY.md appendix B)
+    cells = np.ascontiguousarray(d["topology_vtk"][::13, (0, 1, 3, 2, 4, 5, 7, 6)], dtype=np.int32)
+    P = 3
+    G, dJ = orc.geometry(P, x, cells)
+    co = np.zeros((cells.shape[0], 24))
+    lib = capi.load()
+    assert lib.fus_trilinear_coeffs(cells.shape[0], x, cells, co) == 0
+    G2, dJ2 = np.zeros_like(G), np.zeros_like(dJ)
+    assert lib.fus_trilinear_geometry(P, cells.shape[0], co, capi.optional(G2), capi.optional(dJ2)) == 0
+    assert np.abs(G2 - G).max() <= 1e-12 * np.abs(G).max()
+    assert np.abs(dJ2 - dJ).max() <= 1e-12 * np.abs(dJ).max()
