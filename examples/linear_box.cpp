@@ -2,7 +2,7 @@
 // main.cpp:25-149) on a synthetic box, written against the drop-in headers of this repository.
 // Only the #include lines and the mesh source differ from a driver written for the reference.
 //
-//   g++ -std=c++20 -O2 -Iinclude examples/linear_box.cpp -Lfenicsx-fus_b200/lib -lfus_b200 \
+//   g++ -std=c++20 -O2 -Iinclude examples/linear_box.cpp -Lfenicsx-fus_b200/lib -lfus_b200
 //       -Wl,-rpath,$PWD/fenicsx-fus_b200/lib -o examples/linear_box
 //   ./linear_box [cells_per_direction=8] [steps=20]
 #include <fus/Linear.hpp>

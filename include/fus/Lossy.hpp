@@ -17,8 +17,11 @@ public:
                                            sourceAmplitude, sourceSpeed) {}
 };
 
+#ifndef FUS_HAVE_COMPUTE_DIFFUSIVITY
+#define FUS_HAVE_COMPUTE_DIFFUSIVITY
 /// Lossy.hpp:376-380
 template <typename T>
 const T compute_diffusivity_of_sound(const T w0, const T c0, const T alpha) {
   return 2 * alpha * c0 * c0 * c0 / w0 / w0;
 }
+#endif

@@ -20,9 +20,10 @@ public:
 
 #ifndef FUS_HAVE_COMPUTE_DIFFUSIVITY
 #define FUS_HAVE_COMPUTE_DIFFUSIVITY
-/// Westervelt.hpp:408-413
+/// Westervelt.hpp:408-413 (the reference defines the same function in Lossy.hpp:376-380 as well,
+/// so its two headers cannot be included together; here whichever comes first defines it)
 template <typename T>
-const T compute_diffusivity_of_sound_w(const T w0, const T c0, const T alpha) {
+const T compute_diffusivity_of_sound(const T w0, const T c0, const T alpha) {
   return 2 * alpha * c0 * c0 * c0 / w0 / w0;
 }
 #endif

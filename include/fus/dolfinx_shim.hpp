@@ -203,6 +203,48 @@ private:
   std::vector<V> _values;
 };
 
+/// mesh::h (BM7-SC1/main.cpp:72-73): cell diameter = largest distance between two vertices.
+template <typename T>
+std::vector<T> h(const Mesh<T>& mesh, std::span<const int> entities, int dim) {
+  if (dim != 3)
+    throw std::runtime_error("mesh::h [shim]: cells only");
+  auto x = mesh.geometry().x();
+  auto xd = mesh.geometry().dofmap();
+  std::vector<T> out;
+  out.reserve(entities.size());
+  for (int c : entities) {
+    T d2 = 0;
+    for (int a = 0; a < 8; ++a)
+      for (int b = a + 1; b < 8; ++b) {
+        T s = 0;
+        for (int r = 0; r < 3; ++r) {
+          const T e = x[3 * xd(c, a) + r] - x[3 * xd(c, b) + r];
+          s += e * e;
+        }
+        d2 = std::max(d2, s);
+      }
+    out.push_back(std::sqrt(d2));
+  }
+  return out;
+}
+
+/// [shim] cell tags of the box: `nlayers` slabs of equal thickness along x, tagged 1..nlayers
+/// (stands in for the cell MeshTags the reference drivers read next to their meshes,
+/// BM7-SC1/main.cpp:60-63).  A tag "index" is the local cell index, as in DOLFINx.
+template <typename T>
+MeshTags<std::int32_t> box_cell_layers(const Mesh<T>& mesh, int nlayers) {
+  const auto& n = mesh.box_cells();
+  std::vector<std::int32_t> idx, val;
+  std::int32_t c = 0;
+  for (int i = 0; i < n[0]; ++i)
+    for (int j = 0; j < n[1]; ++j)
+      for (int k = 0; k < n[2]; ++k, ++c) {
+        idx.push_back(c);
+        val.push_back(1 + std::min(nlayers - 1, i * nlayers / n[0]));
+      }
+  return MeshTags<std::int32_t>(std::move(idx), std::move(val));
+}
+
 /// [shim] facet tags of the box: 1 on x = lo, 2 on x = hi
 template <typename T>
 MeshTags<std::int32_t> box_facet_tags(const Mesh<T>& mesh) {

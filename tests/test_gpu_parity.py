@@ -290,6 +290,61 @@ def test_cpp_dropin_driver(fus, gpu):
     assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
 
 
+@pytest.mark.parametrize("kind", ["lossy", "westervelt"])
+def test_cpp_dropin_media_driver(fus, orc, gpu, kind):
+    """examples/media_box.cpp: the reference's BM7-SC1 (lossy, water | cortical bone through cell
+    tags) and W-H131-WATER (Westervelt, degree 6) drivers against include/fus/{Lossy,Westervelt}.hpp.
+    Fields must equal the Python mirror's and the oracle's on the same problem."""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "media_box")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_cpp_example()
+    n, steps = 4, 6
+    res = subprocess.run([exe, kind, str(n), str(steps)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    vals = {ln.split(":")[0]: ln.split(":")[1].strip() for ln in res.stdout.splitlines() if ":" in ln}
+    dt = float(vals["Time step size"])
+    if kind == "lossy":
+        P, L, f0, p0, s0 = 4, 0.12 * n / 54.0, 0.5e6, 60000.0, 1500.0
+        m = fus.BoxMesh((n, n, n), (0, 0, 0), (L, L, L))
+        bone = (np.arange(m.ncells) // (n * n)) * 2 // n >= 1
+        c0, rho0 = np.where(bone, 2800.0, 1500.0), np.where(bone, 1850.0, 1000.0)
+        delta = np.where(bone, fus.compute_diffusivity_of_sound(2 * np.pi * f0, 2800.0,
+                                                                400.0 / 20 * np.log(10)), 0.0)
+        beta = None
+        assert abs(delta.max() - float(vals["Diffusivity of sound"])) <= 1e-15 * delta.max()
+        V = fus.FunctionSpace(m, P, numbering=1)
+        mdl = fus.LossySpectral3D(V, c0, rho0, delta, f0, p0, s0)
+    else:
+        P, L, f0, s0 = 6, 0.08 * n / 100.0, 1.1e6, 1480.0
+        p0 = 1000.0 * 1480.0 * 0.2726428
+        m = fus.BoxMesh((n, n, n), (0, 0, 0), (L, L, L))
+        c0, rho0 = np.full(m.ncells, 1480.0), np.full(m.ncells, 1000.0)
+        delta = np.full(m.ncells, fus.compute_diffusivity_of_sound(2 * np.pi * f0, 1480.0,
+                                                                   0.2 / 20 * np.log(10)))
+        beta = np.full(m.ncells, 3.5)
+        V = fus.FunctionSpace(m, P, numbering=1)
+        mdl = fus.WesterveltSpectral3D(V, c0, rho0, delta, beta, f0, p0, s0)
+    assert int(vals["Degrees of freedom"]) == V.ndofs and vals["Model"] == kind
+    mdl.init()
+    assert mdl.rk4(0.0, (steps - 0.5) * dt, dt) == int(vals["Number of steps"]) == steps
+    u, v = mdl.u_sol(), mdl.v_sol()
+    assert np.linalg.norm(u) > 0
+    assert abs(np.linalg.norm(u) - float(vals["u_l2"])) < 1e-11 * np.linalg.norm(u)
+    assert abs(np.linalg.norm(v) - float(vals["v_l2"])) < 1e-11 * np.linalg.norm(v)
+    # and the oracle, so that the driver's numbers are pinned to the reference's algorithm
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    om = orc.model(kind, P, V.ndofs, V.dofmap, G, dJ, orc.dphi(P), c0, rho0, delta, beta,
+                   m.facets, fn, fs, f0, p0, s0)
+    uo, vo = np.zeros(V.ndofs), np.zeros(V.ndofs)
+    assert om.rk4(0.0, (steps - 0.5) * dt, dt, uo, vo) == steps
+    e = rel_l2(u, uo)
+    note(f"cpp_driver_{kind}_{steps}steps", e)
+    assert e < TOL_STEPS
+
+
 @pytest.mark.parametrize("P", [2, 3, 4, 5, 6, 7])
 def test_affine_geometry_compression(fus, orc, gpu, P):
     """Option geometry_mode=1: parallelepiped cells (here a sheared, anisotropic box) are detected
