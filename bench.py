@@ -265,7 +265,7 @@ def run_gpu_arm(args):
     # local part of the global box, local dof numbering (owned first, then ghosts), halo lists
     part = partition.BoxPartition(P, n_global, pg, rank, lo=(0.0, 0.0, 0.0),
                                   hi=tuple(h * n for n in n_global))
-    V = part.function_space(device=local_rank)
+    V = part.function_space(device=local_rank, lean=args.lean)
     ctx = V.context(local_rank)
     stream = torch.cuda.Stream()         # not the legacy default stream: it cannot be captured
     torch.cuda.set_stream(stream)
@@ -276,6 +276,13 @@ def run_gpu_arm(args):
         transport = "nccl send/recv"
         if os.environ.get("FUS_HALO_TRANSPORT", "peer") == "peer" and part.connect_peers(ctx, dist):
             transport = "peer-direct puts over NVLink (CUDA IPC), NCCL for set-up reductions"
+    if args.geometry_mode and not args.lean:
+        ctx.set_option("geometry_mode", args.geometry_mode)
+    geometry = {0: "G streamed, 48 B/point (the reference's data)",
+                1: "affine cells: Ghat per cell", 2: "rebuilt per point from the trilinear cell map"
+                }[ctx.get_option("geometry_compressed")] + (" (lean context: no G/detJ stored)"
+                                                            if args.lean else "")
+    gmode_used = ctx.get_option("geometry_compressed")
     mdl = fus.LinearSpectral3D(V, C0, RHO0, FREQ, P0, C0, facets=part.facets, device=local_rank)
     dt = timestep(P, h, C0)
     ndofs_global = part.ndofs_global
@@ -367,8 +374,10 @@ def run_gpu_arm(args):
 
     # ---- extra (not the headline): opt-in affine compression of the geometric factors -----------
     extras = {}
-    ctx.set_option("geometry_mode", 1)
-    if ctx.get_option("geometry_compressed"):
+    headline_geometry = not args.lean and not args.geometry_mode
+    if headline_geometry:
+        ctx.set_option("geometry_mode", 1)
+    if headline_geometry and ctx.get_option("geometry_compressed") == 1:
         mdl.rk4(t, t + 2.5 * dt, dt)
         sync_all()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -390,7 +399,8 @@ def run_gpu_arm(args):
             "note": ("option geometry_mode=1: all cells of the box are parallelepipeds, G = w_q*Ghat is "
                      "rebuilt from 6 numbers per cell instead of streamed (48 B/point); not the "
                      "headline because it depends on the mesh")}
-    ctx.set_option("geometry_mode", 0)
+    if headline_geometry:
+        ctx.set_option("geometry_mode", 0)
 
     if rank != 0:
         mdl.destroy()
@@ -410,7 +420,7 @@ def run_gpu_arm(args):
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and world == 1:
+    if os.path.exists(tpath) and world == 1 and gmode_used == 0:
         with open(tpath) as f:
             traffic = json.load(f).get(f"stiffness_line_kernel<{P + 1},false>@P{P}_box{N_BENCH}",
                                        {}).get("dram_bytes_per_launch")
@@ -430,7 +440,7 @@ def run_gpu_arm(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable",
                    "sample": repr(ex)[:200]}
 
-    if world == 1 and not args.no_extras and (P, N_BENCH) == (4, 54):
+    if world == 1 and not args.no_extras and (P, N_BENCH) == (4, 54) and headline_geometry:
         # release this process's device memory first; the child builds its own contexts
         mdl.destroy()
         ctx.destroy()
@@ -449,6 +459,7 @@ def run_gpu_arm(args):
                    "process_grid": list(pg), "dt": dt,
                    "l2": f"inputs_exceed_l2 ({48e-6 * npts_loc:.0f} MB of geometric factors streamed per stage)",
                    "parallelism": f"mesh partition {pg[0]}x{pg[1]}x{pg[2]}", "halo": transport,
+                   "geometry": geometry,
                    "issue": "one captured CUDA graph per RK4 step" if ctx_uses_graph else "eager"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_state / K,
@@ -459,7 +470,8 @@ def run_gpu_arm(args):
                 "wall_s": wall_e2e,
                 "roundtrip_every_step_value": roundtrip_value},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms / K,
-        "roofline": {"bound": "hbm", "kernel": f"stiffness_line_kernel<{P + 1},false>",
+        "roofline": {"bound": "hbm",
+                     "kernel": f"stiffness_line_kernel<{P + 1},false,{gmode_used}>",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "launches": int(n_st),
                      "operator_applications": n_apply, "avg_launch_ms": avg_ms,
@@ -491,6 +503,10 @@ def main():
     # non-headline workloads for our own scaling studies (the driver never passes these)
     ap.add_argument("--degree", type=int, default=P_BENCH)
     ap.add_argument("--cells", type=int, default=N_BENCH, help="cells per direction per GPU")
+    ap.add_argument("--geometry-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="1/2: compressed geometric factors (not the headline: see DESIGN.md)")
+    ap.add_argument("--lean", action="store_true",
+                    help="context without G/detJ on the device (geometry rebuilt on the fly)")
     args = ap.parse_args()
     globals()["P_BENCH"], globals()["N_BENCH"] = args.degree, args.cells
     if args.gpus not in PGRID:

@@ -114,9 +114,11 @@ class FunctionSpace:
         check(lib.fus_box_dofmap(self.P, mesh.n, numbering, self.dofmap), "fus_box_dofmap")
         self._ctx = None
 
-    def context(self, device=0):
+    def context(self, device=0, lean=False):
+        """The device context of this space (created on first use).  lean=True keeps neither G
+        nor detJ on the device: geometric factors are rebuilt from the trilinear cell map."""
         if self._ctx is None:
-            self._ctx = Context.from_mesh(self, device)
+            self._ctx = Context.from_mesh(self, device, lean=lean)
         return self._ctx
 
     def tabulate_dof_coordinates(self):
@@ -148,17 +150,16 @@ class Context:
         self.lib = capi.load()
 
     @classmethod
-    def from_mesh(cls, V, device=0, dofmap=None, ndofs=None, nowned=None):
+    def from_mesh(cls, V, device=0, dofmap=None, ndofs=None, nowned=None, lean=False):
         lib = capi.load()
         m = V.mesh
         dm = V.dofmap if dofmap is None else dofmap
         ndofs = V.ndofs if ndofs is None else ndofs
         nowned = ndofs if nowned is None else nowned
         h = C.c_void_p()
-        check(lib.fus_ctx_create_from_mesh(V.P, dm.shape[0], ndofs, nowned,
-                                           np.ascontiguousarray(dm), m.x.shape[0], m.x,
-                                           m.xdofmap, device, C.byref(h)),
-              "fus_ctx_create_from_mesh")
+        create = lib.fus_ctx_create_from_mesh_lean if lean else lib.fus_ctx_create_from_mesh
+        check(create(V.P, dm.shape[0], ndofs, nowned, np.ascontiguousarray(dm), m.x.shape[0], m.x,
+                     m.xdofmap, device, C.byref(h)), "fus_ctx_create_from_mesh")
         return cls(h, V.P, dm.shape[0], ndofs, nowned, device)
 
     @classmethod

@@ -41,6 +41,8 @@ SIGNATURES = {
     "fus_ctx_create": (_int, [_int, _ll, _ll, _ll, _i32, _p, _p, _f64, _int, C.POINTER(_p)]),
     "fus_ctx_create_from_mesh": (_int, [_int, _ll, _ll, _ll, _i32, _ll, _f64, _i32, _int,
                                         C.POINTER(_p)]),
+    "fus_ctx_create_from_mesh_lean": (_int, [_int, _ll, _ll, _ll, _i32, _ll, _f64, _i32, _int,
+                                             C.POINTER(_p)]),
     "fus_ctx_destroy": (_int, [_p]),
     "fus_ctx_set_stream": (_int, [_p, _p]),
     "fus_ctx_set_option": (_int, [_p, C.c_char_p, _int]),

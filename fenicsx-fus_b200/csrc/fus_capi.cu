@@ -83,6 +83,7 @@ struct fus_ctx {
   double2* d_Ghat = nullptr;
   double* d_tri = nullptr;
   int geom_active = 0;      // what the stiffness operator currently uses: 0 streamed G, 1, 2
+  bool lean = false;        // neither G nor detJ exist on the device: always mode 2
   // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
   // profiles/), 0 column kernel, 1 point kernel, 2 line kernel
   int variant = -1;
@@ -190,7 +191,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   std::memcpy(D.x, c->pts, sizeof(double) * N);
   const bool fuse = (x2 != nullptr);
   const int variant = (c->variant >= 0) ? c->variant : (N >= 5 ? 2 : 0);
-  if (variant == 1) {
+  if (variant == 1 && c->geom_active == 0) {
     ProfScope prof(c, 0, st);
     const int blocks = (int)std::min<long long>(ce - cb, (long long)c->num_sms * 16);
     if (fuse)
@@ -270,7 +271,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
 int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double* coeff,
                      const double* coeff2, double* y, long long cb, long long ce,
                      cudaStream_t st) {
-  if (!c->d_G2) {
+  if (!c->d_G2 && c->geom_active != 2) {
     set_error("context was created without G: stiffness operator unavailable");
     return FUS_ERR_STATE;
   }
@@ -287,8 +288,36 @@ int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double
   return FUS_ERR_UNSUPPORTED;
 }
 
+template <int N>
+int launch_mass_tri_n(fus_ctx* c, const double* x, const double* coeff, double* y, long long cb,
+                      long long ce, cudaStream_t st) {
+  Rule1D<N> R;
+  std::memcpy(R.pts, c->pts, sizeof(double) * N);
+  std::memcpy(R.wts, c->wts, sizeof(double) * N);
+  const long long np = (ce - cb) * c->Nd;
+  mass_tri_kernel<N><<<grid_for(np, 256, c->num_sms * 8), 256, 0, st>>>(x, y, c->d_dofmap, c->d_tri,
+                                                                        coeff, cb, np, R);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
 int launch_mass(fus_ctx* c, const double* x, const double* coeff, double* y, long long cb,
                 long long ce, cudaStream_t st) {
+  if (c->lean && c->d_tri) { // no detJ array: |det J| w from the trilinear cell map
+    if (ce <= cb)
+      return FUS_OK;
+    switch (c->N) {
+    case 2: return launch_mass_tri_n<2>(c, x, coeff, y, cb, ce, st);
+    case 3: return launch_mass_tri_n<3>(c, x, coeff, y, cb, ce, st);
+    case 4: return launch_mass_tri_n<4>(c, x, coeff, y, cb, ce, st);
+    case 5: return launch_mass_tri_n<5>(c, x, coeff, y, cb, ce, st);
+    case 6: return launch_mass_tri_n<6>(c, x, coeff, y, cb, ce, st);
+    case 7: return launch_mass_tri_n<7>(c, x, coeff, y, cb, ce, st);
+    case 8: return launch_mass_tri_n<8>(c, x, coeff, y, cb, ce, st);
+    }
+    set_error("unsupported degree P=%d", c->P);
+    return FUS_ERR_UNSUPPORTED;
+  }
   if (!c->d_detJ) {
     set_error("context was created without detJ: mass operator unavailable");
     return FUS_ERR_STATE;
@@ -541,9 +570,9 @@ int fus_ctx_create(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
   return ctx_fail(out, fill());
 }
 
-int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
-                             const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
-                             const int32_t* xdofmap, int device, fus_ctx** out) {
+static int ctx_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                         const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                         const int32_t* xdofmap, int device, bool lean, fus_ctx** out) {
   if (out)
     *out = nullptr;
   if (!xg || !xdofmap || nverts < 8) {
@@ -556,10 +585,18 @@ int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowne
                 (long long)nverts);
       return FUS_ERR_ARG;
     }
-  int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, true, true, out);
+  int mode_env = 0;
+  if (const char* e = std::getenv("FUS_GEOMETRY_MODE")) { // "2": rebuild G on the fly, "lean": and
+    if (!std::strcmp(e, "lean"))                          // do not even store G / detJ
+      lean = true;
+    else if (!std::strcmp(e, "2"))
+      mode_env = 2;
+  }
+  int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, !lean, !lean, out);
   if (r != FUS_OK)
     return ctx_fail(out, r);
   fus_ctx* c = *out;
+  c->lean = lean;
   auto fill = [&]() -> int {
     FUS_TRY(tabulate_dphi(P, c->dphi));
     DevPtr<double> d_xg;
@@ -570,16 +607,33 @@ int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowne
                              c->stream));
     FUS_CUDA(cudaMemcpyAsync(d_xd.p, xdofmap, sizeof(int32_t) * 8 * ncells,
                              cudaMemcpyHostToDevice, c->stream));
-    FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_n, c, d_xg.p, d_xd.p, true, true));
+    if (!lean)
+      FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_n, c, d_xg.p, d_xd.p, true, true));
     // the trilinear map itself, 192 B per cell: what option geometry_mode = 2 reads instead of G
     FUS_CUDA(cudaMalloc(&c->d_tri, sizeof(double) * FUS_TRI_STRIDE * ncells));
     tri_coeff_kernel<<<grid_for(ncells, 128, 1 << 30), 128, 0, c->stream>>>(d_xg.p, d_xd.p, ncells,
                                                                           c->d_tri);
     FUS_LAUNCHED();
     FUS_CUDA(cudaStreamSynchronize(c->stream));
+    if (lean || mode_env == 2)
+      c->geom_active = 2;
     return FUS_OK;
   };
   return ctx_fail(out, fill());
+}
+
+int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                             const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                             const int32_t* xdofmap, int device, fus_ctx** out) {
+  return ctx_from_mesh(P, ncells, ndofs, nowned, tensor_dofmap, nverts, xg, xdofmap, device, false,
+                       out);
+}
+
+int fus_ctx_create_from_mesh_lean(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                                  const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                                  const int32_t* xdofmap, int device, fus_ctx** out) {
+  return ctx_from_mesh(P, ncells, ndofs, nowned, tensor_dofmap, nverts, xg, xdofmap, device, true,
+                       out);
 }
 
 int fus_ctx_destroy(fus_ctx* c) {
@@ -647,6 +701,10 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
     // 0: stream G per point (default).  1: if EVERY cell is affine, keep one Ghat per cell and
     // rebuild G = w_q * Ghat in the kernel; otherwise stay on the streamed path.  2: rebuild G per
     // point from the trilinear cell map (any mesh; needs a context created from the mesh).
+    if (c->lean && value != 2) {
+      set_error("a lean context holds no G: geometry_mode is fixed at 2");
+      return FUS_ERR_STATE;
+    }
     if (value == 0) {
       c->geom_active = 0;
       return FUS_OK;
@@ -757,6 +815,13 @@ int fus_ctx_get_geometry(fus_ctx* c, double* G, double* detJ) {
   if (!c)
     return FUS_ERR_ARG;
   FUS_TRY(select_device(c));
+  if (c->lean) { // nothing stored: rebuild on the host from the cell map (tests, inspection)
+    std::vector<double> co((size_t)c->ncells * FUS_TRI_STRIDE);
+    FUS_CUDA(cudaMemcpyAsync(co.data(), c->d_tri, sizeof(double) * co.size(),
+                             cudaMemcpyDeviceToHost, c->stream));
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    return trilinear_geometry(c->P, c->ncells, co.data(), G, detJ);
+  }
   if (G) {
     if (!c->d_G2)
       return FUS_ERR_STATE;
@@ -874,7 +939,7 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
     set_error("fus_model_create: delta0/beta0 required for this model kind");
     return FUS_ERR_ARG;
   }
-  if (!c->d_G2 || !c->d_detJ) {
+  if ((!c->d_G2 || !c->d_detJ) && !c->lean) {
     set_error("fus_model_create: context needs both G and detJ");
     return FUS_ERR_STATE;
   }

@@ -715,6 +715,38 @@ static __global__ void __launch_bounds__(256)
   }
 }
 
+// Mass operator of a lean context (no detJ array): |det J| w_q is rebuilt from the trilinear cell
+// map, the same helpers as the geometry_mode = 2 stiffness kernel.  Only used at model creation
+// (lumped mass) and by MassSpectral3D, so it is kept simple: one thread per point, the 21
+// coefficients of a cell are broadcast loads shared by the lanes that work on it.
+template <int N>
+__global__ void __launch_bounds__(256)
+    mass_tri_kernel(const double* __restrict__ x, double* __restrict__ y,
+                    const int32_t* __restrict__ dofmap, const double* __restrict__ tri,
+                    const double* __restrict__ coeff, long long cell_begin, long long npoints,
+                    const __grid_constant__ Rule1D<N> R) {
+  constexpr int NN = N * N, Nd = N * N * N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npoints; p += stride) {
+    const long long cl = p / Nd;
+    const int q = (int)(p - cl * Nd);
+    const int i0 = q / NN, t = q - i0 * NN, a = t / N, b = t - a * N;
+    const long long c = cell_begin + cl;
+    double cq[FUS_TRI_STRIDE];
+#pragma unroll
+    for (int k = 0; k < FUS_TRI_STRIDE / 2; ++k) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(tri) + c * (FUS_TRI_STRIDE / 2) + k);
+      cq[2 * k] = v.x;
+      cq[2 * k + 1] = v.y;
+    }
+    TriLine L;
+    tri_line_setup(cq, R.pts[a], R.pts[b], L);
+    const double dj = tri_abs_det(L, R.pts[i0]) * (R.wts[i0] * (R.wts[a] * R.wts[b]));
+    const int dof = __ldg(dofmap + c * Nd + q);
+    atomicAdd(y + dof, __ldg(coeff + c) * __ldg(x + dof) * dj);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Geometry setup on the device (runs once): per cell and quadrature point
 //   J = sum_v x_v (x) grad phi_v^{Q1}(xi_q),  K = J^-1,  G = K K^T,

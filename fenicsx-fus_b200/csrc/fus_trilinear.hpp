@@ -72,6 +72,19 @@ FUS_HD void tri_cross(const double* u, const double* v, double* r) {
   r[2] = u[0] * v[1] - u[1] * v[0];
 }
 
+// |det J| at xi0 on the line L: what compute_scaled_jacobian_determinant (precompute.hpp:33-94)
+// stores per point, before the quadrature weight.
+FUS_HD double tri_abs_det(const TriLine& L, double xi0) {
+  double j1[3], j2[3], r0[3];
+  for (int i = 0; i < 3; ++i) {
+    j1[i] = L.a0[i] + xi0 * L.da[i];
+    j2[i] = L.b0[i] + xi0 * L.db[i];
+  }
+  tri_cross(j1, j2, r0);
+  const double det = L.j0[0] * r0[0] + L.j0[1] * r0[1] + L.j0[2] * r0[2];
+  return det < 0.0 ? -det : det;
+}
+
 // (t0,t1,t2) = scale_w * |det J| * K K^T (f0,f1,f2) at xi0 on the line L, where scale_w carries the
 // quadrature weight (and the cell coefficient): stiffness::transform (spectral_op.hpp:113-130)
 // with G rebuilt instead of loaded.  Returns |det J|.

@@ -34,7 +34,7 @@ class _PartitionBase:
     n_local = None
 
     # -------------------------------------------------------------------------------------------
-    def function_space(self, device=0):
+    def function_space(self, device=0, lean=False):
         """FunctionSpace-like object over the local block for the operator/model classes."""
         import types
 
@@ -46,7 +46,7 @@ class _PartitionBase:
 
         def context(dev=device):
             if V._ctx is None:
-                V._ctx = Context.from_mesh(V, dev, nowned=self.nowned)
+                V._ctx = Context.from_mesh(V, dev, nowned=self.nowned, lean=lean)
             return V._ctx
         V.context = context
         return V

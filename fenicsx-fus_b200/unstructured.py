@@ -208,10 +208,10 @@ class HexFunctionSpace:
         self.counts = dict(vertices=nv, edges=ne, faces=nf, cells=nc)
         self._ctx = None
 
-    def context(self, device=0):
+    def context(self, device=0, lean=False):
         if self._ctx is None:
             from . import Context
-            self._ctx = Context.from_mesh(self, device)
+            self._ctx = Context.from_mesh(self, device, lean=lean)
         return self._ctx
 
     def tabulate_dof_coordinates(self, return_spread=False):

@@ -118,6 +118,16 @@ int fus_ctx_create_from_mesh(int P, int64_t ncells, int64_t ndofs, int64_t nowne
                              const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
                              const int32_t* xdofmap, int device, fus_ctx** out);
 
+/* Same, but neither G nor detJ is materialised: the context keeps the trilinear cell map
+   (192 B per cell) and the dofmap only, "geometry_mode" is fixed at 2 and the mass operator
+   rebuilds |det J| w the same way.  Device memory per dof drops from ~116 B to ~10 B of cell
+   data at P = 4, so problems ~5x larger fit one GPU.  fus_ctx_get_geometry rebuilds on the host.
+   (Setting the environment variable FUS_GEOMETRY_MODE=lean makes fus_ctx_create_from_mesh behave
+   like this, FUS_GEOMETRY_MODE=2 makes it start in geometry_mode 2: for unmodified drivers.) */
+int fus_ctx_create_from_mesh_lean(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                                  const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                                  const int32_t* xdofmap, int device, fus_ctx** out);
+
 int fus_ctx_destroy(fus_ctx* ctx);
 
 /* Launch all work of this context on the given cudaStream_t (default: a private stream). */

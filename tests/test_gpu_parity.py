@@ -446,6 +446,54 @@ def test_trilinear_geometry_rk4_and_errors(fus, orc, gpu):
         ca.set_option("geometry_mode", 3)
 
 
+@pytest.mark.parametrize("kind,P", [("linear", 3), ("lossy", 4), ("westervelt", 2), ("linear", 5)])
+def test_lean_context_models_vs_oracle(fus, orc, gpu, kind, P):
+    """fus_ctx_create_from_mesh_lean: no G and no detJ on the device (192 B per cell instead of
+    56 B per point).  Operators, lumped mass and RK4 fields against the oracle, which uses the
+    reference's precomputed arrays (precompute.hpp:33-213)."""
+    n, h = (4, 3, 2), 0.002
+    m = fus.BoxMesh(n, (0.1, 0.2, -0.1), tuple(o + h * k for o, k in zip((0.1, 0.2, -0.1), n)),
+                    warp=lambda x: warp_vertices(x, 0.06, 9))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context(lean=True)
+    assert ctx.get_option("geometry_compressed") == 2
+    with pytest.raises(fus.FusError):
+        ctx.set_option("geometry_mode", 0)
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    Gd, dJd = ctx.geometry()
+    assert np.abs(Gd - G).max() <= 1e-12 * np.abs(G).max()
+    assert np.abs(dJd - dJ).max() <= 1e-12 * np.abs(dJ).max()
+    rng = np.random.default_rng(P)
+    nc, nd = m.ncells, V.ndofs
+    x, coeffs = rng.uniform(-1, 1, nd), rng.uniform(0.5, 2, nc)
+    y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(nd))
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(nd))
+    ym = fus.MassSpectral3D(V)(x, coeffs, np.zeros(nd))
+    ymo = orc.mass_apply(P, V.dofmap, dJ, coeffs, x, np.zeros(nd))
+    note(f"lean_stiffness_P{P}", rel_l2(y, yo))
+    note(f"lean_mass_P{P}", rel_l2(ym, ymo))
+    assert rel_l2(y, yo) < TOL_APPLY and rel_l2(ym, ymo) < TOL_APPLY
+    c0, rho0 = rng.uniform(1400, 1600, nc), rng.uniform(900, 1100, nc)
+    delta = rng.uniform(1e-3, 3e-3, nc) if kind != "linear" else None
+    beta = rng.uniform(3, 4, nc) if kind == "westervelt" else None
+    args = [a for a in (c0, rho0, delta, beta) if a is not None]
+    cls = {"linear": fus.LinearSpectral3D, "lossy": fus.LossySpectral3D,
+           "westervelt": fus.WesterveltSpectral3D}[kind]
+    mdl = cls(V, *args, 0.5e6, 6.0e4, 1500.0)
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    om = orc.model(kind, P, nd, V.dofmap, G, dJ, orc.dphi(P), c0, rho0, delta, beta, m.facets, fn,
+                   fs, 0.5e6, 6.0e4, 1500.0)
+    dt = 0.2 * np.sqrt(3) * h / (1600.0 * P * P)
+    u0, v0 = 1e3 * rng.uniform(-1, 1, nd), 1e9 * rng.uniform(-1, 1, nd)
+    u, v = u0.copy(), v0.copy()
+    assert om.rk4(0.0, 7.5 * dt, dt, u, v) == 8
+    mdl.init(u0.copy(), v0.copy())
+    assert mdl.rk4(0.0, 7.5 * dt, dt) == 8
+    e = rel_l2(mdl.u_sol(), u)
+    note(f"lean_{kind}_P{P}_8steps", e)
+    assert e < TOL_STEPS and rel_l2(mdl.v_sol(), v) < TOL_STEPS
+
+
 def test_step_graph_follows_configuration_changes(fus, orc, gpu):
     """fus_model_rk4 replays a captured CUDA graph; switching the kernel variant or the geometry
     mode afterwards must not replay the stale launches.  Same steps, four configurations, and a
