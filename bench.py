@@ -38,12 +38,34 @@ UNIT = "DOF-updates/s"
 PGRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
-def timestep(P, h_edge, c):
+def timestep(P, h_edge, c, cfl=CFL, freq=FREQ):
     """Time step of every reference driver (BM7-SC1/main.cpp:112-118): CFL on the cell diameter,
     snapped to an integer number of steps per period."""
-    dt0 = CFL * (np.sqrt(3.0) * h_edge) / (c * P * P)
-    steps_per_period = int((1.0 / FREQ) / dt0) + 1
-    return (1.0 / FREQ) / steps_per_period
+    dt0 = cfl * (np.sqrt(3.0) * h_edge) / (c * P * P)
+    steps_per_period = int((1.0 / freq) / dt0) + 1
+    return (1.0 / freq) / steps_per_period
+
+
+def make_model(fus, name, V, facets, device):
+    """The solver of the requested BASELINE config on the bench box: (model, dt, vector passes per
+    stage in the SURVEY section 8d byte model).  `linear` is the headline (config 1 physics);
+    `lossy` adds attenuation to it (Lossy.hpp); `westervelt` uses the HITU water parameters of
+    config 4 (W-H131-WATER/main.cpp:32-46) with a planar source on x = 0 -- the bowl meshes are not
+    distributed -- and, like `lossy`, the smaller CFL the all-facet absorbing term needs on a box
+    (DESIGN.md section 6)."""
+    h = BOX_LEN / 54
+    if name == "linear":
+        return (fus.LinearSpectral3D(V, C0, RHO0, FREQ, P0, C0, facets=facets, device=device),
+                timestep(V.P, h, C0), 112.0)
+    if name == "lossy":
+        delta = fus.compute_diffusivity_of_sound(2 * np.pi * FREQ, C0, 5.0)
+        return (fus.LossySpectral3D(V, C0, RHO0, delta, FREQ, P0, C0, facets=facets, device=device),
+                timestep(V.P, h, C0, cfl=0.2), 128.0)
+    f0, c, rho = 1.1e6, 1480.0, 1000.0
+    delta = fus.compute_diffusivity_of_sound(2 * np.pi * f0, c, 0.2 / 20 * np.log(10))
+    return (fus.WesterveltSpectral3D(V, c, rho, delta, 3.5, f0, rho * c * 0.2726428, c,
+                                     facets=facets, device=device),
+            timestep(V.P, h, c, cfl=0.2, freq=f0), 136.0)
 
 
 def measured_peaks():
@@ -283,8 +305,7 @@ def run_gpu_arm(args):
                 }[ctx.get_option("geometry_compressed")] + (" (lean context: no G/detJ stored)"
                                                             if args.lean else "")
     gmode_used = ctx.get_option("geometry_compressed")
-    mdl = fus.LinearSpectral3D(V, C0, RHO0, FREQ, P0, C0, facets=part.facets, device=local_rank)
-    dt = timestep(P, h, C0)
+    mdl, dt, stage_vector_bytes = make_model(fus, args.model, V, part.facets, local_rank)
     ndofs_global = part.ndofs_global
     K, W = args.steps, max(args.warmup, 0)
 
@@ -424,13 +445,14 @@ def run_gpu_arm(args):
         with open(tpath) as f:
             traffic = json.load(f).get(f"stiffness_line_kernel<{P + 1},false>@P{P}_box{N_BENCH}",
                                        {}).get("dram_bytes_per_launch")
-    # whole-step algorithmic bytes: 4 * (52 r + 112) per dof
-    step_bytes = 4.0 * (52.0 * npts_loc + 112.0 * nloc)
+    # whole-step algorithmic bytes: 4 * (52 r + 112) per dof for the linear model,
+    # + 16 (lossy: second gathered vector) or + 24 (Westervelt, fused-minimal flow)
+    step_bytes = 4.0 * (52.0 * npts_loc + stage_vector_bytes * nloc)
     step_gbs = step_bytes * K / (ms_total * 1e-3) / 1e9
 
     # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and (P, N_BENCH) == (4, 54):
+    if world == 1 and not args.no_cpu_baseline and (P, N_BENCH) == (4, 54) and args.model == "linear":
         try:
             val, cores, sdone, snd, kind, el = cpu_linear_rk4(30, 50, 1, budget_s=12.0)
             cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
@@ -440,7 +462,8 @@ def run_gpu_arm(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable",
                    "sample": repr(ex)[:200]}
 
-    if world == 1 and not args.no_extras and (P, N_BENCH) == (4, 54) and headline_geometry:
+    if (world == 1 and not args.no_extras and (P, N_BENCH) == (4, 54) and headline_geometry
+            and args.model == "linear"):
         # release this process's device memory first; the child builds its own contexts
         mdl.destroy()
         ctx.destroy()
@@ -454,7 +477,7 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"linear_rk4_P{P}_box{N_BENCH}_per_gpu", "degree": P,
+        "config": {"workload": f"{args.model}_rk4_P{P}_box{N_BENCH}_per_gpu", "degree": P,
                    "cells_per_gpu": part.ncells, "dofs_global": ndofs_global,
                    "process_grid": list(pg), "dt": dt,
                    "l2": f"inputs_exceed_l2 ({48e-6 * npts_loc:.0f} MB of geometric factors streamed per stage)",
@@ -503,6 +526,8 @@ def main():
     # non-headline workloads for our own scaling studies (the driver never passes these)
     ap.add_argument("--degree", type=int, default=P_BENCH)
     ap.add_argument("--cells", type=int, default=N_BENCH, help="cells per direction per GPU")
+    ap.add_argument("--model", default="linear", choices=["linear", "lossy", "westervelt"],
+                    help="lossy / westervelt: BASELINE configs 3-4 style runs (not the headline)")
     ap.add_argument("--geometry-mode", type=int, default=0, choices=[0, 1, 2],
                     help="1/2: compressed geometric factors (not the headline: see DESIGN.md)")
     ap.add_argument("--lean", action="store_true",
