@@ -214,7 +214,7 @@ def run_reference_arm(args):
     return 0
 
 
-def child_extras(timeout_s=170.0):
+def child_extras(timeout_s=120.0):
     """Secondary measurements in a CHILD process (scripts/bench_sweep.py), after the headline
     numbers are in hand: the degree sweep of BASELINE config 2 (single operator application, P=2..7,
     ~10 M dofs) with the geometric factors streamed and rebuilt on the fly, and the headline RK4

@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 from conftest import ROOT
 
 REQUIRED = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
@@ -60,3 +62,150 @@ def test_child_extras_never_raise():
     assert res["headline_rk4_by_geometry_mode"] == [] and "stderr_tail" in res
     short = bench.child_extras(timeout_s=0.05)
     assert short["exit"] == -9 and "timed out" in short["stderr_tail"]
+
+
+class _FakeEvent:
+    clock = [0.0]
+
+    def __init__(self, enable_timing=True):
+        self.t = None
+
+    def record(self, stream=None):
+        _FakeEvent.clock[0] += 1.5
+        self.t = _FakeEvent.clock[0]
+
+    def elapsed_time(self, other):
+        return other.t - self.t
+
+
+def _fake_torch():
+    """Just enough of torch for bench.py's control flow: streams/events that do nothing and
+    tensors backed by numpy."""
+    import types
+
+    import numpy as np
+
+    class T:
+        def __init__(self, a):
+            self.a = np.asarray(a, dtype=np.float64)
+
+        def pin_memory(self):
+            return self
+
+        def numpy(self):
+            return self.a
+
+        def item(self):
+            return float(self.a.reshape(-1)[0])
+
+    cuda = types.SimpleNamespace(
+        set_device=lambda i: None, synchronize=lambda: None, empty_cache=lambda: None,
+        set_stream=lambda s: None, Stream=lambda: types.SimpleNamespace(cuda_stream=0),
+        Event=_FakeEvent)
+    t = types.ModuleType("torch")
+    t.cuda, t.float64 = cuda, "float64"
+    t.tensor = lambda v, dtype=None, device=None: T(v)
+    t.zeros = lambda n, dtype=None: T(np.zeros(n))
+    t.device = lambda *a: None
+    dist = types.ModuleType("torch.distributed")
+    t.distributed = dist
+    return t, dist
+
+
+@pytest.mark.parametrize("model,extra", [("linear", []), ("westervelt", ["--geometry-mode", "2"]),
+                                         ("lossy", ["--lean"])])
+def test_gpu_arm_control_flow_with_a_stub_device(monkeypatch, capsys, model, extra):
+    """bench.py's GPU arm cannot run in the build container (no GPU) and there is no CPU fallback to
+    run instead, so its Python control flow -- argument plumbing, the JSON line and its keys -- is
+    exercised here with the device library and torch stubbed out.  Numbers are meaningless."""
+    import importlib.util
+    import sys
+    import types
+
+    import numpy as np
+
+    import fenicsx_fus_b200 as fus
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t, dist = _fake_torch()
+    monkeypatch.setitem(sys.modules, "torch", t)
+    monkeypatch.setitem(sys.modules, "torch.distributed", dist)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    calls = {"options": [], "lean": None}
+
+    class Ctx:
+        def __init__(self):
+            self.mode = 0
+
+        def set_stream(self, s):
+            pass
+
+        def set_option(self, name, value):
+            calls["options"].append((name, value))
+            if name == "geometry_mode":
+                self.mode = value
+
+        def get_option(self, name):
+            return self.mode if name == "geometry_compressed" else 0
+
+        def profile(self, kernel):
+            return 8, 2.0
+
+        def destroy(self):
+            pass
+
+    def from_mesh(cls, V, device=0, dofmap=None, ndofs=None, nowned=None, lean=False):
+        calls["lean"] = lean
+        c = Ctx()
+        c.mode = 2 if lean else 0
+        return c
+
+    class Model:
+        def __init__(self, V, *a, **kw):
+            assert "facets" in kw and "device" in kw
+            self.V, self.h = V, 0
+            self.lib = types.SimpleNamespace(fus_model_get_state=lambda h, u, v: 0)
+
+        def init(self, u=None, v=None):
+            pass
+
+        def rk4(self, t0, tf, dt):
+            n, t = 0, t0
+            while t < tf:
+                t += min(dt, tf - t)
+                n += 1
+            return n
+
+        def u_sol(self):
+            return np.ones(self.V.ndofs)
+
+        v_sol = u_sol
+
+        def destroy(self):
+            pass
+
+    monkeypatch.setattr(fus, "device_count", lambda: 1)
+    monkeypatch.setattr(fus, "launch_count", lambda: 0)
+    monkeypatch.setattr(fus.Context, "from_mesh", classmethod(from_mesh))
+    for name in ("LinearSpectral3D", "LossySpectral3D", "WesterveltSpectral3D"):
+        monkeypatch.setattr(fus, name, Model)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--cells", "3",
+                                      "--model", model] + extra)
+    assert bench.main() == 0
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    need = (REQUIRED - {"impl"}) | {"roofline", "clocks", "gpu_launches", "extras"}
+    assert need <= set(d), need - set(d)
+    assert d["steps"] == 2 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["value"] > 0
+    assert d["config"]["workload"] == f"{model}_rk4_P4_box3_per_gpu"
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert calls["lean"] == ("--lean" in extra)
+    if "--geometry-mode" in extra:
+        assert ("geometry_mode", 2) in calls["options"] and "trilinear" in d["config"]["geometry"]
+        assert d["roofline"]["kernel"].endswith(",2>")
+    if model == "linear":
+        assert ("geometry_mode", 1) in calls["options"]          # the affine extra was attempted
