@@ -14,8 +14,10 @@ import numpy as np
 from . import capi
 from .capi import KINDS, FusError, check  # noqa: F401
 
-__all__ = ["BoxMesh", "FunctionSpace", "HexMesh", "HexFunctionSpace", "StiffnessSpectral3D", "MassSpectral3D",
-           "LinearSpectral3D", "LossySpectral3D", "WesterveltSpectral3D", "gll",
+__all__ = ["BoxMesh", "RectMesh", "FunctionSpace", "HexMesh", "HexFunctionSpace",
+           "StiffnessSpectral3D", "MassSpectral3D", "LinearSpectral3D", "LossySpectral3D",
+           "WesterveltSpectral3D", "StiffnessSpectral2D", "MassSpectral2D", "LinearSpectral2D",
+           "LossySpectral2D", "WesterveltSpectral2D", "gll",
            "tabulate_dphi", "compute_diffusivity_of_sound", "launch_count", "device_count"]
 
 
@@ -100,18 +102,56 @@ class BoxMesh:
         return float(np.sqrt((h * h).sum()))
 
 
+class RectMesh:
+    """Structured quadrilateral rectangle (dolfinx::mesh::create_rectangle stand-in) for the 2-D
+    operators of cpp/fenicsx-sf-naive.
+
+    x: (nverts,3) vertex coordinates padded with z = 0 as DOLFINx stores them, xdofmap: (ncells,4)
+    DOLFINx vertex order v = a + 2b, facets: (nfacets,3) exterior edges {cell, local facet, tag}
+    with tag 1 on x=lo, 2 on x=hi.  `warp(x) -> x'` displaces the vertices (bilinear cells)."""
+    dim = 2
+
+    def __init__(self, n, lo=(0.0, 0.0), hi=(1.0, 1.0), warp=None):
+        lib = capi.load()
+        self.n = np.asarray(n, dtype=np.int32)
+        assert self.n.shape == (2,)
+        nx, ny = (int(v) for v in self.n)
+        self.lo = np.asarray(lo, dtype=np.float64)
+        self.hi = np.asarray(hi, dtype=np.float64)
+        self.x = np.zeros(((nx + 1) * (ny + 1), 3))
+        self.xdofmap = np.zeros((nx * ny, 4), dtype=np.int32)
+        check(lib.fus_rect_mesh(self.n, self.lo, self.hi, self.x, self.xdofmap), "fus_rect_mesh")
+        if warp is not None:
+            self.x = np.ascontiguousarray(warp(self.x), dtype=np.float64)
+            self.x[:, 2] = 0.0
+        nf = lib.fus_rect_facets(self.n, None)
+        self.facets = np.zeros((nf, 3), dtype=np.int32)
+        lib.fus_rect_facets(self.n, self.facets.ctypes.data_as(C.c_void_p))
+        self.ncells = nx * ny
+
+    def h_min(self):
+        h = (self.hi - self.lo) / self.n
+        return float(np.sqrt((h * h).sum()))
+
+
 class FunctionSpace:
-    """Degree-P GLL Lagrange space on a BoxMesh with the tensor-product dofmap
-    (create_functionspace + reorder_dofmap, permute.hpp:15-42)."""
+    """Degree-P GLL Lagrange space on a BoxMesh (hexahedra) or a RectMesh (quadrilaterals) with
+    the tensor-product dofmap (create_functionspace + reorder_dofmap, permute.hpp:15-42)."""
 
     def __init__(self, mesh, P, numbering=1):
         lib = capi.load()
         self.mesh, self.P = mesh, int(P)
         self.N = self.P + 1
-        self.ndofs = int(lib.fus_box_num_dofs(self.P, mesh.n))
+        self.dim = getattr(mesh, "dim", 3)
+        if self.dim == 2:
+            self.ndofs = int(lib.fus_rect_num_dofs(self.P, mesh.n))
+            self.dofmap = np.zeros((mesh.ncells, self.N ** 2), dtype=np.int32)
+            check(lib.fus_rect_dofmap(self.P, mesh.n, self.dofmap), "fus_rect_dofmap")
+        else:
+            self.ndofs = int(lib.fus_box_num_dofs(self.P, mesh.n))
+            self.dofmap = np.zeros((mesh.ncells, self.N ** 3), dtype=np.int32)
+            check(lib.fus_box_dofmap(self.P, mesh.n, numbering, self.dofmap), "fus_box_dofmap")
         self.nowned = self.ndofs
-        self.dofmap = np.zeros((mesh.ncells, self.N ** 3), dtype=np.int32)
-        check(lib.fus_box_dofmap(self.P, mesh.n, numbering, self.dofmap), "fus_box_dofmap")
         self._ctx = None
 
     def context(self, device=0, lean=False):
@@ -122,9 +162,19 @@ class FunctionSpace:
         return self._ctx
 
     def tabulate_dof_coordinates(self):
-        """Physical coordinates of every dof (trilinear map of the GLL nodes)."""
+        """Physical coordinates of every dof (tri-/bilinear map of the GLL nodes)."""
         pts, _ = gll(self.P)
         N, m = self.N, self.mesh
+        if self.dim == 2:
+            X = m.x[m.xdofmap]                  # (nc, 4, 3)
+            xi = np.stack(np.meshgrid(pts, pts, indexing="ij"), -1).reshape(-1, 2)
+            acc = 0.0
+            for v in range(4):
+                w = (xi[:, 0] if v & 1 else 1 - xi[:, 0]) * (xi[:, 1] if v >> 1 else 1 - xi[:, 1])
+                acc = acc + w[None, :, None] * X[:, v, None, :]
+            out = np.zeros((self.ndofs, 3))
+            out[self.dofmap.reshape(-1)] = acc.reshape(-1, 3)
+            return out
         X = m.x[m.xdofmap]                      # (nc, 8, 3)
         xi = np.stack(np.meshgrid(pts, pts, pts, indexing="ij"), -1).reshape(-1, 3)  # (Nd,3)
         out = np.zeros((self.ndofs, 3))
@@ -144,9 +194,9 @@ class FunctionSpace:
 class Context:
     """Owner of the device cell data (fus_ctx)."""
 
-    def __init__(self, handle, P, ncells, ndofs, nowned, device):
+    def __init__(self, handle, P, ncells, ndofs, nowned, device, dim=3):
         self.h, self.P, self.ncells, self.ndofs = handle, P, ncells, ndofs
-        self.nowned, self.device = nowned, device
+        self.nowned, self.device, self.dim = nowned, device, dim
         self.lib = capi.load()
 
     @classmethod
@@ -157,20 +207,27 @@ class Context:
         ndofs = V.ndofs if ndofs is None else ndofs
         nowned = ndofs if nowned is None else nowned
         h = C.c_void_p()
-        create = lib.fus_ctx_create_from_mesh_lean if lean else lib.fus_ctx_create_from_mesh
+        dim = getattr(m, "dim", 3)
+        if dim == 2:
+            if lean:
+                raise FusError("lean contexts are a hexahedral feature")
+            create = lib.fus_ctx_create_from_mesh_2d
+        else:
+            create = lib.fus_ctx_create_from_mesh_lean if lean else lib.fus_ctx_create_from_mesh
         check(create(V.P, dm.shape[0], ndofs, nowned, np.ascontiguousarray(dm), m.x.shape[0], m.x,
                      m.xdofmap, device, C.byref(h)), "fus_ctx_create_from_mesh")
-        return cls(h, V.P, dm.shape[0], ndofs, nowned, device)
+        return cls(h, V.P, dm.shape[0], ndofs, nowned, device, dim)
 
     @classmethod
-    def from_arrays(cls, P, dofmap, ndofs, G, detJ, dphi, device=0, nowned=None):
+    def from_arrays(cls, P, dofmap, ndofs, G, detJ, dphi, device=0, nowned=None, dim=3):
         lib = capi.load()
         h = C.c_void_p()
         nowned = ndofs if nowned is None else nowned
-        check(lib.fus_ctx_create(P, dofmap.shape[0], ndofs, nowned, np.ascontiguousarray(dofmap),
-                                 capi.optional(G), capi.optional(detJ), dphi, device,
-                                 C.byref(h)), "fus_ctx_create")
-        return cls(h, P, dofmap.shape[0], ndofs, nowned, device)
+        create = lib.fus_ctx_create if dim == 3 else lib.fus_ctx_create_2d
+        check(create(P, dofmap.shape[0], ndofs, nowned, np.ascontiguousarray(dofmap),
+                     capi.optional(G), capi.optional(detJ), dphi, device, C.byref(h)),
+              "fus_ctx_create")
+        return cls(h, P, dofmap.shape[0], ndofs, nowned, device, dim)
 
     def set_stream(self, cuda_stream):
         check(self.lib.fus_ctx_set_stream(self.h, C.c_void_p(cuda_stream)), "fus_ctx_set_stream")
@@ -194,8 +251,8 @@ class Context:
         return n.value, ms.value
 
     def geometry(self, want_G=True, want_detJ=True):
-        Nd = (self.P + 1) ** 3
-        G = np.zeros((self.ncells, Nd, 6)) if want_G else None
+        Nd = (self.P + 1) ** self.dim
+        G = np.zeros((self.ncells, Nd, 6 if self.dim == 3 else 3)) if want_G else None
         dJ = np.zeros((self.ncells, Nd)) if want_detJ else None
         check(self.lib.fus_ctx_get_geometry(self.h, capi.optional(G), capi.optional(dJ)),
               "fus_ctx_get_geometry")
@@ -285,11 +342,10 @@ class _Model:
         facets = m.facets if facets is None else np.ascontiguousarray(facets, dtype=np.int32)
         src, dsrc, absb, bmass = (np.zeros(nd) for _ in range(4))
         k = KINDS[self.kind]
-        check(lib.fus_boundary_vectors(k, V.P, nc, nd, m.x, m.xdofmap, V.dofmap,
-                                       facets.shape[0], facets, c0, rho0, capi.optional(delta0),
-                                       capi.optional(src), capi.optional(dsrc),
-                                       capi.optional(absb), capi.optional(bmass)),
-              "fus_boundary_vectors")
+        bvec = lib.fus_boundary_vectors_2d if getattr(m, "dim", 3) == 2 else lib.fus_boundary_vectors
+        check(bvec(k, V.P, nc, nd, m.x, m.xdofmap, V.dofmap, facets.shape[0], facets, c0, rho0,
+                   capi.optional(delta0), capi.optional(src), capi.optional(dsrc),
+                   capi.optional(absb), capi.optional(bmass)), "fus_boundary_vectors")
         self.boundary = dict(src=src, dsrc=dsrc, absb=absb, bmass=bmass)
         h = C.c_void_p()
         check(lib.fus_model_create(self.ctx.h, k, c0, rho0, capi.optional(delta0),
@@ -375,3 +431,25 @@ class WesterveltSpectral3D(_Model):
                  sourceFrequency, sourceAmplitude, sourceSpeed, **kw):
         super().__init__(V, speedOfSound, density, diffusivityOfSound, coefficientOfNonlinearity,
                          sourceFrequency, sourceAmplitude, sourceSpeed, **kw)
+
+
+# 2-D quadrilateral variant (cpp/fenicsx-sf-naive/common): the same classes on a RectMesh space --
+# the library dispatches on the dimension of the context.
+class StiffnessSpectral2D(StiffnessSpectral3D):
+    """StiffnessSpectral2D<T,P>::operator() (fenicsx-sf-naive spectral_op.hpp:226-359)."""
+
+
+class MassSpectral2D(MassSpectral3D):
+    """MassSpectral2D<T,P>::operator() (fenicsx-sf-naive spectral_op.hpp:28-107)."""
+
+
+class LinearSpectral2D(LinearSpectral3D):
+    """LinearSpectral2D<T,P> (fenicsx-sf-naive Linear.hpp:52-350)."""
+
+
+class LossySpectral2D(LossySpectral3D):
+    """LossySpectral2D<T,P> (fenicsx-sf-naive Lossy.hpp)."""
+
+
+class WesterveltSpectral2D(WesterveltSpectral3D):
+    """WesterveltSpectral2D<T,P> (fenicsx-sf-naive Westervelt.hpp)."""

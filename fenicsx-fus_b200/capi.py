@@ -43,6 +43,15 @@ SIGNATURES = {
                                         C.POINTER(_p)]),
     "fus_ctx_create_from_mesh_lean": (_int, [_int, _ll, _ll, _ll, _i32, _ll, _f64, _i32, _int,
                                              C.POINTER(_p)]),
+    "fus_rect_mesh": (_int, [_i32, _f64, _f64, _f64, _i32]),
+    "fus_rect_dofmap": (_int, [_int, _i32, _i32]),
+    "fus_rect_num_dofs": (_ll, [_int, _i32]),
+    "fus_rect_facets": (_ll, [_i32, _p]),
+    "fus_boundary_vectors_2d": (_int, [_int, _int, _ll, _ll, _f64, _i32, _i32, _ll, _i32, _f64,
+                                       _f64, _p, _p, _p, _p, _p]),
+    "fus_ctx_create_2d": (_int, [_int, _ll, _ll, _ll, _i32, _p, _p, _f64, _int, C.POINTER(_p)]),
+    "fus_ctx_create_from_mesh_2d": (_int, [_int, _ll, _ll, _ll, _i32, _ll, _f64, _i32, _int,
+                                           C.POINTER(_p)]),
     "fus_ctx_destroy": (_int, [_p]),
     "fus_ctx_set_stream": (_int, [_p, _p]),
     "fus_ctx_set_option": (_int, [_p, C.c_char_p, _int]),

@@ -67,6 +67,7 @@ static inline int grid_for(long long n, int block, int max_blocks) {
 using namespace fus;
 
 struct fus_ctx {
+  int dim = 3;              // 3: hexahedra (cpp/fenicsx-sf), 2: quadrilaterals (cpp/fenicsx-sf-naive)
   int P = 0, N = 0, Nd = 0;
   int64_t ncells = 0, ndofs = 0, nowned = 0;
   int device = 0;
@@ -75,6 +76,7 @@ struct fus_ctx {
   bool own_stream = false;
   int32_t* d_dofmap = nullptr;
   double2* d_G2 = nullptr;
+  double* d_Gq = nullptr;   // dim == 2: Gq[cell][3][N*N]
   double* d_detJ = nullptr;
   double dphi[64];
   double pts[8], wts[8];    // 1-D GLL points and weights
@@ -268,9 +270,50 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
                 C::SMEM_BYTES, C::CPB, configured, bp, bf);
 }
 
+template <int N>
+int launch_stiffness_quad_n(fus_ctx* c, const double* x, const double* x2, const double* coeff,
+                            const double* coeff2, double* y, long long cb, long long ce,
+                            cudaStream_t st) {
+  if (ce <= cb)
+    return FUS_OK;
+  using Q = QuadCfg<N>;
+  DMat<N> D;
+  std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
+  std::memcpy(D.w, c->wts, sizeof(double) * N);
+  std::memcpy(D.x, c->pts, sizeof(double) * N);
+  ProfScope prof(c, 0, st);
+  const long long want = (ce - cb + Q::CPB - 1) / Q::CPB;
+  const int blocks = (int)std::min<long long>(want, (long long)c->num_sms * 8);
+  if (x2)
+    stiffness_quad_kernel<N, true><<<blocks, Q::THREADS, 0, st>>>(x, x2, y, c->d_dofmap, c->d_Gq,
+                                                                  coeff, coeff2, cb, ce, D);
+  else
+    stiffness_quad_kernel<N, false><<<blocks, Q::THREADS, 0, st>>>(x, x2, y, c->d_dofmap, c->d_Gq,
+                                                                   coeff, coeff2, cb, ce, D);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
 int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double* coeff,
                      const double* coeff2, double* y, long long cb, long long ce,
                      cudaStream_t st) {
+  if (c->dim == 2) {
+    if (!c->d_Gq) {
+      set_error("context was created without G: stiffness operator unavailable");
+      return FUS_ERR_STATE;
+    }
+    switch (c->N) {
+    case 2: return launch_stiffness_quad_n<2>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+    case 3: return launch_stiffness_quad_n<3>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+    case 4: return launch_stiffness_quad_n<4>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+    case 5: return launch_stiffness_quad_n<5>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+    case 6: return launch_stiffness_quad_n<6>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+    case 7: return launch_stiffness_quad_n<7>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+    case 8: return launch_stiffness_quad_n<8>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+    }
+    set_error("unsupported degree P=%d", c->P);
+    return FUS_ERR_UNSUPPORTED;
+  }
   if (!c->d_G2 && c->geom_active != 2) {
     set_error("context was created without G: stiffness operator unavailable");
     return FUS_ERR_STATE;
@@ -339,6 +382,16 @@ int launch_geometry_n(fus_ctx* c, const double* d_xg, const int32_t* d_xd, bool 
   FUS_TRY(gll(N - 1, R.pts, R.wts));
   geometry_kernel<N><<<grid_for(c->ncells * c->Nd, 128, c->num_sms * 16), 128, 0, c->stream>>>(
       d_xg, d_xd, c->ncells, want_G ? c->d_G2 : nullptr, want_detJ ? c->d_detJ : nullptr, R);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
+template <int N>
+int launch_geometry_quad_n(fus_ctx* c, const double* d_xg, const int32_t* d_xd) {
+  Rule1D<N> R;
+  FUS_TRY(gll(N - 1, R.pts, R.wts));
+  geometry_quad_kernel<N><<<grid_for(c->ncells * c->Nd, 128, c->num_sms * 16), 128, 0,
+                            c->stream>>>(d_xg, d_xd, c->ncells, c->d_Gq, c->d_detJ, R);
   FUS_LAUNCHED();
   return FUS_OK;
 }
@@ -416,7 +469,7 @@ int affine_detect_n(fus_ctx* c, int* all_affine) {
   }()
 
 int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32_t* dm,
-               int device, bool want_G, bool want_detJ, fus_ctx** out) {
+               int device, bool want_G, bool want_detJ, fus_ctx** out, int dim = 3) {
   if (!out || !dm || ncells < 1 || ndofs < 1 || nowned < 0 || nowned > ndofs) {
     set_error("fus_ctx_create: bad argument");
     return FUS_ERR_ARG;
@@ -442,9 +495,10 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
     return FUS_ERR_CUDA;
   }
   fus_ctx* c = new fus_ctx();
+  c->dim = dim;
   c->P = P;
   c->N = P + 1;
-  c->Nd = c->N * c->N * c->N;
+  c->Nd = (dim == 3) ? c->N * c->N * c->N : c->N * c->N;
   c->ncells = ncells;
   c->ndofs = ndofs;
   c->nowned = nowned;
@@ -475,8 +529,10 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   FUS_CUDA(cudaMalloc(&c->d_dofmap, sizeof(int32_t) * nent));
   FUS_CUDA(cudaMemcpyAsync(c->d_dofmap, dm, sizeof(int32_t) * nent, cudaMemcpyHostToDevice,
                            c->stream));
-  if (want_G)
+  if (want_G && dim == 3)
     FUS_CUDA(cudaMalloc(&c->d_G2, sizeof(double2) * 3 * nent));
+  if (want_G && dim == 2)
+    FUS_CUDA(cudaMalloc(&c->d_Gq, sizeof(double) * 3 * nent));
   if (want_detJ)
     FUS_CUDA(cudaMalloc(&c->d_detJ, sizeof(double) * nent));
   return FUS_OK;
@@ -531,6 +587,21 @@ int fus_trilinear_coeffs(int64_t ncells, const double* xg, const int32_t* xdofma
 }
 int fus_trilinear_geometry(int P, int64_t ncells, const double* coeffs, double* G, double* detJ) {
   return trilinear_geometry(P, ncells, coeffs, G, detJ);
+}
+int fus_rect_mesh(const int n[2], const double lo[2], const double hi[2], double* xg,
+                  int32_t* xdofmap) {
+  return rect_mesh(n, lo, hi, xg, xdofmap);
+}
+int fus_rect_dofmap(int P, const int n[2], int32_t* dm) { return rect_dofmap(P, n, dm); }
+int64_t fus_rect_num_dofs(int P, const int n[2]) { return rect_num_dofs(P, n); }
+int64_t fus_rect_facets(const int n[2], int32_t* facets) { return rect_facets(n, facets); }
+int fus_boundary_vectors_2d(int kind, int P, int64_t ncells, int64_t ndofs, const double* xg,
+                            const int32_t* xdofmap, const int32_t* tensor_dofmap, int64_t nfacets,
+                            const int32_t* facets, const double* c0, const double* rho0,
+                            const double* delta0, double* src, double* dsrc, double* absb,
+                            double* bmass) {
+  return boundary_vectors_2d(kind, P, ncells, ndofs, xg, xdofmap, tensor_dofmap, nfacets, facets,
+                             c0, rho0, delta0, src, dsrc, absb, bmass);
 }
 
 // ---- context ----------------------------------------------------------------------------------
@@ -636,6 +707,79 @@ int fus_ctx_create_from_mesh_lean(int P, int64_t ncells, int64_t ndofs, int64_t 
                        out);
 }
 
+// ---- 2-D quadrilateral contexts (cpp/fenicsx-sf-naive/common/spectral_op.hpp:28-107,226-359) -----
+int fus_ctx_create_2d(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                      const int32_t* tensor_dofmap, const double* G, const double* detJ,
+                      const double* dphi, int device, fus_ctx** out) {
+  if (out)
+    *out = nullptr;
+  if (!dphi || (!G && !detJ)) {
+    set_error("fus_ctx_create_2d: dphi and at least one of G, detJ are required");
+    return FUS_ERR_ARG;
+  }
+  int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, G != nullptr,
+                     detJ != nullptr, out, 2);
+  if (r != FUS_OK)
+    return ctx_fail(out, r);
+  fus_ctx* c = *out;
+  std::memcpy(c->dphi, dphi, sizeof(double) * c->N * c->N);
+  auto fill = [&]() -> int {
+    const int64_t nent = ncells * c->Nd;
+    if (detJ)
+      FUS_CUDA(cudaMemcpyAsync(c->d_detJ, detJ, sizeof(double) * nent, cudaMemcpyHostToDevice,
+                               c->stream));
+    if (G) { // reference layout G[c][q][3] -> Gq[c][p][q]; 2-D data are small: transposed on the host
+      std::vector<double> tmp((size_t)3 * nent);
+      for (int64_t cell = 0; cell < ncells; ++cell)
+        for (int q = 0; q < c->Nd; ++q)
+          for (int p = 0; p < 3; ++p)
+            tmp[(size_t)(cell * 3 + p) * c->Nd + q] = G[(size_t)(cell * c->Nd + q) * 3 + p];
+      FUS_CUDA(cudaMemcpyAsync(c->d_Gq, tmp.data(), sizeof(double) * tmp.size(),
+                               cudaMemcpyHostToDevice, c->stream));
+      FUS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    return FUS_OK;
+  };
+  return ctx_fail(out, fill());
+}
+
+int fus_ctx_create_from_mesh_2d(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                                const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                                const int32_t* xdofmap, int device, fus_ctx** out) {
+  if (out)
+    *out = nullptr;
+  if (!xg || !xdofmap || nverts < 4) {
+    set_error("fus_ctx_create_from_mesh_2d: mesh geometry required");
+    return FUS_ERR_ARG;
+  }
+  for (int64_t i = 0; i < ncells * 4; ++i)
+    if (xdofmap[i] < 0 || xdofmap[i] >= nverts) {
+      set_error("xdofmap[%lld] = %d outside [0,%lld)", (long long)i, xdofmap[i],
+                (long long)nverts);
+      return FUS_ERR_ARG;
+    }
+  int r = ctx_common(P, ncells, ndofs, nowned, tensor_dofmap, device, true, true, out, 2);
+  if (r != FUS_OK)
+    return ctx_fail(out, r);
+  fus_ctx* c = *out;
+  auto fill = [&]() -> int {
+    FUS_TRY(tabulate_dphi(P, c->dphi));
+    DevPtr<double> d_xg;
+    DevPtr<int32_t> d_xd;
+    FUS_CUDA(cudaMalloc(&d_xg.p, sizeof(double) * 3 * nverts));
+    FUS_CUDA(cudaMalloc(&d_xd.p, sizeof(int32_t) * 4 * ncells));
+    FUS_CUDA(cudaMemcpyAsync(d_xg.p, xg, sizeof(double) * 3 * nverts, cudaMemcpyHostToDevice,
+                             c->stream));
+    FUS_CUDA(cudaMemcpyAsync(d_xd.p, xdofmap, sizeof(int32_t) * 4 * ncells,
+                             cudaMemcpyHostToDevice, c->stream));
+    FUS_TRY(FUS_DISPATCH_N(c, launch_geometry_quad_n, c, d_xg.p, d_xd.p));
+    FUS_CUDA(cudaStreamSynchronize(c->stream));
+    return FUS_OK;
+  };
+  return ctx_fail(out, fill());
+}
+
 int fus_ctx_destroy(fus_ctx* c) {
   if (!c)
     return FUS_OK;
@@ -653,6 +797,7 @@ int fus_ctx_destroy(fus_ctx* c) {
   cudaFree(c->d_Ghat);
   cudaFree(c->d_tri);
   cudaFree(c->d_G2);
+  cudaFree(c->d_Gq);
   cudaFree(c->d_detJ);
   if (c->own_stream && c->stream)
     cudaStreamDestroy(c->stream);
@@ -701,6 +846,10 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
     // 0: stream G per point (default).  1: if EVERY cell is affine, keep one Ghat per cell and
     // rebuild G = w_q * Ghat in the kernel; otherwise stay on the streamed path.  2: rebuild G per
     // point from the trilinear cell map (any mesh; needs a context created from the mesh).
+    if (c->dim == 2 && value != 0) {
+      set_error("geometry_mode applies to hexahedral contexts only");
+      return FUS_ERR_UNSUPPORTED;
+    }
     if (c->lean && value != 2) {
       set_error("a lean context holds no G: geometry_mode is fixed at 2");
       return FUS_ERR_STATE;
@@ -815,6 +964,29 @@ int fus_ctx_get_geometry(fus_ctx* c, double* G, double* detJ) {
   if (!c)
     return FUS_ERR_ARG;
   FUS_TRY(select_device(c));
+  if (c->dim == 2) { // Gq[c][p][q] -> reference layout G[c][q][3]
+    const int64_t nent = c->ncells * c->Nd;
+    if (G) {
+      if (!c->d_Gq)
+        return FUS_ERR_STATE;
+      std::vector<double> tmp((size_t)3 * nent);
+      FUS_CUDA(cudaMemcpyAsync(tmp.data(), c->d_Gq, sizeof(double) * tmp.size(),
+                               cudaMemcpyDeviceToHost, c->stream));
+      FUS_CUDA(cudaStreamSynchronize(c->stream));
+      for (int64_t cell = 0; cell < c->ncells; ++cell)
+        for (int q = 0; q < c->Nd; ++q)
+          for (int p = 0; p < 3; ++p)
+            G[(size_t)(cell * c->Nd + q) * 3 + p] = tmp[(size_t)(cell * 3 + p) * c->Nd + q];
+    }
+    if (detJ) {
+      if (!c->d_detJ)
+        return FUS_ERR_STATE;
+      FUS_CUDA(cudaMemcpyAsync(detJ, c->d_detJ, sizeof(double) * nent, cudaMemcpyDeviceToHost,
+                               c->stream));
+      FUS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return FUS_OK;
+  }
   if (c->lean) { // nothing stored: rebuild on the host from the cell map (tests, inspection)
     std::vector<double> co((size_t)c->ncells * FUS_TRI_STRIDE);
     FUS_CUDA(cudaMemcpyAsync(co.data(), c->d_tri, sizeof(double) * co.size(),
@@ -939,7 +1111,7 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
     set_error("fus_model_create: delta0/beta0 required for this model kind");
     return FUS_ERR_ARG;
   }
-  if ((!c->d_G2 || !c->d_detJ) && !c->lean) {
+  if ((!(c->d_G2 || c->d_Gq) || !c->d_detJ) && !c->lean) {
     set_error("fus_model_create: context needs both G and detJ");
     return FUS_ERR_STATE;
   }

@@ -347,4 +347,134 @@ int trilinear_geometry(int P, int64_t ncells, const double* coeffs, double* G, d
   return FUS_OK;
 }
 
+// ---- 2-D quadrilateral variant (cpp/fenicsx-sf-naive/common) ------------
+
+int rect_mesh(const int n[2], const double lo[2], const double hi[2], double* xg,
+              int32_t* xdofmap) {
+  if (n[0] < 1 || n[1] < 1)
+    return FUS_ERR_ARG;
+  const int64_t vy = n[1] + 1;
+  for (int64_t i = 0; i <= n[0]; ++i)
+    for (int64_t j = 0; j <= n[1]; ++j) {
+      double* p = xg + 3 * (i * vy + j); // padded to 3 coordinates, as DOLFINx stores geometry
+      p[0] = lo[0] + (hi[0] - lo[0]) * (double)i / n[0];
+      p[1] = lo[1] + (hi[1] - lo[1]) * (double)j / n[1];
+      p[2] = 0.0;
+    }
+  for (int64_t i = 0; i < n[0]; ++i)
+    for (int64_t j = 0; j < n[1]; ++j)
+      for (int v = 0; v < 4; ++v) // v = a + 2b, x fastest (DOLFINx quadrilateral vertex order)
+        xdofmap[4 * (i * n[1] + j) + v] = (int32_t)((i + (v & 1)) * vy + (j + (v >> 1)));
+  return FUS_OK;
+}
+
+int64_t rect_num_dofs(int P, const int n[2]) {
+  return ((int64_t)n[0] * P + 1) * ((int64_t)n[1] * P + 1);
+}
+
+int rect_dofmap(int P, const int n[2], int32_t* dm) {
+  if (P < 1 || n[0] < 1 || n[1] < 1)
+    return FUS_ERR_ARG;
+  if (rect_num_dofs(P, n) > INT32_MAX)
+    return FUS_ERR_UNSUPPORTED;
+  const int N = P + 1;
+  const int64_t My = (int64_t)n[1] * P + 1;
+  std::vector<int> pos(N);
+  pos[0] = 0;
+  pos[1] = P;
+  for (int i = 2; i < N; ++i)
+    pos[i] = i - 1;
+  for (int64_t i = 0; i < n[0]; ++i)
+    for (int64_t j = 0; j < n[1]; ++j) {
+      int32_t* row = dm + (i * n[1] + j) * N * N;
+      for (int a = 0; a < N; ++a)
+        for (int b = 0; b < N; ++b)
+          row[a * N + b] = (int32_t)((i * P + pos[a]) * My + (j * P + pos[b]));
+    }
+  return FUS_OK;
+}
+
+int64_t rect_facets(const int n[2], int32_t* facets) {
+  // DOLFINx quadrilateral facets: 0: y=0, 1: x=0, 2: x=1, 3: y=1
+  int64_t count = 0;
+  for (int64_t i = 0; i < n[0]; ++i)
+    for (int64_t j = 0; j < n[1]; ++j) {
+      const bool on[4] = {j == 0, i == 0, i == n[0] - 1, j == n[1] - 1};
+      for (int f = 0; f < 4; ++f) {
+        if (!on[f])
+          continue;
+        if (facets) {
+          facets[3 * count + 0] = (int32_t)(i * n[1] + j);
+          facets[3 * count + 1] = f;
+          facets[3 * count + 2] = (f == 1) ? 1 : (f == 2 ? 2 : 0);
+        }
+        ++count;
+      }
+    }
+  return count;
+}
+
+// Edge-lumped boundary vectors: the `ds` forms of the 2-D examples
+// (cpp/fenicsx-sf-naive/examples/linear_planewave2d_1/forms.py:34-40 and the lossy / Westervelt
+// ones) with GLL quadrature are collocated, exactly as in 3-D.
+int boundary_vectors_2d(int kind, int P, int64_t ncells, int64_t ndofs, const double* xg,
+                        const int32_t* xdofmap, const int32_t* dm, int64_t nfacets,
+                        const int32_t* facets, const double* c0, const double* rho0,
+                        const double* delta0, double* src, double* dsrc, double* absb,
+                        double* bmass) {
+  if (kind < 0 || kind > 2 || !xg || !xdofmap || !dm || !c0 || !rho0)
+    return FUS_ERR_ARG;
+  if (kind != FUS_LINEAR && !delta0)
+    return FUS_ERR_ARG;
+  const int N = P + 1, Nd = N * N;
+  std::vector<double> pts(N), wts(N);
+  gll(P, pts.data(), wts.data());
+  for (double* v : {src, dsrc, absb, bmass})
+    if (v)
+      std::fill(v, v + ndofs, 0.0);
+  static const int fdir[4] = {1, 0, 0, 1}, fside[4] = {0, 0, 1, 1};
+  for (int64_t f = 0; f < nfacets; ++f) {
+    const int64_t c = facets[3 * f];
+    const int lf = facets[3 * f + 1], tag = facets[3 * f + 2];
+    if (c < 0 || c >= ncells || lf < 0 || lf > 3)
+      return FUS_ERR_ARG;
+    const int dir = fdir[lf], ta = 1 - dir;
+    double X[4][2];
+    for (int v = 0; v < 4; ++v)
+      for (int r = 0; r < 2; ++r)
+        X[v][r] = xg[3 * (int64_t)xdofmap[4 * c + v] + r];
+    const double rho = rho0[c], cc = c0[c], del = delta0 ? delta0[c] : 0.0;
+    for (int a = 0; a < N; ++a) {
+      int id[2];
+      id[dir] = fside[lf];
+      id[ta] = a;
+      const double xi[2] = {pts[id[0]], pts[id[1]]};
+      // tangent of the bilinear map along reference axis ta
+      double t[2] = {0.0, 0.0};
+      for (int v = 0; v < 4; ++v) {
+        const int bit[2] = {v & 1, v >> 1};
+        const double g = (bit[ta] ? 1.0 : -1.0) * (bit[dir] ? xi[dir] : 1.0 - xi[dir]);
+        t[0] += X[v][0] * g;
+        t[1] += X[v][1] * g;
+      }
+      const double s = wts[a] * std::sqrt(t[0] * t[0] + t[1] * t[1]);
+      const int32_t d = dm[c * Nd + id[0] * N + id[1]];
+      if (tag == 1 && src)
+        src[d] += s / rho;
+      if (kind == FUS_LINEAR) {
+        if (tag == 2 && absb)
+          absb[d] += s / rho / cc;
+      } else {
+        if (absb)
+          absb[d] += s / rho / cc;
+        if (tag == 1 && dsrc)
+          dsrc[d] += s * del / rho / cc / cc;
+        if (bmass)
+          bmass[d] += s * del / rho / cc / cc / cc;
+      }
+    }
+  }
+  return FUS_OK;
+}
+
 } // namespace fus

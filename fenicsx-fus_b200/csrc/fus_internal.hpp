@@ -19,6 +19,16 @@ int boundary_vectors(int kind, int P, int64_t ncells, int64_t ndofs, const doubl
                      const double* delta0, double* src, double* dsrc, double* absb, double* bmass);
 int trilinear_coeffs(int64_t ncells, const double* xg, const int32_t* xdofmap, double* coeffs);
 int trilinear_geometry(int P, int64_t ncells, const double* coeffs, double* G, double* detJ);
+// 2-D quadrilateral variant
+int rect_mesh(const int n[2], const double lo[2], const double hi[2], double* xg, int32_t* xdofmap);
+int rect_dofmap(int P, const int n[2], int32_t* dm);
+int64_t rect_num_dofs(int P, const int n[2]);
+int64_t rect_facets(const int n[2], int32_t* facets);
+int boundary_vectors_2d(int kind, int P, int64_t ncells, int64_t ndofs, const double* xg,
+                        const int32_t* xdofmap, const int32_t* dm, int64_t nfacets,
+                        const int32_t* facets, const double* c0, const double* rho0,
+                        const double* delta0, double* src, double* dsrc, double* absb,
+                        double* bmass);
 
 void set_error(const char* fmt, ...);
 

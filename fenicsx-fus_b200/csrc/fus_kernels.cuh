@@ -920,6 +920,129 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2-D quadrilateral variant: StiffnessSpectral2D::operator(),
+// cpp/fenicsx-sf-naive/common/spectral_op.hpp:275-318 with the 2-D stiffness::transform :196-208.
+//   y[dof] += sum_cells B^T (coeff_c G_c) B x[dof],  G symmetric 2x2 per point
+// One thread per point (i0,i1), whole cells per block, the two contractions of each phase read
+// the cell through shared memory.  2-D problems are a few million dofs at most, so the kernel is
+// written for clarity, not tuned like the hexahedral ones.  Device layout of the geometric
+// factor: Gq[cell][p][q], p = 0..2 <-> {G00, G01, G11}, q = i0*N + i1 (coalesced per component).
+// The mass operator, the boundary terms and the RK4 epilogue are dimension-independent and shared.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+struct QuadCfg {
+  static constexpr int NN = N * N;
+  static constexpr int CPB = (128 / NN) > 0 ? (128 / NN) : 1; // cells per block
+  static constexpr int THREADS = ((CPB * NN + 31) / 32) * 32;
+};
+
+template <int N, bool FUSE2>
+__global__ void __launch_bounds__(QuadCfg<N>::THREADS)
+    stiffness_quad_kernel(const double* __restrict__ x, const double* __restrict__ x2,
+                          double* __restrict__ y, const int32_t* __restrict__ dofmap,
+                          const double* __restrict__ Gq, const double* __restrict__ coeff,
+                          const double* __restrict__ coeff2, long long cell_begin,
+                          long long cell_end, const __grid_constant__ DMat<N> D) {
+  using C = QuadCfg<N>;
+  constexpr int NN = C::NN;
+  __shared__ double xs[C::CPB][NN], t0s[C::CPB][NN], t1s[C::CPB][NN];
+  __shared__ double Ds[NN];
+  const int tid = threadIdx.x;
+  const int slot = tid / NN, t = tid - slot * NN;
+  const bool lane_ok = slot < C::CPB;
+  const int i0 = t / N, i1 = t - i0 * N;
+  if (tid < NN)
+    Ds[tid] = D.d[tid];
+  const long long stride = (long long)gridDim.x * C::CPB;
+  for (long long base = cell_begin + (long long)blockIdx.x * C::CPB; base < cell_end;
+       base += stride) { // uniform over the block: every thread reaches every barrier
+    const long long c = base + slot;
+    const bool valid = lane_ok && c < cell_end;
+    int dof = 0;
+    double cf = 0.0;
+    if (valid) {
+      dof = __ldg(dofmap + c * NN + t);
+      if constexpr (FUSE2) {
+        xs[slot][t] = __ldg(coeff + c) * __ldg(x + dof) + __ldg(coeff2 + c) * __ldg(x2 + dof);
+        cf = 1.0;
+      } else {
+        xs[slot][t] = __ldg(x + dof);
+        cf = __ldg(coeff + c);
+      }
+    }
+    __syncthreads();
+    if (valid) {
+      double d0 = 0.0, d1 = 0.0; // derivatives along reference directions 0 (slow) and 1 (fast)
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        d0 = fma(Ds[i0 * N + k], xs[slot][k * N + i1], d0);
+        d1 = fma(Ds[i1 * N + k], xs[slot][i0 * N + k], d1);
+      }
+      const double* g = Gq + c * (3 * NN) + t;
+      const double g00 = __ldg(g), g01 = __ldg(g + NN), g11 = __ldg(g + 2 * NN);
+      t0s[slot][t] = cf * (g00 * d0 + g01 * d1);
+      t1s[slot][t] = cf * (g01 * d0 + g11 * d1);
+    }
+    __syncthreads();
+    if (valid) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        acc = fma(Ds[k * N + i0], t0s[slot][k * N + i1], acc);
+        acc = fma(Ds[k * N + i1], t1s[slot][i0 * N + k], acc);
+      }
+      atomicAdd(y + dof, acc);
+    }
+    __syncthreads(); // the next pass overwrites xs / t0s / t1s
+  }
+}
+
+// Geometry of bilinear quadrilaterals on the device (runs once):
+//   Gq <- |det J| w_q {G00, G01, G11},  detJ[c][q] = |det J| w_q
+// (cpp/fenicsx-sf-naive/common/precompute.hpp:33-213 with gdim == 2).  xg is padded to 3
+// coordinates per vertex as in DOLFINx; xdofmap has 4 vertices per cell, v = a + 2b.
+template <int N>
+__global__ void __launch_bounds__(128)
+    geometry_quad_kernel(const double* __restrict__ xg, const int32_t* __restrict__ xdofmap,
+                         long long ncells, double* __restrict__ Gq, double* __restrict__ detJ,
+                         const __grid_constant__ Rule1D<N> R) {
+  constexpr int NN = N * N;
+  const long long total = ncells * NN;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+       gid += stride) {
+    const long long c = gid / NN;
+    const int q = (int)(gid - c * NN);
+    const int q0 = q / N, q1 = q - q0 * N;
+    const double xi0 = R.pts[q0], xi1 = R.pts[q1];
+    double J[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int a = v & 1, b = v >> 1;
+      const double l0 = a ? xi0 : 1.0 - xi0, l1 = b ? xi1 : 1.0 - xi1;
+      const double g0 = (a ? 1.0 : -1.0) * l1, g1 = l0 * (b ? 1.0 : -1.0);
+      const double* X = xg + 3 * (long long)__ldg(xdofmap + 4 * c + v);
+      J[0][0] += X[0] * g0;
+      J[0][1] += X[0] * g1;
+      J[1][0] += X[1] * g0;
+      J[1][1] += X[1] * g1;
+    }
+    const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double dj = fabs(det) * (R.wts[q0] * R.wts[q1]);
+    if (detJ)
+      detJ[gid] = dj;
+    if (Gq) {
+      const double id = 1.0 / det;
+      const double k00 = J[1][1] * id, k01 = -J[0][1] * id, k10 = -J[1][0] * id, k11 = J[0][0] * id;
+      double* o = Gq + c * (3 * NN) + q;
+      o[0] = dj * (k00 * k00 + k01 * k01);
+      o[NN] = dj * (k00 * k10 + k01 * k11);
+      o[2 * NN] = dj * (k10 * k10 + k11 * k11);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Boundary terms of the right-hand side over the compacted list of boundary dofs:
 //   b[d] += g * src[k] + dg * dsrc[k] - absb[k] * v[d]
 // -- fem::assemble_vector(b_, *L) with the collocated `ds` forms (Linear.hpp:205, forms.py).

@@ -16,3 +16,20 @@ public:
                                            density, nullptr, nullptr, sourceFrequency,
                                            sourceAmplitude, sourceSpeed) {}
 };
+
+/// LinearSpectral2D<T,P> (cpp/fenicsx-sf-naive/common/Linear.hpp:52-350): quadrilateral mesh, same flow
+template <typename T, int P>
+class LinearSpectral2D : public fus::detail::SpectralModel3D<T, P> {
+public:
+  LinearSpectral2D(basix::FiniteElement<T> element, std::shared_ptr<mesh::Mesh<T>> Mesh,
+                  std::shared_ptr<mesh::MeshTags<std::int32_t>> FacetTags,
+                  std::shared_ptr<fem::Function<T>> speedOfSound,
+                  std::shared_ptr<fem::Function<T>> density,
+                  const T& sourceFrequency, const T& sourceAmplitude, const T& sourceSpeed)
+      : fus::detail::SpectralModel3D<T, P>(FUS_LINEAR, element, Mesh, FacetTags, speedOfSound, density,
+                                           nullptr, nullptr, sourceFrequency, sourceAmplitude,
+                                           sourceSpeed) {
+    if (Mesh->topology()->dim() != 2)
+      throw std::runtime_error("LinearSpectral2D: quadrilateral mesh expected");
+  }
+};

@@ -115,47 +115,56 @@ private:
 } // namespace la
 
 namespace mesh {
-enum class CellType { hexahedron };
+enum class CellType { hexahedron, quadrilateral };
 enum class GhostMode { none };
 
 class Topology {
 public:
-  Topology(std::int64_t ncells) : _cells(std::make_shared<common::IndexMap>(ncells, 0, ncells)) {}
-  int dim() const { return 3; }
+  Topology(std::int64_t ncells, int dim = 3)
+      : _cells(std::make_shared<common::IndexMap>(ncells, 0, ncells)), _dim(dim) {}
+  int dim() const { return _dim; }
   std::shared_ptr<const common::IndexMap> index_map(int) const { return _cells; }
+  void create_connectivity(int, int) const {}
 
 private:
   std::shared_ptr<const common::IndexMap> _cells;
+  int _dim;
 };
 
 template <typename T>
 class Geometry {
 public:
-  Geometry(std::vector<T> x, std::vector<std::int32_t> dofmap)
-      : _x(std::move(x)), _dofmap(std::move(dofmap)) {}
-  int dim() const { return 3; }
+  Geometry(std::vector<T> x, std::vector<std::int32_t> dofmap, int gdim = 3)
+      : _x(std::move(x)), _dofmap(std::move(dofmap)), _gdim(gdim) {}
+  int dim() const { return _gdim; }
+  /// padded to 3 coordinates per vertex whatever the geometric dimension, as in DOLFINx
   std::span<const T> x() const { return std::span<const T>(_x.data(), _x.size()); }
   fus::View2D<const std::int32_t> dofmap() const {
-    return fus::View2D<const std::int32_t>(_dofmap.data(), _dofmap.size() / 8, 8);
+    const std::size_t nv = _gdim == 3 ? 8 : 4;
+    return fus::View2D<const std::int32_t>(_dofmap.data(), _dofmap.size() / nv, nv);
   }
 
 private:
   std::vector<T> _x;
   std::vector<std::int32_t> _dofmap;
+  int _gdim;
 };
 
 template <typename T>
 class Mesh {
 public:
-  Mesh(std::array<int, 3> n, Geometry<T> g, std::vector<std::int32_t> exterior_facets)
+  Mesh(std::array<int, 3> n, Geometry<T> g, std::vector<std::int32_t> exterior_facets,
+       int tdim = 3)
       : _n(n), _geometry(std::move(g)),
-        _topology(std::make_shared<Topology>((std::int64_t)n[0] * n[1] * n[2])),
+        _topology(std::make_shared<Topology>((std::int64_t)n[0] * n[1] * n[2], tdim)),
         _ext(std::move(exterior_facets)) {}
   const Geometry<T>& geometry() const { return _geometry; }
   std::shared_ptr<Topology> topology() const { return _topology; }
   std::shared_ptr<Topology> topology_mutable() const { return _topology; }
-  /// [shim] cells per direction of the structured box
+  /// [shim] cells per direction of the structured box (third entry 1 for a rectangle)
   const std::array<int, 3>& box_cells() const { return _n; }
+  /// [shim] facets per cell: the stride of the facet "index" cell * facets_per_cell + local facet
+  int facets_per_cell() const { return _topology->dim() == 3 ? 6 : 4; }
   /// [shim] exterior facets as {cell, local facet, box tag} triplets
   const std::vector<std::int32_t>& exterior_facets() const { return _ext; }
 
@@ -182,7 +191,23 @@ Mesh<T> create_box(std::array<std::array<T, 3>, 2> p, std::array<std::size_t, 3>
   return Mesh<T>({nn[0], nn[1], nn[2]}, Geometry<T>(std::move(x), std::move(xd)), std::move(f));
 }
 
-/// mesh::MeshTags<int32_t> over exterior facets.  [shim] a facet "index" is cell*6 + local facet.
+/// mesh::create_rectangle (quadrilateral cells) for the 2-D operators of cpp/fenicsx-sf-naive
+template <typename T>
+Mesh<T> create_rectangle(std::array<std::array<T, 2>, 2> p, std::array<std::size_t, 2> n, CellType) {
+  static_assert(std::is_same_v<T, double>, "the B200 path is FP64 only");
+  const int nn[2] = {(int)n[0], (int)n[1]};
+  const std::int64_t nv = (std::int64_t)(nn[0] + 1) * (nn[1] + 1), nc = (std::int64_t)nn[0] * nn[1];
+  std::vector<T> x(3 * nv);
+  std::vector<std::int32_t> xd(4 * nc);
+  fus::check(fus_rect_mesh(nn, p[0].data(), p[1].data(), x.data(), xd.data()), "fus_rect_mesh");
+  const std::int64_t nf = fus_rect_facets(nn, nullptr);
+  std::vector<std::int32_t> f(3 * nf);
+  fus_rect_facets(nn, f.data());
+  return Mesh<T>({nn[0], nn[1], 1}, Geometry<T>(std::move(x), std::move(xd), 2), std::move(f), 2);
+}
+
+/// mesh::MeshTags<int32_t> over exterior facets.  [shim] a facet "index" is
+/// cell * facets_per_cell + local facet.
 template <typename V>
 class MeshTags {
 public:
@@ -206,16 +231,17 @@ private:
 /// mesh::h (BM7-SC1/main.cpp:72-73): cell diameter = largest distance between two vertices.
 template <typename T>
 std::vector<T> h(const Mesh<T>& mesh, std::span<const int> entities, int dim) {
-  if (dim != 3)
+  if (dim != mesh.topology()->dim())
     throw std::runtime_error("mesh::h [shim]: cells only");
   auto x = mesh.geometry().x();
   auto xd = mesh.geometry().dofmap();
+  const int nv = (int)xd.extent(1);
   std::vector<T> out;
   out.reserve(entities.size());
   for (int c : entities) {
     T d2 = 0;
-    for (int a = 0; a < 8; ++a)
-      for (int b = a + 1; b < 8; ++b) {
+    for (int a = 0; a < nv; ++a)
+      for (int b = a + 1; b < nv; ++b) {
         T s = 0;
         for (int r = 0; r < 3; ++r) {
           const T e = x[3 * xd(c, a) + r] - x[3 * xd(c, b) + r];
@@ -252,7 +278,7 @@ MeshTags<std::int32_t> box_facet_tags(const Mesh<T>& mesh) {
   const auto& f = mesh.exterior_facets();
   for (std::size_t k = 0; k < f.size() / 3; ++k)
     if (f[3 * k + 2] != 0) {
-      idx.push_back(f[3 * k] * 6 + f[3 * k + 1]);
+      idx.push_back(f[3 * k] * mesh.facets_per_cell() + f[3 * k + 1]);
       val.push_back(f[3 * k + 2]);
     }
   return MeshTags<std::int32_t>(std::move(idx), std::move(val));
@@ -305,6 +331,14 @@ FunctionSpace<T> create_functionspace(std::shared_ptr<mesh::Mesh<T>> mesh,
     std::iota(dm.begin(), dm.end(), 0);
     auto im = std::make_shared<common::IndexMap>(nc, 0, nc);
     return FunctionSpace<T>(mesh, 0, std::make_shared<DofMap>(std::move(dm), 1, im));
+  }
+  if (mesh->topology()->dim() == 2) {
+    const int Nd2 = (P + 1) * (P + 1);
+    std::vector<std::int32_t> dm2((std::size_t)nc * Nd2);
+    fus::check(fus_rect_dofmap(P, nn, dm2.data()), "fus_rect_dofmap");
+    const std::int64_t nd2 = fus_rect_num_dofs(P, nn);
+    auto im2 = std::make_shared<common::IndexMap>(nd2, 0, nd2);
+    return FunctionSpace<T>(mesh, P, std::make_shared<DofMap>(std::move(dm2), Nd2, im2));
   }
   const int Nd = (P + 1) * (P + 1) * (P + 1);
   std::vector<std::int32_t> dm((std::size_t)nc * Nd);

@@ -6,7 +6,9 @@
 namespace fus::detail {
 
 /// Everything {Linear,Lossy,Westervelt}Spectral3D have in common (Linear.hpp:52-347): function
-/// space, device context, lumped boundary vectors, device model, init / rk4 / u_sol.
+/// space, device context, lumped boundary vectors, device model, init / rk4 / u_sol.  The 2-D
+/// classes of cpp/fenicsx-sf-naive/common (LinearSpectral2D, ...) are the same flow on a
+/// quadrilateral mesh, so they share this base: the dimension comes from the mesh.
 template <typename T, int P>
 class SpectralModel3D {
 public:
@@ -39,13 +41,14 @@ public:
     auto val = ft->values();
     for (std::size_t i = 0; i < idx.size(); ++i)
       for (std::size_t k = 0; k < facets.size() / 3; ++k)
-        if (facets[3 * k] * 6 + facets[3 * k + 1] == idx[i]) {
+        if (facets[3 * k] * mesh->facets_per_cell() + facets[3 * k + 1] == idx[i]) {
           facets[3 * k + 2] = val[i];
           break;
         }
 
     const std::int64_t nd = index_map->size_local() + index_map->num_ghosts();
-    const std::int64_t nc = mesh->topology()->index_map(3)->size_local();
+    const int tdim = mesh->topology()->dim();
+    const std::int64_t nc = mesh->topology()->index_map(tdim)->size_local();
     auto x = mesh->geometry().x();
     auto xd = mesh->geometry().dofmap();
     auto dm = V->dofmap()->map();
@@ -53,7 +56,8 @@ public:
     const T* delta = diffusivityOfSound ? diffusivityOfSound->x()->array().data() : nullptr;
     const T* beta = coefficientOfNonlinearity ? coefficientOfNonlinearity->x()->array().data()
                                               : nullptr;
-    check(fus_boundary_vectors(kind, P, nc, nd, x.data(), xd.data_handle(), dm.data_handle(),
+    auto boundary_vectors = tdim == 2 ? fus_boundary_vectors_2d : fus_boundary_vectors;
+    check(boundary_vectors(kind, P, nc, nd, x.data(), xd.data_handle(), dm.data_handle(),
                                (std::int64_t)facets.size() / 3, facets.data(),
                                speedOfSound->x()->array().data(), density->x()->array().data(),
                                delta, src.data(), dsrc.data(), absb.data(), bmass.data()),

@@ -26,10 +26,11 @@ public:
     auto im = V.dofmap()->index_map;
     auto xd = mesh->geometry().dofmap();
     auto x = mesh->geometry().x();
-    check(fus_ctx_create_from_mesh(V.degree(), (std::int64_t)dm.extent(0),
-                                   im->size_local() + im->num_ghosts(), im->size_local(),
-                                   dm.data_handle(), (std::int64_t)x.size() / 3, x.data(),
-                                   xd.data_handle(), device, &_ctx),
+    auto create = mesh->topology()->dim() == 2 ? fus_ctx_create_from_mesh_2d
+                                               : fus_ctx_create_from_mesh;
+    check(create(V.degree(), (std::int64_t)dm.extent(0), im->size_local() + im->num_ghosts(),
+                 im->size_local(), dm.data_handle(), (std::int64_t)x.size() / 3, x.data(),
+                 xd.data_handle(), device, &_ctx),
           "fus_ctx_create_from_mesh");
   }
   ~SpaceContext() { fus_ctx_destroy(_ctx); }
@@ -88,4 +89,25 @@ public:
 
 private:
   std::shared_ptr<fus::detail::SpaceContext<T>> _ctx;
+};
+
+/// 2D Spectral Mass operator (cpp/fenicsx-sf-naive/common/spectral_op.hpp:28-107): the same
+/// device path on a quadrilateral function space
+template <typename T, int P>
+class MassSpectral2D : public MassSpectral3D<T, P> {
+public:
+  MassSpectral2D(std::shared_ptr<fem::FunctionSpace<T>>& V) : MassSpectral3D<T, P>(V) {
+    if (V->mesh()->topology()->dim() != 2)
+      throw std::runtime_error("MassSpectral2D: quadrilateral mesh expected");
+  }
+};
+
+/// 2D Spectral Stiffness operator (cpp/fenicsx-sf-naive/common/spectral_op.hpp:226-359)
+template <typename T, int P>
+class StiffnessSpectral2D : public StiffnessSpectral3D<T, P> {
+public:
+  StiffnessSpectral2D(std::shared_ptr<fem::FunctionSpace<T>>& V) : StiffnessSpectral3D<T, P>(V) {
+    if (V->mesh()->topology()->dim() != 2)
+      throw std::runtime_error("StiffnessSpectral2D: quadrilateral mesh expected");
+  }
 };

@@ -214,6 +214,34 @@ int64_t fus_launch_count(void);
 int fus_ctx_profile(fus_ctx* ctx, const char* kernel, int64_t* launches, double* total_ms);
 
 /* ------------------------------------------------------------------------------------------
+ * 2-D quadrilateral variant: MassSpectral2D / StiffnessSpectral2D and the 2-D solver classes of
+ * cpp/fenicsx-sf-naive/common/{spectral_op.hpp:28-107,226-359, Linear.hpp:52-350, Lossy.hpp,
+ * Westervelt.hpp}.  Nd = N^2, tensor index i = i0*N + i1, G[c][q][3] = {G00,G01,G11} |detJ| w_q
+ * (precompute.hpp:199-203 there), 4 vertices per cell in DOLFINx order v = a + 2b, vertex
+ * coordinates padded to 3 doubles, local facets (edges) 0: y=0, 1: x=0, 2: x=1, 3: y=1.
+ * A context made by fus_ctx_create_2d / fus_ctx_create_from_mesh_2d works with every operator,
+ * model and halo entry point above (fus_stiffness_apply_*, fus_mass_apply_*, fus_model_*, ...);
+ * the boundary vectors come from fus_boundary_vectors_2d.  "geometry_mode" stays 0.
+ * ---------------------------------------------------------------------------------------- */
+int fus_rect_mesh(const int n[2], const double lo[2], const double hi[2], double* xg,
+                  int32_t* xdofmap);
+int fus_rect_dofmap(int P, const int n[2], int32_t* tensor_dofmap); /* lexicographic numbering */
+int64_t fus_rect_num_dofs(int P, const int n[2]);
+/* exterior edges {cell, local facet, tag}: tag 1 on x=lo, 2 on x=hi, 0 elsewhere */
+int64_t fus_rect_facets(const int n[2], int32_t* facets);
+int fus_boundary_vectors_2d(int kind, int P, int64_t ncells, int64_t ndofs, const double* xg,
+                            const int32_t* xdofmap, const int32_t* tensor_dofmap, int64_t nfacets,
+                            const int32_t* facets, const double* c0, const double* rho0,
+                            const double* delta0, double* src, double* dsrc, double* absb,
+                            double* bmass);
+int fus_ctx_create_2d(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                      const int32_t* tensor_dofmap, const double* G, const double* detJ,
+                      const double* dphi, int device, fus_ctx** out);
+int fus_ctx_create_from_mesh_2d(int P, int64_t ncells, int64_t ndofs, int64_t nowned,
+                                const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
+                                const int32_t* xdofmap, int device, fus_ctx** out);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-GPU halo exchange: replaces la::Vector::scatter_fwd / scatter_rev(std::plus)
  * (call sites Linear.hpp:196,199,206; Westervelt.hpp:243,246,257,265) with NCCL send/recv.
  * One context per GPU/process.  Neighbour k exchanges send_idx[send_off[k]:send_off[k+1]] (local

@@ -470,6 +470,7 @@ int64_t fo_box_facets(int nx, int ny, int nz, int32_t* facets) {
 /* ------------------------------------------------------------------------- */
 typedef struct {
   int kind, P, N, Nd;
+  int dim, nfn; /* 3 (hexahedra) or 2 (quadrilaterals); nodes per facet = N^(dim-1) */
   int64_t nc, ndofs, nowned;
   const int32_t* dofmap;
   const double *G, *detJ, *dphi;
@@ -507,7 +508,7 @@ static double* vec(int64_t n) { return (double*)calloc((size_t)n, sizeof(double)
 
 /* facet part of the bilinear form a (mass-like, applied to u==1) and of L */
 static void assemble_facets_a(const fo_model* M, double* out) {
-  int NN = M->N * M->N;
+  int NN = M->nfn;
   for (int64_t f = 0; f < M->nfacets; ++f) {
     int32_t c = M->facets[3 * f];
     double coef = M->delta0[c] / M->rho0[c] / M->c0[c] / M->c0[c] / M->c0[c];
@@ -519,7 +520,7 @@ static void assemble_facets_a(const fo_model* M, double* out) {
 }
 
 static void assemble_facets_L(const fo_model* M, double* b) {
-  int NN = M->N * M->N;
+  int NN = M->nfn;
   for (int64_t f = 0; f < M->nfacets; ++f) {
     int32_t c = M->facets[3 * f];
     int tag = M->facets[3 * f + 2];
@@ -541,17 +542,24 @@ static void assemble_facets_L(const fo_model* M, double* b) {
   }
 }
 
-fo_model* fo_model_create(int kind, int P, int64_t nc, int64_t ndofs, int64_t nowned,
-                          const int32_t* dofmap, const double* G, const double* detJ,
-                          const double* dphi, const double* c0, const double* rho0,
-                          const double* delta0, const double* beta0, int64_t nfacets,
-                          const int32_t* facets, const int32_t* fnodes, const double* fscale,
-                          double freq, double p0, double s0) {
+void fo_mass_apply_2d(int P, int64_t nc, const int32_t* dofmap, const double* detJ,
+                      const double* coeffs, const double* x, double* y);
+void fo_stiffness_apply_2d(int P, int64_t nc, const int32_t* dofmap, const double* G,
+                           const double* dphi, const double* coeffs, const double* x, double* y);
+
+static fo_model* model_create(int dim, int kind, int P, int64_t nc, int64_t ndofs, int64_t nowned,
+                              const int32_t* dofmap, const double* G, const double* detJ,
+                              const double* dphi, const double* c0, const double* rho0,
+                              const double* delta0, const double* beta0, int64_t nfacets,
+                              const int32_t* facets, const int32_t* fnodes, const double* fscale,
+                              double freq, double p0, double s0) {
   fo_model* M = (fo_model*)calloc(1, sizeof(fo_model));
   M->kind = kind;
   M->P = P;
   M->N = P + 1;
-  M->Nd = M->N * M->N * M->N;
+  M->dim = dim;
+  M->Nd = (dim == 3) ? M->N * M->N * M->N : M->N * M->N;
+  M->nfn = (dim == 3) ? M->N * M->N : M->N;
   M->nc = nc;
   M->ndofs = ndofs;
   M->nowned = nowned;
@@ -573,8 +581,8 @@ fo_model* fo_model_create(int kind, int P, int64_t nc, int64_t ndofs, int64_t no
   M->s0 = s0;
   M->period = 1.0 / freq;
   M->window_length = 4.0;
-  M->stiff = fo_stiffness_apply;
-  M->mass = fo_mass_apply;
+  M->stiff = (dim == 3) ? fo_stiffness_apply : fo_stiffness_apply_2d;
+  M->mass = (dim == 3) ? fo_mass_apply : fo_mass_apply_2d;
   M->src_factor = (kind == 0) ? 1.0 : 2.0; /* Linear.hpp:192 vs Lossy.hpp:216, Westervelt.hpp:237 */
   M->lin_c = vec(nc);
   M->att_c = vec(nc);
@@ -604,12 +612,35 @@ fo_model* fo_model_create(int kind, int P, int64_t nc, int64_t ndofs, int64_t no
   for (int64_t i = 0; i < ndofs; ++i)
     ones[i] = 1.0;
   double* tgt = (kind == 2) ? M->m0 : M->m;
-  fo_mass_apply(P, nc, dofmap, detJ, mcoef, ones, tgt);
+  M->mass(P, nc, dofmap, detJ, mcoef, ones, tgt);
   if (kind >= 1)
     assemble_facets_a(M, tgt);
   free(ones);
   free(mcoef);
   return M;
+}
+
+fo_model* fo_model_create(int kind, int P, int64_t nc, int64_t ndofs, int64_t nowned,
+                          const int32_t* dofmap, const double* G, const double* detJ,
+                          const double* dphi, const double* c0, const double* rho0,
+                          const double* delta0, const double* beta0, int64_t nfacets,
+                          const int32_t* facets, const int32_t* fnodes, const double* fscale,
+                          double freq, double p0, double s0) {
+  return model_create(3, kind, P, nc, ndofs, nowned, dofmap, G, detJ, dphi, c0, rho0, delta0,
+                      beta0, nfacets, facets, fnodes, fscale, freq, p0, s0);
+}
+
+/* {Linear,Lossy,Westervelt}Spectral2D (cpp/fenicsx-sf-naive/common/Linear.hpp:52-350 and the
+   2-D classes of Lossy.hpp / Westervelt.hpp there): the same flow on quadrilaterals; G has 3
+   entries per point, a facet is an edge with N nodes. */
+fo_model* fo_model_create_2d(int kind, int P, int64_t nc, int64_t ndofs, int64_t nowned,
+                             const int32_t* dofmap, const double* G, const double* detJ,
+                             const double* dphi, const double* c0, const double* rho0,
+                             const double* delta0, const double* beta0, int64_t nfacets,
+                             const int32_t* facets, const int32_t* fnodes, const double* fscale,
+                             double freq, double p0, double s0) {
+  return model_create(2, kind, P, nc, ndofs, nowned, dofmap, G, detJ, dphi, c0, rho0, delta0,
+                      beta0, nfacets, facets, fnodes, fscale, freq, p0, s0);
 }
 
 void fo_model_destroy(fo_model* M) {
@@ -728,4 +759,198 @@ int fo_model_rk4(fo_model* M, double startTime, double finalTime, double timeSte
   vcopy(v, v_, n);
   free(u_); free(v_); free(un); free(vn); free(u0); free(v0); free(ku); free(kv);
   return step;
+}
+
+/* ========================================================================= */
+/* 2-D quadrilateral variant.  Reference:            */
+/* cpp/fenicsx-sf-naive/common/{sum_factorisation,spectral_op,precompute}.hpp */
+/* ========================================================================= */
+
+/* transpose<T,Na,Nb,offa,offb> (fenicsx-sf-naive sum_factorisation.hpp:11-19) */
+void fo_transpose_2d(int Na, int Nb, int offa, int offb, const double* A, double* B) {
+  for (int a = 0; a < Na; ++a)
+    for (int b = 0; b < Nb; ++b)
+      B[a * offa + b * offb] = A[a * Nb + b];
+}
+
+/* contract<T,Na,Nb,Nk>: C[a,b] += A[a,k] * B[b,k] (fenicsx-sf-naive sum_factorisation.hpp:29-39) */
+void fo_contract_2d(int Na, int Nb, int Nk, const double* A, const double* B, double* C) {
+  for (int a = 0; a < Na; ++a)
+    for (int b = 0; b < Nb; ++b)
+      for (int k = 0; k < Nk; ++k)
+        C[a * Nb + b] += A[a * Nk + k] * B[b * Nk + k];
+}
+
+/* Rectangle [lo,hi] with nx x ny quadrilaterals.  vertices: id = vx*(ny+1)+vy, coordinates padded
+   to 3 as DOLFINx stores them; cell c = cx*ny+cy; local vertex v = a + 2b <-> (cx+a, cy+b)
+   (DOLFINx quadrilateral order, x fastest). */
+void fo_rect_mesh(int nx, int ny, const double* lo, const double* hi, double* xg,
+                  int32_t* xdofmap) {
+  for (int vx = 0; vx <= nx; ++vx)
+    for (int vy = 0; vy <= ny; ++vy) {
+      size_t id = (size_t)vx * (ny + 1) + vy;
+      xg[3 * id + 0] = lo[0] + (hi[0] - lo[0]) * vx / nx;
+      xg[3 * id + 1] = lo[1] + (hi[1] - lo[1]) * vy / ny;
+      xg[3 * id + 2] = 0.0;
+    }
+  for (int cx = 0; cx < nx; ++cx)
+    for (int cy = 0; cy < ny; ++cy)
+      for (int v = 0; v < 4; ++v)
+        xdofmap[4 * ((size_t)cx * ny + cy) + v]
+            = (int32_t)((size_t)(cx + (v & 1)) * (ny + 1) + (cy + (v >> 1)));
+}
+
+/* tensor_dofmap[c*N*N + i0*N + i1], lexicographic node numbering (x slowest) */
+void fo_rect_dofmap(int P, int nx, int ny, int32_t* dofmap) {
+  int N = P + 1;
+  int64_t My = (int64_t)ny * P + 1;
+  (void)nx;
+  for (int cx = 0; cx < nx; ++cx)
+    for (int cy = 0; cy < ny; ++cy)
+      for (int i0 = 0; i0 < N; ++i0)
+        for (int i1 = 0; i1 < N; ++i1)
+          dofmap[((int64_t)cx * ny + cy) * N * N + i0 * N + i1]
+              = (int32_t)(((int64_t)cx * P + node_pos(i0, P)) * My + cy * P + node_pos(i1, P));
+}
+
+/* J[i][j] = d x_i / d xi_j of the bilinear map */
+static void q1_jacobian_2d(const double X[4][2], const double xi[2], double J[2][2]) {
+  memset(J, 0, sizeof(double) * 4);
+  for (int v = 0; v < 4; ++v) {
+    int a = v & 1, b = v >> 1;
+    double l0 = a ? xi[0] : 1.0 - xi[0], l1 = b ? xi[1] : 1.0 - xi[1];
+    double g[2] = {(a ? 1.0 : -1.0) * l1, l0 * (b ? 1.0 : -1.0)};
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        J[i][j] += X[v][i] * g[j];
+  }
+}
+
+/* G[c][q][3] = |detJ| w_q {G00, G01, G11}, detJ[c][q] = |detJ| w_q, q = q0*N + q1
+   (fenicsx-sf-naive precompute.hpp:101-213 with gdim == 2, :199-203) */
+void fo_geometry_2d(int64_t nc, const double* xg, const int32_t* xdofmap, int N, const double* pts,
+                    const double* wts, double* G, double* detJ) {
+  int Nd = N * N;
+  for (int64_t c = 0; c < nc; ++c) {
+    double X[4][2];
+    for (int v = 0; v < 4; ++v)
+      for (int j = 0; j < 2; ++j)
+        X[v][j] = xg[3 * (size_t)xdofmap[4 * c + v] + j];
+    for (int q0 = 0; q0 < N; ++q0)
+      for (int q1 = 0; q1 < N; ++q1) {
+        int q = q0 * N + q1;
+        double xi[2] = {pts[q0], pts[q1]}, J[2][2];
+        q1_jacobian_2d(X, xi, J);
+        double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        double dj = fabs(det) * wts[q0] * wts[q1];
+        if (detJ)
+          detJ[c * Nd + q] = dj;
+        if (G) {
+          double K[2][2] = {{J[1][1] / det, -J[0][1] / det}, {-J[1][0] / det, J[0][0] / det}};
+          double* o = G + ((size_t)c * Nd + q) * 3;
+          o[0] = dj * (K[0][0] * K[0][0] + K[0][1] * K[0][1]);
+          o[1] = dj * (K[0][0] * K[1][0] + K[0][1] * K[1][1]);
+          o[2] = dj * (K[1][0] * K[1][0] + K[1][1] * K[1][1]);
+        }
+      }
+  }
+}
+
+/* MassSpectral2D::operator() (fenicsx-sf-naive spectral_op.hpp:69-86) */
+void fo_mass_apply_2d(int P, int64_t nc, const int32_t* dofmap, const double* detJ,
+                      const double* coeffs, const double* x, double* y) {
+  int N = P + 1, Nd = N * N;
+  double* x_ = (double*)malloc(sizeof(double) * Nd);
+  for (int64_t c = 0; c < nc; ++c) {
+    for (int i = 0; i < Nd; ++i)
+      x_[i] = x[dofmap[c * Nd + i]];
+    for (int iq = 0; iq < Nd; ++iq)
+      x_[iq] = coeffs[c] * x_[iq] * detJ[c * Nd + iq];
+    for (int i = 0; i < Nd; ++i)
+      y[dofmap[c * Nd + i]] += x_[i];
+  }
+  free(x_);
+}
+
+/* StiffnessSpectral2D::operator() (fenicsx-sf-naive spectral_op.hpp:275-318), call for call;
+   the 2-D stiffness::transform is :196-208 */
+void fo_stiffness_apply_2d(int P, int64_t nc, const int32_t* dofmap, const double* G,
+                           const double* dphi, const double* coeffs, const double* x, double* y) {
+  int N = P + 1, Nd = N * N;
+  size_t bytes = sizeof(double) * Nd;
+  double* buf = (double*)malloc(bytes * 8);
+  double *x_ = buf, *fw0 = buf + Nd, *fw1 = buf + 2 * Nd, *y0 = buf + 3 * Nd, *y1 = buf + 4 * Nd,
+         *T1 = buf + 5 * Nd, *T2 = buf + 6 * Nd, *dphiT = buf + 7 * Nd;
+  fo_transpose_2d(N, N, 1, N, dphi, dphiT); /* :271-272 */
+  for (int64_t c = 0; c < nc; ++c) {
+    for (int i = 0; i < Nd; ++i)
+      x_[i] = x[dofmap[c * Nd + i]];
+    memset(T1, 0, bytes);
+    memset(T2, 0, bytes);
+    memset(fw0, 0, bytes);
+    fo_contract_2d(N, N, N, x_, dphi, fw0); /* [i1,i2] x [q2,i2] -> [i1,q2] */
+    memset(fw1, 0, bytes);
+    fo_transpose_2d(N, N, 1, N, x_, T1);
+    fo_contract_2d(N, N, N, T1, dphi, T2);
+    fo_transpose_2d(N, N, 1, N, T2, fw1);
+    const double* Gc = G + (size_t)c * Nd * 3;
+    double coeff = coeffs[c];
+    for (int iq = 0; iq < Nd; ++iq) {
+      const double* _G = Gc + iq * 3;
+      double w0 = fw0[iq], w1 = fw1[iq];
+      fw0[iq] = coeff * (_G[2] * w0 + _G[1] * w1);
+      fw1[iq] = coeff * (_G[1] * w0 + _G[0] * w1);
+    }
+    memset(T1, 0, bytes);
+    memset(T2, 0, bytes);
+    memset(y0, 0, bytes);
+    fo_contract_2d(N, N, N, fw0, dphiT, y0);
+    memset(y1, 0, bytes);
+    fo_transpose_2d(N, N, 1, N, fw1, T1);
+    fo_contract_2d(N, N, N, T1, dphiT, T2);
+    fo_transpose_2d(N, N, 1, N, T2, y1);
+    for (int i = 0; i < Nd; ++i)
+      y[dofmap[c * Nd + i]] += y0[i] + y1[i];
+  }
+  free(buf);
+}
+
+/* Edge (cell, lf) of a quadrilateral: local tensor indices of its N nodes and w_a * |dx/ds|.
+   DOLFINx quadrilateral facets: 0: xi1=0, 1: xi0=0, 2: xi0=1, 3: xi1=1. */
+void fo_facet_data_2d(int N, const double* xg, const int32_t* xdofmap, const double* pts,
+                      const double* wts, int64_t cell, int lf, int32_t* fnodes, double* fscale) {
+  static const int fdir[4] = {1, 0, 0, 1}, fside[4] = {0, 0, 1, 1};
+  int dir = fdir[lf], side = fside[lf], ta = 1 - dir;
+  double X[4][2];
+  for (int v = 0; v < 4; ++v)
+    for (int j = 0; j < 2; ++j)
+      X[v][j] = xg[3 * (size_t)xdofmap[4 * cell + v] + j];
+  for (int a = 0; a < N; ++a) {
+    int idx[2];
+    idx[dir] = side;
+    idx[ta] = a;
+    double xi[2] = {pts[idx[0]], pts[idx[1]]}, J[2][2];
+    q1_jacobian_2d(X, xi, J);
+    fnodes[a] = idx[0] * N + idx[1];
+    fscale[a] = wts[a] * sqrt(J[0][ta] * J[0][ta] + J[1][ta] * J[1][ta]);
+  }
+}
+
+/* Exterior edges of the rectangle {cell, local facet, tag}: tag 1 on x=lo, 2 on x=hi, 0 elsewhere */
+int64_t fo_rect_facets(int nx, int ny, int32_t* facets) {
+  int64_t k = 0;
+  for (int cx = 0; cx < nx; ++cx)
+    for (int cy = 0; cy < ny; ++cy) {
+      int on[4] = {cy == 0, cx == 0, cx == nx - 1, cy == ny - 1};
+      for (int lf = 0; lf < 4; ++lf)
+        if (on[lf]) {
+          if (facets) {
+            facets[3 * k] = (int32_t)((int64_t)cx * ny + cy);
+            facets[3 * k + 1] = lf;
+            facets[3 * k + 2] = (lf == 1) ? 1 : ((lf == 2) ? 2 : 0);
+          }
+          ++k;
+        }
+    }
+  return k;
 }

@@ -90,7 +90,22 @@ class Oracle:
         L.fo_model_f1.argtypes = [C.c_void_p, _dbl, _f64p, _f64p, _f64p]
         L.fo_model_rk4.argtypes = [C.c_void_p, _dbl, _dbl, _dbl, _f64p, _f64p]
         L.fo_model_rk4.restype = _int
+        # 2-D quadrilateral variant (cpp/fenicsx-sf-naive)
+        L.fo_rect_mesh.argtypes = [_int, _int, _f64p, _f64p, _f64p, _i32p]
+        L.fo_rect_dofmap.argtypes = [_int, _int, _int, _i32p]
+        L.fo_geometry_2d.argtypes = L.fo_geometry.argtypes
+        L.fo_mass_apply_2d.argtypes = L.fo_mass_apply.argtypes
+        L.fo_stiffness_apply_2d.argtypes = L.fo_stiffness_apply.argtypes
+        L.fo_facet_data_2d.argtypes = L.fo_facet_data.argtypes
+        L.fo_rect_facets.argtypes = [_int, _int, C.c_void_p]
+        L.fo_rect_facets.restype = _i64
+        L.fo_model_create_2d.argtypes = L.fo_model_create.argtypes
+        L.fo_model_create_2d.restype = C.c_void_p
+        L.fo_contract_2d.argtypes = [_int, _int, _int, _f64p, _f64p, _f64p]
+        L.fo_transpose_2d.argtypes = [_int, _int, _int, _int, _f64p, _f64p]
         if ref:
+            if hasattr(L, "fr_stiffness_apply_2d"):      # absent from a prebuilt older _ref
+                L.fr_stiffness_apply_2d.argtypes = L.fo_stiffness_apply.argtypes
             L.fr_set_threads.argtypes = [_int]
             L.fr_max_threads.restype = _int
             L.fr_stiffness_apply.argtypes = L.fo_stiffness_apply.argtypes
@@ -165,6 +180,58 @@ class Oracle:
         fn(P, dofmap.shape[0], dofmap, detJ, coeffs, x, y)
         return y
 
+    # ---- 2-D quadrilateral variant ------------------------------------------------------
+    def rect_mesh(self, n, lo=(0.0, 0.0), hi=(1.0, 1.0)):
+        nx, ny = n
+        xg = np.zeros(((nx + 1) * (ny + 1), 3))
+        xd = np.zeros((nx * ny, 4), dtype=np.int32)
+        self.lib.fo_rect_mesh(nx, ny, np.array(lo, dtype=np.float64),
+                              np.array(hi, dtype=np.float64), xg, xd)
+        return xg, xd
+
+    def rect_dofmap(self, P, n):
+        dm = np.zeros((n[0] * n[1], (P + 1) ** 2), dtype=np.int32)
+        self.lib.fo_rect_dofmap(P, n[0], n[1], dm)
+        return dm
+
+    def rect_facets(self, n):
+        k = self.lib.fo_rect_facets(n[0], n[1], None)
+        f = np.zeros((k, 3), dtype=np.int32)
+        self.lib.fo_rect_facets(n[0], n[1], f.ctypes.data_as(C.c_void_p))
+        return f
+
+    def geometry_2d(self, P, xg, xd):
+        N = P + 1
+        pts, wts = self.gll(N)
+        nc = xd.shape[0]
+        G, dJ = np.zeros((nc, N * N, 3)), np.zeros((nc, N * N))
+        self.lib.fo_geometry_2d(nc, xg, xd, N, pts, wts, _opt(G), _opt(dJ))
+        return G, dJ
+
+    def facet_data_2d(self, P, xg, xd, facets):
+        N = P + 1
+        pts, wts = self.gll(N)
+        nf = facets.shape[0]
+        fn, fs = np.zeros((nf, N), dtype=np.int32), np.zeros((nf, N))
+        for k in range(nf):
+            self.lib.fo_facet_data_2d(N, xg, xd, pts, wts, int(facets[k, 0]), int(facets[k, 1]),
+                                      fn[k], fs[k])
+        return fn, fs
+
+    def stiffness_apply_2d(self, P, dofmap, G, dphi, coeffs, x, y, use_ref_kernels=False):
+        fn = self.lib.fr_stiffness_apply_2d if use_ref_kernels else self.lib.fo_stiffness_apply_2d
+        fn(P, dofmap.shape[0], dofmap, G, dphi, coeffs, x, y)
+        return y
+
+    def mass_apply_2d(self, P, dofmap, detJ, coeffs, x, y):
+        self.lib.fo_mass_apply_2d(P, dofmap.shape[0], dofmap, detJ, coeffs, x, y)
+        return y
+
+    def model_2d(self, kind, P, ndofs, dofmap, G, detJ, dphi, c0, rho0, delta0, beta0, facets,
+                 fnodes, fscale, freq, p0, s0):
+        return OracleModel(self, kind, P, ndofs, dofmap, G, detJ, dphi, c0, rho0, delta0, beta0,
+                           facets, fnodes, fscale, freq, p0, s0, None, False, dim=2)
+
     # ---- models -------------------------------------------------------------------------
     def model(self, kind, P, ndofs, dofmap, G, detJ, dphi, c0, rho0, delta0, beta0, facets,
               fnodes, fscale, freq, p0, s0, nowned=None, use_ref_kernels=False):
@@ -176,7 +243,7 @@ class OracleModel:
     KINDS = {"linear": 0, "lossy": 1, "westervelt": 2}
 
     def __init__(self, orc, kind, P, ndofs, dofmap, G, detJ, dphi, c0, rho0, delta0, beta0,
-                 facets, fnodes, fscale, freq, p0, s0, nowned, use_ref_kernels):
+                 facets, fnodes, fscale, freq, p0, s0, nowned, use_ref_kernels, dim=3):
         self.orc = orc
         self.ndofs = ndofs
         kind = self.KINDS.get(kind, kind)
@@ -188,9 +255,10 @@ class OracleModel:
         self._keep = [np.ascontiguousarray(a) for a in
                       (dofmap, G, detJ, dphi, c0, rho0, delta0, beta0, facets, fnodes, fscale)]
         (dofmap, G, detJ, dphi, c0, rho0, delta0, beta0, facets, fnodes, fscale) = self._keep
-        self.h = orc.lib.fo_model_create(kind, P, nc, ndofs, ndofs if nowned is None else nowned,
-                                         dofmap, G, detJ, dphi, c0, rho0, delta0, beta0,
-                                         facets.shape[0], facets, fnodes, fscale, freq, p0, s0)
+        create = orc.lib.fo_model_create if dim == 3 else orc.lib.fo_model_create_2d
+        self.h = create(kind, P, nc, ndofs, ndofs if nowned is None else nowned, dofmap, G, detJ,
+                        dphi, c0, rho0, delta0, beta0, facets.shape[0], facets, fnodes, fscale,
+                        freq, p0, s0)
         if use_ref_kernels:
             L = orc.lib
             orc.lib.fo_model_set_ops(self.h, C.cast(L.fr_stiffness_apply, C.c_void_p),

@@ -86,3 +86,32 @@ def dense_stiffness_apply(P, xg, xd, dofmap, coeffs, x):
         K, _ = element_matrices(P, xg[xd[c]], coeffs[c])
         y[dofmap[c]] += K @ x[dofmap[c]]
     return y
+
+
+def element_matrices_2d(P, X, coeff):
+    """Dense element stiffness (Nd x Nd, Nd = N^2) and lumped mass diagonal of one bilinear
+    quadrilateral; X: (4,2) vertices in tensor order v = a + 2b."""
+    N = P + 1
+    pts, wts = gll_basix_order(N)
+    phi1, dphi1 = lagrange_tables(pts)
+    Nd = N * N
+    K = np.zeros((Nd, Nd))
+    mdiag = np.zeros(Nd)
+    for q0 in range(N):
+        for q1 in range(N):
+            q = q0 * N + q1
+            grad = np.stack([np.outer(dphi1[q0], phi1[q1]).reshape(-1),
+                             np.outer(phi1[q0], dphi1[q1]).reshape(-1)], axis=1)      # (Nd, 2)
+            xi = (pts[q0], pts[q1])
+            J = np.zeros((2, 2))
+            for v in range(4):
+                b = (v & 1, v >> 1)
+                l = [xi[d] if b[d] else 1 - xi[d] for d in range(2)]
+                s = [1.0 if b[d] else -1.0 for d in range(2)]
+                J[:, 0] += X[v] * s[0] * l[1]
+                J[:, 1] += X[v] * l[0] * s[1]
+            w = wts[q0] * wts[q1] * abs(np.linalg.det(J))
+            pg = grad @ np.linalg.inv(J)
+            K += coeff * w * (pg @ pg.T)
+            mdiag[q] = w
+    return K, mdiag

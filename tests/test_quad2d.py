@@ -1,0 +1,249 @@
+"""2-D quadrilateral variant: MassSpectral2D / StiffnessSpectral2D and the
+2-D solvers of cpp/fenicsx-sf-naive/common.  CPU part: the oracle's restatement against the
+reference's own 2-D tensor kernels (oracle/_ref), an independent dense evaluation and analytic
+identities; the host set-up of the library against the oracle.  GPU part: the CUDA path against the
+oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+
+TOL_APPLY, TOL_STEPS = 1e-12, 1e-10
+
+
+def warped_rect(fus, n, lo=(0.1, -0.2), hi=(1.3, 0.7), amp=0.12, seed=3):
+    rng = np.random.default_rng(seed)
+    h = (np.asarray(hi) - np.asarray(lo)) / np.asarray(n)
+
+    def warp(x):
+        y = x.copy()
+        y[:, :2] += amp * h * rng.uniform(-1, 1, (x.shape[0], 2))
+        return y
+    return fus.RectMesh(n, lo, hi, warp=warp)
+
+
+# ---------------------------------------------------------------------------------------- CPU
+@pytest.mark.parametrize("P", range(1, 8))
+def test_oracle_2d_vs_reference_naive_header(fus, orc, orc_ref, P):
+    """fo_stiffness_apply_2d (plain C) against the same cell loop instantiated on the reference's
+    unmodified cpp/fenicsx-sf-naive/common/sum_factorisation.hpp (oracle/ref_driver2d.cpp)."""
+    if not hasattr(orc_ref.lib, "fr_stiffness_apply_2d"):
+        pytest.skip("prebuilt oracle/_ref predates the 2-D driver")
+    m = warped_rect(fus, (4, 3))
+    V = fus.FunctionSpace(m, P)
+    G, dJ = orc.geometry_2d(P, m.x, m.xdofmap)
+    rng = np.random.default_rng(P)
+    x, c = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)
+    y = orc.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c, x, np.zeros(V.ndofs))
+    yr = orc_ref.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c, x, np.zeros(V.ndofs),
+                                    use_ref_kernels=True)
+    assert rel_l2(y, yr) < 1e-14
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 5])
+def test_oracle_2d_vs_dense_and_identities(fus, orc, P):
+    from dense_ref import element_matrices_2d
+    m = warped_rect(fus, (3, 2))
+    V = fus.FunctionSpace(m, P)
+    nd, nc = V.ndofs, m.ncells
+    G, dJ = orc.geometry_2d(P, m.x, m.xdofmap)
+    assert np.abs(G[:, :, 1]).max() > 1e-3 * np.abs(G).max()            # genuinely non-diagonal
+    rng = np.random.default_rng(10 + P)
+    x, c = rng.uniform(-1, 1, nd), rng.uniform(0.5, 2, nc)
+    y = orc.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c, x, np.zeros(nd))
+    yd, md = np.zeros(nd), np.zeros(nd)
+    for cell in range(nc):
+        K, mdiag = element_matrices_2d(P, m.x[m.xdofmap[cell], :2], c[cell])
+        yd[V.dofmap[cell]] += K @ x[V.dofmap[cell]]
+        md[V.dofmap[cell]] += c[cell] * mdiag * x[V.dofmap[cell]]
+    assert rel_l2(y, yd) < 1e-12
+    ym = orc.mass_apply_2d(P, V.dofmap, dJ, c, x, np.zeros(nd))
+    assert rel_l2(ym, md) < 1e-13
+    one = np.ones(nd)
+    assert np.abs(orc.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c, one, np.zeros(nd))).max() \
+        < 1e-12 * np.abs(y).max()                                       # K 1 = 0
+    z = rng.uniform(-1, 1, nd)
+    Kz = orc.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c, z, np.zeros(nd))
+    assert abs(x @ Kz - z @ y) < 1e-12 * abs(z @ y)                      # symmetry
+    # sum of the lumped mass = area of the (polygonal) mesh
+    quad = m.x[m.xdofmap][:, (0, 1, 3, 2), :2]
+    area = 0.5 * np.abs((quad[:, :, 0] * np.roll(quad[:, :, 1], -1, 1)
+                         - np.roll(quad[:, :, 0], -1, 1) * quad[:, :, 1]).sum(1)).sum()
+    assert abs(orc.mass_apply_2d(P, V.dofmap, dJ, np.ones(nc), one, np.zeros(nd)).sum() - area) \
+        < 1e-13 * area
+
+
+@pytest.mark.parametrize("kind", ["linear", "lossy", "westervelt"])
+def test_host_setup_2d_vs_oracle(fus, orc, kind):
+    """fus_rect_mesh / fus_rect_dofmap / fus_rect_facets bit-exact against the oracle's generators;
+    fus_boundary_vectors_2d against an edge-by-edge assembly of the oracle's facet data."""
+    from fenicsx_fus_b200 import capi
+    P, n = 3, (4, 3)
+    m0 = fus.RectMesh(n, (0.1, -0.2), (1.3, 0.7))
+    xg, xd = orc.rect_mesh(n, (0.1, -0.2), (1.3, 0.7))
+    V0 = fus.FunctionSpace(m0, P)
+    assert np.array_equal(m0.x, xg) and np.array_equal(m0.xdofmap, xd)
+    assert np.array_equal(V0.dofmap, orc.rect_dofmap(P, n))
+    assert np.array_equal(m0.facets, orc.rect_facets(n)) and m0.facets.shape[0] == 2 * (4 + 3)
+    m = warped_rect(fus, n)
+    V = fus.FunctionSpace(m, P)
+    nc, nd = m.ncells, V.ndofs
+    rng = np.random.default_rng(0)
+    c0, rho0 = rng.uniform(1400, 1600, nc), rng.uniform(900, 1100, nc)
+    delta = rng.uniform(1e-3, 2e-3, nc)
+    k = capi.KINDS[kind]
+    src, dsrc, absb, bmass = (np.zeros(nd) for _ in range(4))
+    assert capi.load().fus_boundary_vectors_2d(
+        k, P, nc, nd, m.x, m.xdofmap, V.dofmap, m.facets.shape[0], m.facets, c0, rho0,
+        capi.optional(delta), capi.optional(src), capi.optional(dsrc), capi.optional(absb),
+        capi.optional(bmass)) == 0
+    fn, fs = orc.facet_data_2d(P, m.x, m.xdofmap, m.facets)
+    r_src, r_abs, r_ds, r_bm = (np.zeros(nd) for _ in range(4))
+    for f in range(m.facets.shape[0]):
+        c, tag = m.facets[f, 0], m.facets[f, 2]
+        d = V.dofmap[c, fn[f]]
+        if tag == 1:
+            np.add.at(r_src, d, fs[f] / rho0[c])
+        if kind == "linear":
+            if tag == 2:
+                np.add.at(r_abs, d, fs[f] / rho0[c] / c0[c])
+        else:
+            np.add.at(r_abs, d, fs[f] / rho0[c] / c0[c])
+            np.add.at(r_bm, d, fs[f] * delta[c] / rho0[c] / c0[c] ** 3)
+            if tag == 1:
+                np.add.at(r_ds, d, fs[f] * delta[c] / rho0[c] / c0[c] ** 2)
+    for a, b in ((src, r_src), (absb, r_abs), (dsrc, r_ds), (bmass, r_bm)):
+        assert np.allclose(a, b, rtol=1e-13, atol=1e-30)
+
+
+def test_oracle_2d_plane_wave_physics(fus, orc):
+    """LinearSpectral2D on a strip reproduces p0 sin(w(t - x/c)) behind the front (the analytic
+    solution of python/tests/test_linearspectral_1d.py:72-90; natural conditions on y = const)."""
+    P, nx = 4, 24
+    c, rho, f, p0 = 1500.0, 1000.0, 0.5e6, 1.0
+    Lx = 6 * c / f
+    h = Lx / nx
+    m = fus.RectMesh((nx, 2), (0, 0), (Lx, 2 * h))
+    V = fus.FunctionSpace(m, P)
+    G, dJ = orc.geometry_2d(P, m.x, m.xdofmap)
+    fn, fs = orc.facet_data_2d(P, m.x, m.xdofmap, m.facets)
+    nc, nd = m.ncells, V.ndofs
+    mdl = orc.model_2d("linear", P, nd, V.dofmap, G, dJ, orc.dphi(P), np.full(nc, c),
+                       np.full(nc, rho), None, None, m.facets, fn, fs, f, p0, c)
+    dt, tf = 0.3 * h / (c * P * P), 5.0 / f
+    u, v = np.zeros(nd), np.zeros(nd)
+    mdl.rk4(0.0, tf, dt, u, v)
+    xs = V.tabulate_dof_coordinates()[:, 0]
+    sel = xs < 0.9 * c * (tf - 4.0 / f)
+    exact = p0 * np.sin(2 * np.pi * f * (tf - xs / c))
+    assert np.sqrt(((u - exact)[sel] ** 2).sum() / (exact[sel] ** 2).sum()) < 2e-2
+
+
+def test_2d_context_needs_a_gpu(fus):
+    if fus.device_count() > 0:
+        pytest.skip("a GPU is present")
+    V = fus.FunctionSpace(fus.RectMesh((2, 2)), 2)
+    with pytest.raises(fus.FusError):
+        V.context()
+
+
+# ---------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_gpu_operators_2d_vs_oracle(fus, orc, gpu, P):
+    """stiffness_quad_kernel / mass_kernel / geometry_quad_kernel through the C ABI: a cell count
+    that is not a multiple of the cells-per-block packing, warped bilinear cells."""
+    m = warped_rect(fus, (7, 5))
+    V = fus.FunctionSpace(m, P)
+    nd, nc = V.ndofs, m.ncells
+    G, dJ = orc.geometry_2d(P, m.x, m.xdofmap)
+    Gd, dJd = V.context().geometry()
+    assert rel_l2(Gd, G) < 1e-13 and rel_l2(dJd, dJ) < 1e-13
+    rng = np.random.default_rng(P)
+    x, c = rng.uniform(-1, 1, nd), rng.uniform(0.5, 2, nc)
+    y = fus.StiffnessSpectral2D(V)(x, c, np.zeros(nd))
+    yo = orc.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c, x, np.zeros(nd))
+    ym = fus.MassSpectral2D(V)(x, c, np.zeros(nd))
+    ymo = orc.mass_apply_2d(P, V.dofmap, dJ, c, x, np.zeros(nd))
+    assert rel_l2(y, yo) < TOL_APPLY and rel_l2(ym, ymo) < TOL_APPLY
+    # accumulate semantics (y += A x) and integer data bit-exactness of the gather/scatter
+    y2 = fus.StiffnessSpectral2D(V)(x, c, y.copy())
+    assert rel_l2(y2, 2 * yo) < TOL_APPLY
+    xi = rng.integers(-8, 9, nd).astype(np.float64)
+    one = np.ones(nc)
+    a = fus.MassSpectral2D(fus.Context.from_arrays(P, V.dofmap, nd, None, np.ones_like(dJ),
+                                                   orc.dphi(P), dim=2))(xi, one, np.zeros(nd))
+    b = orc.mass_apply_2d(P, V.dofmap, np.ones_like(dJ), one, xi, np.zeros(nd))
+    assert np.array_equal(a, b)
+    # the reference-layout constructor (G[c][q][3] from precompute.hpp) gives the same operator
+    ca = fus.Context.from_arrays(P, V.dofmap, nd, G, dJ, orc.dphi(P), dim=2)
+    ya = fus.StiffnessSpectral2D(ca)(x, c, np.zeros(nd))
+    assert rel_l2(ya, yo) < TOL_APPLY
+    with pytest.raises(fus.FusError):
+        ca.set_option("geometry_mode", 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,P", [("linear", 4), ("lossy", 3), ("westervelt", 5)])
+def test_gpu_models_2d_vs_oracle(fus, orc, gpu, kind, P):
+    """{Linear,Lossy,Westervelt}Spectral2D: 10 RK4 steps from a random state, heterogeneous media."""
+    n, h = (6, 4), 0.002
+    m = warped_rect(fus, n, (0, 0), (h * n[0], h * n[1]), amp=0.05)
+    V = fus.FunctionSpace(m, P)
+    nc, nd = m.ncells, V.ndofs
+    rng = np.random.default_rng(7)
+    c0, rho0 = rng.uniform(1400, 1600, nc), rng.uniform(900, 1100, nc)
+    delta = rng.uniform(1e-3, 3e-3, nc) if kind != "linear" else None
+    beta = rng.uniform(3, 4, nc) if kind == "westervelt" else None
+    args = [a for a in (c0, rho0, delta, beta) if a is not None]
+    cls = {"linear": fus.LinearSpectral2D, "lossy": fus.LossySpectral2D,
+           "westervelt": fus.WesterveltSpectral2D}[kind]
+    mdl = cls(V, *args, 0.5e6, 6.0e4, 1500.0)
+    G, dJ = orc.geometry_2d(P, m.x, m.xdofmap)
+    fn, fs = orc.facet_data_2d(P, m.x, m.xdofmap, m.facets)
+    om = orc.model_2d(kind, P, nd, V.dofmap, G, dJ, orc.dphi(P), c0, rho0, delta, beta, m.facets,
+                      fn, fs, 0.5e6, 6.0e4, 1500.0)
+    assert rel_l2(mdl.mass(), om.mass()) < 1e-13
+    dt = 0.2 * np.sqrt(2) * h / (1600.0 * P * P)
+    u0, v0 = 1e3 * rng.uniform(-1, 1, nd), 1e9 * rng.uniform(-1, 1, nd)
+    k_gpu, k_orc = mdl.f1(3e-7, u0, v0), om.f1(3e-7, u0, v0)
+    assert rel_l2(k_gpu, k_orc) < TOL_APPLY
+    u, v = u0.copy(), v0.copy()
+    assert om.rk4(0.0, 9.5 * dt, dt, u, v) == 10
+    mdl.init(u0.copy(), v0.copy())
+    assert mdl.rk4(0.0, 9.5 * dt, dt) == 10
+    assert rel_l2(mdl.u_sol(), u) < TOL_STEPS and rel_l2(mdl.v_sol(), v) < TOL_STEPS
+
+
+@pytest.mark.gpu
+def test_gpu_cpp_dropin_2d_driver(fus, orc, gpu):
+    """examples/planewave2d.cpp (linear_planewave2d_1/main.cpp against include/fus/Linear.hpp and
+    spectral_op.hpp: LinearSpectral2D, StiffnessSpectral2D, MassSpectral2D) vs the Python mirror."""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "planewave2d")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_cpp_example()
+    n, steps = 6, 8
+    res = subprocess.run([exe, str(n), str(steps)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    vals = {ln.split(":")[0]: ln.split(":")[1].strip() for ln in res.stdout.splitlines() if ":" in ln}
+    L = 0.12 * n / 54.0
+    m = fus.RectMesh((n, n), (0, 0), (L, L))
+    V = fus.FunctionSpace(m, 4)
+    assert int(vals["Degrees of freedom"]) == V.ndofs
+    dt = float(vals["Time step size"])
+    mdl = fus.LinearSpectral2D(V, 1500.0, 1000.0, 0.5e6, 60000.0, 1500.0)
+    mdl.init()
+    assert mdl.rk4(0.0, (steps - 0.5) * dt, dt) == int(vals["Number of steps"]) == steps
+    u = mdl.u_sol()
+    assert np.linalg.norm(u) > 0
+    assert abs(np.linalg.norm(u) - float(vals["u_l2"])) < 1e-11 * np.linalg.norm(u)
+    x = np.sin(0.01 * np.arange(V.ndofs))
+    c = np.full(m.ncells, -1e-3)
+    y = fus.StiffnessSpectral2D(V)(x, c, np.zeros(V.ndofs))
+    z = fus.MassSpectral2D(V)(x, c, np.zeros(V.ndofs))
+    assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
+    assert abs(np.linalg.norm(z) - float(vals["Mx_l2"])) < 1e-11 * np.linalg.norm(z)
