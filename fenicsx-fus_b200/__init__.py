@@ -277,8 +277,9 @@ class Context:
               "fus_dev_download")
 
     def destroy(self):
-        if self.h:
-            self.lib.fus_ctx_destroy(self.h)
+        """Release the device data.  Refused (the handle stays valid) while models built on this
+        context are alive: destroy them first."""
+        if self.h and self.lib.fus_ctx_destroy(self.h) == 0:
             self.h = None
 
     def __del__(self):

@@ -86,6 +86,7 @@ struct fus_ctx {
   double* d_tri = nullptr;
   int geom_active = 0;      // what the stiffness operator currently uses: 0 streamed G, 1, 2
   bool lean = false;        // neither G nor detJ exist on the device: always mode 2
+  int live_models = 0;      // fus_model objects that still point at this context
   // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
   // profiles/), 0 column kernel, 1 point kernel, 2 line kernel
   int variant = -1;
@@ -104,6 +105,14 @@ struct fus_ctx {
 };
 
 namespace {
+// cudaFuncSetAttribute and the occupancy query are per device: a process that drives several GPUs
+// (one context each) must configure every kernel on every device it launches it on.
+constexpr int kMaxDevices = 64;
+struct KernelCfg {
+  bool configured[kMaxDevices] = {};
+  int blocks_plain[kMaxDevices] = {}, blocks_fuse[kMaxDevices] = {};
+};
+
 // RAII event bracket around one launch; a no-op unless profiling is on.
 struct ProfScope {
   fus_ctx* c;
@@ -208,7 +217,9 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   // variant 0: column kernel, variant 2: line kernel (same launch geometry rules)
   const double2* Gptr = c->d_G2;
   auto launch = [&](auto kern_plain, auto kern_fuse, int threads, int smem_bytes, int cpb,
-                    bool& configured, int& bps_plain, int& bps_fuse) -> int {
+                    KernelCfg& cfg) -> int {
+    bool& configured = cfg.configured[c->device];
+    int &bps_plain = cfg.blocks_plain[c->device], &bps_fuse = cfg.blocks_fuse[c->device];
     if (!configured) {
       FUS_CUDA(cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     smem_bytes));
@@ -242,32 +253,28 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   };
   if (c->geom_active == 1) { // all cells are parallelepipeds: Ghat per cell instead of G per point
     using L = LineCfg<N>;
-    static bool configured = false;
-    static int bp = 1, bf = 1;
+    static KernelCfg cfg;
     Gptr = c->d_Ghat;
     return launch(stiffness_line_kernel<N, false, 1>, stiffness_line_kernel<N, true, 1>,
-                  L::THREADS, L::SMEM_BYTES, L::CPB, configured, bp, bf);
+                  L::THREADS, L::SMEM_BYTES, L::CPB, cfg);
   }
   if (c->geom_active == 2) { // trilinear cells: G rebuilt per point from 192 B per cell
     using L = LineCfg<N>;
-    static bool configured = false;
-    static int bp = 1, bf = 1;
+    static KernelCfg cfg;
     Gptr = reinterpret_cast<const double2*>(c->d_tri);
     return launch(stiffness_line_kernel<N, false, 2>, stiffness_line_kernel<N, true, 2>,
-                  L::THREADS, L::SMEM_BYTES, L::CPB, configured, bp, bf);
+                  L::THREADS, L::SMEM_BYTES, L::CPB, cfg);
   }
   if (variant == 2) {
     using L = LineCfg<N>;
-    static bool configured = false;
-    static int bp = 1, bf = 1;
+    static KernelCfg cfg;
     return launch(stiffness_line_kernel<N, false>, stiffness_line_kernel<N, true>, L::THREADS,
-                  L::SMEM_BYTES, L::CPB, configured, bp, bf);
+                  L::SMEM_BYTES, L::CPB, cfg);
   }
   using C = ColCfg<N>;
-  static bool configured = false;
-  static int bp = 1, bf = 1;
+  static KernelCfg cfg;
   return launch(stiffness_col_kernel<N, false>, stiffness_col_kernel<N, true>, C::THREADS,
-                C::SMEM_BYTES, C::CPB, configured, bp, bf);
+                C::SMEM_BYTES, C::CPB, cfg);
 }
 
 template <int N>
@@ -483,7 +490,8 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
     return FUS_ERR_UNSUPPORTED;
   }
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device >= ndev) {
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev
+      || device >= kMaxDevices) {
     set_error("no usable CUDA device (requested %d of %d); there is no CPU fallback", device, ndev);
     return FUS_ERR_CUDA;
   }
@@ -783,6 +791,11 @@ int fus_ctx_create_from_mesh_2d(int P, int64_t ncells, int64_t ndofs, int64_t no
 int fus_ctx_destroy(fus_ctx* c) {
   if (!c)
     return FUS_OK;
+  if (c->live_models > 0) { // their device vectors live on this context's device and stream
+    set_error("fus_ctx_destroy: %d model(s) still use this context; destroy them first",
+              c->live_models);
+    return FUS_ERR_STATE;
+  }
   cudaSetDevice(c->device);
   if (c->stream)
     cudaStreamSynchronize(c->stream);
@@ -1118,6 +1131,7 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
   FUS_TRY(select_device(c));
   fus_model* m = new fus_model();
   m->ctx = c;
+  ++c->live_models;
   m->kind = kind;
   m->freq = freq;
   m->p0 = p0;
@@ -1223,6 +1237,7 @@ int fus_model_destroy(fus_model* m) {
                   (void*)m->d_u0, (void*)m->d_v0, (void*)m->d_ua, (void*)m->d_va, (void*)m->d_un,
                   (void*)m->d_vn, (void*)m->d_b})
     cudaFree(p);
+  --m->ctx->live_models;
   delete m;
   return FUS_OK;
 }

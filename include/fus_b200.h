@@ -128,6 +128,7 @@ int fus_ctx_create_from_mesh_lean(int P, int64_t ncells, int64_t ndofs, int64_t 
                                   const int32_t* tensor_dofmap, int64_t nverts, const double* xg,
                                   const int32_t* xdofmap, int device, fus_ctx** out);
 
+/* FUS_ERR_STATE (and nothing released) while fus_model objects created on it are alive. */
 int fus_ctx_destroy(fus_ctx* ctx);
 
 /* Launch all work of this context on the given cudaStream_t (default: a private stream). */
