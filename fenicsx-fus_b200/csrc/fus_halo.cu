@@ -97,8 +97,6 @@ struct PhaseProf {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
 };
 bool g_prof = std::getenv("FUS_HALO_PROF") != nullptr;
-// FUS_HALO_SKIP=1: timing experiment only -- issue no exchange at all (results are wrong)
-bool g_skip = std::getenv("FUS_HALO_SKIP") != nullptr;
 // FUS_HALO_LIGHTFENCE=1: one system fence per block (thread 0, after the block barrier)
 bool g_lightfence = std::getenv("FUS_HALO_LIGHTFENCE") != nullptr;
 PhaseProf g_phase[6] = {{"put_fwd", {}}, {"wait_fwd", {}}, {"put_rev", {}},
@@ -374,7 +372,7 @@ inline OffTables tables(Halo* h) { return OffTables{h->d_soff, h->d_roff}; }
 } // namespace
 
 int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty() || g_skip)
+  if (h->neigh.empty())
     return FUS_OK;
   const int nv = b ? 2 : 1, nn = (int)h->neigh.size();
   const OffTables T = tables(h);
@@ -607,7 +605,7 @@ int halo_peer_error(Halo* h) {
 }
 
 int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty() || g_skip)
+  if (h->neigh.empty())
     return FUS_OK;
   if (h->peer) { // one-sided put on the side stream, concurrent with the next cells on `st`
     FUS_CUDA_H(cudaEventRecord(h->ev_fwd_ready, st));
@@ -630,7 +628,7 @@ int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
 }
 
 int halo_forward_end(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty() || g_skip)
+  if (h->neigh.empty())
     return FUS_OK;
   if (h->peer) {
     // our own put has read a/b before anything later on `st` may overwrite them
@@ -660,13 +658,13 @@ static int reverse_on(Halo* h, double* a, double* b, cudaStream_t st) {
 }
 
 int halo_reverse(Halo* h, double* a, double* b, cudaStream_t st) {
-  if (h->neigh.empty() || g_skip)
+  if (h->neigh.empty())
     return FUS_OK;
   return reverse_on(h, a, b, st);
 }
 
 int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
-  if (h->neigh.empty() || g_skip)
+  if (h->neigh.empty())
     return FUS_OK;
   if (h->peer) {
     FUS_CUDA_H(cudaEventRecord(h->ev_ready, st));
@@ -689,7 +687,7 @@ int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
 }
 
 int halo_reverse_end(Halo* h, double* a, cudaStream_t st) {
-  if (h->neigh.empty() || g_skip)
+  if (h->neigh.empty())
     return FUS_OK;
   if (h->peer) {
     FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_done, 0)); // ghost partial sums have been read
