@@ -13,13 +13,14 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfus_b200.so")
-SOURCES = ["fus_capi.cu", "fus_halo.cu", "fus_host.cpp"]
-HEADERS = ["fus_kernels.cuh", "fus_internal.hpp", "fus_halo.hpp"]
+SOURCES = ["fus_capi.cu", "fus_halo.cu", "fus_host.cpp", "fus_partition.cpp"]
+HEADERS = ["fus_kernels.cuh", "fus_internal.hpp", "fus_halo.hpp", "fus_trilinear.hpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fopenmp",          # host set-up loops (fus_partition.cpp)
 ]
 
 
@@ -59,7 +60,7 @@ def build_library(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + [
         "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", LIB,
-    ] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
+    ] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl", "-lgomp"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)

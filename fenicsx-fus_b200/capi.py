@@ -82,6 +82,10 @@ SIGNATURES = {
     "fus_halo_setup": (_int, [_p, _int, _int, _p, _int, _p, _p, _p, _p, _p, _ll]),
     "fus_halo_peer_export": (_int, [_p, _p, _p]),
     "fus_halo_peer_connect": (_int, [_p, _p, _p]),
+    "fus_box_partition_create": (_int, [_int, _i32, _i32, _int, _int, C.POINTER(_p)]),
+    "fus_box_partition_info": (_int, [_p, _i64, _i32, _i32]),
+    "fus_box_partition_arrays": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "fus_box_partition_destroy": (_int, [_p]),
     "fus_scatter_fwd_dev": (_int, [_p, _p]),
     "fus_scatter_rev_dev": (_int, [_p, _p]),
 }

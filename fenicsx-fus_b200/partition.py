@@ -150,14 +150,21 @@ class _PartitionBase:
 
 
 class BoxPartition(_PartitionBase):
+    """One rank's block of the global box.  The index work runs in the library
+    (fus_box_partition_create, csrc/fus_partition.cpp); `native=False` selects the numpy
+    implementation below, kept as the cross-check the tests compare it with array by array."""
+
     def __init__(self, P, n_global, pgrid, rank, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0),
-                 numbering=1):
+                 numbering=1, native=True):
         lib = capi.load()
         self.P, self.N = int(P), int(P) + 1
         self.n_global = tuple(int(v) for v in n_global)
         self.pgrid = tuple(int(v) for v in pgrid)
         self.rank = int(rank)
         self.nranks = int(np.prod(self.pgrid))
+        if native:
+            self._init_native(lib, lo, hi, numbering)
+            return
         Px, Py, Pz = self.pgrid
         self.rcoord = (rank // (Py * Pz), (rank // Pz) % Py, rank % Pz)
         rng = [_split(self.n_global[d], self.pgrid[d], self.rcoord[d]) for d in range(3)]
@@ -292,6 +299,55 @@ class BoxPartition(_PartitionBase):
         f = f[keep]
         f[:, 0] = inv[f[:, 0]]
         self.facets = np.ascontiguousarray(f)
+
+
+    def _init_native(self, lib, lo, hi, numbering):
+        h = C.c_void_p()
+        ng = np.array(self.n_global, dtype=np.int32)
+        pg = np.array(self.pgrid, dtype=np.int32)
+        rc = lib.fus_box_partition_create(self.P, ng, pg, self.rank, int(numbering), C.byref(h))
+        if rc != 0:
+            msg = lib.fus_last_error().decode(errors="replace")
+            if "no cells" in msg:
+                raise ValueError("a rank has no cells")
+            raise capi.FusError(f"fus_box_partition_create failed with code {rc}: {msg}")
+        try:
+            sizes = np.zeros(9, dtype=np.int64)
+            self.n_local = np.zeros(3, dtype=np.int32)
+            cell_lo = np.zeros(3, dtype=np.int32)
+            capi.check(lib.fus_box_partition_info(h, sizes, self.n_local, cell_lo), "partition info")
+            ncells, ndofs, nowned, nf, nn, ns, nr, nif, ndg = (int(v) for v in sizes)
+            self.cell_lo = cell_lo.astype(np.int64)
+            Px, Py, Pz = self.pgrid
+            self.rcoord = (self.rank // (Py * Pz), (self.rank // Pz) % Py, self.rank % Pz)
+            self.has_lower = [self.rcoord[d] > 0 for d in range(3)]
+            self.has_upper = [self.rcoord[d] < self.pgrid[d] - 1 for d in range(3)]
+            self.ncells, self.ndofs, self.nowned = ncells, ndofs, nowned
+            self.ninterface_cells, self.ndofs_global = nif, ndg
+            self.dofmap = np.zeros((ncells, self.N ** 3), dtype=np.int32)
+            self.xdofmap = np.zeros((ncells, 8), dtype=np.int32)
+            self.cell_global = np.zeros(ncells, dtype=np.int64)
+            self.global_key = np.zeros(ndofs, dtype=np.int64)
+            self.facets = np.zeros((nf, 3), dtype=np.int32)
+            neigh = np.zeros(nn, dtype=np.int32)
+            soff, roff = np.zeros(nn + 1, dtype=np.int64), np.zeros(nn + 1, dtype=np.int64)
+            sidx, ridx = np.zeros(ns, dtype=np.int32), np.zeros(nr, dtype=np.int32)
+            p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+            capi.check(lib.fus_box_partition_arrays(
+                h, p(self.dofmap), p(self.xdofmap), p(self.cell_global), p(self.global_key),
+                p(self.facets), p(neigh), p(soff), p(sidx), p(roff), p(ridx)), "partition arrays")
+        finally:
+            lib.fus_box_partition_destroy(h)
+        self.neigh = [int(q) for q in neigh]
+        self.send_lists = [sidx[soff[k]:soff[k + 1]] for k in range(nn)]
+        self.recv_lists = [ridx[roff[k]:roff[k + 1]] for k in range(nn)]
+        # vertex coordinates from the GLOBAL formula (bitwise identical to the unpartitioned box)
+        lo, hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+        nv = self.n_local + 1
+        ax = [lo[d] + (hi[d] - lo[d]) * (self.cell_lo[d] + np.arange(nv[d])) / self.n_global[d]
+              for d in range(3)]
+        X, Y, Z = np.meshgrid(*ax, indexing="ij")
+        self.x = np.ascontiguousarray(np.stack([X, Y, Z], -1).reshape(-1, 3))
 
 
 class HexPartition(_PartitionBase):

@@ -267,6 +267,28 @@ int fus_halo_setup(fus_ctx* ctx, int rank, int nranks, const void* nccl_unique_i
 int fus_halo_peer_export(fus_ctx* ctx, void* ipc_handle64, int64_t* layout3);
 int fus_halo_peer_connect(fus_ctx* ctx, const void* handles, const int64_t* byte_off);
 
+/* Partition of the structured box over a pgrid[0] x pgrid[1] x pgrid[2] process grid for rank
+ * `rank` (host, once per rank): what DOLFINx's mesh partitioner and common::IndexMap provide to the
+ * reference.  Cells are split in contiguous blocks without ghost cells; an interface node is owned
+ * by the block with the lowest grid coordinates sharing it; local numbering is owned entries first,
+ * then ghosts grouped by owner rank; cells touching a shared dof come first.
+ * fus_box_partition_info: sizes = {ncells, ndofs, nowned, nfacets, nneigh, nsend, nrecv,
+ * ninterface_cells, ndofs_global}.  fus_box_partition_arrays copies out (any pointer may be NULL):
+ * dofmap[ncells][Nd], xdofmap[ncells][8] (vertex numbering of fus_box_mesh on the local block),
+ * cell_global[ncells], global_key[ndofs] (global lexicographic node id of every local dof),
+ * facets[nfacets][3], neigh[nneigh], send_off[nneigh+1], send_idx[nsend], recv_off[nneigh+1],
+ * recv_idx[nrecv] -- the arguments of fus_halo_setup. */
+typedef struct fus_partition fus_partition;
+int fus_box_partition_create(int P, const int n_global[3], const int pgrid[3], int rank,
+                             int numbering, fus_partition** out);
+int fus_box_partition_info(const fus_partition* p, int64_t sizes[9], int32_t n_local[3],
+                           int32_t cell_lo[3]);
+int fus_box_partition_arrays(const fus_partition* p, int32_t* dofmap, int32_t* xdofmap,
+                             int64_t* cell_global, int64_t* global_key, int32_t* facets,
+                             int32_t* neigh, int64_t* send_off, int32_t* send_idx,
+                             int64_t* recv_off, int32_t* recv_idx);
+int fus_box_partition_destroy(fus_partition* p);
+
 /* Stand-alone collectives on device vectors (tests): owner -> ghost, ghost -> owner (+=). */
 int fus_scatter_fwd_dev(fus_ctx* ctx, double* x);
 int fus_scatter_rev_dev(fus_ctx* ctx, double* x);

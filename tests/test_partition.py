@@ -52,6 +52,31 @@ def test_ownership_and_halo_lists(fus, P, n, pg):
     assert nf == 2 * (n[0] * n[1] + n[1] * n[2] + n[0] * n[2])
 
 
+@pytest.mark.parametrize("P,n,pg", [(2, (4, 3, 5), (2, 1, 1)), (3, (4, 4, 4), (2, 2, 2)),
+                                    (1, (5, 3, 2), (1, 3, 2)), (4, (6, 4, 2), (3, 2, 1)),
+                                    (2, (3, 3, 3), (1, 1, 1))])
+def test_native_partitioner_equals_numpy_reference(fus, P, n, pg):
+    """fus_box_partition_create (csrc/fus_partition.cpp, what bench.py and the GPU checks use) against
+    the numpy implementation of the same rules: every array and list identical on every rank."""
+    from fenicsx_fus_b200.partition import BoxPartition
+    for rank in range(int(np.prod(pg))):
+        for numbering in (0, 1):
+            a = BoxPartition(P, n, pg, rank, lo=(0.1, 0, 0), hi=(1, 2, 3), numbering=numbering)
+            b = BoxPartition(P, n, pg, rank, lo=(0.1, 0, 0), hi=(1, 2, 3), numbering=numbering,
+                             native=False)
+            for k in ("dofmap", "xdofmap", "cell_global", "global_key", "facets", "x", "n_local"):
+                assert np.array_equal(getattr(a, k), getattr(b, k)), (rank, numbering, k)
+            for k in ("ncells", "ndofs", "nowned", "ninterface_cells", "ndofs_global", "neigh"):
+                assert getattr(a, k) == getattr(b, k), (rank, numbering, k)
+            assert len(a.send_lists) == len(b.send_lists) == len(a.neigh)
+            for la, lb in zip(a.send_lists + a.recv_lists, b.send_lists + b.recv_lists):
+                assert np.array_equal(la, lb)
+    with pytest.raises(ValueError):
+        BoxPartition(2, (1, 2, 2), (2, 1, 1), 1)                       # this rank would have no cells
+    with pytest.raises(ValueError):
+        BoxPartition(2, (1, 2, 2), (2, 1, 1), 1, native=False)
+
+
 def test_single_rank_partition_is_trivial(fus, orc):
     from fenicsx_fus_b200.partition import BoxPartition
     p = BoxPartition(3, (3, 2, 2), (1, 1, 1), 0)
