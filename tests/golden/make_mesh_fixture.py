@@ -58,5 +58,48 @@ def main():
           "bytes", os.path.getsize(os.path.join(HERE, "ref_mesh_hex6312.npz")))
 
 
+SRC_2D = "/root/reference/cpp/fenicsx-sf-naive/examples/linear_planewave2d_1/mesh.h5"
+
+
+def main_2d():
+    """The mesh of the reference's 2-D example linear_planewave2d_1 (8 400 quadrilaterals on
+    [0,0.12] x [-0.035,0.035], facet tags 1 = source edge, 2 = absorbing edge, 3 = walls) with
+    outputs of the 2-D operators of cpp/fenicsx-sf-naive computed by oracle/_ref, i.e. the cell loop
+    of spectral_op.hpp:275-318 on the reference's own 2-D contract<>/transpose<> (P = 4,
+    u = sin(40 x) cos(30 pi y), the coefficients of the example: c0 = 1500, rho0 = 1000)."""
+    from fenicsx_fus_b200.unstructured2d import QuadFunctionSpace, QuadMesh
+    f = hdf5min.File(SRC_2D)
+    name = "planewave_2d_1"
+    topo = f.read(f"/Mesh/{name}/topology").astype(np.int32)
+    geom = f.read(f"/Mesh/{name}/geometry")
+    fl = f.read(f"/MeshTags/{name}_facets/topology").astype(np.int32)
+    fv = f.read(f"/MeshTags/{name}_facets/Values").astype(np.int32)
+    cv = f.read(f"/MeshTags/{name}_cells/Values").astype(np.int32)
+    assert np.array_equal(f.read(f"/MeshTags/{name}_cells/topology"), topo)
+    mesh = QuadMesh(geom, topo[:, (0, 1, 3, 2)], fl, fv, cv)
+    P = 4
+    V = QuadFunctionSpace(mesh, P)
+    ref = Oracle(ref=True)
+    G, dJ = ref.geometry_2d(P, mesh.x, mesh.xdofmap)
+    X = V.tabulate_dof_coordinates()
+    u = np.sin(40 * X[:, 0]) * np.cos(30 * np.pi * X[:, 1])
+    c0, rho0 = 1500.0, 1000.0
+    ym = ref.mass_apply_2d(P, V.dofmap, dJ, np.full(mesh.ncells, 1.0 / rho0 / c0 / c0), u,
+                           np.zeros(V.ndofs))
+    ys = ref.stiffness_apply_2d(P, V.dofmap, G, ref.dphi(P), np.full(mesh.ncells, -1.0 / rho0), u,
+                                np.zeros(V.ndofs), use_ref_kernels=True)
+    rng = np.random.default_rng(2048)
+    sample = np.sort(rng.choice(V.ndofs, 2048, replace=False))
+    out = os.path.join(HERE, "ref_mesh_quad8400.npz")
+    np.savez_compressed(out, topology_vtk=topo, geometry=geom, facet_lines=fl, facet_values=fv,
+                        cell_values=cv, P=P, ndofs=V.ndofs, sample=sample, sample_xy=X[sample, :2],
+                        mass_sample=ym[sample], stiff_sample=ys[sample],
+                        mass_l2=np.linalg.norm(ym), stiff_l2=np.linalg.norm(ys), area=dJ.sum())
+    print("2-D: ndofs", V.ndofs, "mass_l2", np.linalg.norm(ym), "stiff_l2", np.linalg.norm(ys),
+          "bytes", os.path.getsize(out))
+
+
 if __name__ == "__main__":
-    main()
+    if "--2d-only" not in sys.argv:
+        main()
+    main_2d()
