@@ -242,3 +242,43 @@ def test_rk4_plane_wave_physics(orc):
     exact = p0 * np.sin(2 * np.pi * f * (tf - xs / c))
     err = np.sqrt(((u - exact)[sel] ** 2).sum() / (exact[sel] ** 2).sum())
     assert err < 2e-2
+
+
+def _plane_wave_error(orc, P, nx):
+    """Relative L2 error of LinearSpectral3D on a column of nx cells (6 wavelengths) against
+    p0 sin(w (t - x/c)) behind the front, small time step (spatial error dominates)."""
+    c, rho, f, p0 = 1500.0, 1000.0, 0.5e6, 1.0
+    Lx = 6 * c / f
+    n, h = (nx, 1, 1), Lx / nx
+    xg, xd = orc.box_mesh(n, (0, 0, 0), (Lx, h, h))
+    dm = orc.box_dofmap(P, n, 0)
+    nd = dm.max() + 1
+    G, dJ = orc.geometry(P, xg, xd)
+    facets = orc.box_facets(n)
+    fn, fs = orc.facet_data(P, xg, xd, facets)
+    nc = dm.shape[0]
+    mdl = orc.model("linear", P, nd, dm, G, dJ, orc.dphi(P), np.full(nc, c), np.full(nc, rho),
+                    None, None, facets, fn, fs, f, p0, c)
+    dt, tf = 0.1 * h / (c * P * P), 5.0 / f
+    u, v = np.zeros(nd), np.zeros(nd)
+    mdl.rk4(0.0, tf, dt, u, v)
+    pts, _ = orc.gll(P + 1)
+    xs = np.zeros(nd)
+    for cx in range(nx):
+        for i0 in range(P + 1):
+            xs[dm[cx].reshape(P + 1, P + 1, P + 1)[i0]] = (cx + pts[i0]) * h
+    sel = xs < 0.9 * c * (tf - 4.0 / f)
+    exact = p0 * np.sin(2 * np.pi * f * (tf - xs / c))
+    return np.sqrt(((u - exact)[sel] ** 2).sum() / (exact[sel] ** 2).sum())
+
+
+def test_plane_wave_spectral_convergence(orc):
+    """An anchor outside this repository for the numbers Basix/DOLFINx/FFCx would supply (GLL
+    rule, derivative table, geometry, the lumped boundary terms): halving h must reduce the error
+    against the analytic plane wave (python/tests/test_linearspectral_1d.py:72-90) at the
+    dispersion rate h^(2P) of a GLL spectral element method -- 2^4 for P = 2, 2^8 for P = 4.
+    Wrong nodes, weights or derivative entries destroy that rate."""
+    e2 = [_plane_wave_error(orc, 2, nx) for nx in (24, 48)]
+    assert e2[1] < 1e-3 and 10.0 < e2[0] / e2[1] < 40.0             # measured 18.5
+    e4 = [_plane_wave_error(orc, 4, nx) for nx in (12, 24)]
+    assert e4[1] < 5e-5 and e4[0] / e4[1] > 150.0                   # measured 412
