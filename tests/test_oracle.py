@@ -282,3 +282,75 @@ def test_plane_wave_spectral_convergence(orc):
     assert e2[1] < 1e-3 and 10.0 < e2[0] / e2[1] < 40.0             # measured 18.5
     e4 = [_plane_wave_error(orc, 4, nx) for nx in (12, 24)]
     assert e4[1] < 5e-5 and e4[0] / e4[1] > 150.0                   # measured 412
+
+
+def _column(orc, P, nx, L):
+    """A column of nx hexahedra along x whose only boundary facets are the two end faces (tag 1 at
+    x = 0, tag 2 at x = L): the lateral walls stay natural, which makes the 3-D models one-dimensional,
+    the setting of the reference's python/tests/*_1d.py."""
+    n, h = (nx, 1, 1), L / nx
+    xg, xd = orc.box_mesh(n, (0, 0, 0), (L, h, h))
+    dm = orc.box_dofmap(P, n, 0)
+    nd = dm.max() + 1
+    G, dJ = orc.geometry(P, xg, xd)
+    facets = orc.box_facets(n)
+    facets = np.ascontiguousarray(facets[facets[:, 2] > 0])
+    fn, fs = orc.facet_data(P, xg, xd, facets)
+    pts, _ = orc.gll(P + 1)
+    xs = np.zeros(nd)
+    for cx in range(nx):
+        for i0 in range(P + 1):
+            xs[dm[cx].reshape(P + 1, P + 1, P + 1)[i0]] = (cx + pts[i0]) * h
+    return dm, nd, G, dJ, facets, fn, fs, xs, h
+
+
+def test_reference_analytic_test_lossy(orc):
+    """python/tests/test_lossyspectral_1d.py:13-118 (degree 4, 4 elements per wavelength, f0 = 10,
+    c0 = 1, rho0 = 4, 5 dB/m, CFL 0.5, t_end = L/c0 + 16/f0) with the oracle's LossySpectral3D:
+    the attenuated plane wave p0 exp(-alpha x) sin(w t - w x / c0) within the reference's own
+    threshold of 1e-2.  Covers what the linear test cannot: the second stiffness term, the
+    d g/dt source term, the boundary mass term and the source factor 2 of Lossy.hpp:216."""
+    P, epw = 4, 4
+    f0, c0, rho0, alphadB, L = 10.0, 1.0, 4.0, 5.0, 1.0
+    w0 = 2 * np.pi * f0
+    aNp = alphadB / 20 * np.log(10)
+    delta0 = 2 * aNp * c0 ** 3 / w0 / w0            # compute_diffusivity_of_sound, Lossy.hpp:376-380
+    p0 = rho0 * c0 * 1.0
+    nx = int(epw * L / (c0 / f0) + 1)
+    dm, nd, G, dJ, facets, fn, fs, xs, h = _column(orc, P, nx, L)
+    nc = dm.shape[0]
+    mdl = orc.model("lossy", P, nd, dm, G, dJ, orc.dphi(P), np.full(nc, c0), np.full(nc, rho0),
+                    np.full(nc, delta0), None, facets, fn, fs, f0, p0, c0)
+    dt, tend = 0.5 * h / (c0 * P * P), L / c0 + 16 / f0
+    u, v = np.zeros(nd), np.zeros(nd)
+    mdl.rk4(0.0, tend, dt, u, v)
+    exact = p0 * np.exp(-aNp * xs) * np.sin(w0 * tend - w0 / c0 * xs)
+    assert np.linalg.norm(u - exact) / np.linalg.norm(exact) < 1e-2      # measured 5.6e-3
+
+
+def test_reference_analytic_test_westervelt(orc):
+    """python/tests/test_westerveltspectral_1d.py:13-128 (degree 4, 8 elements per wavelength,
+    beta = 0.01, delta = 0, CFL 0.9, t_end = L/c0 + 8/f0) with the oracle's
+    WesterveltSpectral3D: the Fubini solution.  The reference accepts 1e-1; the linear solution
+    alone is 0.18 away, so the two nonlinear mass terms of Westervelt.hpp:249-265 are what is
+    being checked."""
+    from scipy.special import jv
+    P, epw = 4, 8
+    f0, c0, rho0, beta0, L = 10.0, 1.0, 1.0, 0.01, 1.0
+    w0, p0 = 2 * np.pi * f0, 1.0
+    nx = int(epw * L / (c0 / f0) + 1)
+    dm, nd, G, dJ, facets, fn, fs, xs, h = _column(orc, P, nx, L)
+    nc = dm.shape[0]
+    mdl = orc.model("westervelt", P, nd, dm, G, dJ, orc.dphi(P), np.full(nc, c0), np.full(nc, rho0),
+                    np.zeros(nc), np.full(nc, beta0), facets, fn, fs, f0, p0, c0)
+    dt, tend = 0.9 * h / (c0 * P * P), L / c0 + 8 / f0
+    u, v = np.zeros(nd), np.zeros(nd)
+    mdl.rk4(0.0, tend, dt, u, v)
+    sigma = (xs + 1e-7) / (c0 ** 2 / w0 / beta0 / (p0 / rho0 / c0))
+    exact = np.zeros(nd)
+    for term in range(1, 50):
+        exact += 2 / term / sigma * jv(term, term * sigma) * np.sin(term * w0 * (tend - xs / c0))
+    exact *= p0
+    linear = p0 * np.sin(w0 * (tend - xs / c0))
+    err = np.linalg.norm(u - exact) / np.linalg.norm(exact)
+    assert err < 1e-2 and np.linalg.norm(linear - exact) / np.linalg.norm(exact) > 0.1   # 3.8e-3
