@@ -12,7 +12,11 @@
  * the reference obtains from Basix / DOLFINx / FFCx at run time (GLL rule, 1-D
  * derivative table, Jacobians, facet integrals) has NO golden vector anywhere in the
  * reference tree: for those numbers this oracle is "parity unpinned" and is instead
- * self-validated by closed-form known answers and a dense O(N^6) evaluation in tests/.
+ * self-validated by closed-form known answers and a dense O(N^6) evaluation in tests/, and
+ * anchored outside this repository by the reference's own analytic tests
+ * (python/tests/test_{linear,lossy,westervelt}spectral_1d.py: plane wave, attenuated plane
+ * wave, Fubini solution -- all within the reference's thresholds), by h^(2P) convergence, and
+ * by the reference's 2-D example run on its own shipped mesh and tags.
  *
  * Every function cites the reference lines it follows (paths relative to
  * cpp/fenicsx-sf/common/ unless stated).
