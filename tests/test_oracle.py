@@ -354,3 +354,23 @@ def test_reference_analytic_test_westervelt(orc):
     linear = p0 * np.sin(w0 * (tend - xs / c0))
     err = np.linalg.norm(u - exact) / np.linalg.norm(exact)
     assert err < 1e-2 and np.linalg.norm(linear - exact) / np.linalg.norm(exact) > 0.1   # 3.8e-3
+
+
+@pytest.mark.parametrize("P", [2, 3, 4, 5, 6, 7])
+def test_gll_element_mass_matrix_is_diagonal(orc, P):
+    """python/tests/test_element_mass_matrix.py:13-72: a GLL-variant Lagrange element integrated
+    with the GLL rule of matching degree has a diagonal mass matrix (dimensions 1, 2, 3) -- the
+    property that lets MassSpectral3D multiply nodal values by detJ[c][q] (spectral_op.hpp:75-85).
+    Basis functions are built independently of the oracle (monomial coefficients)."""
+    from dense_ref import lagrange_tables
+    pts, wts = orc.gll(P + 1)
+    phi, _ = lagrange_tables(pts)
+    M1 = phi.T @ np.diag(wts) @ phi
+    assert np.abs(M1 - np.diag(wts)).max() < 1e-12 and abs(wts.sum() - 1.0) < 1e-14
+    if P <= 4:
+        M2 = np.kron(M1, M1)
+        assert np.abs(M2 - np.diag(np.diag(M2))).max() < 1e-12
+    if P <= 3:
+        M3 = np.kron(M2, M1)
+        assert np.abs(M3 - np.diag(np.diag(M3))).max() < 1e-12
+        assert np.allclose(np.diag(M3), np.einsum("a,b,c->abc", wts, wts, wts).reshape(-1))

@@ -213,3 +213,42 @@ def test_gpu_models_on_reference_mesh(fus, orc, gpu, ref_mesh, kind):
     assert om.rk4(t0, tf, dt, u, v) == steps
     assert np.isfinite(u).all() and 0 < np.abs(u).max() < 1e3 * p0     # a stable run
     assert rel_l2(mdl.u_sol(), u) < 1e-10 and rel_l2(mdl.v_sol(), v) < 1e-10
+
+
+def test_reference_five_operator_checks_vs_dense(fus, orc, ref_mesh):
+    """The five checks of cpp/fenicsx-sf-naive/tests/test_operators3d/main.cpp:104-339 on the
+    reference's unstructured mesh, with its parameters (c0 = 1.5, rho0 = 1, delta0 = 10, beta0 = 10;
+    u = 1, u_n = 2, w_n = u_n^2, v_n = cos x sin(pi y) cos(2 pi z)): the reference compares each
+    spectral operator with an independently assembled FFCx form; here the independent side is the
+    dense evaluation of the same GLL-quadrature forms (tests/dense_ref.py) on a subset of cells."""
+    from dense_ref import element_matrices
+    from fenicsx_fus_b200.unstructured import HexFunctionSpace
+    m, _ = ref_mesh
+    P = 2
+    V = HexFunctionSpace(m, P)
+    cells = np.arange(0, m.ncells, 97)                       # 66 general hexahedra
+    dm = np.ascontiguousarray(V.dofmap[cells])
+    xd = np.ascontiguousarray(m.xdofmap[cells])
+    G, dJ = orc.geometry(P, m.x, xd)
+    X = V.tabulate_dof_coordinates()
+    nd, nc = V.ndofs, cells.size
+    c0, rho0, delta0, beta0 = 1.5, 1.0, 10.0, 10.0
+    u, un = np.ones(nd), np.full(nd, 2.0)
+    wn = un * un
+    vn = np.cos(X[:, 0]) * np.sin(np.pi * X[:, 1]) * np.cos(2 * np.pi * X[:, 2])
+    checks = [("m1", "mass", 1.0 / rho0 / c0 ** 2, u),                          # main.cpp:104-160
+              ("m2", "mass", -2.0 * beta0 / rho0 ** 2 / c0 ** 4, un),           # :162-207
+              ("m3", "mass", 2.0 * beta0 / rho0 ** 2 / c0 ** 4, wn),            # :209-254
+              ("b1", "stiff", -1.0 / rho0, vn),                                 # :256-297
+              ("b2", "stiff", -delta0 / rho0 / c0 ** 2, vn)]                    # :299-339
+    for name, op, coef, x in checks:
+        cf = np.full(nc, coef)
+        if op == "mass":
+            y = orc.mass_apply(P, dm, dJ, cf, x, np.zeros(nd))
+        else:
+            y = orc.stiffness_apply(P, dm, G, orc.dphi(P), cf, x, np.zeros(nd))
+        yd = np.zeros(nd)
+        for k in range(nc):
+            K, mdiag = element_matrices(P, m.x[xd[k]], coef)
+            yd[dm[k]] += (coef * mdiag * x[dm[k]]) if op == "mass" else K @ x[dm[k]]
+        assert rel_l2(y, yd) < 1e-12, name
