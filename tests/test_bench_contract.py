@@ -98,6 +98,10 @@ def _fake_torch():
         def item(self):
             return float(self.a.reshape(-1)[0])
 
+        def zero_(self):
+            self.a[...] = 0.0
+            return self
+
     cuda = types.SimpleNamespace(
         set_device=lambda i: None, synchronize=lambda: None, empty_cache=lambda: None,
         set_stream=lambda s: None, Stream=lambda: types.SimpleNamespace(cuda_stream=0),
@@ -106,6 +110,10 @@ def _fake_torch():
     t.cuda, t.float64 = cuda, "float64"
     t.tensor = lambda v, dtype=None, device=None: T(v)
     t.zeros = lambda n, dtype=None: T(np.zeros(n))
+    t.rand = lambda n, dtype=None, device=None: T(np.random.default_rng(0).uniform(size=n))
+    t.zeros_like = lambda x: T(np.zeros_like(x.a))
+    t.full = lambda shape, v, dtype=None, device=None: T(np.full(shape, v))
+    t.linalg = types.SimpleNamespace(vector_norm=lambda x: T([np.linalg.norm(x.a)]))
     t.device = lambda *a: None
     dist = types.ModuleType("torch.distributed")
     t.distributed = dist
@@ -209,3 +217,80 @@ def test_gpu_arm_control_flow_with_a_stub_device(monkeypatch, capsys, model, ext
         assert d["roofline"]["kernel"].endswith(",2>")
     if model == "linear":
         assert ("geometry_mode", 1) in calls["options"]          # the affine extra was attempted
+
+
+def test_child_sweep_script_control_flow_with_a_stub_device(monkeypatch, capsys):
+    """scripts/bench_sweep.py is what bench.py runs in a child process for its `extras`; like the
+    GPU arm it cannot run here, so its control flow is exercised with the device stubbed out:
+    every (degree, geometry mode) row and every RK4-by-mode row comes out as JSON."""
+    import importlib.util
+    import sys
+
+    import numpy as np
+
+    import fenicsx_fus_b200 as fus
+    spec = importlib.util.spec_from_file_location("sweep_mod",
+                                                  os.path.join(ROOT, "scripts", "bench_sweep.py"))
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)
+    t, dist = _fake_torch()
+    monkeypatch.setitem(sys.modules, "torch", t)
+    monkeypatch.setattr(sweep, "SWEEP", {P: 3 for P in range(2, 8)})
+
+    class Ctx:
+        mode = 0
+
+        def set_stream(self, s):
+            pass
+
+        def set_option(self, name, value):
+            if name == "geometry_mode":
+                self.mode = value
+
+        def get_option(self, name):
+            return self.mode
+
+        def profile(self, kernel):
+            return 80, 16.0
+
+        def destroy(self):
+            pass
+
+    class Op:
+        def __init__(self, V):
+            pass
+
+        def __call__(self, x, c, y):
+            return y
+
+    class Model:
+        def __init__(self, V, *a, **kw):
+            self.V = V
+
+        def init(self, u=None, v=None):
+            pass
+
+        def rk4(self, t0, tf, dt):
+            return int(round((tf - t0) / dt + 0.5))
+
+        def u_sol(self):
+            return np.ones(self.V.ndofs)
+
+        def destroy(self):
+            pass
+
+    monkeypatch.setattr(fus.Context, "from_mesh", classmethod(lambda cls, V, device=0, **kw: Ctx()))
+    monkeypatch.setattr(fus, "StiffnessSpectral3D", Op)
+    monkeypatch.setattr(fus, "LinearSpectral3D", Model)
+    monkeypatch.setattr(sys, "argv", ["bench_sweep.py", "--degrees", "2,3,4,5,6,7", "--variants=-1",
+                                      "--geometry-modes", "0,1,2", "--rk4-geometry-modes", "0,1,2",
+                                      "--models", "", "--repeats", "2"])
+    sweep.main()
+    rows = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    deg = [r for r in rows if r["config"] == "degree_sweep"]
+    rk = [r for r in rows if r["config"] == "headline_rk4_by_geometry_mode"]
+    assert sorted((r["P"], r["geometry_mode"]) for r in deg) == [(P, g) for P in range(2, 8)
+                                                                 for g in (0, 1, 2)]
+    assert [r["geometry_mode"] for r in rk] == [0, 1, 2] and all(r["steps"] == 20 for r in rk)
+    assert all({"ms_min", "gdof_per_s", "frac_of_measured_peak"} <= set(r) for r in deg)
+    assert all({"ms_per_step", "operator_ms", "rel_l2_vs_first_mode"} <= set(r) for r in rk)
