@@ -290,6 +290,30 @@ def test_cpp_dropin_driver(fus, gpu):
     assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
 
 
+def test_c_abi_from_plain_c(fus, gpu):
+    """examples/c_abi_minimal.c: the C ABI driven from C11 (stiffness application, boundary vectors,
+    model, rk4, destroy order) gives the numbers of the Python mirror."""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "c_abi_minimal")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_cpp_example()
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    vals = {ln.split(":")[0]: ln.split(":")[1].strip() for ln in res.stdout.splitlines() if ":" in ln}
+    m = fus.BoxMesh((4, 3, 2), (0, 0, 0), (0.008, 0.006, 0.004))
+    V = fus.FunctionSpace(m, 3, numbering=1)
+    x = np.sin(0.01 * np.arange(V.ndofs))
+    y = fus.StiffnessSpectral3D(V)(x, np.full(m.ncells, -1e-3), np.zeros(V.ndofs))
+    assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
+    mdl = fus.LinearSpectral3D(V, 1500.0, 1000.0, 0.5e6, 60000.0, 1500.0)
+    mdl.init()
+    assert mdl.rk4(0.0, 9.5 * 4.0e-8, 4.0e-8) == int(vals["Number of steps"]) == 10
+    u = mdl.u_sol()
+    assert np.linalg.norm(u) > 0
+    assert abs(np.linalg.norm(u) - float(vals["u_l2"])) < 1e-11 * np.linalg.norm(u)
+
+
 @pytest.mark.parametrize("kind", ["lossy", "westervelt"])
 def test_cpp_dropin_media_driver(fus, orc, gpu, kind):
     """examples/media_box.cpp: the reference's BM7-SC1 (lossy, water | cortical bone through cell

@@ -203,3 +203,24 @@ def test_trilinear_map_on_the_reference_mesh(fus, orc):
     assert lib.fus_trilinear_geometry(P, cells.shape[0], co, capi.optional(G2), capi.optional(dJ2)) == 0
     assert np.abs(G2 - G).max() <= 1e-12 * np.abs(G).max()
     assert np.abs(dJ2 - dJ).max() <= 1e-12 * np.abs(dJ).max()
+
+
+def test_header_is_valid_c_and_c_example_links(fus, tmp_path):
+    """include/fus_b200.h is a C header (no C++ in the signatures): gcc -std=c11 -pedantic accepts
+    it and examples/c_abi_minimal.c links against the library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "fus_b200.h")
+    res = subprocess.run(["/usr/bin/gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                          "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    exe = str(tmp_path / "c_abi_minimal")
+    res = subprocess.run(["/usr/bin/gcc", "-std=c11", "-O1", "-Wall", "-Werror",
+                          "-I" + os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "examples", "c_abi_minimal.c"),
+                          "-L" + os.path.join(ROOT, "fenicsx-fus_b200", "lib"), "-lfus_b200", "-lm",
+                          "-Wl,-rpath," + os.path.join(ROOT, "fenicsx-fus_b200", "lib"), "-o", exe],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    if fus.device_count() == 0:                  # no GPU here: it must fail loudly, not fall back
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode != 0 and "no CPU fallback" in run.stderr
