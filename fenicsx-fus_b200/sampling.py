@@ -15,24 +15,26 @@ from . import capi
 
 
 def _trilinear(X, xi):
-    """x(xi) and Jacobian for cells X (n,8,3) at reference points xi (n,3)."""
-    n = X.shape[0]
-    x = np.zeros((n, 3))
-    J = np.zeros((n, 3, 3))
-    for v in range(8):
-        b = (v & 1, (v >> 1) & 1, (v >> 2) & 1)
-        l = [xi[:, d] if b[d] else 1.0 - xi[:, d] for d in range(3)]
-        dl = [1.0 if b[d] else -1.0 for d in range(3)]
-        w = l[0] * l[1] * l[2]
+    """x(xi) and Jacobian for cells X (n, 2^d, d) at reference points xi (n, d), d = 2 or 3
+    (bilinear quadrilaterals, trilinear hexahedra; vertex v = a + 2b [+ 4c])."""
+    n, d = X.shape[0], xi.shape[1]
+    x = np.zeros((n, d))
+    J = np.zeros((n, d, d))
+    for v in range(1 << d):
+        b = [(v >> k) & 1 for k in range(d)]
+        l = [xi[:, k] if b[k] else 1.0 - xi[:, k] for k in range(d)]
+        dl = [1.0 if b[k] else -1.0 for k in range(d)]
+        w = np.prod(l, axis=0)
         x += w[:, None] * X[:, v]
-        g = np.stack([dl[0] * l[1] * l[2], l[0] * dl[1] * l[2], l[0] * l[1] * dl[2]], axis=1)
+        g = np.stack([dl[k] * np.prod([l[j] for j in range(d) if j != k], axis=0)
+                      for k in range(d)], axis=1)
         J += X[:, v, :, None] * g[:, None, :]
     return x, J
 
 
 def pull_back(X, pts, iters=30, tol=1e-14):
-    """Reference coordinates of physical points pts (n,3) in cells X (n,8,3) by Newton."""
-    xi = np.full((X.shape[0], 3), 0.5)
+    """Reference coordinates of physical points pts (n,d) in cells X (n,2^d,d) by Newton."""
+    xi = np.full((X.shape[0], pts.shape[1]), 0.5)
     for _ in range(iters):
         x, J = _trilinear(X, xi)
         r = pts - x
@@ -47,26 +49,26 @@ def compute_eval_params(mesh, points, padding=1e-12):
     """points: (3, n) like the reference helper (or (n, 3)).  Returns (points_on_proc (m,3),
     cells (m,), reference coordinates (m,3), indices of the kept points (m,))."""
     pts = np.asarray(points, dtype=np.float64)
-    if pts.ndim != 2 or 3 not in pts.shape:
-        raise ValueError("points must be (3, n) or (n, 3)")
-    if pts.shape[0] == 3 and pts.shape[1] != 3:
+    d = getattr(mesh, "dim", 3)                                # 2: quadrilateral meshes (z ignored)
+    if pts.ndim != 2 or not ({3, d} & set(pts.shape)):
+        raise ValueError("points must be (3, n) or (n, 3)" + (" or (2, n) / (n, 2)" if d == 2 else ""))
+    if pts.shape[0] in (3, d) and pts.shape[1] not in (3, d):
         pts = pts.T
-    pts = np.ascontiguousarray(pts)
-    X = mesh.x[mesh.xdofmap]                                   # (nc, 8, 3)
+    pts = np.ascontiguousarray(pts[:, :d])
+    X = mesh.x[mesh.xdofmap][:, :, :d]                         # (nc, 2^d, d)
     lo, hi = X.min(axis=1) - padding, X.max(axis=1) + padding
     # uniform background grid over the mesh bounding box: cells registered in every bin they touch
     glo, ghi = lo.min(axis=0), hi.max(axis=0)
     nc = X.shape[0]
-    nb = max(1, int(round(nc ** (1.0 / 3.0))))
+    nb = max(1, int(round(nc ** (1.0 / d))))
     h = np.where(ghi > glo, (ghi - glo) / nb, 1.0)
     b0 = np.clip(((lo - glo) / h).astype(np.int64), 0, nb - 1)
     b1 = np.clip(((hi - glo) / h).astype(np.int64), 0, nb - 1)
     bins = {}
+    import itertools
     for c in range(nc):
-        for i in range(b0[c, 0], b1[c, 0] + 1):
-            for j in range(b0[c, 1], b1[c, 1] + 1):
-                for k in range(b0[c, 2], b1[c, 2] + 1):
-                    bins.setdefault((i, j, k), []).append(c)
+        for key in itertools.product(*(range(b0[c, k], b1[c, k] + 1) for k in range(d))):
+            bins.setdefault(key, []).append(c)
     keep, cells, xis = [], [], []
     pb = np.clip(((pts - glo) / h).astype(np.int64), 0, nb - 1)
     inside_box = np.all((pts >= glo) & (pts <= ghi), axis=1)
@@ -87,7 +89,7 @@ def compute_eval_params(mesh, points, padding=1e-12):
             xis.append(np.clip(xi[k], 0.0, 1.0))
     keep = np.array(keep, dtype=np.int64)
     return (pts[keep], np.array(cells, dtype=np.int32),
-            np.array(xis).reshape(-1, 3), keep)
+            np.array(xis).reshape(-1, d), keep)
 
 
 def lagrange_1d(P, s):
@@ -104,9 +106,12 @@ def lagrange_1d(P, s):
 
 
 def eval_function(V, u, cells, xi):
-    """u at reference points xi (m,3) of the given cells: sum_i u[dofmap[c,i]] phi_i0 phi_i1 phi_i2
+    """u at reference points xi (m,d) of the given cells: sum_i u[dofmap[c,i]] phi_i0 phi_i1 [phi_i2]
     (fem::Function::eval)."""
     P, N = V.P, V.P + 1
+    if xi.shape[1] == 2:
+        l0, l1 = (lagrange_1d(P, xi[:, k]) for k in range(2))
+        return np.einsum("mab,ma,mb->m", np.asarray(u)[V.dofmap[cells]].reshape(-1, N, N), l0, l1)
     l0, l1, l2 = (lagrange_1d(P, xi[:, d]) for d in range(3))
     coeff = np.asarray(u)[V.dofmap[cells]].reshape(-1, N, N, N)
     return np.einsum("mabc,ma,mb,mc->m", coeff, l0, l1, l2)

@@ -4,7 +4,8 @@ The reference's examples dump `u_n` with `dolfinx::io::VTXWriter` (ADIOS2 BP, e.
 `cpp/fenicsx-sf-naive/examples/linear_planewave2d_1/main.cpp:144-158`) for ParaView.  ADIOS2 is a
 third-party library that is not in this image, so the same step is offered as VTK XML
 unstructured-grid files (`.vtu`, plus a `.pvd` collection for time series), which ParaView and
-VisIt read natively.  A degree-P cell is written as P^3 linear hexahedra on its GLL lattice: every
+VisIt read natively.  A degree-P cell is written as P^3 linear hexahedra (P^2 quadrilaterals for the
+2-D variant, where the reference's examples actually write their output) on its GLL lattice: every
 nodal value is kept exactly and no high-order cell support is needed in the reader.
 
 Host-side post-processing only: fields come from `model.u_sol()` / `model.v_sol()`.
@@ -27,11 +28,21 @@ def gll_lattice_order(P):
     return np.argsort(pts, kind="stable")
 
 
-def subcell_connectivity(dofmap, P):
-    """(ncells * P^3, 8) linear hexahedra in VTK vertex order from the tensor dofmap
-    `dofmap[c, i0*N*N + i1*N + i2]` (permute.hpp:15-42 ordering)."""
+_VTK_QUAD = ((0, 0), (1, 0), (1, 1), (0, 1))
+
+
+def subcell_connectivity(dofmap, P, dim=3):
+    """(ncells * P^3, 8) linear hexahedra -- or (ncells * P^2, 4) quadrilaterals for dim = 2 -- in
+    VTK vertex order from the tensor dofmap `dofmap[c, i0*N*N + i1*N + i2]` / `dofmap[c, i0*N + i1]`
+    (permute.hpp:15-42 ordering)."""
     N = P + 1
     order = gll_lattice_order(P)                       # lattice position -> 1-D node index
+    if dim == 2:
+        dm2 = np.asarray(dofmap).reshape(-1, N, N)[:, order][:, :, order]
+        conn2 = np.empty((dm2.shape[0], P, P, 4), dtype=np.int64)
+        for k, (dx, dy) in enumerate(_VTK_QUAD):
+            conn2[..., k] = dm2[:, dx:dx + P, dy:dy + P]
+        return conn2.reshape(-1, 4)
     dm = np.asarray(dofmap).reshape(-1, N, N, N)[:, order][:, :, order][:, :, :, order]
     conn = np.empty((dm.shape[0], P, P, P, 8), dtype=np.int64)
     for k, (dx, dy, dz) in enumerate(_VTK_HEX):
@@ -61,8 +72,9 @@ def write_vtu(path, V, fields, binary=True, dof_coordinates=None):
     X = np.asarray(X, dtype=np.float64)
     if X.shape != (V.ndofs, 3):
         raise ValueError("dof coordinates must be (ndofs, 3)")
-    conn = subcell_connectivity(V.dofmap, V.P)
-    nsub = conn.shape[0]
+    dim = getattr(V, "dim", 3)
+    conn = subcell_connectivity(V.dofmap, V.P, dim)
+    nsub, nvc = conn.shape                             # sub-cells, vertices per sub-cell
     for name, f in fields.items():
         if np.asarray(f).shape != (V.ndofs,):
             raise ValueError(f"field {name!r} must have {V.ndofs} entries")
@@ -73,8 +85,9 @@ def write_vtu(path, V, fields, binary=True, dof_coordinates=None):
         out.write("<Points>\n" + _data_array("Points", X, 3, binary) + "</Points>\n")
         out.write("<Cells>\n")
         out.write(_data_array("connectivity", conn.reshape(-1), None, binary))
-        out.write(_data_array("offsets", 8 * np.arange(1, nsub + 1, dtype=np.int64), None, binary))
-        out.write(_data_array("types", np.full(nsub, 12, dtype=np.uint8), None, binary))
+        out.write(_data_array("offsets", nvc * np.arange(1, nsub + 1, dtype=np.int64), None, binary))
+        out.write(_data_array("types", np.full(nsub, 12 if dim == 3 else 9, dtype=np.uint8), None,
+                              binary))                 # VTK_HEXAHEDRON / VTK_QUAD
         out.write("</Cells>\n")
         first = next(iter(fields), None)
         out.write(f'<PointData Scalars="{first}">\n' if first else "<PointData>\n")

@@ -62,3 +62,26 @@ def test_eval_on_warped_box_reproduces_nodal_values(fus):
     pk, cells, xi, keep = sampling.compute_eval_params(m, X[sel])
     assert len(keep) == 60                                   # nodes (also boundary ones) are found
     assert np.abs(sampling.eval_function(V, u, cells, xi) - u[sel]).max() < 1e-10
+
+
+def test_eval_on_the_reference_2d_example_mesh(fus):
+    """Line sampling as in the reference's 2-D examples (python/src/fenicsxfus/utils.py:10-47 on the
+    axis of the planar-wave runs): a degree-P polynomial is reproduced exactly on the example's mesh."""
+    from fenicsx_fus_b200 import sampling
+    from fenicsx_fus_b200.unstructured2d import QuadFunctionSpace, QuadMesh
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_mesh_quad8400.npz"))
+    m = QuadMesh(g["geometry"], g["topology_vtk"][:, (0, 1, 3, 2)])
+    P = 3
+    V = QuadFunctionSpace(m, P)
+    X = V.tabulate_dof_coordinates()
+    f = lambda x: 1 + 50 * x[:, 0] ** 3 - 200 * x[:, 0] * x[:, 1] ** 2 + x[:, 1]  # noqa: E731
+    u = f(X)
+    pl, vl = sampling.eval_line(V, u, (0.0, 0.001), (0.12, 0.001), 60)
+    assert pl.shape == (60, 2) and np.abs(vl - f(pl)).max() < 1e-12
+    rng = np.random.default_rng(1)
+    pts = rng.uniform([0, -0.035, 0], [0.12, 0.035, 0], (100, 3))         # (n,3) with z = 0 accepted
+    pk, cells, xi, keep = sampling.compute_eval_params(m, pts)
+    assert len(keep) == 100 and xi.shape == (100, 2)
+    assert np.abs(sampling.eval_function(V, u, cells, xi) - f(pts)).max() < 1e-12
+    pk, cells, xi, keep = sampling.compute_eval_params(m, np.array([[0.2, 0.0], [0.06, 0.0]]))
+    assert keep.tolist() == [1]

@@ -60,3 +60,32 @@ def test_pvd_time_series_on_the_reference_mesh(fus, tmp_path):
     assert last["connectivity"].size == 8 * m.ncells * 8                  # P^3 = 8 sub-cells per cell
     with pytest.raises(ValueError):
         vtkio.write_vtu(str(tmp_path / "bad.vtu"), V, {"u": np.zeros(3)})
+
+
+def test_vtu_2d_on_the_reference_example_mesh(fus, tmp_path):
+    """The reference writes its output in the 2-D examples (VTXWriter in
+    cpp/fenicsx-sf-naive/examples/linear_planewave2d_1/main.cpp:147-149): quadrilateral spaces are
+    written as P^2 VTK_QUAD sub-cells per cell, here on that example's own mesh."""
+    from fenicsx_fus_b200 import vtkio
+    from fenicsx_fus_b200.unstructured2d import QuadFunctionSpace, QuadMesh
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_mesh_quad8400.npz"))
+    m = QuadMesh(g["geometry"], g["topology_vtk"][:, (0, 1, 3, 2)], g["facet_lines"],
+                 g["facet_values"], g["cell_values"])
+    P = 3
+    V = QuadFunctionSpace(m, P)
+    X = V.tabulate_dof_coordinates()
+    u = np.sin(50 * X[:, 0]) + X[:, 1]
+    path = str(tmp_path / "u2d.vtu")
+    npts, ncell = vtkio.write_vtu(path, V, {"u": u})
+    assert (npts, ncell) == (V.ndofs, m.ncells * P * P)
+    d = vtkio.read_vtu_arrays(path)
+    assert np.array_equal(d["u"], u) and np.array_equal(d["Points"], X) and (d["types"] == 9).all()
+    conn = d["connectivity"].reshape(-1, 4)
+    assert np.array_equal(d["offsets"], 4 * np.arange(1, ncell + 1))
+    Y = X[conn][:, :, :2]
+    area = 0.5 * ((Y[:, :, 0] * np.roll(Y[:, :, 1], -1, 1)
+                   - np.roll(Y[:, :, 0], -1, 1) * Y[:, :, 1]).sum(1))      # signed, counter-clockwise
+    assert (area > 0).all() and abs(area.sum() - 0.12 * 0.07) < 1e-15
+    # a structured RectMesh space goes through the same path
+    Vr = fus.FunctionSpace(fus.RectMesh((3, 2)), 2)
+    assert vtkio.write_vtu(str(tmp_path / "r.vtu"), Vr, {"one": np.ones(Vr.ndofs)}) == (Vr.ndofs, 24)
