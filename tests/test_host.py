@@ -224,3 +224,40 @@ def test_header_is_valid_c_and_c_example_links(fus, tmp_path):
     if fus.device_count() == 0:                  # no GPU here: it must fail loudly, not fall back
         run = subprocess.run([exe], capture_output=True, text=True)
         assert run.returncode != 0 and "no CPU fallback" in run.stderr
+
+
+def test_bad_arguments_of_the_newer_entry_points(fus):
+    """Host-side entry points added for the trilinear, 2-D and partition paths return error codes
+    (never crash) on malformed input; device entry points still fail loudly without a GPU."""
+    from fenicsx_fus_b200 import capi
+    lib = capi.load()
+    i32, f64 = np.int32, np.float64
+    assert lib.fus_trilinear_coeffs(-1, np.zeros(3), np.zeros(8, dtype=i32), np.zeros(24)) < 0
+    assert lib.fus_trilinear_geometry(16, 1, np.zeros(24), None, None) < 0
+    assert lib.fus_rect_mesh(np.array([0, 2], dtype=i32), np.zeros(2), np.ones(2), np.zeros(9),
+                             np.zeros(4, dtype=i32)) < 0
+    assert lib.fus_rect_dofmap(0, np.array([1, 1], dtype=i32), np.zeros(4, dtype=i32)) < 0
+    assert lib.fus_rect_num_dofs(2, np.array([3, 2], dtype=i32)) == 7 * 5
+    assert lib.fus_rect_facets(np.array([3, 2], dtype=i32), None) == 10
+    h = C.c_void_p()
+    ng, pg = np.array([4, 4, 4], dtype=i32), np.array([2, 2, 1], dtype=i32)
+    assert lib.fus_box_partition_create(2, ng, pg, 4, 1, C.byref(h)) < 0        # rank outside the grid
+    assert not h.value and b"rank" in lib.fus_last_error()
+    assert lib.fus_box_partition_create(0, ng, pg, 0, 1, C.byref(h)) < 0        # degree
+    assert lib.fus_box_partition_create(2, ng, pg, 0, 7, C.byref(h)) < 0        # numbering
+    assert lib.fus_box_partition_create(2, ng, pg, 3, 1, C.byref(h)) == 0 and h.value
+    sizes = np.zeros(9, dtype=np.int64)
+    nl, lo = np.zeros(3, dtype=i32), np.zeros(3, dtype=i32)
+    assert lib.fus_box_partition_info(h, sizes, nl, lo) == 0
+    assert nl.tolist() == [2, 2, 4] and lo.tolist() == [2, 2, 0] and sizes[0] == 16
+    assert sizes[8] == 9 ** 3 and sizes[2] < sizes[1]                           # it has ghosts
+    assert lib.fus_box_partition_arrays(h, *([None] * 10)) == 0                 # all outputs optional
+    assert lib.fus_box_partition_destroy(h) == 0
+    if fus.device_count() == 0:
+        m = fus.RectMesh((2, 2))
+        V = fus.FunctionSpace(m, 2)
+        rc = lib.fus_ctx_create_from_mesh_2d(2, m.ncells, V.ndofs, V.ndofs, V.dofmap, m.x.shape[0],
+                                             m.x, m.xdofmap, 0, C.byref(h))
+        assert rc < 0 and not h.value and b"no CPU fallback" in lib.fus_last_error()
+        with pytest.raises(fus.FusError):
+            fus.FunctionSpace(fus.BoxMesh((1, 1, 1)), 2).context(lean=True)
