@@ -178,13 +178,16 @@ private:
 /// mesh::create_box (experiments/measure_fraction_of_peak_performance/main.cpp:61-65)
 template <typename T>
 Mesh<T> create_box(std::array<std::array<T, 3>, 2> p, std::array<std::size_t, 3> n, CellType) {
-  static_assert(std::is_same_v<T, double>, "the B200 path is FP64 only");
+  static_assert(std::is_floating_point_v<T>, "real scalar types only");
   const int nn[3] = {(int)n[0], (int)n[1], (int)n[2]};
   const std::int64_t nv = (std::int64_t)(nn[0] + 1) * (nn[1] + 1) * (nn[2] + 1);
   const std::int64_t nc = (std::int64_t)nn[0] * nn[1] * nn[2];
-  std::vector<T> x(3 * nv);
+  std::vector<double> xdbl(3 * nv);
   std::vector<std::int32_t> xd(8 * nc);
-  fus::check(fus_box_mesh(nn, p[0].data(), p[1].data(), x.data(), xd.data()), "fus_box_mesh");
+  const double lo[3] = {(double)p[0][0], (double)p[0][1], (double)p[0][2]};
+  const double hi[3] = {(double)p[1][0], (double)p[1][1], (double)p[1][2]};
+  fus::check(fus_box_mesh(nn, lo, hi, xdbl.data(), xd.data()), "fus_box_mesh");
+  std::vector<T> x(xdbl.begin(), xdbl.end()); // the mesh stores coordinates in its own scalar type
   const std::int64_t nf = fus_box_facets(nn, nullptr);
   std::vector<std::int32_t> f(3 * nf);
   fus_box_facets(nn, f.data());
@@ -194,12 +197,14 @@ Mesh<T> create_box(std::array<std::array<T, 3>, 2> p, std::array<std::size_t, 3>
 /// mesh::create_rectangle (quadrilateral cells) for the 2-D operators of cpp/fenicsx-sf-naive
 template <typename T>
 Mesh<T> create_rectangle(std::array<std::array<T, 2>, 2> p, std::array<std::size_t, 2> n, CellType) {
-  static_assert(std::is_same_v<T, double>, "the B200 path is FP64 only");
+  static_assert(std::is_floating_point_v<T>, "real scalar types only");
   const int nn[2] = {(int)n[0], (int)n[1]};
   const std::int64_t nv = (std::int64_t)(nn[0] + 1) * (nn[1] + 1), nc = (std::int64_t)nn[0] * nn[1];
-  std::vector<T> x(3 * nv);
+  std::vector<double> xdbl(3 * nv);
   std::vector<std::int32_t> xd(4 * nc);
-  fus::check(fus_rect_mesh(nn, p[0].data(), p[1].data(), x.data(), xd.data()), "fus_rect_mesh");
+  const double lo[2] = {(double)p[0][0], (double)p[0][1]}, hi[2] = {(double)p[1][0], (double)p[1][1]};
+  fus::check(fus_rect_mesh(nn, lo, hi, xdbl.data(), xd.data()), "fus_rect_mesh");
+  std::vector<T> x(xdbl.begin(), xdbl.end());
   const std::int64_t nf = fus_rect_facets(nn, nullptr);
   std::vector<std::int32_t> f(3 * nf);
   fus_rect_facets(nn, f.data());

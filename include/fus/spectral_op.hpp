@@ -7,7 +7,11 @@
 //                                                                             (:69-70, :173-174)
 // with the same semantics: y += A(coeffs) x over the local cells, no communication, the caller
 // zero-fills y and refreshes the ghosts of x.  The arithmetic runs in the CUDA library through the
-// C ABI (fus_b200.h); T must be double.  Construction uploads the cell data once (the reference
+// C ABI (fus_b200.h) in FP64.  T = float (the reference's test_operators3d and its float timing
+// runs instantiate the operators with it) is accepted by the two operator classes: vectors and
+// geometry are widened on the way in and the result is rounded once on the way out, so float
+// drivers get at least the accuracy of the reference's float arithmetic, not its speed (there are
+// no FP32 kernels yet).  Construction uploads the cell data once (the reference
 // precomputes G / detJ in its constructor too); each call moves x, coeffs and y across PCIe --
 // the solver classes (fus/Linear.hpp, ...) keep everything resident instead.
 #pragma once
@@ -20,12 +24,13 @@ template <typename T>
 class SpaceContext {
 public:
   explicit SpaceContext(const dolfinx::fem::FunctionSpace<T>& V, int device = 0) {
-    static_assert(std::is_same_v<T, double>, "the B200 path is FP64 only");
+    static_assert(std::is_floating_point_v<T>, "real scalar types only");
     auto mesh = V.mesh();
     auto dm = V.dofmap()->map();
     auto im = V.dofmap()->index_map;
     auto xd = mesh->geometry().dofmap();
-    auto x = mesh->geometry().x();
+    auto xT = mesh->geometry().x();
+    const std::vector<double> x(xT.begin(), xT.end()); // the device path is FP64
     auto create = mesh->topology()->dim() == 2 ? fus_ctx_create_from_mesh_2d
                                                : fus_ctx_create_from_mesh;
     check(create(V.degree(), (std::int64_t)dm.extent(0), im->size_local() + im->num_ghosts(),
@@ -41,6 +46,21 @@ public:
 private:
   fus_ctx* _ctx = nullptr;
 };
+
+/// y += A(coeffs) x through a `*_apply_host` entry point; scalar types other than double are
+/// widened first and the accumulated result is rounded back once.
+template <typename T>
+void apply_host(int (*entry)(fus_ctx*, const double*, const double*, double*), const char* what,
+                fus_ctx* ctx, std::span<const T> x, std::span<T> coeffs, std::span<T> y) {
+  if constexpr (std::is_same_v<T, double>) {
+    check(entry(ctx, x.data(), coeffs.data(), y.data()), what);
+  } else {
+    const std::vector<double> xd(x.begin(), x.end()), cd(coeffs.begin(), coeffs.end());
+    std::vector<double> yd(y.begin(), y.end());
+    check(entry(ctx, xd.data(), cd.data(), yd.data()), what);
+    std::transform(yd.begin(), yd.end(), y.begin(), [](double v) { return (T)v; });
+  }
+}
 } // namespace fus::detail
 
 using namespace dolfinx;
@@ -59,9 +79,8 @@ public:
   /// Operator y += M x
   template <typename Alloc>
   void operator()(const la::Vector<T, Alloc>& x, std::span<T> coeffs, la::Vector<T, Alloc>& y) {
-    fus::check(fus_mass_apply_host(_ctx->get(), x.array().data(), coeffs.data(),
-                                   y.mutable_array().data()),
-               "fus_mass_apply_host");
+    fus::detail::apply_host<T>(fus_mass_apply_host, "fus_mass_apply_host", _ctx->get(), x.array(),
+                               coeffs, y.mutable_array());
   }
 
 private:
@@ -82,9 +101,8 @@ public:
   /// Operator y += K x
   template <typename Alloc>
   void operator()(const la::Vector<T, Alloc>& x, std::span<T> coeffs, la::Vector<T, Alloc>& y) {
-    fus::check(fus_stiffness_apply_host(_ctx->get(), x.array().data(), coeffs.data(),
-                                        y.mutable_array().data()),
-               "fus_stiffness_apply_host");
+    fus::detail::apply_host<T>(fus_stiffness_apply_host, "fus_stiffness_apply_host", _ctx->get(),
+                               x.array(), coeffs, y.mutable_array());
   }
 
 private:

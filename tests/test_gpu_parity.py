@@ -290,6 +290,24 @@ def test_cpp_dropin_driver(fus, gpu):
     assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
 
 
+def test_cpp_float_operator_instantiation(fus, gpu):
+    """examples/float_operators.cpp: MassSpectral3D<float,P> / StiffnessSpectral3D<float,P> (the
+    scalar type of the reference's tests/test_operators3d/main.cpp:13) next to the double classes.
+    The float classes widen at the boundary and run the FP64 device path, so they agree with the
+    double result to float rounding of the inputs and of the output."""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "float_operators")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build_cpp_example()
+    res = subprocess.run([exe, "5"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    vals = {ln.split(":")[0]: float(ln.split(":")[1]) for ln in res.stdout.splitlines() if ":" in ln}
+    for op in ("mass", "stiffness"):
+        f, d = vals[f"float_{op}_l2"], vals[f"double_{op}_l2"]
+        assert d > 0 and abs(f - d) < 1e-5 * d, (op, f, d)
+
+
 def test_c_abi_from_plain_c(fus, gpu):
     """examples/c_abi_minimal.c: the C ABI driven from C11 (stiffness application, boundary vectors,
     model, rk4, destroy order) gives the numbers of the Python mirror."""
