@@ -1,0 +1,33 @@
+#!/bin/bash
+# First GPU call of the next round (1 GPU): everything this round's last hours could not run.
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_next_round.sh r2a'
+# 1. full GPU suite (incl. the tests written after the budget ran out: reference 2-D mesh, C ABI from C,
+#    float operator classes), smoke, bench (with the child-process sweep: degree sweep x geometry modes)
+# 2. ncu --set full of the on-the-fly geometry kernel (mode 2) to confirm the latency-bound reading
+# 3. BASELINE config 5 (1.0 G dofs, P=5) on ONE GPU with a lean context
+TAG=${1:-r2a}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit,memory.total --format=csv > $OUT/gpu_${TAG}.txt 2>&1
+echo "== pytest -m gpu"
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $OUT/pytest_gpu_${TAG}.log 2>&1
+echo "pytest exit $?" | tee -a $OUT/pytest_gpu_${TAG}.log
+tail -n 15 $OUT/pytest_gpu_${TAG}.log
+echo "== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 3 | tee $OUT/smoke_${TAG}.log
+echo "== bench"
+timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err
+echo "bench exit $?"; tail -c 2500 $OUT/bench_${TAG}.json; tail -n 3 $OUT/bench_${TAG}.err
+echo "== probe (all degrees, modes 0 and 2)"
+timeout 300 python scripts/probe_geometry_modes.py 2:107 3:71 4:54 5:43 6:36 7:31 > $OUT/probe_${TAG}.jsonl 2> $OUT/probe_${TAG}.err
+cat $OUT/probe_${TAG}.jsonl
+echo "== ncu full, mode-2 kernel"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:stiffness_line -s 6 -c 2 \
+    -f -o $OUT/prof_stiffness_mode2_${TAG} python bench.py --steps 2 --warmup 1 --geometry-mode 2 \
+    --no-cpu-baseline --no-extras > $OUT/ncu_mode2_${TAG}.log 2>&1
+echo "ncu exit $?"
+echo "== config 5 (1.0 G dofs, P=5, 200^3 cells) on one GPU, lean context"
+timeout 1200 python bench.py --degree 5 --cells 200 --lean --steps 5 --warmup 2 --no-cpu-baseline --no-extras \
+    > $OUT/bench_c5_lean_1gpu_${TAG}.json 2> $OUT/bench_c5_lean_1gpu_${TAG}.err
+echo "config-5 lean exit $?"; tail -c 1500 $OUT/bench_c5_lean_1gpu_${TAG}.json; tail -n 3 $OUT/bench_c5_lean_1gpu_${TAG}.err
+ls -la $OUT | tail -n 12
