@@ -15,8 +15,23 @@ def _parts(P, n, pg):
     return [BoxPartition(P, n, pg, r, lo=(0, 0, 0), hi=(1.0, 0.7, 0.9)) for r in range(nr)]
 
 
+def _random_partition_cases(count=10, seed=2026):
+    """Seeded random (degree, box, process grid) triples: uneven splits, 3- and 4-way splits,
+    single-cell blocks -- grids the 8-GPU runs (2x2x2) never exercise."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < count:
+        pg = tuple(int(v) for v in rng.integers(1, 5, 3))
+        if np.prod(pg) > 12:
+            continue
+        n = tuple(int(pg[d] + rng.integers(0, 4)) for d in range(3))
+        cases.append((int(rng.integers(1, 5)), n, pg))
+    return cases
+
+
 @pytest.mark.parametrize("P,n,pg", [(2, (4, 4, 4), (2, 2, 2)), (3, (5, 3, 2), (2, 1, 1)),
-                                    (4, (4, 6, 2), (2, 2, 1)), (1, (3, 3, 3), (3, 1, 3))])
+                                    (4, (4, 6, 2), (2, 2, 1)), (1, (3, 3, 3), (3, 1, 3))]
+                         + _random_partition_cases())
 def test_ownership_and_halo_lists(fus, P, n, pg):
     parts = _parts(P, n, pg)
     nglob = np.prod([n[d] * P + 1 for d in range(3)])
