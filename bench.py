@@ -283,6 +283,10 @@ def run_gpu_arm(args):
 
     P = P_BENCH
     pg = PGRID[world]
+    if args.pgrid:                       # e.g. 8,1,1: slabs (2 neighbours per rank) instead of 2x2x2
+        pg = tuple(int(v) for v in args.pgrid.split(","))
+        if len(pg) != 3 or pg[0] * pg[1] * pg[2] != world:
+            raise SystemExit("--pgrid must be three factors of the number of GPUs")
     h = BOX_LEN / 54            # same cell size whatever the box
     n_global = tuple(N_BENCH * p for p in pg)
     # local part of the global box, local dof numbering (owned first, then ghosts), halo lists
@@ -527,6 +531,8 @@ def main():
     # non-headline workloads for our own scaling studies (the driver never passes these)
     ap.add_argument("--degree", type=int, default=P_BENCH)
     ap.add_argument("--cells", type=int, default=N_BENCH, help="cells per direction per GPU")
+    ap.add_argument("--pgrid", default="", help="process grid px,py,pz (default 1x1x1, 2x1x1, "
+                    "2x2x1, 2x2x2); our own scaling studies only")
     ap.add_argument("--model", default="linear", choices=["linear", "lossy", "westervelt"],
                     help="lossy / westervelt: BASELINE configs 3-4 style runs (not the headline)")
     ap.add_argument("--geometry-mode", type=int, default=0, choices=[0, 1, 2],
