@@ -146,13 +146,17 @@ def _worker(rank, world, port, P, n, pg, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("P,n,pg", [(3, (4, 3, 2), (2, 1, 1)), (2, (3, 4, 3), (1, 2, 1))])
+@pytest.mark.parametrize("P,n,pg", [(3, (4, 3, 2), (2, 1, 1)), (2, (3, 4, 3), (1, 2, 1)),
+                                    (2, (5, 2, 2), (3, 1, 1)), (2, (3, 3, 2), (2, 2, 1))])
 def test_distributed_operator_gloo_world2(fus, orc, tmp_path, P, n, pg):
-    """Two processes over gloo run the partitioned algorithm (scatter_fwd, local cells with the
-    interface cells first, scatter_rev) and reproduce the single-domain operator."""
+    """Two (or three, four) processes over gloo run the partitioned algorithm (scatter_fwd, local
+    cells with the interface cells first, scatter_rev) and reproduce the single-domain operator.
+    The 3x1x1 slab case has a middle rank with both a lower and an upper neighbour, the 2x2x1 case
+    edge neighbours -- topologies beyond the 2-rank ones."""
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, P, n, pg, str(tmp_path)), nprocs=2, join=True)
+    world = int(np.prod(pg))
+    mp.spawn(_worker, args=(world, port, P, n, pg, str(tmp_path)), nprocs=world, join=True)
     hi = (1.0, 0.7, 0.9)
     xg, xd = orc.box_mesh(n, (0, 0, 0), hi)
     dm = orc.box_dofmap(P, n, 0)                                   # lexicographic: dof id == global key
@@ -163,7 +167,7 @@ def test_distributed_operator_gloo_world2(fus, orc, tmp_path, P, n, pg):
     y = orc.stiffness_apply(P, dm, G, orc.dphi(P), coeffs, x, np.zeros(nd))
     m = orc.mass_apply(P, dm, dJ, coeffs, np.ones(nd), np.zeros(nd))
     got_y, got_m = np.full(nd, np.nan), np.full(nd, np.nan)
-    for r in range(2):
+    for r in range(world):
         d = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
         got_y[d["key"]] = d["y"]
         got_m[d["key"]] = d["m"]
