@@ -174,6 +174,102 @@ def test_distributed_operator_gloo_world2(fus, orc, tmp_path, P, n, pg):
     assert rel_l2(got_y, y) < 1e-14 and rel_l2(got_m, m) < 1e-14
 
 
+def _model_worker(rank, world, port, P, n, pg, steps, out_dir):
+    """One rank of the partitioned RK4 loop as fus_model_rk4 issues it (csrc/fus_capi.cu): lumped
+    mass reduced once, per stage owner->ghost update of the stage input, local cells, boundary
+    terms of the local facets, ghost->owner sum of b, epilogue on the owned dofs only.  Oracle
+    kernels and host scatters over gloo stand in for the GPU kernels and the halo layer."""
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fenicsx_fus_b200 import capi
+    from fenicsx_fus_b200.partition import BoxPartition
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    h = 0.002
+    hi = tuple(h * k for k in n)
+    p = BoxPartition(P, n, pg, rank, lo=(0, 0, 0), hi=hi)
+    nc, nd, no = p.ncells, p.ndofs, p.nowned
+    G, dJ = orc.geometry(P, p.x, p.xdofmap)
+    dphi = orc.dphi(P)
+    c0 = 1450.0 + 10.0 * (p.cell_global % 11)                   # heterogeneous, defined globally
+    rho0 = 950.0 + 5.0 * (p.cell_global % 13)
+    src, dsrc, absb, bmass = (np.zeros(nd) for _ in range(4))
+    assert capi.load().fus_boundary_vectors(
+        capi.KINDS["linear"], P, nc, nd, p.x, p.xdofmap, p.dofmap, p.facets.shape[0], p.facets, c0,
+        rho0, None, capi.optional(src), capi.optional(dsrc), capi.optional(absb),
+        capi.optional(bmass)) == 0
+    m = orc.mass_apply(P, p.dofmap, dJ, 1.0 / rho0 / c0 ** 2, np.ones(nd), np.zeros(nd))
+    p.scatter_rev_host(dist, m)                                  # once (Linear.hpp:134)
+    f0, p0, s0 = 0.5e6, 6.0e4, 1500.0
+    w0, dt = 2 * np.pi * f0, 0.5 * np.sqrt(3) * h / (1560.0 * P * P)
+    u = np.zeros(nd)
+    v = np.zeros(nd)
+    u[:no] = 1e3 * np.sin(0.37 * p.global_key[:no])
+    v[:no] = 1e9 * np.cos(0.23 * p.global_key[:no])
+    a_r, b_r = (0.0, 0.5, 0.5, 1.0), (1 / 6, 1 / 3, 1 / 3, 1 / 6)
+    t, tf, dt_full = 0.0, (steps - 0.5) * dt, dt
+    while t < tf:                                                # Linear.hpp:270-298
+        dt = min(dt, tf - t)                                     # the last step lands on tf
+        u0, v0 = u.copy(), v.copy()
+        ku, kv = np.zeros(nd), np.zeros(nd)
+        for i in range(4):
+            un, vn = u0.copy(), v0.copy()
+            un[:no] += a_r[i] * dt * ku[:no]
+            vn[:no] += a_r[i] * dt * kv[:no]
+            tn = t + a_r[i] * dt
+            window = 0.5 * (1 - np.cos(f0 * np.pi * tn / 4.0)) if tn < 4.0 / f0 else 1.0
+            g = window * p0 * w0 / s0 * np.cos(w0 * tn)
+            p.scatter_fwd_host(dist, un)
+            p.scatter_fwd_host(dist, vn)
+            b = orc.stiffness_apply(P, p.dofmap, G, dphi, -1.0 / rho0, un, np.zeros(nd))
+            b += g * src - absb * vn
+            p.scatter_rev_host(dist, b)
+            ku = vn.copy()
+            kv = np.zeros(nd)
+            kv[:no] = b[:no] / m[:no]
+            u[:no] += b_r[i] * dt * ku[:no]
+            v[:no] += b_r[i] * dt * kv[:no]
+        t += dt
+    np.savez(os.path.join(out_dir, f"model_rank{rank}.npz"), key=p.global_key[:no], u=u[:no],
+             v=v[:no], dt=dt_full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P,n,pg", [(3, (4, 3, 2), (2, 1, 1)), (2, (5, 2, 2), (3, 1, 1))])
+def test_distributed_rk4_model_gloo(fus, orc, tmp_path, P, n, pg):
+    """The partitioned RK4 stage flow (what fus_model_rk4 issues on N GPUs) over gloo with oracle
+    kernels: heterogeneous linear model from a random state, against the oracle's single-domain
+    LinearSpectral3D."""
+    import torch.multiprocessing as mp
+    world, steps = int(np.prod(pg)), 4
+    mp.spawn(_model_worker, args=(world, _free_port(), P, n, pg, steps, str(tmp_path)), nprocs=world,
+             join=True)
+    h = 0.002
+    xg, xd = orc.box_mesh(n, (0, 0, 0), tuple(h * k for k in n))
+    dm = orc.box_dofmap(P, n, 0)                                   # lexicographic: dof id == global key
+    nd, nc = dm.max() + 1, dm.shape[0]
+    G, dJ = orc.geometry(P, xg, xd)
+    facets = orc.box_facets(n)
+    fn, fs = orc.facet_data(P, xg, xd, facets)
+    cg = np.arange(nc)
+    c0, rho0 = 1450.0 + 10.0 * (cg % 11), 950.0 + 5.0 * (cg % 13)
+    om = orc.model("linear", P, nd, dm, G, dJ, orc.dphi(P), c0, rho0, None, None, facets, fn, fs,
+                   0.5e6, 6.0e4, 1500.0)
+    key = np.arange(nd)
+    u, v = 1e3 * np.sin(0.37 * key), 1e9 * np.cos(0.23 * key)
+    got_u, got_v = np.full(nd, np.nan), np.full(nd, np.nan)
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), f"model_rank{r}.npz"))
+        got_u[d["key"]], got_v[d["key"]], dt = d["u"], d["v"], float(d["dt"])
+    assert om.rk4(0.0, (steps - 0.5) * dt, dt, u, v) == steps
+    assert rel_l2(got_u, u) < 1e-12 and rel_l2(got_v, v) < 1e-12
+
+
 # ---- unstructured meshes ----------------------------------------------------------------------
 def _ref_mesh():
     from fenicsx_fus_b200.unstructured import HexMesh
