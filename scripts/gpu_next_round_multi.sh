@@ -30,4 +30,8 @@ run n4_slabs 4 --pgrid 4,1,1
 run n8_slabs 8 --pgrid 8,1,1
 run n8_slabs_yz 8 --pgrid 1,2,4
 run c5_n8 8 --degree 5 --cells 100
+# BASELINE config 4: Westervelt, P=4, 1/2/4/8 GPUs
+python bench.py --model westervelt --steps 40 --warmup 5 --no-cpu-baseline --no-extras \
+    > $OUT/bench_westervelt_n1_${TAG}.json 2> $OUT/bench_westervelt_n1_${TAG}.err
+for n in 2 4 8; do run westervelt_n${n} $n --model westervelt; done
 ls -la $OUT | tail -n 12
