@@ -481,7 +481,10 @@ def run_gpu_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        # the only published time-loop figure is the Lossy solver at P=4: 122 M
+        # DOF-updates/s on 76 Ice Lake ranks; the headline (linear) workload has none
+        "vs_baseline": (value / 122.0e6 if (args.model, P) == ("lossy", 4) else None),
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.model}_rk4_P{P}_box{N_BENCH}_per_gpu", "degree": P,
                    "cells_per_gpu": part.ncells, "dofs_global": ndofs_global,
                    "process_grid": list(pg), "dt": dt,
