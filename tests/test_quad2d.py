@@ -404,3 +404,53 @@ def test_gpu_reference_2d_example_mesh(fus, orc, gpu, ref_quad_mesh):
     assert mdl.rk4(0.0, 24.5 * dt, dt) == 25
     assert np.linalg.norm(uo) > 0
     assert rel_l2(mdl.u_sol(), uo) < TOL_STEPS and rel_l2(mdl.v_sol(), vo) < TOL_STEPS
+
+
+def _strip(fus, orc, P, nx, L):
+    """A strip of nx quadrilaterals whose only boundary facets are the two end edges (tag 1 at
+    x = 0, tag 2 at x = L): natural walls, i.e. the 1-D setting of python/tests/*_1d.py."""
+    m = fus.RectMesh((nx, 1), (0, 0), (L, L / nx))
+    V = fus.FunctionSpace(m, P)
+    G, dJ = orc.geometry_2d(P, m.x, m.xdofmap)
+    facets = np.ascontiguousarray(m.facets[m.facets[:, 2] > 0])
+    fn, fs = orc.facet_data_2d(P, m.x, m.xdofmap, facets)
+    return m, V, G, dJ, facets, fn, fs, V.tabulate_dof_coordinates()[:, 0]
+
+
+def test_reference_analytic_tests_on_the_2d_solvers(fus, orc):
+    """The reference's analytic tests for the lossy and Westervelt models
+    (python/tests/test_lossyspectral_1d.py:13-118, test_westerveltspectral_1d.py:13-128; same
+    parameters and thresholds as tests/test_oracle.py::test_reference_analytic_test_*) on the
+    oracle's LossySpectral2D / WesterveltSpectral2D (cpp/fenicsx-sf-naive/common/Lossy.hpp,
+    Westervelt.hpp, 2-D classes)."""
+    from scipy.special import jv
+    P = 4
+    # lossy: attenuated plane wave
+    f0, c0, rho0, L = 10.0, 1.0, 4.0, 1.0
+    w0, aNp, p0 = 2 * np.pi * f0, 5.0 / 20 * np.log(10), 4.0
+    delta0 = 2 * aNp * c0 ** 3 / w0 / w0
+    nx = int(4 * L / (c0 / f0) + 1)
+    m, V, G, dJ, facets, fn, fs, xs = _strip(fus, orc, P, nx, L)
+    nc, nd = m.ncells, V.ndofs
+    mdl = orc.model_2d("lossy", P, nd, V.dofmap, G, dJ, orc.dphi(P), np.full(nc, c0),
+                       np.full(nc, rho0), np.full(nc, delta0), None, facets, fn, fs, f0, p0, c0)
+    dt, tend = 0.5 * (L / nx) / (c0 * P * P), L / c0 + 16 / f0
+    u, v = np.zeros(nd), np.zeros(nd)
+    mdl.rk4(0.0, tend, dt, u, v)
+    exact = p0 * np.exp(-aNp * xs) * np.sin(w0 * tend - w0 / c0 * xs)
+    assert np.linalg.norm(u - exact) / np.linalg.norm(exact) < 1e-2
+    # Westervelt: Fubini solution
+    rho0, beta0, p0 = 1.0, 0.01, 1.0
+    nx = int(8 * L / (c0 / f0) + 1)
+    m, V, G, dJ, facets, fn, fs, xs = _strip(fus, orc, P, nx, L)
+    nc, nd = m.ncells, V.ndofs
+    mdl = orc.model_2d("westervelt", P, nd, V.dofmap, G, dJ, orc.dphi(P), np.full(nc, c0),
+                       np.full(nc, rho0), np.zeros(nc), np.full(nc, beta0), facets, fn, fs, f0, p0, c0)
+    dt, tend = 0.9 * (L / nx) / (c0 * P * P), L / c0 + 8 / f0
+    u, v = np.zeros(nd), np.zeros(nd)
+    mdl.rk4(0.0, tend, dt, u, v)
+    sigma = (xs + 1e-7) / (c0 ** 2 / w0 / beta0 / (p0 / rho0 / c0))
+    exact = np.zeros(nd)
+    for term in range(1, 50):
+        exact += 2 / term / sigma * jv(term, term * sigma) * np.sin(term * w0 * (tend - xs / c0))
+    assert np.linalg.norm(u - p0 * exact) / np.linalg.norm(p0 * exact) < 1e-2
