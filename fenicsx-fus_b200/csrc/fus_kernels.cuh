@@ -8,9 +8,15 @@
 //   t = i1*N + i2, i.e. for one cell and one i0-level the N*N points of a component pair are
 //   contiguous: a thread column (i1,i2) streams its 3*N double2 with 16-byte coalesced loads.
 #pragma once
+// FUS_HOST_EMULATION: defined only by tests/emu (a SIMT emulator that runs these kernels on host
+// threads so that their indexing, staging and barrier logic is exercised by the CPU test suite).
+// The guarded alternatives replace inline PTX and CUDA-only declarations; device builds never see
+// them.
 #include "fus_trilinear.hpp"
 
+#ifndef FUS_HOST_EMULATION
 #include <cuda_runtime.h>
+#endif
 
 #include <cstdint>
 
@@ -32,9 +38,13 @@ struct Rule1D {
 // Streaming 16-byte load for data that is used exactly once (G): read-only path, do not keep
 // the line in L1 so that L1 stays available for the gathered dofs.
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
+#ifdef FUS_HOST_EMULATION
+  return *p;
+#else
   double2 v;
   asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -78,7 +88,11 @@ __global__ void __launch_bounds__(ColCfg<N>::THREADS)
                          long long cell_end, const __grid_constant__ DMat<N> D) {
   using C = ColCfg<N>;
   constexpr int NN = C::NN, NS = C::NS, PL = C::PL;
+#ifdef FUS_HOST_EMULATION
+  double* smem = fus_emu::dynamic_shared();
+#else
   extern __shared__ double smem[];
+#endif
 
   const int tid = threadIdx.x;
   int slot, t;
@@ -329,7 +343,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
   constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
   static_assert(GEOM >= 0 && GEOM <= 2, "unknown geometry mode");
+#ifdef FUS_HOST_EMULATION
+  double* smem = fus_emu::dynamic_shared();
+#else
   extern __shared__ double smem[];
+#endif
 
   const int tid = threadIdx.x;
   const int group = tid / (C::GW * 32), lg = tid - group * (C::GW * 32);
@@ -354,7 +372,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
     if constexpr (C::WARP)
       __syncwarp();
     else
+#ifdef FUS_HOST_EMULATION
+      fus_emu::named_barrier(group + 1, C::GW * 32);
+#else
       asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(C::GW * 32) : "memory");
+#endif
   };
 
   const long long stride = (long long)gridDim.x * C::CPB;
@@ -393,8 +415,12 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
   };
   auto tri_prefetch = [&](long long cell) {
     const double2* q = G2 + cell * TQ;
+#ifdef FUS_HOST_EMULATION
+    (void)q;
+#else
     asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(q + TQ - 1));
+#endif
   };
 #pragma unroll
   for (int p = 0; p < 3; ++p)

@@ -1,0 +1,196 @@
+// emu_kernels.cpp -- TEST INFRASTRUCTURE: the kernels of fus_kernels.cuh compiled for the host
+// through tests/emu/simt_emu.hpp, behind a small C interface for tests/test_kernel_emulation.py.
+// Launch geometry follows fus_capi.cu (same block sizes, shared-memory sizes and cells per block);
+// the grid is capped low so that the grid-stride loops and their tails are exercised.
+#include "simt_emu.hpp"
+
+#include "fus_kernels.cuh"
+
+using namespace fus;
+
+namespace {
+template <int N>
+DMat<N> make_dmat(const double* dphi, const double* pts, const double* wts) {
+  DMat<N> D;
+  std::memcpy(D.d, dphi, sizeof(double) * N * N);
+  std::memcpy(D.w, wts, sizeof(double) * N);
+  std::memcpy(D.x, pts, sizeof(double) * N);
+  return D;
+}
+
+// reference layout G[c][q][6] -> device layout G2[cell][i0][p][t] (g_to_device_layout_kernel)
+template <int N>
+std::vector<double2> device_layout(const double* G, long long ncells) {
+  constexpr int NN = N * N, Nd = N * NN;
+  std::vector<double2> out((size_t)ncells * 3 * Nd);
+  gridDim.x = 1;
+  blockDim.x = 1;
+  fus_emu::launch(1, 1, 0, [&] { g_to_device_layout_kernel<N>(G, ncells, out.data()); });
+  return out;
+}
+
+template <int N>
+int stiffness_n(int variant, int geom, const double* x, const double* x2, double* y,
+                const int32_t* dofmap, const double* G, const double* aux, const double* coeff,
+                const double* coeff2, long long ncells, const double* dphi, const double* pts,
+                const double* wts, int max_blocks, long long cb, long long ce) {
+  const DMat<N> D = make_dmat<N>(dphi, pts, wts);
+  const bool fuse = x2 != nullptr;
+  std::vector<double2> G2;
+  const double2* gptr = nullptr;
+  if (geom == 0) {
+    G2 = device_layout<N>(G, ncells);
+    gptr = G2.data();
+  } else {
+    gptr = reinterpret_cast<const double2*>(aux); // Ghat[cell][3] double2, or the cell-map coefficients
+  }
+  auto blocks_for = [&](int cpb) {
+    return (unsigned)std::max<long long>(1, std::min<long long>((ce - cb + cpb - 1) / cpb, max_blocks));
+  };
+  if (variant == 1) {
+    auto run = [&](auto kern) {
+      fus_emu::launch(blocks_for(1), N * N * N, 0, [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D); });
+    };
+    if (fuse)
+      run(stiffness_point_kernel<N, true>);
+    else
+      run(stiffness_point_kernel<N, false>);
+    return 0;
+  }
+  if (variant == 0) {
+    using C = ColCfg<N>;
+    auto run = [&](auto kern) {
+      fus_emu::launch(blocks_for(C::CPB), C::THREADS, C::SMEM_BYTES,
+                      [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D); });
+    };
+    if (fuse)
+      run(stiffness_col_kernel<N, true>);
+    else
+      run(stiffness_col_kernel<N, false>);
+    return 0;
+  }
+  using L = LineCfg<N>;
+  auto run = [&](auto kern) {
+    fus_emu::launch(blocks_for(L::CPB), L::THREADS, L::SMEM_BYTES,
+                    [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D); });
+  };
+  if (geom == 0)
+    fuse ? run(stiffness_line_kernel<N, true, 0>) : run(stiffness_line_kernel<N, false, 0>);
+  else if (geom == 1)
+    fuse ? run(stiffness_line_kernel<N, true, 1>) : run(stiffness_line_kernel<N, false, 1>);
+  else
+    fuse ? run(stiffness_line_kernel<N, true, 2>) : run(stiffness_line_kernel<N, false, 2>);
+  return 0;
+}
+
+template <int N>
+int quad_n(const double* x, const double* x2, double* y, const int32_t* dofmap, const double* Gq,
+           const double* coeff, const double* coeff2, long long ncells, const double* dphi,
+           const double* pts, const double* wts, int max_blocks) {
+  using Q = QuadCfg<N>;
+  const DMat<N> D = make_dmat<N>(dphi, pts, wts);
+  const unsigned blocks
+      = (unsigned)std::max<long long>(1, std::min<long long>((ncells + Q::CPB - 1) / Q::CPB, max_blocks));
+  if (x2)
+    fus_emu::launch(blocks, Q::THREADS, 0, [&] {
+      stiffness_quad_kernel<N, true>(x, x2, y, dofmap, Gq, coeff, coeff2, 0, ncells, D);
+    });
+  else
+    fus_emu::launch(blocks, Q::THREADS, 0, [&] {
+      stiffness_quad_kernel<N, false>(x, x2, y, dofmap, Gq, coeff, coeff2, 0, ncells, D);
+    });
+  return 0;
+}
+
+template <int N>
+int tri_n(const double* xg, const int32_t* xdofmap, long long ncells, double* coeffs,
+          const double* x, double* y, const int32_t* dofmap, const double* coeff,
+          const double* pts, const double* wts) {
+  fus_emu::launch((unsigned)((ncells + 127) / 128), 128, 0,
+                  [&] { tri_coeff_kernel(xg, xdofmap, ncells, coeffs); });
+  Rule1D<N> R;
+  std::memcpy(R.pts, pts, sizeof(double) * N);
+  std::memcpy(R.wts, wts, sizeof(double) * N);
+  const long long np = ncells * N * N * N;
+  fus_emu::launch(2, 256, 0, [&] { mass_tri_kernel<N>(x, y, dofmap, coeffs, coeff, 0, np, R); });
+  return 0;
+}
+
+#define EMU_DISPATCH(N, fn, ...)                                                                   \
+  switch (N) {                                                                                     \
+  case 2: return fn<2>(__VA_ARGS__);                                                               \
+  case 3: return fn<3>(__VA_ARGS__);                                                               \
+  case 4: return fn<4>(__VA_ARGS__);                                                               \
+  case 5: return fn<5>(__VA_ARGS__);                                                               \
+  case 6: return fn<6>(__VA_ARGS__);                                                               \
+  case 7: return fn<7>(__VA_ARGS__);                                                               \
+  case 8: return fn<8>(__VA_ARGS__);                                                               \
+  }                                                                                                \
+  return -1
+} // namespace
+
+extern "C" {
+
+// y += K x with the production kernels: variant 0 column, 1 point, 2 line; geom 0 streamed G
+// (reference layout in, re-laid-out here), 1 affine (aux = Ghat[cell][6]), 2 trilinear (aux =
+// FUS_TRI_STRIDE doubles per cell).  x2/coeff2 non-NULL selects the fused two-vector gather.
+// Only cells [cell_begin, cell_end) are applied: the split launches of a partitioned stage.
+int emu_stiffness(int N, int variant, int geom, const double* x, const double* x2, double* y,
+                  const int32_t* dofmap, const double* G, const double* aux, const double* coeff,
+                  const double* coeff2, long long ncells, const double* dphi, const double* pts,
+                  const double* wts, int max_blocks, long long cell_begin, long long cell_end) {
+  EMU_DISPATCH(N, stiffness_n, variant, geom, x, x2, y, dofmap, G, aux, coeff, coeff2, ncells, dphi,
+               pts, wts, max_blocks, cell_begin, cell_end);
+}
+
+int emu_stiffness_quad(int N, const double* x, const double* x2, double* y, const int32_t* dofmap,
+                       const double* Gq, const double* coeff, const double* coeff2, long long ncells,
+                       const double* dphi, const double* pts, const double* wts, int max_blocks) {
+  EMU_DISPATCH(N, quad_n, x, x2, y, dofmap, Gq, coeff, coeff2, ncells, dphi, pts, wts, max_blocks);
+}
+
+// tri_coeff_kernel (coeffs out) followed by mass_tri_kernel (y += M x)
+int emu_tri_coeffs_and_mass(int N, const double* xg, const int32_t* xdofmap, long long ncells,
+                            double* coeffs, const double* x, double* y, const int32_t* dofmap,
+                            const double* coeff, const double* pts, const double* wts) {
+  EMU_DISPATCH(N, tri_n, xg, xdofmap, ncells, coeffs, x, y, dofmap, coeff, pts, wts);
+}
+
+int emu_mass(const double* x, double* y, const int32_t* dofmap, const double* detJ,
+             const double* coeff, long long npoints, int Nd) {
+  fus_emu::launch(3, 256, 0, [&] { mass_kernel(x, y, dofmap, detJ, coeff, npoints, Nd); });
+  return 0;
+}
+
+// one fused RK4 stage epilogue; vectors are updated in place
+int emu_rk4_stage(int stage, int westervelt, double* b, const double* m, const double* dnl,
+                  double* u0, double* v0, double* ua, double* va, double* un, double* vn,
+                  long long nowned, long long ntotal, double a_next_dt, double bw_dt) {
+  StageArgs A;
+  A.b = b, A.m = m, A.dnl = dnl, A.u0 = u0, A.v0 = v0, A.ua = ua, A.va = va, A.un = un, A.vn = vn;
+  A.nowned = nowned, A.ntotal = ntotal, A.a_next_dt = a_next_dt, A.bw_dt = bw_dt;
+  A.step_ctr = nullptr;
+  auto go = [&](auto kern) { fus_emu::launch(2, 256, 0, [&] { kern(A); }); };
+  switch (stage * 2 + (westervelt ? 1 : 0)) {
+  case 0: go(rk4_stage_kernel<0, false>); break;
+  case 1: go(rk4_stage_kernel<0, true>); break;
+  case 2: go(rk4_stage_kernel<1, false>); break;
+  case 3: go(rk4_stage_kernel<1, true>); break;
+  case 4: go(rk4_stage_kernel<2, false>); break;
+  case 5: go(rk4_stage_kernel<2, true>); break;
+  case 6: go(rk4_stage_kernel<3, false>); break;
+  case 7: go(rk4_stage_kernel<3, true>); break;
+  default: return -1;
+  }
+  return 0;
+}
+
+int emu_boundary(double* b, const double* v, const int32_t* bidx, const double* bsrc,
+                 const double* bdsrc, const double* babs, long long nb, double g, double dg) {
+  fus_emu::launch((unsigned)((nb + 255) / 256), 256, 0, [&] {
+    boundary_kernel(b, v, bidx, bsrc, bdsrc, babs, nb, g, dg, nullptr, nullptr, 0);
+  });
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,107 @@
+// simt_emu.hpp -- TEST INFRASTRUCTURE: a small SIMT emulator for the kernels in
+// fenicsx-fus_b200/csrc/fus_kernels.cuh.
+//
+// The build container has no GPU.  To keep the kernels' *logic* (thread-to-data mapping, shared
+// memory staging, software pipelining, barriers, tail handling) under test on the CPU, this header
+// lets the very same kernel source compile as host C++: every CUDA thread of a block runs as an OS
+// thread, __syncthreads / __syncwarp / named barriers are real barriers, atomics are atomics, blocks
+// run one after another.  Threads of a warp are NOT in lockstep here, so code that silently relies
+// on warp-synchronous execution without a __syncwarp shows up as a race.  What it cannot show:
+// anything about the memory model of the device, performance, or PTX-level behaviour.
+// Only tests/ may use it; the product never loads it (there is no CPU fallback).
+#pragma once
+#define FUS_HOST_EMULATION 1
+
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+struct double2 {
+  double x, y;
+};
+inline double2 make_double2(double a, double b) { return double2{a, b}; }
+
+struct emu_dim3 {
+  unsigned x = 1, y = 1, z = 1;
+};
+inline thread_local emu_dim3 threadIdx, blockIdx;
+inline emu_dim3 blockDim, gridDim; // one launch at a time
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __shared__ static // blocks run one after another, so one copy per kernel instantiation
+
+namespace fus_emu {
+struct BlockState {
+  std::unique_ptr<std::barrier<>> block;
+  std::vector<std::unique_ptr<std::barrier<>>> warps;
+  std::map<int, std::unique_ptr<std::barrier<>>> named;
+  std::mutex mu;
+  std::vector<double> dyn;
+};
+inline BlockState* g_block = nullptr;
+
+inline double* dynamic_shared() { return g_block->dyn.data(); }
+inline void named_barrier(int id, int count) {
+  std::barrier<>* b;
+  {
+    std::lock_guard<std::mutex> lk(g_block->mu);
+    auto& slot = g_block->named[id];
+    if (!slot)
+      slot = std::make_unique<std::barrier<>>(count);
+    b = slot.get();
+  }
+  b->arrive_and_wait();
+}
+
+// kernel<<<grid, block, smem_bytes>>>(args...)  ->  launch(grid, block, smem_bytes, [&]{ kernel(args...); })
+inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::function<void()>& body) {
+  gridDim.x = grid;
+  blockDim.x = block;
+  for (unsigned b = 0; b < grid; ++b) {
+    BlockState st;
+    st.block = std::make_unique<std::barrier<>>(block);
+    for (unsigned w = 0; w < (block + 31) / 32; ++w)
+      st.warps.push_back(std::make_unique<std::barrier<>>(std::min(32u, block - 32 * w)));
+    st.dyn.assign(smem_bytes / sizeof(double) + 1, 0.0);
+    g_block = &st;
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; ++t)
+      th.emplace_back([&, t, b] {
+        threadIdx.x = t;
+        blockIdx.x = b;
+        body();
+      });
+    for (auto& x : th)
+      x.join();
+    g_block = nullptr;
+  }
+}
+} // namespace fus_emu
+
+inline void __syncthreads() { fus_emu::g_block->block->arrive_and_wait(); }
+inline void __syncwarp() { fus_emu::g_block->warps[threadIdx.x / 32]->arrive_and_wait(); }
+template <typename T>
+inline T __ldg(const T* p) {
+  return *p;
+}
+inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
+inline int atomicExch(int* p, int v) { return std::atomic_ref<int>(*p).exchange(v); }
+using std::fabs;
+using std::fma;
+using std::fmax;

@@ -1,0 +1,241 @@
+"""The CUDA kernels of fenicsx-fus_b200/csrc/fus_kernels.cuh executed on the CPU by a SIMT emulator
+(tests/emu/simt_emu.hpp: one OS thread per CUDA thread, real barriers, real atomics) and compared with
+the oracle.  The build container has no GPU; this keeps the kernels' indexing, shared-memory staging,
+software pipelining, barrier placement and tail handling under test in the CPU suite.  It says
+nothing about the device's memory model or speed -- the `-m gpu` tests remain the parity tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2, warp_vertices
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+_f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_p, _ll, _int, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data_as(_p)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib = os.path.join(EMU_DIR, "libfus_emu.so")
+    deps = [os.path.join(EMU_DIR, f) for f in ("emu_kernels.cpp", "simt_emu.hpp")] + [
+        os.path.join(ROOT, "fenicsx-fus_b200", "csrc", f) for f in ("fus_kernels.cuh", "fus_trilinear.hpp")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC",
+                        "-I" + os.path.join(ROOT, "include"),
+                        "-I" + os.path.join(ROOT, "fenicsx-fus_b200", "csrc"), "-I" + EMU_DIR,
+                        os.path.join(EMU_DIR, "emu_kernels.cpp"), "-o", lib], check=True)
+    L = C.CDLL(lib)
+    L.emu_stiffness.argtypes = [_int, _int, _int, _f64, _p, _f64, _i32, _p, _p, _f64, _p, _ll, _f64,
+                                _f64, _f64, _int, _ll, _ll]
+    L.emu_stiffness_quad.argtypes = [_int, _f64, _p, _f64, _i32, _f64, _f64, _p, _ll, _f64, _f64,
+                                     _f64, _int]
+    L.emu_tri_coeffs_and_mass.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _i32, _f64, _f64,
+                                          _f64]
+    L.emu_mass.argtypes = [_f64, _f64, _i32, _f64, _f64, _ll, _int]
+    L.emu_rk4_stage.argtypes = [_int, _int, _f64, _f64, _p, _f64, _f64, _f64, _f64, _f64, _f64, _ll,
+                                _ll, _dbl, _dbl]
+    L.emu_boundary.argtypes = [_f64, _f64, _i32, _f64, _f64, _f64, _ll, _dbl, _dbl]
+    return L
+
+
+def _case(fus, orc, P, n=(5, 3, 2), warp=True, numbering=1):
+    m = fus.BoxMesh(n, (0.2, -0.1, 0.3), (1.2, 0.5, 0.7),
+                    warp=(lambda x: warp_vertices(x, 0.08, 3)) if warp else None)
+    V = fus.FunctionSpace(m, P, numbering=numbering)
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    pts, wts = orc.gll(P + 1)
+    return m, V, G, dJ, pts, wts
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_emulated_stiffness_kernels_vs_oracle(fus, orc, emu, P, variant):
+    """stiffness_col_kernel / stiffness_point_kernel / stiffness_line_kernel with streamed G, plain
+    and fused two-vector gather, 30 warped cells on at most 2 blocks (grid-stride loop, ragged tail,
+    the look-ahead pipeline across cells)."""
+    m, V, G, dJ, pts, wts = _case(fus, orc, P, numbering=P % 2)
+    nd, nc = V.ndofs, m.ncells
+    rng = np.random.default_rng(100 * P + variant)
+    x, x2 = rng.uniform(-1, 1, nd), rng.uniform(-1, 1, nd)
+    c1, c2 = rng.uniform(0.5, 2, nc), rng.uniform(-1, 1, nc)
+    dphi = orc.dphi(P)
+    y = np.zeros(nd)
+    assert emu.emu_stiffness(P + 1, variant, 0, x, None, y, V.dofmap, _opt(G), None, c1, None, nc,
+                             dphi, pts, wts, 2, 0, nc) == 0
+    yo = orc.stiffness_apply(P, V.dofmap, G, dphi, c1, x, np.zeros(nd))
+    assert rel_l2(y, yo) < 1e-13
+    yf = np.zeros(nd)
+    assert emu.emu_stiffness(P + 1, variant, 0, x, _opt(x2), yf, V.dofmap, _opt(G), None, c1,
+                             _opt(c2), nc, dphi, pts, wts, 2, 0, nc) == 0
+    yfo = orc.stiffness_apply(P, V.dofmap, G, dphi, c1, x, np.zeros(nd))
+    yfo = orc.stiffness_apply(P, V.dofmap, G, dphi, c2, x2, yfo)
+    assert rel_l2(yf, yfo) < 1e-13
+    # integer data: gather/scatter indexing bit-exact (sums of small integers are exact)
+    xi = rng.integers(-4, 5, nd).astype(np.float64)
+    Gi = np.zeros_like(G)
+    Gi[:, :, [0, 3, 5]] = 1.0
+    di = np.rint(4 * dphi) / 4                                   # exactly representable table
+    yi = np.zeros(nd)
+    emu.emu_stiffness(P + 1, variant, 0, xi, None, yi, V.dofmap, _opt(Gi), None, np.ones(nc), None,
+                      nc, di, pts, wts, 2, 0, nc)
+    assert np.array_equal(yi, orc.stiffness_apply(P, V.dofmap, Gi, di, np.ones(nc), xi, np.zeros(nd)))
+
+
+@pytest.mark.parametrize("variant,P", [(0, 2), (0, 3), (2, 4), (2, 5), (2, 6), (2, 7), (1, 3)])
+def test_emulated_split_launches_of_a_partitioned_stage(fus, orc, emu, variant, P):
+    """A partitioned stage applies the cells in three launches -- interior A [ni, mid), interface
+    [0, ni), interior B [mid, nc) (assemble_rhs in csrc/fus_capi.cu) -- with sub-ranges that are
+    not multiples of the cells-per-block packing; together they must equal one full application."""
+    m, V, G, dJ, pts, wts = _case(fus, orc, P)
+    nd, nc = V.ndofs, m.ncells
+    rng = np.random.default_rng(7 * P + variant)
+    x, c1 = rng.uniform(-1, 1, nd), rng.uniform(0.5, 2, nc)
+    dphi = orc.dphi(P)
+    ni, mid = 7, 7 + (nc - 7) // 2
+    y = np.zeros(nd)
+    for cb, ce in ((ni, mid), (0, ni), (mid, nc)):
+        assert emu.emu_stiffness(P + 1, variant, 0, x, None, y, V.dofmap, _opt(G), None, c1, None, nc,
+                                 dphi, pts, wts, 3, cb, ce) == 0
+    assert rel_l2(y, orc.stiffness_apply(P, V.dofmap, G, dphi, c1, x, np.zeros(nd))) < 1e-13
+    # an empty range launches nothing harmful
+    y2 = y.copy()
+    emu.emu_stiffness(P + 1, variant, 0, x, None, y2, V.dofmap, _opt(G), None, c1, None, nc, dphi, pts,
+                      wts, 3, 5, 6)
+    one = orc.stiffness_apply(P, V.dofmap[5:6], G[5:6], dphi, c1[5:6], x, np.zeros(nd))
+    assert rel_l2(y2 - y, one) < 1e-12
+
+
+@pytest.mark.parametrize("P", [1, 2, 4, 5, 7])
+def test_emulated_compressed_geometry_kernels(fus, orc, emu, P):
+    """stiffness_line_kernel<N,FUSE2,1> (one Ghat per affine cell) and <N,FUSE2,2> (G rebuilt from
+    the trilinear cell map), tri_coeff_kernel and mass_tri_kernel."""
+    from fenicsx_fus_b200 import capi
+    rng = np.random.default_rng(P)
+    dphi = orc.dphi(P)
+    # mode 2 on warped cells
+    m, V, G, dJ, pts, wts = _case(fus, orc, P)
+    nd, nc = V.ndofs, m.ncells
+    x, x2 = rng.uniform(-1, 1, nd), rng.uniform(-1, 1, nd)
+    c1, c2 = rng.uniform(0.5, 2, nc), rng.uniform(-1, 1, nc)
+    co_ref = np.zeros((nc, 24))
+    assert capi.load().fus_trilinear_coeffs(nc, m.x, m.xdofmap, co_ref) == 0
+    co, ym = np.zeros((nc, 24)), np.zeros(nd)
+    assert emu.emu_tri_coeffs_and_mass(P + 1, m.x, m.xdofmap, nc, co, x, ym, V.dofmap, c1, pts,
+                                       wts) == 0
+    assert np.array_equal(co, co_ref)                             # same helper, same arithmetic
+    assert rel_l2(ym, orc.mass_apply(P, V.dofmap, dJ, c1, x, np.zeros(nd))) < 1e-12
+    for fuse in (False, True):
+        y = np.zeros(nd)
+        emu.emu_stiffness(P + 1, 2, 2, x, _opt(x2) if fuse else None, y, V.dofmap, None, _opt(co),
+                          c1, _opt(c2) if fuse else None, nc, dphi, pts, wts, 2, 0, nc)
+        yo = orc.stiffness_apply(P, V.dofmap, G, dphi, c1, x, np.zeros(nd))
+        if fuse:
+            yo = orc.stiffness_apply(P, V.dofmap, G, dphi, c2, x2, yo)
+        assert rel_l2(y, yo) < 1e-12
+    # mode 1 on a sheared box: Ghat = G / w at any point of the cell
+    A = np.array([[1.0, 0.3, 0.1], [0.0, 0.8, 0.25], [0.05, 0.0, 1.2]])
+    ma = fus.BoxMesh((4, 3, 2), (0, 0, 0), (1.0, 0.6, 0.5), warp=lambda z: z @ A.T)
+    Va = fus.FunctionSpace(ma, P, numbering=1)
+    Ga, _ = orc.geometry(P, ma.x, ma.xdofmap)
+    ghat = np.ascontiguousarray(Ga[:, 0, :] / (wts[0] ** 3))
+    xa, ca = rng.uniform(-1, 1, Va.ndofs), rng.uniform(0.5, 2, ma.ncells)
+    ya = np.zeros(Va.ndofs)
+    emu.emu_stiffness(P + 1, 2, 1, xa, None, ya, Va.dofmap, None, _opt(ghat), ca, None, ma.ncells,
+                      dphi, pts, wts, 2, 0, ma.ncells)
+    assert rel_l2(ya, orc.stiffness_apply(P, Va.dofmap, Ga, dphi, ca, xa, np.zeros(Va.ndofs))) < 1e-12
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_emulated_quad_kernel_vs_oracle(fus, orc, emu, P):
+    """stiffness_quad_kernel<N,FUSE2> (2-D variant): 35 warped cells on 2 blocks, so the block loop
+    with its trailing barrier iterates several times."""
+    rng = np.random.default_rng(P)
+    h = np.array([1.2, 0.9]) / np.array([7, 5])
+
+    def warp(z):
+        w = z.copy()
+        w[:, :2] += 0.1 * h * rng.uniform(-1, 1, (z.shape[0], 2))
+        return w
+    m = fus.RectMesh((7, 5), (0.1, -0.2), (1.3, 0.7), warp=warp)
+    V = fus.FunctionSpace(m, P)
+    nd, nc = V.ndofs, m.ncells
+    G, dJ = orc.geometry_2d(P, m.x, m.xdofmap)
+    Gq = np.ascontiguousarray(G.transpose(0, 2, 1))              # device layout Gq[cell][p][q]
+    pts, wts = orc.gll(P + 1)
+    x, x2 = rng.uniform(-1, 1, nd), rng.uniform(-1, 1, nd)
+    c1, c2 = rng.uniform(0.5, 2, nc), rng.uniform(-1, 1, nc)
+    y = np.zeros(nd)
+    assert emu.emu_stiffness_quad(P + 1, x, None, y, V.dofmap, Gq, c1, None, nc, orc.dphi(P), pts,
+                                  wts, 2) == 0
+    yo = orc.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c1, x, np.zeros(nd))
+    assert rel_l2(y, yo) < 1e-13
+    yf = np.zeros(nd)
+    emu.emu_stiffness_quad(P + 1, x, _opt(x2), yf, V.dofmap, Gq, c1, _opt(c2), nc, orc.dphi(P), pts,
+                           wts, 2)
+    yfo = orc.stiffness_apply_2d(P, V.dofmap, G, orc.dphi(P), c2, x2, yo.copy())
+    assert rel_l2(yf, yfo) < 1e-13
+
+
+def test_emulated_mass_boundary_and_rk4_stage_kernels(fus, orc, emu):
+    """mass_kernel, boundary_kernel and the four fused RK4 epilogues (linear and Westervelt) against
+    the formulas they fuse (Linear.hpp:203-221,279-294; Westervelt.hpp:249-265)."""
+    P = 3
+    m, V, G, dJ, pts, wts = _case(fus, orc, P)
+    nd, nc = V.ndofs, m.ncells
+    rng = np.random.default_rng(9)
+    x, c1 = rng.uniform(-1, 1, nd), rng.uniform(0.5, 2, nc)
+    y = np.zeros(nd)
+    emu.emu_mass(x, y, np.ascontiguousarray(V.dofmap.reshape(-1)), np.ascontiguousarray(dJ.reshape(-1)),
+                 c1, nc * (P + 1) ** 3, (P + 1) ** 3)
+    assert rel_l2(y, orc.mass_apply(P, V.dofmap, dJ, c1, x, np.zeros(nd))) < 1e-14
+    # boundary terms over a compacted list
+    nb = 300
+    bidx = np.sort(rng.choice(nd, nb, replace=False)).astype(np.int32)
+    bs, bd, ba = rng.uniform(0, 1, nb), rng.uniform(0, 1, nb), rng.uniform(0, 1, nb)
+    b, v = rng.uniform(-1, 1, nd), rng.uniform(-1, 1, nd)
+    want = b.copy()
+    want[bidx] += 0.7 * bs + (-0.3) * bd - ba * v[bidx]
+    emu.emu_boundary(b, v, bidx, bs, bd, ba, nb, 0.7, -0.3)
+    assert np.allclose(b, want, rtol=1e-15, atol=0)
+    # RK4 epilogues: owned entries updated, every entry of b zeroed, ghosts untouched elsewhere
+    nowned = nd - 37
+    dt = 1e-3
+    a_r, b_r = (0.0, 0.5, 0.5, 1.0), (1 / 6, 1 / 3, 1 / 3, 1 / 6)
+    for west in (0, 1):
+        mvec, dnl = rng.uniform(1, 2, nd), rng.uniform(0.01, 0.02, nd)
+        u0, v0 = rng.uniform(-1, 1, nd), rng.uniform(-1, 1, nd)
+        st = dict(u0=u0.copy(), v0=v0.copy(), ua=np.zeros(nd), va=np.zeros(nd), un=np.zeros(nd),
+                  vn=np.zeros(nd))
+        ref = {k: a.copy() for k, a in st.items()}
+        for i in range(4):
+            b = rng.uniform(-1, 1, nd)
+            o = slice(0, nowned)
+            un_in = ref["u0"][o] if i == 0 else ref["un"][o]
+            vn_in = ref["v0"][o] if i == 0 else ref["vn"][o]
+            mm, bb = mvec[o].copy(), b[o].copy()
+            if west:
+                mm = mm - dnl[o] * un_in
+                bb = bb + dnl[o] * vn_in * vn_in
+            kv, ku = bb / mm, vn_in.copy()
+            ua = (ref["u0"][o] if i == 0 else ref["ua"][o]) + b_r[i] * dt * ku
+            va = (ref["v0"][o] if i == 0 else ref["va"][o]) + b_r[i] * dt * kv
+            if i < 3:
+                ref["un"][o] = ref["u0"][o] + a_r[i + 1] * dt * ku
+                ref["vn"][o] = ref["v0"][o] + a_r[i + 1] * dt * kv
+                ref["ua"][o], ref["va"][o] = ua, va
+            else:
+                ref["u0"][o], ref["v0"][o] = ua, va
+            emu.emu_rk4_stage(i, west, b, mvec, _opt(dnl) if west else None, st["u0"], st["v0"],
+                              st["ua"], st["va"], st["un"], st["vn"], nowned, nd,
+                              a_r[i + 1] * dt if i < 3 else 0.0, b_r[i] * dt)
+            assert not b.any()
+            for k in st:
+                assert np.allclose(st[k], ref[k], rtol=1e-14, atol=1e-15), (west, i, k)
