@@ -116,6 +116,35 @@ int tri_n(const double* xg, const int32_t* xdofmap, long long ncells, double* co
   return 0;
 }
 
+template <int N>
+int geometry_n(const double* xg, const int32_t* xdofmap, long long ncells, double* G, double* detJ,
+               const double* pts, const double* wts, double* Ghat, int* all_affine) {
+  constexpr int Nd = N * N * N;
+  Rule1D<N> R;
+  std::memcpy(R.pts, pts, sizeof(double) * N);
+  std::memcpy(R.wts, wts, sizeof(double) * N);
+  std::vector<double2> G2((size_t)ncells * 3 * Nd);
+  fus_emu::launch(3, 128, 0, [&] { geometry_kernel<N>(xg, xdofmap, ncells, G2.data(), detJ, R); });
+  fus_emu::launch(2, 256, 0, [&] { g_from_device_layout_kernel<N>(G2.data(), ncells, G); });
+  DMat<N> D{};
+  std::memcpy(D.w, wts, sizeof(double) * N);
+  *all_affine = 1;
+  fus_emu::launch((unsigned)((ncells + 127) / 128), 128, 0, [&] {
+    affine_detect_kernel<N>(G2.data(), ncells, 1e-13, reinterpret_cast<double2*>(Ghat), all_affine, D);
+  });
+  return 0;
+}
+
+template <int N>
+int geometry_quad_n(const double* xg, const int32_t* xdofmap, long long ncells, double* Gq,
+                    double* detJ, const double* pts, const double* wts) {
+  Rule1D<N> R;
+  std::memcpy(R.pts, pts, sizeof(double) * N);
+  std::memcpy(R.wts, wts, sizeof(double) * N);
+  fus_emu::launch(2, 128, 0, [&] { geometry_quad_kernel<N>(xg, xdofmap, ncells, Gq, detJ, R); });
+  return 0;
+}
+
 #define EMU_DISPATCH(N, fn, ...)                                                                   \
   switch (N) {                                                                                     \
   case 2: return fn<2>(__VA_ARGS__);                                                               \
@@ -154,6 +183,18 @@ int emu_tri_coeffs_and_mass(int N, const double* xg, const int32_t* xdofmap, lon
                             double* coeffs, const double* x, double* y, const int32_t* dofmap,
                             const double* coeff, const double* pts, const double* wts) {
   EMU_DISPATCH(N, tri_n, xg, xdofmap, ncells, coeffs, x, y, dofmap, coeff, pts, wts);
+}
+
+// geometry_kernel -> G2 -> g_from_device_layout_kernel (reference layout out), then
+// affine_detect_kernel on the same G2 (Ghat[ncells][6] and the all-affine flag out)
+int emu_geometry(int N, const double* xg, const int32_t* xdofmap, long long ncells, double* G,
+                 double* detJ, const double* pts, const double* wts, double* Ghat, int* all_affine) {
+  EMU_DISPATCH(N, geometry_n, xg, xdofmap, ncells, G, detJ, pts, wts, Ghat, all_affine);
+}
+
+int emu_geometry_quad(int N, const double* xg, const int32_t* xdofmap, long long ncells, double* Gq,
+                      double* detJ, const double* pts, const double* wts) {
+  EMU_DISPATCH(N, geometry_quad_n, xg, xdofmap, ncells, Gq, detJ, pts, wts);
 }
 
 int emu_mass(const double* x, double* y, const int32_t* dofmap, const double* detJ,

@@ -40,6 +40,8 @@ def emu():
     L.emu_tri_coeffs_and_mass.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _i32, _f64, _f64,
                                           _f64]
     L.emu_mass.argtypes = [_f64, _f64, _i32, _f64, _f64, _ll, _int]
+    L.emu_geometry.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64, _f64, C.POINTER(_int)]
+    L.emu_geometry_quad.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64]
     L.emu_rk4_stage.argtypes = [_int, _int, _f64, _f64, _p, _f64, _f64, _f64, _f64, _f64, _f64, _ll,
                                 _ll, _dbl, _dbl]
     L.emu_boundary.argtypes = [_f64, _f64, _i32, _f64, _f64, _f64, _ll, _dbl, _dbl]
@@ -239,3 +241,28 @@ def test_emulated_mass_boundary_and_rk4_stage_kernels(fus, orc, emu):
             assert not b.any()
             for k in st:
                 assert np.allclose(st[k], ref[k], rtol=1e-14, atol=1e-15), (west, i, k)
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_emulated_setup_kernels(fus, orc, emu, P):
+    """geometry_kernel (G in the device layout, detJ), g_from_device_layout_kernel (back to the
+    reference layout), affine_detect_kernel and geometry_quad_kernel against precompute.hpp as the
+    oracle restates it."""
+    m, V, G, dJ, pts, wts = _case(fus, orc, P, n=(3, 2, 2))
+    nc = m.ncells
+    Gk, dJk, ghat, flag = np.zeros_like(G), np.zeros_like(dJ), np.zeros((nc, 6)), C.c_int(-1)
+    assert emu.emu_geometry(P + 1, m.x, m.xdofmap, nc, Gk, dJk, pts, wts, ghat, C.byref(flag)) == 0
+    assert rel_l2(Gk, G) < 1e-14 and rel_l2(dJk, dJ) < 1e-14 and flag.value == 0     # warped: not affine
+    A = np.array([[1.0, 0.3, 0.1], [0.0, 0.8, 0.25], [0.05, 0.0, 1.2]])
+    ma = fus.BoxMesh((3, 2, 2), (0, 0, 0), (1.0, 0.6, 0.5), warp=lambda z: z @ A.T)
+    Ga, dJa = orc.geometry(P, ma.x, ma.xdofmap)
+    Gk, dJk = np.zeros_like(Ga), np.zeros_like(dJa)
+    emu.emu_geometry(P + 1, ma.x, ma.xdofmap, ma.ncells, Gk, dJk, pts, wts, ghat, C.byref(flag))
+    assert flag.value == 1 and rel_l2(Gk, Ga) < 1e-14
+    assert np.allclose(ghat, Ga[:, 0, :] / wts[0] ** 3, rtol=1e-13)
+    mq = fus.RectMesh((4, 3), (0.1, -0.2), (1.3, 0.7),
+                      warp=lambda z: z + 0.03 * np.sin(7 * z[:, ::-1]) * np.array([1, 1, 0]))
+    Gq_ref, dJq_ref = orc.geometry_2d(P, mq.x, mq.xdofmap)
+    Gq, dJq = np.zeros((mq.ncells, 3, (P + 1) ** 2)), np.zeros_like(dJq_ref)
+    assert emu.emu_geometry_quad(P + 1, mq.x, mq.xdofmap, mq.ncells, Gq, dJq, pts, wts) == 0
+    assert rel_l2(Gq.transpose(0, 2, 1), Gq_ref) < 1e-14 and rel_l2(dJq, dJq_ref) < 1e-14
