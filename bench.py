@@ -222,7 +222,7 @@ def child_extras(timeout_s=120.0):
     time-out -- can cost the headline line."""
     cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_sweep.py"), "--degrees",
            "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,1,2", "--rk4-geometry-modes",
-           "0,1,2", "--models", "", "--repeats", "20"]
+           "0,1,2", "--models", "", "--repeats", "20", "--fp32"]
     env = dict(os.environ)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -242,12 +242,16 @@ def child_extras(timeout_s=120.0):
                 pass
     keep = ("P", "dofs", "geometry_mode", "ms_min", "ms_median", "gdof_per_s",
             "frac_of_measured_peak", "ms_per_step", "dof_updates_per_s", "operator_ms",
-            "rel_l2_vs_first_mode")
+            "rel_l2_vs_first_mode", "rel_l2_vs_fp64")
     res = {"wall_s": time.perf_counter() - t0, "exit": rc,
            "degree_sweep_operator_apply": [{k: r[k] for k in keep if k in r} for r in rows
                                            if r.get("config") == "degree_sweep"],
            "headline_rk4_by_geometry_mode": [{k: r[k] for k in keep if k in r} for r in rows
                                              if r.get("config") == "headline_rk4_by_geometry_mode"],
+           # FP32 operator instantiation (float data, 28 B/point + 8 B/dof algorithmic): first
+           # hardware run of these kernels -- their logic is covered by the host emulation tests
+           "degree_sweep_operator_apply_fp32": [{k: r[k] for k in keep if k in r} for r in rows
+                                                if r.get("config") == "degree_sweep_fp32"],
            "note": ("geometry_mode 0 streams the reference's G (48 B/point; the roofline's bytes), "
                     "1 keeps one Ghat per affine cell (the box qualifies), "
                     "2 rebuilds G per point from the trilinear cell map (192 B/cell); "

@@ -304,13 +304,16 @@ class _Operator:
         """y += A(coeffs) x.  numpy arrays go through the host entry point (copies included);
         CUDA tensors (float64, contiguous) through the device entry point on the context stream."""
         lib = self.ctx.lib
+        # float32 data selects the FP32 instantiation (the reference's T = float operators)
+        f32 = "float32" in str(x.dtype)
         if _is_device_tensor(x):
-            check(getattr(lib, self._dev_fn)(self.ctx.h, C.c_void_p(x.data_ptr()),
-                                             C.c_void_p(coeffs.data_ptr()),
-                                             C.c_void_p(y.data_ptr())), self._dev_fn)
+            fn = self._dev_fn.replace("_dev", "_f32_dev") if f32 else self._dev_fn
+            check(getattr(lib, fn)(self.ctx.h, C.c_void_p(x.data_ptr()), C.c_void_p(coeffs.data_ptr()),
+                                   C.c_void_p(y.data_ptr())), fn)
         else:
-            check(getattr(lib, self._host_fn)(self.ctx.h, x, np.ascontiguousarray(coeffs), y),
-                  self._host_fn)
+            fn = self._host_fn.replace("_host", "_f32_host") if f32 else self._host_fn
+            coeffs = np.ascontiguousarray(coeffs, dtype=np.float32 if f32 else np.float64)
+            check(getattr(lib, fn)(self.ctx.h, x, coeffs, y), fn)
         return y
 
 

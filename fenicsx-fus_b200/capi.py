@@ -17,6 +17,7 @@ KINDS = {"linear": FUS_LINEAR, "lossy": FUS_LOSSY, "westervelt": FUS_WESTERVELT}
 
 _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _i64 = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 _p = C.c_void_p
 _ll = C.c_int64
@@ -62,6 +63,10 @@ SIGNATURES = {
     "fus_stiffness_apply_host": (_int, [_p, _f64, _f64, _f64]),
     "fus_mass_apply_dev": (_int, [_p, _p, _p, _p]),
     "fus_mass_apply_host": (_int, [_p, _f64, _f64, _f64]),
+    "fus_stiffness_apply_f32_dev": (_int, [_p, _p, _p, _p]),
+    "fus_stiffness_apply_f32_host": (_int, [_p, _f32, _f32, _f32]),
+    "fus_mass_apply_f32_dev": (_int, [_p, _p, _p, _p]),
+    "fus_mass_apply_f32_host": (_int, [_p, _f32, _f32, _f32]),
     "fus_dev_alloc": (_int, [_p, C.c_size_t, C.POINTER(_p)]),
     "fus_dev_free": (_int, [_p, _p]),
     "fus_dev_upload": (_int, [_p, _p, _p, C.c_size_t]),

@@ -84,6 +84,9 @@ struct fus_ctx {
   // 2 = trilinear map coefficients per cell, G rebuilt in the kernel (fus_trilinear.hpp)
   double2* d_Ghat = nullptr;
   double* d_tri = nullptr;
+  // float copies of G2 / detJ for the FP32 operator entry points, made on first use
+  float* d_G2f = nullptr;
+  float* d_detJf = nullptr;
   int geom_active = 0;      // what the stiffness operator currently uses: 0 streamed G, 1, 2
   bool lean = false;        // neither G nor detJ exist on the device: always mode 2
   int live_models = 0;      // fus_model objects that still point at this context
@@ -336,6 +339,69 @@ int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double
   }
   set_error("unsupported degree P=%d", c->P);
   return FUS_ERR_UNSUPPORTED;
+}
+
+// ---- FP32 operators (float copies of the cell data; 3-D, streamed geometry only) ------------------
+int ensure_f32(fus_ctx* c, bool want_G, bool want_detJ) {
+  if (c->dim != 3 || c->lean) {
+    set_error("the FP32 operators need a hexahedral context that stores G / detJ");
+    return FUS_ERR_UNSUPPORTED;
+  }
+  const long long nent = c->ncells * c->Nd;
+  if (want_G && !c->d_G2f) {
+    if (!c->d_G2) {
+      set_error("context was created without G: stiffness operator unavailable");
+      return FUS_ERR_STATE;
+    }
+    FUS_CUDA(cudaMalloc(&c->d_G2f, sizeof(float) * 6 * nent));
+    narrow_kernel<<<grid_for(6 * nent, 256, c->num_sms * 8), 256, 0, c->stream>>>(
+        reinterpret_cast<const double*>(c->d_G2), c->d_G2f, 6 * nent); // same [cell][i0][p][t] order
+    FUS_LAUNCHED();
+  }
+  if (want_detJ && !c->d_detJf) {
+    if (!c->d_detJ) {
+      set_error("context was created without detJ: mass operator unavailable");
+      return FUS_ERR_STATE;
+    }
+    FUS_CUDA(cudaMalloc(&c->d_detJf, sizeof(float) * nent));
+    narrow_kernel<<<grid_for(nent, 256, c->num_sms * 8), 256, 0, c->stream>>>(c->d_detJ,
+                                                                              c->d_detJf, nent);
+    FUS_LAUNCHED();
+  }
+  return FUS_OK;
+}
+
+template <int N>
+int launch_stiffness_f32_n(fus_ctx* c, const float* x, const float* coeff, float* y) {
+  using L = LineCfg<N>;
+  static KernelCfg cfg;
+  DMatT<float, N> D;
+  for (int i = 0; i < N * N; ++i)
+    D.d[i] = (float)c->dphi[i];
+  for (int i = 0; i < N; ++i) {
+    D.w[i] = (float)c->wts[i];
+    D.x[i] = (float)c->pts[i];
+  }
+  auto kern = stiffness_line_kernel<N, false, 0, float>;
+  if (!cfg.configured[c->device]) {
+    FUS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
+    FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.blocks_plain[c->device], kern,
+                                                          L::THREADS, L::SMEM_BYTES));
+    if (cfg.blocks_plain[c->device] < 1) {
+      set_error("FP32 stiffness kernel <N=%d> does not fit on an SM", N);
+      return FUS_ERR_CUDA;
+    }
+    cfg.configured[c->device] = true;
+  }
+  ProfScope prof(c, 0, c->stream);
+  const long long want = (c->ncells + L::CPB - 1) / L::CPB;
+  const int blocks
+      = (int)std::min<long long>(want, (long long)c->num_sms * cfg.blocks_plain[c->device]);
+  kern<<<blocks, L::THREADS, L::SMEM_BYTES, c->stream>>>(
+      x, nullptr, y, c->d_dofmap, reinterpret_cast<const float2*>(c->d_G2f), coeff, nullptr, 0,
+      c->ncells, D);
+  FUS_LAUNCHED();
+  return FUS_OK;
 }
 
 template <int N>
@@ -809,6 +875,8 @@ int fus_ctx_destroy(fus_ctx* c) {
   cudaFree(c->d_dofmap);
   cudaFree(c->d_Ghat);
   cudaFree(c->d_tri);
+  cudaFree(c->d_G2f);
+  cudaFree(c->d_detJf);
   cudaFree(c->d_G2);
   cudaFree(c->d_Gq);
   cudaFree(c->d_detJ);
@@ -1061,6 +1129,53 @@ int fus_stiffness_apply_host(fus_ctx* c, const double* x, const double* coeffs, 
 }
 int fus_mass_apply_host(fus_ctx* c, const double* x, const double* coeffs, double* y) {
   return apply_host(c, x, coeffs, y, false);
+}
+
+// ---- FP32 operator entry points -------------------------------------------------------------------
+int fus_stiffness_apply_f32_dev(fus_ctx* c, const float* x, const float* coeffs, float* y) {
+  if (!c || !x || !coeffs || !y)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_TRY(ensure_f32(c, true, false));
+  return FUS_DISPATCH_N(c, launch_stiffness_f32_n, c, x, coeffs, y);
+}
+
+int fus_mass_apply_f32_dev(fus_ctx* c, const float* x, const float* coeffs, float* y) {
+  if (!c || !x || !coeffs || !y)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  FUS_TRY(ensure_f32(c, false, true));
+  const long long np = c->ncells * c->Nd;
+  mass_kernel_f32<<<grid_for(np, 256, c->num_sms * 8), 256, 0, c->stream>>>(
+      x, y, c->d_dofmap, c->d_detJf, coeffs, np, c->Nd);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
+static int apply_host_f32(fus_ctx* c, const float* x, const float* coeffs, float* y, bool stiff) {
+  if (!c || !x || !coeffs || !y)
+    return FUS_ERR_ARG;
+  FUS_TRY(select_device(c));
+  DevPtr<float> dx, dy, dc;
+  const size_t vb = sizeof(float) * c->ndofs, cbytes = sizeof(float) * c->ncells;
+  FUS_CUDA(cudaMalloc(&dx.p, vb));
+  FUS_CUDA(cudaMalloc(&dy.p, vb));
+  FUS_CUDA(cudaMalloc(&dc.p, cbytes));
+  FUS_CUDA(cudaMemcpyAsync(dx.p, x, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(dy.p, y, vb, cudaMemcpyHostToDevice, c->stream));
+  FUS_CUDA(cudaMemcpyAsync(dc.p, coeffs, cbytes, cudaMemcpyHostToDevice, c->stream));
+  FUS_TRY(stiff ? fus_stiffness_apply_f32_dev(c, dx.p, dc.p, dy.p)
+                : fus_mass_apply_f32_dev(c, dx.p, dc.p, dy.p));
+  FUS_CUDA(cudaMemcpyAsync(y, dy.p, vb, cudaMemcpyDeviceToHost, c->stream));
+  FUS_CUDA(cudaStreamSynchronize(c->stream));
+  return FUS_OK;
+}
+
+int fus_stiffness_apply_f32_host(fus_ctx* c, const float* x, const float* coeffs, float* y) {
+  return apply_host_f32(c, x, coeffs, y, true);
+}
+int fus_mass_apply_f32_host(fus_ctx* c, const float* x, const float* coeffs, float* y) {
+  return apply_host_f32(c, x, coeffs, y, false);
 }
 
 // ---- device memory helpers ----------------------------------------------------------------------

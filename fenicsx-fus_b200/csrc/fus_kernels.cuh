@@ -22,12 +22,34 @@
 
 namespace fus {
 
-template <int N>
-struct DMat {
-  double d[N * N]; // d[q*N+k] = phi_k'(xi_q)
-  double w[N];     // 1-D GLL weights (only read by the compressed-geometry kernels)
-  double x[N];     // 1-D GLL points  (only read by the trilinear-geometry kernel)
+// Scalar type of an operator instantiation: double everywhere in the solvers; float exists for
+// the operator classes only (the reference's float runs).
+template <typename T>
+struct Vec2;
+template <>
+struct Vec2<double> {
+  using type = double2;
 };
+template <>
+struct Vec2<float> {
+  using type = float2;
+};
+template <typename T>
+__device__ __forceinline__ typename Vec2<T>::type make_v2(T a, T b) {
+  typename Vec2<T>::type v;
+  v.x = a;
+  v.y = b;
+  return v;
+}
+
+template <typename T, int N>
+struct DMatT {
+  T d[N * N]; // d[q*N+k] = phi_k'(xi_q)
+  T w[N];     // 1-D GLL weights (only read by the compressed-geometry kernels)
+  T x[N];     // 1-D GLL points  (only read by the trilinear-geometry kernel)
+};
+template <int N>
+using DMat = DMatT<double, N>;
 
 template <int N>
 struct Rule1D {
@@ -43,6 +65,15 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
 #else
   double2 v;
   asm("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#endif
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+#ifdef FUS_HOST_EMULATION
+  return *p;
+#else
+  float2 v;
+  asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
 #endif
 }
@@ -330,23 +361,28 @@ struct LineCfg {
 //                per CELL, fus_trilinear.hpp) and |det J| w K K^T f is evaluated per point from
 //                them: exact for every mesh with a degree-1 coordinate element, 192 B per cell
 //                instead of 48 B per point, ~45 more FP64 operations per point.
-template <int N, bool FUSE2, int GEOM = 0>
+template <int N, bool FUSE2, int GEOM = 0, typename T = double>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3 : 0)
-    stiffness_line_kernel(const double* __restrict__ x, const double* __restrict__ x2,
-                          double* __restrict__ y, const int32_t* __restrict__ dofmap,
-                          const double2* __restrict__ G2, const double* __restrict__ coeff,
-                          const double* __restrict__ coeff2, long long cell_begin,
-                          long long cell_end, const __grid_constant__ DMat<N> D) {
+    stiffness_line_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
+                          const int32_t* __restrict__ dofmap,
+                          const typename Vec2<T>::type* __restrict__ G2,
+                          const T* __restrict__ coeff, const T* __restrict__ coeff2,
+                          long long cell_begin, long long cell_end,
+                          const __grid_constant__ DMatT<T, N> D) {
   using C = LineCfg<N>;
+  using V2 = typename Vec2<T>::type;
+  static_assert(GEOM != 2 || sizeof(T) == sizeof(double),
+                "the trilinear cell map is evaluated in FP64 only");
   constexpr int NN = C::NN, GPF = C::GPF;
   constexpr bool AFFINE = (GEOM == 1), TRI = (GEOM == 2);
   constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
   static_assert(GEOM >= 0 && GEOM <= 2, "unknown geometry mode");
 #ifdef FUS_HOST_EMULATION
-  double* smem = fus_emu::dynamic_shared();
+  T* smem = reinterpret_cast<T*>(fus_emu::dynamic_shared());
 #else
-  extern __shared__ double smem[];
+  extern __shared__ double smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
 #endif
 
   const int tid = threadIdx.x;
@@ -356,17 +392,17 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
   const bool lane_ok = cg < C::GC;
   const int slot = group * C::GC + (lane_ok ? cg : 0);
   const int a = t / N, b = t - a * N;
-  double* Sx = smem + slot * C::CS;
-  double* S1 = Sx + C::X_SZ;
-  double* S2 = S1 + C::B1_SZ;
+  T* Sx = smem + slot * C::CS;
+  T* S1 = Sx + C::X_SZ;
+  T* S2 = S1 + C::B1_SZ;
   // per-thread base offsets of the three access patterns
-  double* SxA = Sx + a * C::X_S1 + b;   // + k*X_S0
-  double* SxB = Sx + a * C::X_S0 + b;   // + k*X_S1
-  double* SxC = Sx + a * C::X_S0 + b * C::X_S1; // + k
-  double* S1A = S1 + a * C::B1_S1 + b;  // + k*B1_S0
-  double* S1B = S1 + a * C::B1_S0 + b;  // + k*B1_S1
-  double* S2A = S2 + a * C::B2_S1 + b;  // + k*B2_S0
-  double* S2C = S2 + a * C::B2_S0 + b * C::B2_S1; // + k
+  T* SxA = Sx + a * C::X_S1 + b;   // + k*X_S0
+  T* SxB = Sx + a * C::X_S0 + b;   // + k*X_S1
+  T* SxC = Sx + a * C::X_S0 + b * C::X_S1; // + k
+  T* S1A = S1 + a * C::B1_S1 + b;  // + k*B1_S0
+  T* S1B = S1 + a * C::B1_S0 + b;  // + k*B1_S1
+  T* S2A = S2 + a * C::B2_S1 + b;  // + k*B2_S0
+  T* S2C = S2 + a * C::B2_S0 + b * C::B2_S1; // + k
 
   auto sync = [group] {
     if constexpr (C::WARP)
@@ -385,16 +421,16 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
   long long c = cell_begin + (long long)blockIdx.x * C::CPB + slot;
 
   int idx[N], idxn[N];
-  double xv[N];
-  double2 g[GEOM != 0 ? 1 : GPF][3];
-  double2 gh[3], ghn[3]; // AFFINE: Ghat of the current and of the next cell
+  T xv[N];
+  V2 g[GEOM != 0 ? 1 : GPF][3];
+  V2 gh[3], ghn[3]; // AFFINE: Ghat of the current and of the next cell
   // TRI: the pieces of J on this thread's line (xi1,xi2) = (x[a],x[b]) for the current cell.  The
   // 192 B of a cell are read by all its threads at the same addresses, so there is nothing to keep
   // in flight: the next cell's two lines are prefetched into L2 and loaded when it becomes current.
   TriLine tl;
-  const double wab = (GEOM != 0) ? D.w[a] * D.w[b] : 0.0;
-  const double xia = TRI ? D.x[a] : 0.0, xib = TRI ? D.x[b] : 0.0;
-  double cf = 0.0;
+  const T wab = (GEOM != 0) ? D.w[a] * D.w[b] : T(0);
+  const double xia = TRI ? (double)D.x[a] : 0.0, xib = TRI ? (double)D.x[b] : 0.0;
+  T cf = T(0);
   if constexpr (TRI) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) { // identity map: padding lanes stay finite
@@ -404,17 +440,19 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
   }
   // coefficients of cell `cell` -> line pieces
   auto tri_setup = [&](long long cell) {
-    double cq[FUS_TRI_STRIDE];
+    if constexpr (TRI) {
+      double cq[FUS_TRI_STRIDE];
 #pragma unroll
-    for (int k = 0; k < TQ; ++k) {
-      const double2 v = __ldg(G2 + cell * TQ + k);
-      cq[2 * k] = v.x;
-      cq[2 * k + 1] = v.y;
+      for (int k = 0; k < TQ; ++k) {
+        const double2 v = __ldg(G2 + cell * TQ + k);
+        cq[2 * k] = v.x;
+        cq[2 * k + 1] = v.y;
+      }
+      tri_line_setup(cq, xia, xib, tl);
     }
-    tri_line_setup(cq, xia, xib, tl);
   };
   auto tri_prefetch = [&](long long cell) {
-    const double2* q = G2 + cell * TQ;
+    const V2* q = G2 + cell * TQ;
 #ifdef FUS_HOST_EMULATION
     (void)q;
 #else
@@ -424,18 +462,18 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
   };
 #pragma unroll
   for (int p = 0; p < 3; ++p)
-    gh[p] = ghn[p] = make_double2(0.0, 0.0);
+    gh[p] = ghn[p] = make_v2<T>(T(0), T(0));
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     idx[k] = 0;
     idxn[k] = 0;
-    xv[k] = 0.0;
+    xv[k] = T(0);
   }
 #pragma unroll
   for (int k = 0; k < (GEOM != 0 ? 1 : GPF); ++k)
 #pragma unroll
     for (int p = 0; p < 3; ++p)
-      g[k][p] = make_double2(0.0, 0.0);
+      g[k][p] = make_v2<T>(T(0), T(0));
 
   bool valid = lane_ok && (c < cell_end);
   if (valid) {
@@ -444,11 +482,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
     for (int k = 0; k < N; ++k)
       idx[k] = __ldg(dm + k * NN);
     if constexpr (FUSE2) {
-      const double ca = __ldg(coeff + c), cb = __ldg(coeff2 + c);
+      const T ca = __ldg(coeff + c), cb = __ldg(coeff2 + c);
 #pragma unroll
       for (int k = 0; k < N; ++k)
         xv[k] = ca * __ldg(x + idx[k]) + cb * __ldg(x2 + idx[k]);
-      cf = 1.0;
+      cf = T(1);
     } else {
 #pragma unroll
       for (int k = 0; k < N; ++k)
@@ -462,7 +500,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
     } else if constexpr (TRI) {
       tri_setup(c);
     } else {
-      const double2* gp = G2 + c * (3 * N * NN) + t;
+      const V2* gp = G2 + c * (3 * N * NN) + t;
 #pragma unroll
       for (int k = 0; k < GPF; ++k)
 #pragma unroll
@@ -493,19 +531,19 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
       for (int k = 0; k < N; ++k)
         SxA[k * C::X_S0] = xv[k];
     }
-    double f0[N];
+    T f0[N];
 #pragma unroll
     for (int q = 0; q < N; ++q) {
-      double s = 0.0;
+      T s = T(0);
 #pragma unroll
       for (int k = 0; k < N; ++k)
         s = fma(D.d[q * N + k], xv[k], s);
       f0[q] = s;
     }
-    const double cfc = cf;
+    const T cfc = cf;
     if (validn) {
       if constexpr (FUSE2) {
-        const double ca = __ldg(coeff + cn), cb = __ldg(coeff2 + cn);
+        const T ca = __ldg(coeff + cn), cb = __ldg(coeff2 + cn);
 #pragma unroll
         for (int k = 0; k < N; ++k)
           xv[k] = ca * __ldg(x + idxn[k]) + cb * __ldg(x2 + idxn[k]);
@@ -522,13 +560,13 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
     // Padding lanes are predicated off for loads too: their aliased addresses would add bank
     // conflicts (ncu: 3-4 wavefronts per LDS.64 instead of 2).
     if (lane_ok) {
-      double l[N];
+      T l[N];
 #pragma unroll
       for (int k = 0; k < N; ++k)
         l[k] = SxB[k * C::X_S1];
 #pragma unroll
       for (int q = 0; q < N; ++q) {
-        double s = 0.0;
+        T s = T(0);
 #pragma unroll
         for (int k = 0; k < N; ++k)
           s = fma(D.d[q * N + k], l[k], s);
@@ -539,7 +577,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
         l[k] = SxC[k];
 #pragma unroll
       for (int q = 0; q < N; ++q) {
-        double s = 0.0;
+        T s = T(0);
 #pragma unroll
         for (int k = 0; k < N; ++k)
           s = fma(D.d[q * N + k], l[k], s);
@@ -549,25 +587,25 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
     sync();
 
     // (3) back in layout A: G transform per level, transposed direction 0 in registers
-    double yv[N];
+    T yv[N];
 #pragma unroll
     for (int m = 0; m < N; ++m)
-      yv[m] = 0.0;
-    const double2* gpc = G2 + c * (3 * N * NN) + t;
-    const double2* gpn = G2 + cn * (3 * N * NN) + t;
+      yv[m] = T(0);
+    const V2* gpc = G2 + c * (3 * N * NN) + t;
+    const V2* gpn = G2 + cn * (3 * N * NN) + t;
 #pragma unroll
     for (int i0 = 0; i0 < N; ++i0) {
-      double f1 = 0.0, f2 = 0.0;
+      T f1 = T(0), f2 = T(0);
       if (lane_ok) {
         f1 = S1A[i0 * C::B1_S0];
         f2 = S2A[i0 * C::B2_S0];
       }
-      double t0, t1, t2;
+      T t0, t1, t2;
       if constexpr (TRI) {
         tri_transform(tl, D.x[i0], cfc * (D.w[i0] * wab), f0[i0], f1, f2, t0, t1, t2);
       } else {
-        double2 ga, gb, gc;
-        double scale;
+        V2 ga, gb, gc;
+        T scale;
         if constexpr (AFFINE) {
           ga = gh[0], gb = gh[1], gc = gh[2];
           scale = cfc * (D.w[i0] * wab);
@@ -604,13 +642,13 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
 
     // (4) transposed direction 1 and 2 along the thread's own lines, results back in place
     if (lane_ok) {
-      double l[N];
+      T l[N];
 #pragma unroll
       for (int q = 0; q < N; ++q)
         l[q] = S1B[q * C::B1_S1];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        double s = 0.0;
+        T s = T(0);
 #pragma unroll
         for (int q = 0; q < N; ++q)
           s = fma(D.d[q * N + j], l[q], s);
@@ -621,7 +659,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
         l[q] = S2C[q];
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        double s = 0.0;
+        T s = T(0);
 #pragma unroll
         for (int q = 0; q < N; ++q)
           s = fma(D.d[q * N + j], l[q], s);
@@ -634,7 +672,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
 #pragma unroll
     for (int j0 = 0; j0 < N; ++j0) {
       if (valid) {
-        const double acc = yv[j0] + S1A[j0 * C::B1_S0] + S2A[j0 * C::B2_S0];
+        const T acc = yv[j0] + S1A[j0 * C::B1_S0] + S2A[j0 * C::B2_S0];
         atomicAdd(y + idx[j0], acc);
       }
     }
@@ -739,6 +777,29 @@ static __global__ void __launch_bounds__(256)
     const double v = __ldg(coeff + c) * __ldg(x + dof) * __ldg(detJ + p);
     atomicAdd(y + dof, v);
   }
+}
+
+// FP32 instantiation of the operators (the reference's float runs,
+// tests/test_operators3d/main.cpp:13): the stiffness operator is stiffness_line_kernel<N,FUSE2,0,
+// float> on float copies of the cell data (24 B of G per point instead of 48), the mass operator
+// the kernel below; the two conversion kernels make those copies once per context.
+static __global__ void __launch_bounds__(256)
+    mass_kernel_f32(const float* __restrict__ x, float* __restrict__ y,
+                    const int32_t* __restrict__ dofmap, const float* __restrict__ detJ,
+                    const float* __restrict__ coeff, long long npoints, int Nd) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npoints; p += stride) {
+    const long long c = p / Nd;
+    const int dof = __ldg(dofmap + p);
+    atomicAdd(y + dof, __ldg(coeff + c) * __ldg(x + dof) * __ldg(detJ + p));
+  }
+}
+
+static __global__ void __launch_bounds__(256)
+    narrow_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (float)in[i];
 }
 
 // Mass operator of a lean context (no detJ array): |det J| w_q is rebuilt from the trilinear cell

@@ -169,6 +169,15 @@ int fus_stiffness_apply_host(fus_ctx* ctx, const double* x, const double* coeffs
 int fus_mass_apply_dev(fus_ctx* ctx, const double* x, const double* coeffs, double* y);
 int fus_mass_apply_host(fus_ctx* ctx, const double* x, const double* coeffs, double* y);
 
+/* The same two operators in FP32 (StiffnessSpectral3D<float,P> / MassSpectral3D<float,P>, the
+   scalar type of the reference's tests/test_operators3d/main.cpp:13 and of its float timing runs):
+   float vectors and coefficients, float copies of G / detJ made on the first call (24 B of G per
+   point instead of 48).  Hexahedral contexts that store G / detJ only; geometry mode 0. */
+int fus_stiffness_apply_f32_dev(fus_ctx* ctx, const float* x, const float* coeffs, float* y);
+int fus_stiffness_apply_f32_host(fus_ctx* ctx, const float* x, const float* coeffs, float* y);
+int fus_mass_apply_f32_dev(fus_ctx* ctx, const float* x, const float* coeffs, float* y);
+int fus_mass_apply_f32_host(fus_ctx* ctx, const float* x, const float* coeffs, float* y);
+
 /* Device buffers for callers without a CUDA runtime of their own (C, ctypes). */
 int fus_dev_alloc(fus_ctx* ctx, size_t bytes, void** ptr);
 int fus_dev_free(fus_ctx* ctx, void* ptr);

@@ -30,6 +30,50 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
+def sweep_fp32(args, fus, torch, stream, pk):
+    """FP32 operator instantiation per degree (StiffnessSpectral3D<float,P>: float data select the
+    FP32 kernels), after everything else -- it is the newest code: if it fails, the rows printed
+    before it are already out."""
+    for P in [int(s) for s in args.degrees.split(",") if s]:
+        n = SWEEP[P]
+        m = fus.BoxMesh((n, n, n))
+        V = fus.FunctionSpace(m, P, numbering=args.numbering)
+        ctx = V.context()
+        ctx.set_stream(stream.cuda_stream)
+        x = torch.rand(V.ndofs, dtype=torch.float64, device="cuda")
+        coeffs = torch.full((m.ncells,), -1.0 / 1000.0, dtype=torch.float64, device="cuda")
+        K = fus.StiffnessSpectral3D(V)
+        x32, c32 = x.float(), coeffs.float()
+        y32, y64 = torch.zeros_like(x32), torch.zeros_like(x)
+        K(x, coeffs, y64)
+        K(x32, c32, y32)
+        torch.cuda.synchronize()
+        err = float((torch.linalg.vector_norm(y32.double() - y64)
+                     / torch.linalg.vector_norm(y64)).item())
+        for _ in range(3):
+            K(x32, c32, y32)
+        times = []
+        for _ in range(args.repeats):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            K(x32, c32, y32)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        tmin, tmed = min(times), float(np.median(times))
+        alg32 = 28.0 * m.ncells * (P + 1) ** 3 + 8.0 * V.ndofs      # 24 B G + 4 B dofmap; x, y
+        print(json.dumps({"config": "degree_sweep_fp32", "P": P, "n": n, "dofs": V.ndofs,
+                          "ms_min": tmin, "ms_median": tmed,
+                          "gdof_per_s": V.ndofs / (tmin * 1e-3) / 1e9,
+                          "alg_gbs_median": alg32 / (tmed * 1e-3) / 1e9,
+                          "frac_of_measured_peak": alg32 / (tmed * 1e-3) / 1e9 / pk,
+                          "rel_l2_vs_fp64": err}), flush=True)
+        del K, x, coeffs, x32, c32, y32, y64
+        V._ctx = None
+        ctx.destroy()
+        torch.cuda.empty_cache()
+
+
 def main():
     import torch
 
@@ -41,6 +85,8 @@ def main():
     ap.add_argument("--variants", default="0", help="-1 = the library's own choice per degree")
     ap.add_argument("--geometry-modes", default="0")
     ap.add_argument("--rk4-geometry-modes", default="")
+    ap.add_argument("--fp32", action="store_true",
+                    help="also time the FP32 operator instantiation and report its error vs FP64")
     ap.add_argument("--numbering", type=int, default=1)
     args = ap.parse_args()
     pk = peak()
@@ -191,6 +237,8 @@ def main():
                               "finite": bool(np.isfinite(u).all()),
                               "u_norm": float(np.linalg.norm(u))}), flush=True)
             mdl.destroy()
+    if args.fp32:
+        sweep_fp32(args, fus, torch, stream, pk)
 
 
 if __name__ == "__main__":

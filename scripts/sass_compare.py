@@ -35,8 +35,9 @@ def demangle(names):
 
 def norm(n):
     n = re.sub(r"\(.*", "", n).replace("void fus::", "")
-    # bool template arguments print as true/false, ints as digits: make them comparable
-    return n.replace("true", "1").replace("false", "0")
+    # bool template arguments print as true/false, ints as digits: make them comparable; a trailing
+    # default scalar type (added when the line kernel was templated on it) is not part of the name
+    return n.replace("true", "1").replace("false", "0").replace(", double>", ">")
 
 
 a, b = kernels(sys.argv[1]), kernels(sys.argv[2])

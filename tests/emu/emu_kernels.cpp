@@ -116,6 +116,40 @@ int tri_n(const double* xg, const int32_t* xdofmap, long long ncells, double* co
   return 0;
 }
 
+// FP32 instantiation: float copies of G (narrow_kernel on the device-layout array, as fus_capi.cu
+// does), then stiffness_line_kernel<N,false,0,float> and mass_kernel_f32
+template <int N>
+int f32_n(const float* x, float* y, float* ym, const int32_t* dofmap, const double* G,
+          const double* detJ, const float* coeff, long long ncells, const double* dphi,
+          const double* pts, const double* wts, int max_blocks) {
+  using L = LineCfg<N>;
+  constexpr int Nd = N * N * N;
+  const std::vector<double2> G2 = device_layout<N>(G, ncells);
+  std::vector<float> G2f((size_t)ncells * Nd * 6), dJf((size_t)ncells * Nd);
+  fus_emu::launch(2, 256, 0, [&] {
+    narrow_kernel(reinterpret_cast<const double*>(G2.data()), G2f.data(), (long long)G2f.size());
+  });
+  fus_emu::launch(2, 256, 0, [&] { narrow_kernel(detJ, dJf.data(), (long long)dJf.size()); });
+  DMatT<float, N> D;
+  for (int i = 0; i < N * N; ++i)
+    D.d[i] = (float)dphi[i];
+  for (int i = 0; i < N; ++i) {
+    D.w[i] = (float)wts[i];
+    D.x[i] = (float)pts[i];
+  }
+  const unsigned blocks
+      = (unsigned)std::max<long long>(1, std::min<long long>((ncells + L::CPB - 1) / L::CPB, max_blocks));
+  fus_emu::launch(blocks, L::THREADS, L::SMEM_BYTES, [&] {
+    stiffness_line_kernel<N, false, 0, float>(x, nullptr, y, dofmap,
+                                              reinterpret_cast<const float2*>(G2f.data()), coeff,
+                                              nullptr, 0, ncells, D);
+  });
+  fus_emu::launch(3, 256, 0, [&] {
+    mass_kernel_f32(x, ym, dofmap, dJf.data(), coeff, ncells * Nd, Nd);
+  });
+  return 0;
+}
+
 template <int N>
 int geometry_n(const double* xg, const int32_t* xdofmap, long long ncells, double* G, double* detJ,
                const double* pts, const double* wts, double* Ghat, int* all_affine) {
@@ -195,6 +229,13 @@ int emu_geometry(int N, const double* xg, const int32_t* xdofmap, long long ncel
 int emu_geometry_quad(int N, const double* xg, const int32_t* xdofmap, long long ncells, double* Gq,
                       double* detJ, const double* pts, const double* wts) {
   EMU_DISPATCH(N, geometry_quad_n, xg, xdofmap, ncells, Gq, detJ, pts, wts);
+}
+
+// y += K x and ym += M x in FP32 (float data in and out; G / detJ given in FP64 reference layouts)
+int emu_operators_f32(int N, const float* x, float* y, float* ym, const int32_t* dofmap,
+                      const double* G, const double* detJ, const float* coeff, long long ncells,
+                      const double* dphi, const double* pts, const double* wts, int max_blocks) {
+  EMU_DISPATCH(N, f32_n, x, y, ym, dofmap, G, detJ, coeff, ncells, dphi, pts, wts, max_blocks);
 }
 
 int emu_mass(const double* x, double* y, const int32_t* dofmap, const double* detJ,

@@ -29,6 +29,9 @@ struct double2 {
   double x, y;
 };
 inline double2 make_double2(double a, double b) { return double2{a, b}; }
+struct float2 {
+  float x, y;
+};
 
 struct emu_dim3 {
   unsigned x = 1, y = 1, z = 1;
@@ -101,6 +104,7 @@ inline T __ldg(const T* p) {
   return *p;
 }
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
+inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
 inline int atomicExch(int* p, int v) { return std::atomic_ref<int>(*p).exchange(v); }
 using std::fabs;
 using std::fma;

@@ -102,6 +102,17 @@ def _fake_torch():
             self.a[...] = 0.0
             return self
 
+        def float(self):
+            return T(self.a)
+
+        double = float
+
+        def __sub__(self, o):
+            return T(self.a - o.a)
+
+        def __truediv__(self, o):
+            return T(self.a / np.maximum(np.abs(o.a), 1e-300))
+
     cuda = types.SimpleNamespace(
         set_device=lambda i: None, synchronize=lambda: None, empty_cache=lambda: None,
         set_stream=lambda s: None, Stream=lambda: types.SimpleNamespace(cuda_stream=0),
@@ -284,7 +295,7 @@ def test_child_sweep_script_control_flow_with_a_stub_device(monkeypatch, capsys)
     monkeypatch.setattr(fus, "LinearSpectral3D", Model)
     monkeypatch.setattr(sys, "argv", ["bench_sweep.py", "--degrees", "2,3,4,5,6,7", "--variants=-1",
                                       "--geometry-modes", "0,1,2", "--rk4-geometry-modes", "0,1,2",
-                                      "--models", "", "--repeats", "2"])
+                                      "--models", "", "--repeats", "2", "--fp32"])
     sweep.main()
     rows = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     deg = [r for r in rows if r["config"] == "degree_sweep"]
@@ -293,4 +304,6 @@ def test_child_sweep_script_control_flow_with_a_stub_device(monkeypatch, capsys)
                                                                  for g in (0, 1, 2)]
     assert [r["geometry_mode"] for r in rk] == [0, 1, 2] and all(r["steps"] == 20 for r in rk)
     assert all({"ms_min", "gdof_per_s", "frac_of_measured_peak"} <= set(r) for r in deg)
+    f32 = [r for r in rows if r["config"] == "degree_sweep_fp32"]
+    assert [r["P"] for r in f32] == list(range(2, 8)) and all("rel_l2_vs_fp64" in r for r in f32)
     assert all({"ms_per_step", "operator_ms", "rel_l2_vs_first_mode"} <= set(r) for r in rk)

@@ -40,6 +40,9 @@ def emu():
     L.emu_tri_coeffs_and_mass.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _i32, _f64, _f64,
                                           _f64]
     L.emu_mass.argtypes = [_f64, _f64, _i32, _f64, _f64, _ll, _int]
+    f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    L.emu_operators_f32.argtypes = [_int, f32, f32, f32, _i32, _f64, _f64, f32, _ll, _f64, _f64, _f64,
+                                    _int]
     L.emu_geometry.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64, _f64, C.POINTER(_int)]
     L.emu_geometry_quad.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64]
     L.emu_rk4_stage.argtypes = [_int, _int, _f64, _f64, _p, _f64, _f64, _f64, _f64, _f64, _f64, _ll,
@@ -266,3 +269,22 @@ def test_emulated_setup_kernels(fus, orc, emu, P):
     Gq, dJq = np.zeros((mq.ncells, 3, (P + 1) ** 2)), np.zeros_like(dJq_ref)
     assert emu.emu_geometry_quad(P + 1, mq.x, mq.xdofmap, mq.ncells, Gq, dJq, pts, wts) == 0
     assert rel_l2(Gq.transpose(0, 2, 1), Gq_ref) < 1e-14 and rel_l2(dJq, dJq_ref) < 1e-14
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
+def test_emulated_fp32_operators(fus, orc, emu, P):
+    """stiffness_line_kernel<N,false,0,float> and mass_kernel_f32 on float copies of the cell data
+    (SURVEY.md section 8f-4): the FP64 oracle on the same float-rounded inputs, to float accuracy."""
+    m, V, G, dJ, pts, wts = _case(fus, orc, P)
+    nd, nc = V.ndofs, m.ncells
+    rng = np.random.default_rng(50 + P)
+    x = rng.uniform(-1, 1, nd).astype(np.float32)
+    c = rng.uniform(0.5, 2, nc).astype(np.float32)
+    y, ym = np.zeros(nd, dtype=np.float32), np.zeros(nd, dtype=np.float32)
+    assert emu.emu_operators_f32(P + 1, x, y, ym, np.ascontiguousarray(V.dofmap), G, dJ, c, nc,
+                                 orc.dphi(P), pts, wts, 2) == 0
+    x64, c64 = x.astype(np.float64), c.astype(np.float64)
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), c64, x64, np.zeros(nd))
+    mo = orc.mass_apply(P, V.dofmap, dJ, c64, x64, np.zeros(nd))
+    assert rel_l2(y, yo) < 2e-6 and rel_l2(ym, mo) < 1e-6
+    assert y.dtype == np.float32 and np.isfinite(y).all()
