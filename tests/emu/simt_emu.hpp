@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <atomic>
 #include <barrier>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -49,6 +51,7 @@ inline emu_dim3 blockDim, gridDim; // one launch at a time
 #define __shared__ static // blocks run one after another, so one copy per kernel instantiation
 
 namespace fus_emu {
+inline void jitter();
 struct BlockState {
   std::unique_ptr<std::barrier<>> block;
   std::vector<std::unique_ptr<std::barrier<>>> warps;
@@ -69,6 +72,7 @@ inline void named_barrier(int id, int count) {
     b = slot.get();
   }
   b->arrive_and_wait();
+  jitter();
 }
 
 // kernel<<<grid, block, smem_bytes>>>(args...)  ->  launch(grid, block, smem_bytes, [&]{ kernel(args...); })
@@ -97,8 +101,30 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
 }
 } // namespace fus_emu
 
-inline void __syncthreads() { fus_emu::g_block->block->arrive_and_wait(); }
-inline void __syncwarp() { fus_emu::g_block->warps[threadIdx.x / 32]->arrive_and_wait(); }
+// FUS_EMU_JITTER=<microseconds>: every thread sleeps a pseudo-random time below that bound after
+// each barrier, so that threads run far apart and a missing barrier is very likely to be observed.
+namespace fus_emu {
+inline void jitter() {
+  static const int bound = [] {
+    const char* e = std::getenv("FUS_EMU_JITTER");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (bound > 0) {
+    thread_local unsigned state = 2654435761u * (threadIdx.x + 1) + blockIdx.x;
+    state = state * 1664525u + 1013904223u;
+    std::this_thread::sleep_for(std::chrono::microseconds((state >> 8) % (unsigned)bound));
+  }
+}
+} // namespace fus_emu
+
+inline void __syncthreads() {
+  fus_emu::g_block->block->arrive_and_wait();
+  fus_emu::jitter();
+}
+inline void __syncwarp() {
+  fus_emu::g_block->warps[threadIdx.x / 32]->arrive_and_wait();
+  fus_emu::jitter();
+}
 template <typename T>
 inline T __ldg(const T* p) {
   return *p;

@@ -288,3 +288,39 @@ def test_emulated_fp32_operators(fus, orc, emu, P):
     mo = orc.mass_apply(P, V.dofmap, dJ, c64, x64, np.zeros(nd))
     assert rel_l2(y, yo) < 2e-6 and rel_l2(ym, mo) < 1e-6
     assert y.dtype == np.float32 and np.isfinite(y).all()
+
+
+def test_emulation_with_scheduling_jitter(fus, orc, emu):
+    """The stiffness kernels once more with every emulated thread sleeping a pseudo-random time after
+    each barrier (FUS_EMU_JITTER): threads of a warp and of a block then run far apart, which makes
+    a missing __syncwarp / __syncthreads / named barrier all but certain to corrupt the result."""
+    import sys
+    code = (
+        "import os, sys, ctypes as C, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        "import fenicsx_fus_b200 as fus\n"
+        "from conftest import warp_vertices, rel_l2\n"
+        "from oracle.oracle import Oracle\n"
+        "orc = Oracle()\n"
+        f"L = C.CDLL({os.path.join(EMU_DIR, 'libfus_emu.so')!r})\n"
+        "f64 = np.ctypeslib.ndpointer(dtype=np.float64, flags='C_CONTIGUOUS')\n"
+        "i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags='C_CONTIGUOUS')\n"
+        "L.emu_stiffness.argtypes = [C.c_int] * 3 + [f64, C.c_void_p, f64, i32, C.c_void_p, C.c_void_p,"
+        " f64, C.c_void_p, C.c_int64, f64, f64, f64, C.c_int, C.c_int64, C.c_int64]\n"
+        "for P, variant in ((2, 0), (4, 2), (5, 2), (6, 2), (3, 1)):\n"
+        "    m = fus.BoxMesh((3, 2, 2), warp=lambda x: warp_vertices(x, 0.08, 3))\n"
+        "    V = fus.FunctionSpace(m, P, numbering=1)\n"
+        "    G, dJ = orc.geometry(P, m.x, m.xdofmap)\n"
+        "    pts, wts = orc.gll(P + 1)\n"
+        "    rng = np.random.default_rng(P)\n"
+        "    x, c = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)\n"
+        "    y = np.zeros(V.ndofs)\n"
+        "    L.emu_stiffness(P + 1, variant, 0, x, None, y, V.dofmap, G.ctypes.data_as(C.c_void_p), None,"
+        " c, None, m.ncells, orc.dphi(P), pts, wts, 1, 0, m.ncells)\n"
+        "    e = rel_l2(y, orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), c, x, np.zeros(V.ndofs)))\n"
+        "    assert e < 1e-13, (P, variant, e)\n"
+        "print('jitter ok')\n")
+    env = dict(os.environ, FUS_EMU_JITTER="200")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert res.returncode == 0 and "jitter ok" in res.stdout, res.stdout + res.stderr
