@@ -156,6 +156,13 @@ def test_emulated_compressed_geometry_kernels(fus, orc, emu, P):
     emu.emu_stiffness(P + 1, 2, 1, xa, None, ya, Va.dofmap, None, _opt(ghat), ca, None, ma.ncells,
                       dphi, pts, wts, 2, 0, ma.ncells)
     assert rel_l2(ya, orc.stiffness_apply(P, Va.dofmap, Ga, dphi, ca, xa, np.zeros(Va.ndofs))) < 1e-12
+    xb, cb2 = rng.uniform(-1, 1, Va.ndofs), rng.uniform(-1, 1, ma.ncells)
+    yb = np.zeros(Va.ndofs)                                       # affine + fused two-vector gather
+    emu.emu_stiffness(P + 1, 2, 1, xa, _opt(xb), yb, Va.dofmap, None, _opt(ghat), ca, _opt(cb2),
+                      ma.ncells, dphi, pts, wts, 2, 0, ma.ncells)
+    yref = orc.stiffness_apply(P, Va.dofmap, Ga, dphi, ca, xa, np.zeros(Va.ndofs))
+    yref = orc.stiffness_apply(P, Va.dofmap, Ga, dphi, cb2, xb, yref)
+    assert rel_l2(yb, yref) < 1e-12
 
 
 @pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
