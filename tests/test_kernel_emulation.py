@@ -331,3 +331,79 @@ def test_emulation_with_scheduling_jitter(fus, orc, emu):
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
                          timeout=600)
     assert res.returncode == 0 and "jitter ok" in res.stdout, res.stdout + res.stderr
+
+
+@pytest.mark.parametrize("kind", ["linear", "westervelt"])
+def test_emulated_fused_rk4_step_vs_reference_flow(fus, orc, emu, kind):
+    """The fused stage flow of fus_model_rk4 (csrc/fus_capi.cu: operator with the fused two-vector
+    gather, boundary_kernel, rk4_stage_kernel<STAGE,WESTERVELT>; 41 vector passes per step) executed
+    with the emulated kernels, against the oracle's literal restatement of the reference loop
+    (Linear.hpp:228-314, Westervelt.hpp:216-373; ~30 passes per stage).  Same fields after 3 steps."""
+    from fenicsx_fus_b200 import capi
+    P, n, h = 3, (3, 2, 2), 0.002
+    m = fus.BoxMesh(n, (0, 0, 0), tuple(h * k for k in n), warp=lambda x: warp_vertices(x, 0.05, 5))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    nd, nc = V.ndofs, m.ncells
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    pts, wts = orc.gll(P + 1)
+    dphi = orc.dphi(P)
+    rng = np.random.default_rng(3)
+    c0, rho0 = rng.uniform(1400, 1600, nc), rng.uniform(900, 1100, nc)
+    west = kind == "westervelt"
+    delta = rng.uniform(1e-3, 3e-3, nc) if west else None
+    beta = rng.uniform(3, 4, nc) if west else None
+    f0, p0, s0 = 0.5e6, 6.0e4, 1500.0
+    fn, fs = orc.facet_data(P, m.x, m.xdofmap, m.facets)
+    om = orc.model(kind, P, nd, V.dofmap, G, dJ, dphi, c0, rho0, delta, beta, m.facets, fn, fs, f0, p0,
+                   s0)
+    dt = 0.2 * np.sqrt(3) * h / (1600.0 * P * P)
+    u0, v0 = 1e3 * rng.uniform(-1, 1, nd), 1e9 * rng.uniform(-1, 1, nd)
+    u_ref, v_ref = u0.copy(), v0.copy()
+    steps, tf = 3, 2.5 * dt                # the reference loop shortens the last step to land on tf
+    assert om.rk4(0.0, tf, dt, u_ref, v_ref) == steps
+    # ---- model set-up as fus_model_create does it
+    src, dsrc, absb, bmass = (np.zeros(nd) for _ in range(4))
+    assert capi.load().fus_boundary_vectors(
+        capi.KINDS[kind], P, nc, nd, m.x, m.xdofmap, V.dofmap, m.facets.shape[0], m.facets, c0, rho0,
+        _opt(delta), capi.optional(src), capi.optional(dsrc), capi.optional(absb),
+        capi.optional(bmass)) == 0
+    Nd = (P + 1) ** 3
+    dmf, dJf = np.ascontiguousarray(V.dofmap.reshape(-1)), np.ascontiguousarray(dJ.reshape(-1))
+    mvec = np.zeros(nd)
+    emu.emu_mass(np.ones(nd), mvec, dmf, dJf, 1.0 / rho0 / c0 ** 2, nc * Nd, Nd)
+    mvec += bmass
+    dnl = None
+    if west:
+        dnl = np.zeros(nd)
+        emu.emu_mass(np.ones(nd), dnl, dmf, dJf, 2.0 * beta / rho0 ** 2 / c0 ** 4, nc * Nd, Nd)
+    lin = -1.0 / rho0
+    att = (-delta / rho0 / c0 ** 2) if west else None
+    bidx = np.flatnonzero((src != 0) | (dsrc != 0) | (absb != 0)).astype(np.int32)
+    bs, bd, ba = src[bidx].copy(), dsrc[bidx].copy(), absb[bidx].copy()
+    # ---- the time loop as fus_model_rk4 / issue_step issue it
+    st = dict(u0=u0.copy(), v0=v0.copy(), ua=np.zeros(nd), va=np.zeros(nd), un=np.zeros(nd),
+              vn=np.zeros(nd))
+    b = np.zeros(nd)
+    a_r, b_r = (0.0, 0.5, 0.5, 1.0), (1 / 6, 1 / 3, 1 / 3, 1 / 6)
+    t, dt_full = 0.0, dt
+    while t < tf:                          # Linear.hpp:270-298, as fus_model_rk4 tabulates it
+        dt = min(dt_full, tf - t)
+        for i in range(4):
+            u_in = st["u0"] if i == 0 else st["un"]
+            v_in = st["v0"] if i == 0 else st["vn"]
+            tn = t + a_r[i] * dt
+            win = 0.5 * (1 - np.cos(f0 * np.pi * tn / 4.0)) if tn < 4.0 / f0 else 1.0
+            dwin = 0.5 * np.pi * f0 / 4.0 * np.sin(f0 * np.pi * tn / 4.0) if tn < 4.0 / f0 else 0.0
+            w0 = 2 * np.pi * f0
+            kappa = 2.0 if west else 1.0
+            g = kappa * win * p0 * w0 / s0 * np.cos(w0 * tn)
+            dg = (kappa * (dwin * p0 * w0 / s0 * np.cos(w0 * tn) - win * p0 * w0 * w0 / s0 * np.sin(w0 * tn))
+                  if west else 0.0)
+            emu.emu_stiffness(P + 1, 0, 0, u_in, _opt(v_in) if west else None, b, V.dofmap, _opt(G),
+                              None, lin, _opt(att), nc, dphi, pts, wts, 2, 0, nc)
+            emu.emu_boundary(b, v_in, bidx, bs, bd, ba, bidx.size, g, dg)
+            emu.emu_rk4_stage(i, int(west), b, mvec, _opt(dnl), st["u0"], st["v0"], st["ua"],
+                              st["va"], st["un"], st["vn"], nd, nd,
+                              a_r[i + 1] * dt if i < 3 else 0.0, b_r[i] * dt)
+        t += dt
+    assert rel_l2(st["u0"], u_ref) < 1e-12 and rel_l2(st["v0"], v_ref) < 1e-12
