@@ -221,8 +221,8 @@ def child_extras(timeout_s=120.0):
     workload per geometry mode.  A child so that nothing it does -- a fault in a newer kernel, a
     time-out -- can cost the headline line."""
     cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_sweep.py"), "--degrees",
-           "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,1,2", "--rk4-geometry-modes",
-           "0,1,2", "--models", "", "--repeats", "20", "--fp32"]
+           "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,1,2,3", "--rk4-geometry-modes",
+           "0,1,2,3", "--models", "", "--repeats", "20", "--fp32"]
     env = dict(os.environ)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -254,7 +254,8 @@ def child_extras(timeout_s=120.0):
                                                 if r.get("config") == "degree_sweep_fp32"],
            "note": ("geometry_mode 0 streams the reference's G (48 B/point; the roofline's bytes), "
                     "1 keeps one Ghat per affine cell (the box qualifies), "
-                    "2 rebuilds G per point from the trilinear cell map (192 B/cell); "
+                    "2 rebuilds G per point from the trilinear cell map (192 B/cell), 3 is the same "
+                    "kernel compiled under a 128-register cap (occupancy experiment); "
                     "frac_of_measured_peak always uses the streamed algorithmic bytes")}
     if rc != 0:
         res["stderr_tail"] = err
@@ -310,7 +311,8 @@ def run_gpu_arm(args):
     if args.geometry_mode and not args.lean:
         ctx.set_option("geometry_mode", args.geometry_mode)
     geometry = {0: "G streamed, 48 B/point (the reference's data)",
-                1: "affine cells: Ghat per cell", 2: "rebuilt per point from the trilinear cell map"
+                1: "affine cells: Ghat per cell", 2: "rebuilt per point from the trilinear cell map",
+                3: "rebuilt per point from the trilinear cell map (128-register build)"
                 }[ctx.get_option("geometry_compressed")] + (" (lean context: no G/detJ stored)"
                                                             if args.lean else "")
     gmode_used = ctx.get_option("geometry_compressed")
@@ -542,7 +544,7 @@ def main():
                     "2x2x1, 2x2x2); our own scaling studies only")
     ap.add_argument("--model", default="linear", choices=["linear", "lossy", "westervelt"],
                     help="lossy / westervelt: BASELINE configs 3-4 style runs (not the headline)")
-    ap.add_argument("--geometry-mode", type=int, default=0, choices=[0, 1, 2],
+    ap.add_argument("--geometry-mode", type=int, default=0, choices=[0, 1, 2, 3],
                     help="1/2: compressed geometric factors (not the headline: see DESIGN.md)")
     ap.add_argument("--lean", action="store_true",
                     help="context without G/detJ on the device (geometry rebuilt on the fly)")

@@ -268,6 +268,13 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     return launch(stiffness_line_kernel<N, false, 2>, stiffness_line_kernel<N, true, 2>,
                   L::THREADS, L::SMEM_BYTES, L::CPB, cfg);
   }
+  if (c->geom_active == 3) { // same, compiled under a 128-register cap (occupancy experiment)
+    using L = LineCfg<N>;
+    static KernelCfg cfg;
+    Gptr = reinterpret_cast<const double2*>(c->d_tri);
+    return launch(stiffness_line_kernel<N, false, 3>, stiffness_line_kernel<N, true, 3>,
+                  L::THREADS, L::SMEM_BYTES, L::CPB, cfg);
+  }
   if (variant == 2) {
     using L = LineCfg<N>;
     static KernelCfg cfg;
@@ -324,7 +331,7 @@ int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double
     set_error("unsupported degree P=%d", c->P);
     return FUS_ERR_UNSUPPORTED;
   }
-  if (!c->d_G2 && c->geom_active != 2) {
+  if (!c->d_G2 && c->geom_active < 2) {
     set_error("context was created without G: stiffness operator unavailable");
     return FUS_ERR_STATE;
   }
@@ -931,7 +938,7 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
       set_error("geometry_mode applies to hexahedral contexts only");
       return FUS_ERR_UNSUPPORTED;
     }
-    if (c->lean && value != 2) {
+    if (c->lean && value != 2 && value != 3) {
       set_error("a lean context holds no G: geometry_mode is fixed at 2");
       return FUS_ERR_STATE;
     }
@@ -939,17 +946,17 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
       c->geom_active = 0;
       return FUS_OK;
     }
-    if (value == 2) {
+    if (value == 2 || value == 3) { // 3: mode 2 under a 128-register cap (occupancy experiment)
       if (!c->d_tri) {
         set_error("geometry_mode 2 needs the cell vertices: create the context with "
                   "fus_ctx_create_from_mesh");
         return FUS_ERR_STATE;
       }
-      c->geom_active = 2;
+      c->geom_active = value;
       return FUS_OK;
     }
     if (value != 1) {
-      set_error("geometry_mode must be 0, 1 or 2");
+      set_error("geometry_mode must be 0, 1, 2 (or 3, the occupancy experiment of mode 2)");
       return FUS_ERR_ARG;
     }
     if (!c->d_G2)

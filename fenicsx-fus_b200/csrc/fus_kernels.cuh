@@ -361,8 +361,12 @@ struct LineCfg {
 //                per CELL, fus_trilinear.hpp) and |det J| w K K^T f is evaluated per point from
 //                them: exact for every mesh with a degree-1 coordinate element, 192 B per cell
 //                instead of 48 B per point, ~45 more FP64 operations per point.
+//   3  the same code as 2 compiled under a 128-register cap (4 blocks/SM for P <= 4 instead of 3:
+//                16 warps/SM at the price of a few spilled values) -- an occupancy experiment that
+//                bench.py's child sweep measures next to mode 2.
 template <int N, bool FUSE2, int GEOM = 0, typename T = double>
-__global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3 : 0)
+__global__ void __launch_bounds__(LineCfg<N>::THREADS,
+                                  (GEOM == 2 && N <= 5) ? 3 : ((GEOM == 3 && N <= 5) ? 4 : 0))
     stiffness_line_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                           const int32_t* __restrict__ dofmap,
                           const typename Vec2<T>::type* __restrict__ G2,
@@ -371,13 +375,13 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS, (GEOM == 2 && N <= 5) ? 3
                           const __grid_constant__ DMatT<T, N> D) {
   using C = LineCfg<N>;
   using V2 = typename Vec2<T>::type;
-  static_assert(GEOM != 2 || sizeof(T) == sizeof(double),
+  static_assert(GEOM < 2 || sizeof(T) == sizeof(double),
                 "the trilinear cell map is evaluated in FP64 only");
   constexpr int NN = C::NN, GPF = C::GPF;
-  constexpr bool AFFINE = (GEOM == 1), TRI = (GEOM == 2);
+  constexpr bool AFFINE = (GEOM == 1), TRI = (GEOM == 2 || GEOM == 3);
   constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
-  static_assert(GEOM >= 0 && GEOM <= 2, "unknown geometry mode");
+  static_assert(GEOM >= 0 && GEOM <= 3, "unknown geometry mode");
 #ifdef FUS_HOST_EMULATION
   T* smem = reinterpret_cast<T*>(fus_emu::dynamic_shared());
 #else

@@ -149,7 +149,8 @@ int fus_ctx_set_option(fus_ctx* ctx, const char* name, int value);
    (off by default; falls back to streaming when any cell is not affine).
    "geometry_mode" 2 rebuilds |det J| w K K^T at every point from the trilinear cell map (192 B per
    cell, fus_trilinear_coeffs): valid for any mesh with a degree-1 coordinate element, needs a
-   context made by fus_ctx_create_from_mesh (FUS_ERR_STATE otherwise).
+   context made by fus_ctx_create_from_mesh (FUS_ERR_STATE otherwise).  Value 3 selects the same
+   kernel compiled under a 128-register cap: an occupancy experiment, same results.
    fus_ctx_get_option reads back "geometry_compressed" (the mode in use: 0, 1 or 2),
    "stiffness_variant", "halo_mode". */
 int fus_ctx_get_option(fus_ctx* ctx, const char* name, int* value);

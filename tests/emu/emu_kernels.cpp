@@ -78,8 +78,10 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
     fuse ? run(stiffness_line_kernel<N, true, 0>) : run(stiffness_line_kernel<N, false, 0>);
   else if (geom == 1)
     fuse ? run(stiffness_line_kernel<N, true, 1>) : run(stiffness_line_kernel<N, false, 1>);
-  else
+  else if (geom == 2)
     fuse ? run(stiffness_line_kernel<N, true, 2>) : run(stiffness_line_kernel<N, false, 2>);
+  else
+    fuse ? run(stiffness_line_kernel<N, true, 3>) : run(stiffness_line_kernel<N, false, 3>);
   return 0;
 }
 

@@ -294,15 +294,15 @@ def test_child_sweep_script_control_flow_with_a_stub_device(monkeypatch, capsys)
     monkeypatch.setattr(fus, "StiffnessSpectral3D", Op)
     monkeypatch.setattr(fus, "LinearSpectral3D", Model)
     monkeypatch.setattr(sys, "argv", ["bench_sweep.py", "--degrees", "2,3,4,5,6,7", "--variants=-1",
-                                      "--geometry-modes", "0,1,2", "--rk4-geometry-modes", "0,1,2",
-                                      "--models", "", "--repeats", "2", "--fp32"])
+                                      "--geometry-modes", "0,1,2,3", "--rk4-geometry-modes",
+                                      "0,1,2,3", "--models", "", "--repeats", "2", "--fp32"])
     sweep.main()
     rows = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     deg = [r for r in rows if r["config"] == "degree_sweep"]
     rk = [r for r in rows if r["config"] == "headline_rk4_by_geometry_mode"]
     assert sorted((r["P"], r["geometry_mode"]) for r in deg) == [(P, g) for P in range(2, 8)
-                                                                 for g in (0, 1, 2)]
-    assert [r["geometry_mode"] for r in rk] == [0, 1, 2] and all(r["steps"] == 20 for r in rk)
+                                                                 for g in (0, 1, 2, 3)]
+    assert [r["geometry_mode"] for r in rk] == [0, 1, 2, 3] and all(r["steps"] == 20 for r in rk)
     assert all({"ms_min", "gdof_per_s", "frac_of_measured_peak"} <= set(r) for r in deg)
     f32 = [r for r in rows if r["config"] == "degree_sweep_fp32"]
     assert [r["P"] for r in f32] == list(range(2, 8)) and all("rel_l2_vs_fp64" in r for r in f32)

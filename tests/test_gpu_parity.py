@@ -485,7 +485,7 @@ def test_trilinear_geometry_rk4_and_errors(fus, orc, gpu):
         ca.set_option("geometry_mode", 2)
     assert ca.get_option("geometry_compressed") == 0
     with pytest.raises(fus.FusError):
-        ca.set_option("geometry_mode", 3)
+        ca.set_option("geometry_mode", 7)
 
 
 @pytest.mark.parametrize("kind,P", [("linear", 3), ("lossy", 4), ("westervelt", 2), ("linear", 5)])

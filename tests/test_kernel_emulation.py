@@ -137,9 +137,9 @@ def test_emulated_compressed_geometry_kernels(fus, orc, emu, P):
                                        wts) == 0
     assert np.array_equal(co, co_ref)                             # same helper, same arithmetic
     assert rel_l2(ym, orc.mass_apply(P, V.dofmap, dJ, c1, x, np.zeros(nd))) < 1e-12
-    for fuse in (False, True):
+    for fuse, mode in ((False, 2), (True, 2), (False, 3)):   # 3: the same code under a register cap
         y = np.zeros(nd)
-        emu.emu_stiffness(P + 1, 2, 2, x, _opt(x2) if fuse else None, y, V.dofmap, None, _opt(co),
+        emu.emu_stiffness(P + 1, 2, mode, x, _opt(x2) if fuse else None, y, V.dofmap, None, _opt(co),
                           c1, _opt(c2) if fuse else None, nc, dphi, pts, wts, 2, 0, nc)
         yo = orc.stiffness_apply(P, V.dofmap, G, dphi, c1, x, np.zeros(nd))
         if fuse:
