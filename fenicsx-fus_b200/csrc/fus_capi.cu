@@ -1758,6 +1758,13 @@ int fus_halo_setup(fus_ctx* c, int rank, int nranks, const void* uid, int nneigh
   return rc;
 }
 
+int fus_halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout4) {
+  if (nsend < 0 || nrecv < 0 || nneigh < 0 || !layout4)
+    return FUS_ERR_ARG;
+  halo_mailbox_layout(nsend, nrecv, nneigh, layout4);
+  return FUS_OK;
+}
+
 int fus_halo_peer_export(fus_ctx* c, void* ipc_handle64, int64_t* layout3) {
   if (!c || !c->halo) {
     set_error("fus_halo_peer_export: call fus_halo_setup first");

@@ -5,6 +5,7 @@
 // libnccl.so.2 already loaded in the process (torch's) or found by the loader, so that the
 // single-GPU path has no NCCL dependency.
 #include "fus_halo.hpp"
+#include "fus_halo_kernels.cuh"
 #include "fus_internal.hpp"
 
 #include <dlfcn.h>
@@ -167,14 +168,6 @@ struct Halo {
                                              // so that a captured CUDA graph can replay the step
 };
 
-constexpr int kMaxNeigh = 26;
-struct PeerTable {
-  double* fwd_dst[kMaxNeigh];               // where my packed owner values go on neighbour k
-  double* rev_dst[kMaxNeigh];               // where my ghost partial sums go on neighbour k
-  unsigned long long* fwd_flag[kMaxNeigh];  // flag on neighbour k that I raise after a forward put
-  unsigned long long* rev_flag[kMaxNeigh];
-};
-
 int halo_unique_id(void* id128) {
   if (!id128)
     return FUS_ERR_ARG;
@@ -321,48 +314,6 @@ static int exchange(Halo* h, bool fwd, int nv, cudaStream_t st) {
   return FUS_OK;
 }
 
-// pack/unpack with the per-neighbour [vector][entry] interleave
-__global__ void __launch_bounds__(256)
-    halo_pack_kernel(const double* __restrict__ a, const double* __restrict__ b,
-                     const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
-                     double* __restrict__ buf, long long n, int nv) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  int k = 0;
-  while (k + 1 < nneigh && i >= off[k + 1])
-    ++k;
-  const long long base = nv * off[k], len = off[k + 1] - off[k], j = i - off[k];
-  const int d = idx[i];
-  buf[base + j] = a[d];
-  if (nv == 2)
-    buf[base + len + j] = b[d];
-}
-
-template <bool ADD>
-__global__ void __launch_bounds__(256)
-    halo_unpack_kernel(double* __restrict__ a, double* __restrict__ b,
-                       const int32_t* __restrict__ idx, const int64_t* __restrict__ off,
-                       int nneigh, const double* __restrict__ buf, long long n, int nv) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  int k = 0;
-  while (k + 1 < nneigh && i >= off[k + 1])
-    ++k;
-  const long long base = nv * off[k], len = off[k + 1] - off[k], j = i - off[k];
-  const int d = idx[i];
-  if (ADD) {
-    atomicAdd(a + d, buf[base + j]); // an owned dof may be a ghost on several neighbours
-    if (nv == 2)
-      atomicAdd(b + d, buf[base + len + j]);
-  } else {
-    a[d] = buf[base + j];
-    if (nv == 2)
-      b[d] = buf[base + len + j];
-  }
-}
-
 namespace {
 // device copies of the per-neighbour offset tables (owned by the Halo, made in halo_create)
 struct OffTables {
@@ -401,91 +352,6 @@ int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
 // stage s+1 before it has received the reverse message of stage s, which the ghost side only
 // sends after it has unpacked the forward message of stage s (and symmetrically).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void __launch_bounds__(256)
-    peer_put_kernel(const double* __restrict__ a, const double* __restrict__ b,
-                    const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
-                    long long n, int nv, const PeerTable* __restrict__ tab, int forward,
-                    unsigned int* counter, unsigned long long* epoch_ctr, int lightfence) {
-  // every block reads the counter before it can be advanced: the last block only advances it
-  // after all blocks have passed their atomicAdd below
-  const unsigned long long epoch = *(volatile unsigned long long*)epoch_ctr + 1ull;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    int k = 0;
-    while (k + 1 < nneigh && i >= off[k + 1])
-      ++k;
-    const long long len = off[k + 1] - off[k], j = i - off[k];
-    double* dst = forward ? tab->fwd_dst[k] : tab->rev_dst[k];
-    const int d = idx[i];
-    dst[j] = a[d];
-    if (nv == 2)
-      dst[len + j] = b[d];
-  }
-  if (!lightfence)
-    __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (lightfence)
-      __threadfence_system(); // cumulative over the block's stores ordered by the barrier
-    const unsigned int prev = atomicAdd(counter, 1u);
-    if (prev == gridDim.x - 1) { // every block's stores are fenced before its increment
-      *counter = 0;
-      *epoch_ctr = epoch;
-      __threadfence_system();
-      for (int k = 0; k < nneigh; ++k)
-        if (off[k + 1] > off[k])
-          st_release_sys(forward ? tab->fwd_flag[k] : tab->rev_flag[k], epoch);
-    }
-  }
-}
-
-template <bool ADD>
-__global__ void __launch_bounds__(256)
-    peer_wait_kernel(double* __restrict__ a, double* __restrict__ b,
-                     const int32_t* __restrict__ idx, const int64_t* __restrict__ off, int nneigh,
-                     long long n, int nv, const double* mbox_data,
-                     const unsigned long long* flags, const unsigned long long* epoch_ctr,
-                     int* error) {
-  // the local put of this exchange is ordered before this kernel and has advanced the counter
-  const unsigned long long epoch = *(volatile const unsigned long long*)epoch_ctr;
-  if (threadIdx.x < nneigh && off[threadIdx.x + 1] > off[threadIdx.x]) {
-    const long long t0 = clock64();
-    while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
-      if (clock64() - t0 > 4000000000ll) { // ~2 s: a peer died; report instead of hanging the GPU
-        atomicExch(error, 1);
-        break;
-      }
-      __nanosleep(100);
-    }
-  }
-  __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n)
-    return;
-  int k = 0;
-  while (k + 1 < nneigh && i >= off[k + 1])
-    ++k;
-  const long long base = nv * off[k], len = off[k + 1] - off[k], j = i - off[k];
-  const int d = idx[i];
-  const double va = __ldcg(mbox_data + base + j); // written by a peer: never trust L1
-  if (ADD) {
-    atomicAdd(a + d, va);
-  } else {
-    a[d] = va;
-    if (nv == 2)
-      b[d] = __ldcg(mbox_data + base + len + j);
-  }
-}
-
 static int peer_put(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
   if (fwd && !b) {
     set_error("peer transport: the forward update always carries two vectors");
@@ -525,6 +391,16 @@ static int peer_wait(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
   return FUS_OK;
 }
 
+// mailbox = [fwd data: 2*nrecv doubles][rev data: nsend doubles][fwd flags][rev flags];
+// layout4 = byte offsets {reverse data, forward flags, reverse flags, total size}
+void halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout4) {
+  const int64_t nn = std::max(1, nneigh);
+  layout4[0] = (int64_t)sizeof(double) * 2 * std::max<int64_t>(1, nrecv);
+  layout4[1] = layout4[0] + (int64_t)sizeof(double) * std::max<int64_t>(1, nsend);
+  layout4[2] = layout4[1] + (int64_t)sizeof(unsigned long long) * nn;
+  layout4[3] = layout4[2] + (int64_t)sizeof(unsigned long long) * nn;
+}
+
 int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3) {
   if (!h || !ipc_handle64 || !layout3)
     return FUS_ERR_ARG;
@@ -535,11 +411,12 @@ int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   FUS_CUDA_H(cudaSetDevice(h->device));
   if (!h->d_mbox) {
-    const size_t nn = std::max<size_t>(1, h->neigh.size());
-    h->off_rev = sizeof(double) * 2 * (size_t)std::max<int64_t>(1, h->nrecv);
-    h->off_fflag = h->off_rev + sizeof(double) * (size_t)std::max<int64_t>(1, h->nsend);
-    h->off_rflag = h->off_fflag + sizeof(unsigned long long) * nn;
-    h->mbox_bytes = h->off_rflag + sizeof(unsigned long long) * nn;
+    int64_t lay[4];
+    halo_mailbox_layout(h->nsend, h->nrecv, (int)h->neigh.size(), lay);
+    h->off_rev = (size_t)lay[0];
+    h->off_fflag = (size_t)lay[1];
+    h->off_rflag = (size_t)lay[2];
+    h->mbox_bytes = (size_t)lay[3];
     FUS_CUDA_H(cudaMalloc(&h->d_mbox, h->mbox_bytes));
     FUS_CUDA_H(cudaMemset(h->d_mbox, 0, h->mbox_bytes));
     FUS_CUDA_H(cudaMalloc(&h->d_counter, 2 * sizeof(unsigned int)));

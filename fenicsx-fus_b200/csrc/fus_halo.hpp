@@ -29,6 +29,8 @@ int halo_forward_end(Halo* h, double* a, double* b, cudaStream_t st);
 int halo_overlap(const Halo* h);
 // modes: 0 NCCL in stream order, 1 NCCL on a side stream (overlapped), 2 peer-direct one-sided puts
 int halo_mode(const Halo* h);
+// byte layout of a rank's mailbox (host arithmetic only)
+void halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout4);
 // peer-direct transport: export this rank's mailbox, then connect to the neighbours' mailboxes
 int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3);
 int halo_peer_connect(Halo* h, const void* handles, const int64_t* byte_off);

@@ -27,6 +27,15 @@ def _split(n, parts, r):
     return start, start + base + (1 if r < rem else 0)
 
 
+def peer_byte_offsets(q_neigh, q_soff, q_roff, q_layout, my_rank):
+    """Where this rank's messages go inside neighbour q's mailbox (bytes): {forward data, forward
+    flag, reverse data, reverse flag}, from q's neighbour list, offset tables and mailbox layout
+    {off_rev, off_fflag, off_rflag} (fus_halo_peer_connect in include/fus_b200.h)."""
+    j = list(q_neigh).index(my_rank)
+    off_rev, off_fflag, off_rflag = (int(v) for v in q_layout[:3])
+    return (8 * 2 * int(q_roff[j]), off_fflag + 8 * j, off_rev + 8 * int(q_soff[j]), off_rflag + 8 * j)
+
+
 class _PartitionBase:
     """What the operator / model / halo layers need from a partition of any mesh:
     x, xdofmap, dofmap (local numbering, owned first), ndofs, nowned, ncells, facets, P, N, rank,
@@ -102,11 +111,9 @@ class _PartitionBase:
         boff = np.zeros((max(nn, 1), 4), dtype=np.int64)
         for k, q in enumerate(self.neigh):
             info = allinfo[q]
-            j = info["neigh"].index(self.rank)
-            off_rev, off_fflag, off_rflag = info["layout"]
             handles[k] = np.frombuffer(info["handle"], dtype=np.uint8)
-            boff[k] = (8 * 2 * info["roff"][j], off_fflag + 8 * j,
-                       off_rev + 8 * info["soff"][j], off_rflag + 8 * j)
+            boff[k] = peer_byte_offsets(info["neigh"], info["soff"], info["roff"], info["layout"],
+                                        self.rank)
         rc = lib.fus_halo_peer_connect(ctx.h, p(handles), p(boff))
         flags = [None] * self.nranks
         dist.all_gather_object(flags, rc == 0)

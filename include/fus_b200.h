@@ -275,6 +275,10 @@ int fus_halo_setup(fus_ctx* ctx, int rank, int nranks, const void* nccl_unique_i
  *   {8*2*recv_off_q[j], off_fflag_q + 8*j, off_rev_q + 8*send_off_q[j], off_rflag_q + 8*j}
  * where j is this rank's position in q's neighbour list. */
 int fus_halo_peer_export(fus_ctx* ctx, void* ipc_handle64, int64_t* layout3);
+/* Byte layout of a rank's mailbox for given list sizes (host arithmetic, no device): layout4 =
+ * {off_rev, off_fflag, off_rflag, total bytes}; the first three are what fus_halo_peer_export
+ * reports. */
+int fus_halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout4);
 int fus_halo_peer_connect(fus_ctx* ctx, const void* handles, const int64_t* byte_off);
 
 /* Partition of the structured box over a pgrid[0] x pgrid[1] x pgrid[2] process grid for rank

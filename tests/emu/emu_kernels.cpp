@@ -4,6 +4,7 @@
 // the grid is capped low so that the grid-stride loops and their tails are exercised.
 #include "simt_emu.hpp"
 
+#include "fus_halo_kernels.cuh"
 #include "fus_kernels.cuh"
 
 using namespace fus;
@@ -273,6 +274,56 @@ int emu_boundary(double* b, const double* v, const int32_t* bidx, const double* 
                  const double* bdsrc, const double* babs, long long nb, double g, double dg) {
   fus_emu::launch((unsigned)((nb + 255) / 256), 256, 0, [&] {
     boundary_kernel(b, v, bidx, bsrc, bdsrc, babs, nb, g, dg, nullptr, nullptr, 0);
+  });
+  return 0;
+}
+
+// ---- halo kernels (fus_halo_kernels.cuh) ----------------------------------------------------------
+// NCCL transport: pack the interface values of one or two vectors / unpack (insert or add)
+int emu_halo_pack(const double* a, const double* b, const int32_t* idx, const int64_t* off,
+                  int nneigh, double* buf, long long n, int nv) {
+  fus_emu::launch((unsigned)((n + 255) / 256), 256, 0,
+                  [&] { halo_pack_kernel(a, b, idx, off, nneigh, buf, n, nv); });
+  return 0;
+}
+int emu_halo_unpack(int add, double* a, double* b, const int32_t* idx, const int64_t* off,
+                    int nneigh, const double* buf, long long n, int nv) {
+  fus_emu::launch((unsigned)((n + 255) / 256), 256, 0, [&] {
+    if (add)
+      halo_unpack_kernel<true>(a, b, idx, off, nneigh, buf, n, nv);
+    else
+      halo_unpack_kernel<false>(a, b, idx, off, nneigh, buf, n, nv);
+  });
+  return 0;
+}
+
+// peer-direct transport: one rank's put into its neighbours' mailboxes (dst[4*k..] = addresses of
+// {forward data, forward flag, reverse data, reverse flag} inside neighbour k's mailbox), and one
+// rank's wait + unpack from its own mailbox
+int emu_peer_put(const double* a, const double* b, const int32_t* idx, const int64_t* off,
+                 int nneigh, long long n, int nv, const unsigned long long* dst, int forward,
+                 unsigned* counter, unsigned long long* epoch_ctr, int lightfence) {
+  PeerTable tab;
+  std::memset(&tab, 0, sizeof(tab));
+  for (int k = 0; k < nneigh; ++k) {
+    tab.fwd_dst[k] = reinterpret_cast<double*>(dst[4 * k + 0]);
+    tab.fwd_flag[k] = reinterpret_cast<unsigned long long*>(dst[4 * k + 1]);
+    tab.rev_dst[k] = reinterpret_cast<double*>(dst[4 * k + 2]);
+    tab.rev_flag[k] = reinterpret_cast<unsigned long long*>(dst[4 * k + 3]);
+  }
+  fus_emu::launch((unsigned)std::max<long long>(1, (n + 255) / 256), 256, 0, [&] {
+    peer_put_kernel(a, b, idx, off, nneigh, n, nv, &tab, forward, counter, epoch_ctr, lightfence);
+  });
+  return 0;
+}
+int emu_peer_wait(int add, double* a, double* b, const int32_t* idx, const int64_t* off, int nneigh,
+                  long long n, int nv, const double* mbox_data, const unsigned long long* flags,
+                  const unsigned long long* epoch_ctr, int* error) {
+  fus_emu::launch((unsigned)((n + 255) / 256), 256, 0, [&] {
+    if (add)
+      peer_wait_kernel<true>(a, b, idx, off, nneigh, n, nv, mbox_data, flags, epoch_ctr, error);
+    else
+      peer_wait_kernel<false>(a, b, idx, off, nneigh, n, nv, mbox_data, flags, epoch_ctr, error);
   });
   return 0;
 }

@@ -132,6 +132,19 @@ inline T __ldg(const T* p) {
 inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v); }
 inline int atomicExch(int* p, int v) { return std::atomic_ref<int>(*p).exchange(v); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_add(v); }
+// device-only intrinsics of the halo kernels
+inline long long clock64() {
+  return std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch())
+      .count();
+}
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+template <typename T>
+inline T __ldcg(const T* p) {
+  return *p;
+}
 using std::fabs;
 using std::fma;
 using std::fmax;

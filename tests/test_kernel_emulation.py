@@ -26,7 +26,8 @@ def _opt(a):
 def emu():
     lib = os.path.join(EMU_DIR, "libfus_emu.so")
     deps = [os.path.join(EMU_DIR, f) for f in ("emu_kernels.cpp", "simt_emu.hpp")] + [
-        os.path.join(ROOT, "fenicsx-fus_b200", "csrc", f) for f in ("fus_kernels.cuh", "fus_trilinear.hpp")]
+        os.path.join(ROOT, "fenicsx-fus_b200", "csrc", f)
+        for f in ("fus_kernels.cuh", "fus_trilinear.hpp", "fus_halo_kernels.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC",
                         "-I" + os.path.join(ROOT, "include"),
@@ -43,6 +44,12 @@ def emu():
     f32 = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
     L.emu_operators_f32.argtypes = [_int, f32, f32, f32, _i32, _f64, _f64, f32, _ll, _f64, _f64, _f64,
                                     _int]
+    u64 = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+    i64 = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+    L.emu_halo_pack.argtypes = [_f64, _p, _i32, i64, _int, _f64, _ll, _int]
+    L.emu_halo_unpack.argtypes = [_int, _f64, _p, _i32, i64, _int, _f64, _ll, _int]
+    L.emu_peer_put.argtypes = [_f64, _p, _i32, i64, _int, _ll, _int, u64, _int, _p, _p, _int]
+    L.emu_peer_wait.argtypes = [_int, _f64, _p, _i32, i64, _int, _ll, _int, _p, _p, _p, _p]
     L.emu_geometry.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64, _f64, C.POINTER(_int)]
     L.emu_geometry_quad.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64]
     L.emu_rk4_stage.argtypes = [_int, _int, _f64, _f64, _p, _f64, _f64, _f64, _f64, _f64, _f64, _ll,
@@ -407,3 +414,121 @@ def test_emulated_fused_rk4_step_vs_reference_flow(fus, orc, emu, kind):
                               a_r[i + 1] * dt if i < 3 else 0.0, b_r[i] * dt)
         t += dt
     assert rel_l2(st["u0"], u_ref) < 1e-12 and rel_l2(st["v0"], v_ref) < 1e-12
+
+
+class _EmuRank:
+    """One rank of an emulated peer-direct halo: its partition, its mailbox (laid out by
+    fus_halo_mailbox_layout, the function halo_peer_export uses) and its device-side counters."""
+
+    def __init__(self, part):
+        from fenicsx_fus_b200 import capi
+        self.p = part
+        self.neigh, self.soff, self.sidx, self.roff, self.ridx = part.halo_arrays()
+        self.nsend, self.nrecv = int(self.sidx.size), int(self.ridx.size)
+        self.layout = np.zeros(4, dtype=np.int64)
+        assert capi.load().fus_halo_mailbox_layout(self.nsend, self.nrecv, len(self.neigh),
+                                                   self.layout) == 0
+        self.mbox = np.zeros(int(self.layout[3]) // 8 + 1, dtype=np.uint64)      # 8-byte aligned
+        self.counter = np.zeros(2, dtype=np.uint32)
+        self.epoch = np.zeros(2, dtype=np.uint64)
+        self.error = np.zeros(1, dtype=np.int32)
+
+    def connect(self, ranks):
+        from fenicsx_fus_b200.partition import peer_byte_offsets
+        self.dst = np.zeros(4 * max(1, len(self.neigh)), dtype=np.uint64)
+        for k, q in enumerate(self.neigh):
+            o = ranks[int(q)]
+            offs = peer_byte_offsets(o.neigh, o.soff, o.roff, o.layout, self.p.rank)
+            assert all(0 <= b < o.layout[3] for b in offs)
+            self.dst[4 * k:4 * k + 4] = [o.mbox.ctypes.data + b for b in offs]
+
+    def put(self, emu, fwd, a, b, lightfence=0):
+        idx, off = (self.sidx, self.soff) if fwd else (self.ridx, self.roff)
+        emu.emu_peer_put(a, _opt(b), idx if idx.size else np.zeros(1, np.int32), off, len(self.neigh),
+                         idx.size, 2 if fwd else 1, self.dst, int(fwd),
+                         self.counter[0 if fwd else 1:].ctypes.data_as(_p),
+                         self.epoch[0 if fwd else 1:].ctypes.data_as(_p), lightfence)
+
+    def wait(self, emu, fwd, a, b):
+        idx, off = (self.ridx, self.roff) if fwd else (self.sidx, self.soff)
+        if not idx.size:
+            return
+        base = self.mbox.ctypes.data
+        emu.emu_peer_wait(0 if fwd else 1, a, _opt(b), idx, off, len(self.neigh), idx.size,
+                          2 if fwd else 1, C.c_void_p(base + (0 if fwd else int(self.layout[0]))),
+                          C.c_void_p(base + int(self.layout[1 if fwd else 2])),
+                          self.epoch[0 if fwd else 1:].ctypes.data_as(_p),
+                          self.error.ctypes.data_as(_p))
+        assert self.error[0] == 0
+
+
+@pytest.mark.parametrize("P,n,pg", [(2, (4, 3, 2), (2, 1, 1)), (2, (5, 2, 2), (3, 1, 1)),
+                                    (1, (4, 4, 2), (4, 1, 1)), (2, (3, 3, 2), (2, 2, 1)),
+                                    (1, (2, 2, 2), (2, 2, 2)), (1, (2, 3, 4), (1, 3, 2))])
+def test_emulated_peer_direct_halo_exchange(fus, emu, P, n, pg):
+    """peer_put_kernel / peer_wait_kernel (csrc/fus_halo_kernels.cuh) for every rank of a process
+    grid, with the partition lists of the native partitioner, the mailbox layout of
+    fus_halo_mailbox_layout and the byte offsets of partition.peer_byte_offsets -- the pieces the
+    multi-GPU runs connect over CUDA IPC.  Three stages of forward (owner -> ghost, two vectors)
+    and reverse (ghost -> owner, add) exchanges; slabs (a middle rank with two neighbours), 2x2
+    (edge neighbours) and 2x2x2 (corner neighbours) grids."""
+    from fenicsx_fus_b200.partition import BoxPartition
+    R = int(np.prod(pg))
+    ranks = [_EmuRank(BoxPartition(P, n, pg, r)) for r in range(R)]
+    for rk in ranks:
+        rk.connect(ranks)
+    for stage in range(3):
+        # forward: owners hold f(global id, stage), ghosts hold garbage
+        us, vs = [], []
+        for rk in ranks:
+            key = rk.p.global_key.astype(np.float64)
+            u, v = np.full(rk.p.ndofs, -7.0), np.full(rk.p.ndofs, -9.0)
+            u[:rk.p.nowned] = np.sin(key[:rk.p.nowned] + stage)
+            v[:rk.p.nowned] = 3.0 * key[:rk.p.nowned] - stage
+            us.append(u)
+            vs.append(v)
+        for rk, u, v in zip(ranks, us, vs):
+            rk.put(emu, True, u, v, lightfence=stage % 2)
+        for rk, u, v in zip(ranks, us, vs):
+            rk.wait(emu, True, u, v)
+            key = rk.p.global_key.astype(np.float64)
+            assert np.array_equal(u, np.sin(key + stage)) and np.array_equal(v, 3.0 * key - stage)
+        # reverse: every rank contributes 1 + rank to each of its dofs; owners end with the sum over
+        # all ranks that hold the dof
+        bs = [np.full(rk.p.ndofs, 1.0 + rk.p.rank) for rk in ranks]
+        for rk, b in zip(ranks, bs):
+            rk.put(emu, False, b, None)
+        for rk, b in zip(ranks, bs):
+            rk.wait(emu, False, b, None)
+        total = {}
+        for rk in ranks:
+            for k in rk.p.global_key:
+                total[int(k)] = total.get(int(k), 0.0) + 1.0 + rk.p.rank
+        for rk, b in zip(ranks, bs):
+            want = np.array([total[int(k)] for k in rk.p.global_key[:rk.p.nowned]])
+            assert np.array_equal(b[:rk.p.nowned], want)
+        assert all(int(rk.epoch[0]) == stage + 1 and int(rk.epoch[1]) == stage + 1 for rk in ranks)
+
+
+def test_emulated_nccl_pack_unpack(fus, emu):
+    """halo_pack_kernel / halo_unpack_kernel (NCCL transport): pack on the sender, a host copy in
+    place of ncclSend/ncclRecv, unpack (insert forward, add reverse) on the receiver."""
+    from fenicsx_fus_b200.partition import BoxPartition
+    P, n, pg = 2, (4, 3, 3), (2, 1, 1)
+    parts = [BoxPartition(P, n, pg, r) for r in range(2)]
+    arr = [p.halo_arrays() for p in parts]
+    u = [np.where(np.arange(p.ndofs) < p.nowned, np.cos(p.global_key.astype(float)), -5.0) for p in parts]
+    v = [np.where(np.arange(p.ndofs) < p.nowned, p.global_key.astype(float), -6.0) for p in parts]
+    bufs = []
+    for r in range(2):
+        neigh, soff, sidx, roff, ridx = arr[r]
+        buf = np.zeros(2 * max(1, sidx.size))
+        if sidx.size:
+            emu.emu_halo_pack(u[r], _opt(v[r]), sidx, soff, len(neigh), buf, sidx.size, 2)
+        bufs.append(buf)
+    for r in range(2):
+        neigh, soff, sidx, roff, ridx = arr[r]
+        if ridx.size:                                             # two ranks: one neighbour each
+            emu.emu_halo_unpack(0, u[r], _opt(v[r]), ridx, roff, len(neigh), bufs[1 - r], ridx.size, 2)
+        key = parts[r].global_key.astype(float)
+        assert np.array_equal(u[r], np.cos(key)) and np.array_equal(v[r], key)
