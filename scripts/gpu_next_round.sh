@@ -13,9 +13,6 @@ echo "== pytest -m gpu"
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $OUT/pytest_gpu_${TAG}.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/pytest_gpu_${TAG}.log
 tail -n 15 $OUT/pytest_gpu_${TAG}.log
-echo "== FP32 operator tests (first hardware run)"
-FUS_TEST_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k fp32 \
-    2>&1 | tail -n 8 | tee $OUT/pytest_fp32_${TAG}.log
 echo "== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 3 | tee $OUT/smoke_${TAG}.log
 echo "== bench"

@@ -9,8 +9,60 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_addoption(parser):
+    parser.addoption("--emulated-device", action="store_true", default=False,
+                     help="run the -m gpu tests against tests/emu/libfus_b200_emulated.so: the whole "
+                          "library built for the CPU on the SIMT emulator (host plumbing + kernel "
+                          "logic; no statement about the device).  Test infrastructure only.")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "emu_skip: too large or hardware-specific for --emulated-device")
+    if config.getoption("--emulated-device"):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "build_emulated_library", os.path.join(ROOT, "tests", "emu", "build_emulated_library.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        if mod.stale():
+            mod.build()
+        from fenicsx_fus_b200 import capi
+        capi.LIB_PATH, capi._lib = mod.LIB, None            # tests only: the product never does this
+        libdir = os.path.join(ROOT, "tests", "emu", "_gen", "lib")
+        os.makedirs(libdir, exist_ok=True)
+        link = os.path.join(libdir, "libfus_b200.so")
+        if os.path.lexists(link):
+            os.remove(link)
+        os.symlink(mod.LIB, link)
+        _EMU["libdir"] = libdir
+
+
+def pytest_collection_modifyitems(config, items):
+    if config.getoption("--emulated-device"):
+        skip = pytest.mark.skip(reason="not meaningful / too large on the emulated device")
+        for item in items:
+            if "emu_skip" in item.keywords:
+                item.add_marker(skip)
+
+
+_EMU = {"libdir": None}
+
+
+def exe_env():
+    """Environment for the example executables (examples/*): unchanged on a GPU box; with
+    --emulated-device a directory holding the emulated build under the product library's name is put
+    on LD_LIBRARY_PATH (searched before the executables' RUNPATH), so that they run on it."""
+    env = dict(os.environ)
+    if _EMU["libdir"]:
+        env["LD_LIBRARY_PATH"] = _EMU["libdir"] + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    return env
+
+
+@pytest.fixture(scope="session")
+def emulated(request):
+    """True when the -m gpu tests run against the emulated device (smaller workloads then)."""
+    return bool(request.config.getoption("--emulated-device"))
 
 
 @pytest.fixture(scope="session")
