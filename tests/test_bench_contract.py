@@ -307,3 +307,40 @@ def test_child_sweep_script_control_flow_with_a_stub_device(monkeypatch, capsys)
     f32 = [r for r in rows if r["config"] == "degree_sweep_fp32"]
     assert [r["P"] for r in f32] == list(range(2, 8)) and all("rel_l2_vs_fp64" in r for r in f32)
     assert all({"ms_per_step", "operator_ms", "rel_l2_vs_first_mode"} <= set(r) for r in rk)
+
+
+@pytest.mark.parametrize("extra", [[], ["--model", "westervelt", "--lean"]])
+def test_gpu_arm_on_the_emulated_device(extra):
+    """bench.py's GPU arm against the REAL library built for the CPU (tests/emu: every entry point,
+    the RK4 loop, per-kernel profiling, the affine extra) with only torch stubbed out -- a small box,
+    meaningless timings, but the actual call sequence the driver will run on the B200."""
+    code = (
+        "import os, sys, importlib.util, json\n"
+        f"ROOT = {ROOT!r}\n"
+        "sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))\n"
+        "spec = importlib.util.spec_from_file_location('bel', os.path.join(ROOT, 'tests', 'emu', "
+        "'build_emulated_library.py'))\n"
+        "bel = importlib.util.module_from_spec(spec); spec.loader.exec_module(bel)\n"
+        "if bel.stale(): bel.build()\n"
+        "from fenicsx_fus_b200 import capi\n"
+        "capi.LIB_PATH, capi._lib = bel.LIB, None\n"
+        "import test_bench_contract as tb\n"
+        "t, dist = tb._fake_torch()\n"
+        "sys.modules['torch'] = t; sys.modules['torch.distributed'] = dist\n"
+        "for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'): os.environ.pop(k, None)\n"
+        "spec = importlib.util.spec_from_file_location('bench_emu', os.path.join(ROOT, 'bench.py'))\n"
+        "bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)\n"
+        f"sys.argv = ['bench.py', '--steps', '3', '--warmup', '1', '--cells', '3'] + {extra!r}\n"
+        "sys.exit(bench.main())\n")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900,
+                         cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] > 0
+    assert d["roofline"]["launches"] == 12 and d["roofline"]["operator_applications"] == 12
+    if not extra:                               # headline geometry: the affine extra ran as well
+        assert "affine_compressed_geometry" in d["extras"]
+    if "--lean" in extra or "--geometry-mode" in extra:
+        assert d["roofline"]["kernel"].endswith(",2>")
