@@ -88,6 +88,7 @@ def main():
     ap.add_argument("--fp32", action="store_true",
                     help="also time the FP32 operator instantiation and report its error vs FP64")
     ap.add_argument("--numbering", type=int, default=1)
+    ap.add_argument("--rk4-cells", type=int, default=54, help="cells per direction of the RK4 runs")
     args = ap.parse_args()
     pk = peak()
     stream = torch.cuda.Stream()        # the legacy default stream cannot be graph-captured
@@ -140,7 +141,8 @@ def main():
         torch.cuda.empty_cache()
 
     # ---- models at P=4 on the 54^3 box ----------------------------------------------------
-    P, n, L = 4, 54, 0.12
+    P, n = 4, args.rk4_cells
+    L = 0.12 * n / 54.0                             # same cell size whatever the box
     h = L / n
     models = [s for s in args.models.split(",") if s]
     rk4_modes = [int(s) for s in args.rk4_geometry_modes.split(",") if s]

@@ -86,8 +86,18 @@ def _fake_torch():
     import numpy as np
 
     class T:
+        is_cuda = True                       # "device" tensors: the emulated device shares host memory
+
         def __init__(self, a):
-            self.a = np.asarray(a, dtype=np.float64)
+            a = np.asarray(a)
+            self.a = np.ascontiguousarray(a if a.dtype == np.float32 else a.astype(np.float64))
+
+        @property
+        def dtype(self):
+            return self.a.dtype
+
+        def data_ptr(self):
+            return self.a.ctypes.data
 
         def pin_memory(self):
             return self
@@ -103,9 +113,10 @@ def _fake_torch():
             return self
 
         def float(self):
-            return T(self.a)
+            return T(self.a.astype(np.float32))
 
-        double = float
+        def double(self):
+            return T(self.a.astype(np.float64))
 
         def __sub__(self, o):
             return T(self.a - o.a)
@@ -344,3 +355,42 @@ def test_gpu_arm_on_the_emulated_device(extra):
         assert "affine_compressed_geometry" in d["extras"]
     if "--lean" in extra or "--geometry-mode" in extra:
         assert d["roofline"]["kernel"].endswith(",2>")
+
+
+def test_child_sweep_script_on_the_emulated_device():
+    """scripts/bench_sweep.py (bench.py's child process) against the real library on the emulated
+    device, torch stubbed: degree sweep in every geometry mode, the RK4 runs per mode, and the FP32
+    operator sweep through the Python dispatch on float32 tensors -- tiny boxes."""
+    code = (
+        "import os, sys, importlib.util\n"
+        f"ROOT = {ROOT!r}\n"
+        "sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))\n"
+        "spec = importlib.util.spec_from_file_location('bel', os.path.join(ROOT, 'tests', 'emu', "
+        "'build_emulated_library.py'))\n"
+        "bel = importlib.util.module_from_spec(spec); spec.loader.exec_module(bel)\n"
+        "if bel.stale(): bel.build()\n"
+        "from fenicsx_fus_b200 import capi\n"
+        "capi.LIB_PATH, capi._lib = bel.LIB, None\n"
+        "import test_bench_contract as tb\n"
+        "t, dist = tb._fake_torch()\n"
+        "sys.modules['torch'] = t\n"
+        "spec = importlib.util.spec_from_file_location('sweep_emu', os.path.join(ROOT, 'scripts', "
+        "'bench_sweep.py'))\n"
+        "sweep = importlib.util.module_from_spec(spec); spec.loader.exec_module(sweep)\n"
+        "sweep.SWEEP = {P: 3 for P in range(2, 8)}\n"
+        "sys.argv = ['bench_sweep.py', '--degrees', '2,4,5', '--variants=-1', '--geometry-modes', "
+        "'0,1,2,3', '--rk4-geometry-modes', '0,1,2,3', '--rk4-cells', '3', '--models', '', "
+        "'--repeats', '2', '--fp32']\n"
+        "sweep.main()\n")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1200,
+                         cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    rows = [json.loads(ln) for ln in res.stdout.splitlines() if ln.startswith("{")]
+    deg = [r for r in rows if r["config"] == "degree_sweep"]
+    assert sorted((r["P"], r["geometry_mode"]) for r in deg) == [(P, g) for P in (2, 4, 5)
+                                                                 for g in (0, 1, 2, 3)]
+    rk = [r for r in rows if r["config"] == "headline_rk4_by_geometry_mode"]
+    assert [r["geometry_mode"] for r in rk] == [0, 1, 2, 3]
+    assert all(r["rel_l2_vs_first_mode"] < 1e-10 for r in rk)              # same fields in every mode
+    f32 = [r for r in rows if r["config"] == "degree_sweep_fp32"]
+    assert [r["P"] for r in f32] == [2, 4, 5] and all(0 < r["rel_l2_vs_fp64"] < 1e-5 for r in f32)
