@@ -19,6 +19,9 @@ def pytest_addoption(parser):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
     config.addinivalue_line("markers", "emu_skip: too large or hardware-specific for --emulated-device")
+    config.addinivalue_line("markers", "first_hw_run: written after the round's GPU budget was spent "
+                            "(verified on the emulated device only): collected after the tests that "
+                            "already passed on a B200, so that under -x they cannot hide them")
     if config.getoption("--emulated-device"):
         import importlib.util
         spec = importlib.util.spec_from_file_location(
@@ -39,6 +42,7 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=lambda item: "first_hw_run" in item.keywords)          # stable: order otherwise kept
     if config.getoption("--emulated-device"):
         skip = pytest.mark.skip(reason="not meaningful / too large on the emulated device")
         for item in items:

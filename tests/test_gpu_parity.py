@@ -292,6 +292,7 @@ def test_cpp_dropin_driver(fus, gpu):
     assert abs(np.linalg.norm(y) - float(vals["Kx_l2"])) < 1e-11 * np.linalg.norm(y)
 
 
+@pytest.mark.first_hw_run
 def test_cpp_float_operator_instantiation(fus, gpu):
     """examples/float_operators.cpp: MassSpectral3D<float,P> / StiffnessSpectral3D<float,P> (the
     scalar type of the reference's tests/test_operators3d/main.cpp:13) next to the double classes.
@@ -310,6 +311,7 @@ def test_cpp_float_operator_instantiation(fus, gpu):
         assert d > 0 and abs(f - d) < 1e-5 * d, (op, f, d)
 
 
+@pytest.mark.first_hw_run
 def test_c_abi_from_plain_c(fus, gpu):
     """examples/c_abi_minimal.c: the C ABI driven from C11 (stiffness application, boundary vectors,
     model, rk4, destroy order) gives the numbers of the Python mirror."""
@@ -542,6 +544,7 @@ def test_lean_context_models_vs_oracle(fus, orc, gpu, kind, P):
 # hardware run they passed the host emulation twice over -- the kernels alone
 # (tests/test_kernel_emulation.py) and this very test through the whole library built for the CPU
 # (pytest -m gpu --emulated-device).
+@pytest.mark.first_hw_run
 @pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
 def test_fp32_operators_vs_oracle(fus, orc, gpu, P):
     """StiffnessSpectral3D / MassSpectral3D on float32 data (the reference's T = float operators,

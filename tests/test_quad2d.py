@@ -366,6 +366,7 @@ def test_boundary_vectors_on_the_reference_2d_mesh(fus, orc, ref_quad_mesh):
 
 
 @pytest.mark.gpu
+@pytest.mark.first_hw_run
 def test_gpu_reference_2d_example_mesh(fus, orc, gpu, ref_quad_mesh, emulated):
     """The reference's 2-D example mesh on the GPU: more cells than one pass of the grid (the
     kernel's block loop iterates), an unstructured conforming numbering, tagged edges.  Operators
