@@ -4,7 +4,8 @@
 # 1. full GPU suite (incl. the tests written after the budget ran out: reference 2-D mesh, C ABI from C,
 #    float operator classes), smoke, bench (with the child-process sweep: degree sweep x geometry modes)
 # 2. ncu --set full of the on-the-fly geometry kernel (mode 2) to confirm the latency-bound reading
-# 3. BASELINE config 5 (1.0 G dofs, P=5) on ONE GPU with a lean context
+# 3. ncu --set full of the streamed kernel at P=6 and P=7
+# 4. BASELINE config 5 (1.0 G dofs, P=5) on ONE GPU with a lean context
 TAG=${1:-r2a}
 OUT=gpurun_out
 mkdir -p $OUT
@@ -26,6 +27,15 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:stif
     -f -o $OUT/prof_stiffness_mode2_${TAG} python bench.py --steps 2 --warmup 1 --geometry-mode 2 \
     --no-cpu-baseline --no-extras > $OUT/ncu_mode2_${TAG}.log 2>&1
 echo "ncu exit $?"
+echo "== ncu full, streamed kernels at P=6 and P=7 (0.70 of the HBM peak in round 1: find the stall)"
+for P in 6 7; do
+  timeout 300 python scripts/bench_sweep.py --degrees $P --variants=-1 --geometry-modes 0 --models "" --repeats 3 \
+      > $OUT/sweep_P${P}_${TAG}.jsonl 2> $OUT/sweep_P${P}_${TAG}.err &&
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:stiffness_line -s 2 -c 1 \
+      -f -o $OUT/prof_stiffness_P${P}_${TAG} python scripts/bench_sweep.py --degrees $P --variants=-1 \
+      --geometry-modes 0 --models "" --repeats 3 > $OUT/ncu_P${P}_${TAG}.log 2>&1
+  echo "ncu P=$P exit $?"
+done
 echo "== config 5 (1.0 G dofs, P=5, 200^3 cells) on one GPU, lean context"
 timeout 1200 python bench.py --degree 5 --cells 200 --lean --steps 5 --warmup 2 --no-cpu-baseline --no-extras \
     > $OUT/bench_c5_lean_1gpu_${TAG}.json 2> $OUT/bench_c5_lean_1gpu_${TAG}.err
