@@ -89,6 +89,7 @@ def main():
                     help="also time the FP32 operator instantiation and report its error vs FP64")
     ap.add_argument("--numbering", type=int, default=1)
     ap.add_argument("--rk4-cells", type=int, default=54, help="cells per direction of the RK4 runs")
+    ap.add_argument("--rk4-steps", type=int, default=20, help="timed steps of the RK4 runs per mode")
     args = ap.parse_args()
     pk = peak()
     stream = torch.cuda.Stream()        # the legacy default stream cannot be graph-captured
@@ -154,7 +155,7 @@ def main():
         mdl = fus.LinearSpectral3D(V, 1500.0, 1000.0, 0.5e6, 6e4, 1500.0)
         dt0 = 0.65 * np.sqrt(3) * h / (1500.0 * P * P)
         dt = 2e-6 / (int(2e-6 / dt0) + 1)
-        K, ref = 20, None
+        K, ref = args.rk4_steps, None
         for gmode in rk4_modes:
             ctx.set_option("geometry_mode", gmode)
             if ctx.get_option("geometry_compressed") != gmode:
