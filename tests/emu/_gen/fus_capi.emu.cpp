@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -88,7 +89,7 @@ struct fus_ctx {
   // float copies of G2 / detJ for the FP32 operator entry points, made on first use
   float* d_G2f = nullptr;
   float* d_detJf = nullptr;
-  int geom_active = 0;      // what the stiffness operator currently uses: 0 streamed G, 1, 2
+  int geom_active = 0;      // what the stiffness operator currently uses: 0 streamed G, 1, 2, 3
   bool lean = false;        // neither G nor detJ exist on the device: always mode 2
   int live_models = 0;      // fus_model objects that still point at this context
   // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
@@ -111,9 +112,12 @@ struct fus_ctx {
 namespace {
 // cudaFuncSetAttribute and the occupancy query are per device: a process that drives several GPUs
 // (one context each) must configure every kernel on every device it launches it on.
+// Contexts on different devices may be driven from different host threads, so the first-use
+// configuration is done under a lock and published through an atomic flag.
 constexpr int kMaxDevices = 64;
 struct KernelCfg {
-  bool configured[kMaxDevices] = {};
+  std::mutex mu;
+  std::atomic<bool> configured[kMaxDevices] = {};
   int blocks_plain[kMaxDevices] = {}, blocks_fuse[kMaxDevices] = {};
 };
 
@@ -220,22 +224,25 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   const double2* Gptr = c->d_G2;
   auto launch = [&](auto kern_plain, auto kern_fuse, int threads, int smem_bytes, int cpb,
                     KernelCfg& cfg) -> int {
-    bool& configured = cfg.configured[c->device];
+    std::atomic<bool>& configured = cfg.configured[c->device];
     int &bps_plain = cfg.blocks_plain[c->device], &bps_fuse = cfg.blocks_fuse[c->device];
-    if (!configured) {
-      FUS_CUDA(cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    smem_bytes));
-      FUS_CUDA(cudaFuncSetAttribute(kern_fuse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    smem_bytes));
-      FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_plain, kern_plain, threads,
-                                                            smem_bytes));
-      FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_fuse, kern_fuse, threads,
-                                                            smem_bytes));
-      if (bps_plain < 1 || bps_fuse < 1) {
-        set_error("stiffness kernel <N=%d> does not fit on an SM", N);
-        return FUS_ERR_CUDA;
+    if (!configured.load(std::memory_order_acquire)) {
+      std::lock_guard<std::mutex> lock(cfg.mu);
+      if (!configured.load(std::memory_order_relaxed)) {
+        FUS_CUDA(cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      smem_bytes));
+        FUS_CUDA(cudaFuncSetAttribute(kern_fuse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      smem_bytes));
+        FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_plain, kern_plain, threads,
+                                                              smem_bytes));
+        FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_fuse, kern_fuse, threads,
+                                                              smem_bytes));
+        if (bps_plain < 1 || bps_fuse < 1) {
+          set_error("stiffness kernel <N=%d> does not fit on an SM", N);
+          return FUS_ERR_CUDA;
+        }
+        configured.store(true, std::memory_order_release);
       }
-      configured = true;
     }
     ProfScope prof(c, 0, st);
     int bps = fuse ? bps_fuse : bps_plain;
@@ -388,15 +395,19 @@ int launch_stiffness_f32_n(fus_ctx* c, const float* x, const float* coeff, float
     D.x[i] = (float)c->pts[i];
   }
   auto kern = stiffness_line_kernel<N, false, 0, float>;
-  if (!cfg.configured[c->device]) {
-    FUS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_BYTES));
-    FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.blocks_plain[c->device], kern,
-                                                          L::THREADS, L::SMEM_BYTES));
-    if (cfg.blocks_plain[c->device] < 1) {
-      set_error("FP32 stiffness kernel <N=%d> does not fit on an SM", N);
-      return FUS_ERR_CUDA;
+  if (!cfg.configured[c->device].load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lock(cfg.mu);
+    if (!cfg.configured[c->device].load(std::memory_order_relaxed)) {
+      FUS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::SMEM_BYTES));
+      FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cfg.blocks_plain[c->device], kern,
+                                                            L::THREADS, L::SMEM_BYTES));
+      if (cfg.blocks_plain[c->device] < 1) {
+        set_error("FP32 stiffness kernel <N=%d> does not fit on an SM", N);
+        return FUS_ERR_CUDA;
+      }
+      cfg.configured[c->device].store(true, std::memory_order_release);
     }
-    cfg.configured[c->device] = true;
   }
   ProfScope prof(c, 0, c->stream);
   const long long want = (c->ncells + L::CPB - 1) / L::CPB;
