@@ -529,8 +529,9 @@ int affine_detect_n(fus_ctx* c, int* all_affine) {
   std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
   std::memcpy(D.w, c->wts, sizeof(double) * N);
   std::memcpy(D.x, c->pts, sizeof(double) * N);
-  int* d_flag = nullptr;
-  FUS_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+  DevPtr<int> flag;
+  FUS_CUDA(cudaMalloc(&flag.p, sizeof(int)));
+  int* d_flag = flag.p;
   const int one = 1;
   FUS_CUDA(cudaMemcpyAsync(d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (!c->d_Ghat)
@@ -540,7 +541,6 @@ int affine_detect_n(fus_ctx* c, int* all_affine) {
   FUS_LAUNCHED();
   FUS_CUDA(cudaMemcpyAsync(all_affine, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   FUS_CUDA(cudaStreamSynchronize(c->stream));
-  FUS_CUDA(cudaFree(d_flag));
   return FUS_OK;
 }
 
@@ -581,7 +581,7 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   }
   cudaDeviceProp prop;
   FUS_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) {
+  if (prop.major != 10 || prop.minor != 0) { // arch-specific SASS only: no other target can load it
     set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
               prop.minor);
     return FUS_ERR_CUDA;
@@ -647,7 +647,7 @@ int fus_device_count(void) {
   int ok = 0;
   for (int d = 0; d < n; ++d) {
     cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major >= 10)
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10 && p.minor == 0)
       ++ok;
   }
   return ok;
@@ -970,8 +970,10 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
       set_error("geometry_mode must be 0, 1, 2 (or 3, the occupancy experiment of mode 2)");
       return FUS_ERR_ARG;
     }
-    if (!c->d_G2)
+    if (!c->d_G2) {
+      set_error("geometry_mode 1 needs the stored G of the context");
       return FUS_ERR_STATE;
+    }
     FUS_TRY(select_device(c));
     int all_affine = 0;
     FUS_TRY(FUS_DISPATCH_N(c, affine_detect_n, c, &all_affine));
@@ -1066,8 +1068,10 @@ int fus_ctx_get_geometry(fus_ctx* c, double* G, double* detJ) {
   if (c->dim == 2) { // Gq[c][p][q] -> reference layout G[c][q][3]
     const int64_t nent = c->ncells * c->Nd;
     if (G) {
-      if (!c->d_Gq)
+      if (!c->d_Gq) {
+        set_error("fus_ctx_get_geometry: the context holds no G");
         return FUS_ERR_STATE;
+      }
       std::vector<double> tmp((size_t)3 * nent);
       FUS_CUDA(cudaMemcpyAsync(tmp.data(), c->d_Gq, sizeof(double) * tmp.size(),
                                cudaMemcpyDeviceToHost, c->stream));
@@ -1078,8 +1082,10 @@ int fus_ctx_get_geometry(fus_ctx* c, double* G, double* detJ) {
             G[(size_t)(cell * c->Nd + q) * 3 + p] = tmp[(size_t)(cell * 3 + p) * c->Nd + q];
     }
     if (detJ) {
-      if (!c->d_detJ)
+      if (!c->d_detJ) {
+        set_error("fus_ctx_get_geometry: the context holds no detJ");
         return FUS_ERR_STATE;
+      }
       FUS_CUDA(cudaMemcpyAsync(detJ, c->d_detJ, sizeof(double) * nent, cudaMemcpyDeviceToHost,
                                c->stream));
       FUS_CUDA(cudaStreamSynchronize(c->stream));
@@ -1094,13 +1100,17 @@ int fus_ctx_get_geometry(fus_ctx* c, double* G, double* detJ) {
     return trilinear_geometry(c->P, c->ncells, co.data(), G, detJ);
   }
   if (G) {
-    if (!c->d_G2)
+    if (!c->d_G2) {
+      set_error("fus_ctx_get_geometry: the context holds no G");
       return FUS_ERR_STATE;
+    }
     FUS_TRY(FUS_DISPATCH_N(c, g_download_n, c, G));
   }
   if (detJ) {
-    if (!c->d_detJ)
+    if (!c->d_detJ) {
+      set_error("fus_ctx_get_geometry: the context holds no detJ");
       return FUS_ERR_STATE;
+    }
     FUS_CUDA(cudaMemcpyAsync(detJ, c->d_detJ, sizeof(double) * c->ncells * c->Nd,
                              cudaMemcpyDeviceToHost, c->stream));
     FUS_CUDA(cudaStreamSynchronize(c->stream));
