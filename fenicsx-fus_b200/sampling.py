@@ -1,7 +1,8 @@
 """Point evaluation of a GLL field after the time loop.
 
 Host-side post-processing, the step the reference's examples run right after `rk4`
-(`cpp/mwe/parallel_eval_line/main.cpp:47-106`, `python/src/fenicsxfus/utils.py:10-47`):
+(`cpp/mwe/parallel_eval_line/main.cpp:47-106`, `cpp/mwe/parallel_eval_surface/main.cpp:50-104`,
+`python/src/fenicsxfus/utils.py:10-47`):
 find the cell containing each point, then evaluate the tensor-product Lagrange expansion there.
 
 `compute_eval_params(mesh, points)` mirrors the reference helper of the same name: it returns the
@@ -124,3 +125,27 @@ def eval_line(V, u, start, end, num_points=100):
     pts = (1 - tt) * np.asarray(start, float)[None, :] + tt * np.asarray(end, float)[None, :]
     pk, cells, xi, _ = compute_eval_params(V.mesh, pts)
     return pk, eval_function(V, u, cells, xi)
+
+
+def eval_surface(V, u, origin, edge_u, edge_v, num_points=100, path=None):
+    """Sample u on the parallelogram origin + s*edge_u + t*edge_v, s,t in [0,1], on a
+    num_points x num_points grid (the reference's parallel_eval_surface example,
+    main.cpp:50-62: a 100 x 100 grid over the plane z = 0 of a rectangle).  Points outside the
+    local mesh are dropped.  Returns (points kept, values); with `path` the rows "x,y[,z],value" are
+    APPENDED to that text file, as each rank of the reference appends to surface_data.txt
+    (main.cpp:91-104)."""
+    num = (num_points, num_points) if np.isscalar(num_points) else tuple(num_points)
+    o, eu, ev = (np.asarray(a, float) for a in (origin, edge_u, edge_v))
+    ss, tt = np.meshgrid(np.linspace(0.0, 1.0, num[0]), np.linspace(0.0, 1.0, num[1]), indexing="xy")
+    pts = o[None, :] + ss.reshape(-1, 1) * eu[None, :] + tt.reshape(-1, 1) * ev[None, :]
+    if pts.shape[1] == 2:
+        pts = np.concatenate([pts, np.zeros((pts.shape[0], 1))], axis=1)
+    pk, cells, xi, _ = compute_eval_params(V.mesh, pts)
+    vals = eval_function(V, u, cells, xi)
+    if path is not None:
+        ncoord = 2 if getattr(V.mesh, "dim", 3) == 2 else 3
+        with open(path, "a") as f:
+            for p, v in zip(pk, vals):
+                f.write(",".join(repr(float(c)) for c in p[:ncoord]) + "," + repr(float(v)) + "\n")
+    return pk, vals
+

@@ -85,3 +85,30 @@ def test_eval_on_the_reference_2d_example_mesh(fus):
     assert np.abs(sampling.eval_function(V, u, cells, xi) - f(pts)).max() < 1e-12
     pk, cells, xi, keep = sampling.compute_eval_params(m, np.array([[0.2, 0.0], [0.06, 0.0]]))
     assert keep.tolist() == [1]
+
+
+def test_eval_surface_like_the_reference_example(fus, tmp_path):
+    """cpp/mwe/parallel_eval_surface: u = sin(2 pi x) cos(2 pi y) on [-1,1]^2 (32 x 32 cells), sampled
+    on a 100 x 100 grid and appended to a text file; and a tilted plane through a 3-D box."""
+    from fenicsx_fus_b200 import sampling
+    m = fus.RectMesh((32, 32), (-1.0, -1.0), (1.0, 1.0))
+    V = fus.FunctionSpace(m, 4)
+    X = V.tabulate_dof_coordinates()
+    f2 = lambda x: np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1])  # noqa: E731
+    out = tmp_path / "surface_data.txt"
+    pk, vals = sampling.eval_surface(V, f2(X), (-1.0, -1.0), (2.0, 0.0), (0.0, 2.0), 100, path=str(out))
+    assert len(vals) == 100 * 100 and np.abs(vals - f2(pk)).max() < 2e-5       # interpolation error
+    rows = np.loadtxt(out, delimiter=",")
+    assert rows.shape == (10000, 3) and np.array_equal(rows[:, 2], vals)
+    assert np.allclose(rows[:100, 1], -1.0) and np.allclose(rows[:100, 0], np.linspace(-1, 1, 100))
+    # 3-D: a polynomial of the space is reproduced exactly on a tilted plane; corners outside the box drop
+    m3 = fus.BoxMesh((3, 2, 2), (0, 0, 0), (1.5, 1.0, 0.8))
+    V3 = fus.FunctionSpace(m3, 3)
+    f3 = lambda x: 1 + x[:, 0] ** 3 - x[:, 1] * x[:, 2] ** 2                   # noqa: E731
+    u3 = f3(V3.tabulate_dof_coordinates())
+    pk, vals = sampling.eval_surface(V3, u3, (0.0, 0.0, 0.1), (1.5, 0.0, 0.6), (0.0, 1.0, 0.0), (20, 10))
+    assert len(vals) == 200 and np.abs(vals - f3(pk)).max() < 1e-12
+    pk, vals = sampling.eval_surface(V3, u3, (0.0, 0.0, 0.5), (3.0, 0.0, 0.0), (0.0, 1.0, 0.0), (21, 5))
+    assert 0 < len(vals) < 105 and pk[:, 0].max() <= 1.5 + 1e-12
+    assert np.abs(vals - f3(pk)).max() < 1e-12
+
