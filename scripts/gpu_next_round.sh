@@ -37,7 +37,20 @@ for P in 6 7; do
   echo "ncu P=$P exit $?"
 done
 echo "== config 5 (1.0 G dofs, P=5, 200^3 cells) on one GPU, lean context"
-timeout 1200 python bench.py --degree 5 --cells 200 --lean --steps 5 --warmup 2 --no-cpu-baseline --no-extras \
-    > $OUT/bench_c5_lean_1gpu_${TAG}.json 2> $OUT/bench_c5_lean_1gpu_${TAG}.err
-echo "config-5 lean exit $?"; tail -c 1500 $OUT/bench_c5_lean_1gpu_${TAG}.json; tail -n 3 $OUT/bench_c5_lean_1gpu_${TAG}.err
+# host side of a 1.0 G-dof mesh: ~7 GB dofmap, 4 x 8 GB boundary vectors, pinned state copies: ~100 GB
+AVAIL_GB=$(awk '/MemAvailable/ {print int($2/1048576)}' /proc/meminfo)
+LIMIT=$(cat /sys/fs/cgroup/memory.max 2>/dev/null || echo max)
+echo "host memory available: ${AVAIL_GB} GB, cgroup limit: ${LIMIT}"
+if [ "$AVAIL_GB" -ge 250 ] && { [ "$LIMIT" = "max" ] || [ "$LIMIT" -ge 268435456000 ]; }; then
+  timeout 1200 python bench.py --degree 5 --cells 200 --lean --steps 5 --warmup 2 --no-cpu-baseline --no-extras \
+      > $OUT/bench_c5_lean_1gpu_${TAG}.json 2> $OUT/bench_c5_lean_1gpu_${TAG}.err
+  echo "config-5 lean exit $?"; tail -c 1500 $OUT/bench_c5_lean_1gpu_${TAG}.json; tail -n 3 $OUT/bench_c5_lean_1gpu_${TAG}.err
+elif [ "$AVAIL_GB" -lt 130 ]; then
+  echo "skipped: not enough host memory for a 0.5-1.0 G-dof mesh on the host side"
+else
+  echo "not enough host memory for the 1.0 G-dof host arrays; running 160^3 cells (0.51 G dofs) instead"
+  timeout 1200 python bench.py --degree 5 --cells 160 --lean --steps 5 --warmup 2 --no-cpu-baseline --no-extras \
+      > $OUT/bench_c5_lean_1gpu_${TAG}.json 2> $OUT/bench_c5_lean_1gpu_${TAG}.err
+  echo "160^3 lean exit $?"; tail -c 1500 $OUT/bench_c5_lean_1gpu_${TAG}.json; tail -n 3 $OUT/bench_c5_lean_1gpu_${TAG}.err
+fi
 ls -la $OUT | tail -n 12
