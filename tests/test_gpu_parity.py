@@ -456,6 +456,35 @@ def test_trilinear_geometry_on_the_fly(fus, orc, gpu, P):
     assert rel_l2(k2, k0) < TOL_APPLY
 
 
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("P", [2, 4])
+def test_trilinear_geometry_register_capped_build(fus, orc, gpu, P):
+    """Option geometry_mode=3: the mode-2 kernel compiled under a 128-register cap (4 blocks/SM for
+    P <= 4, a few spilled values) -- the occupancy experiment bench.py's child sweep times.  Same
+    numbers as mode 2 are required: one application and the fused two-vector stage on warped cells."""
+    m = fus.BoxMesh((5, 3, 2), (0.4, -0.3, 1.0), (0.9, 0.0, 1.2),
+                    warp=lambda x: warp_vertices(x, 0.08, 3))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context()
+    ctx.set_option("geometry_mode", 3)
+    assert ctx.get_option("geometry_compressed") == 3
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    rng = np.random.default_rng(300 + P)
+    x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)
+    y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(V.ndofs))
+    note(f"trilinear_capped_stiffness_P{P}", rel_l2(y, yo))
+    assert rel_l2(y, yo) < TOL_APPLY
+    mdl = fus.LossySpectral3D(V, 1500.0, 1000.0, 3e-3, 0.5e6, 1e5, 1500.0)
+    u, v = rng.uniform(-1, 1, V.ndofs), 1e6 * rng.uniform(-1, 1, V.ndofs)
+    k3 = mdl.f1(1e-6, u, v)
+    ctx.set_option("geometry_mode", 2)
+    k2 = mdl.f1(1e-6, u, v)
+    ctx.set_option("geometry_mode", 0)
+    k0 = mdl.f1(1e-6, u, v)
+    assert rel_l2(k3, k2) < 1e-13 and rel_l2(k3, k0) < TOL_APPLY
+
+
 def test_trilinear_geometry_rk4_and_errors(fus, orc, gpu):
     """geometry_mode=2 inside the captured RK4 loop (linear model, warped mesh) against the oracle;
     a context made from precomputed arrays has no vertices and must refuse the mode."""
