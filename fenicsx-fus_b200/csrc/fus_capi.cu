@@ -1307,9 +1307,8 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
     for (double** v : {&m->d_m, &m->d_u0, &m->d_v0, &m->d_ua, &m->d_va, &m->d_un, &m->d_vn, &m->d_b})
       FUS_TRY(model_alloc_vec(c, v));
     // lumped mass: the form `a` assembled with u == 1 (Linear.hpp:127-134), + facet mass term
-    std::vector<double> ones(nd, 1.0);
-    FUS_CUDA(cudaMemcpyAsync(m->d_un, ones.data(), sizeof(double) * nd, cudaMemcpyHostToDevice,
-                             c->stream));
+    fill_kernel<<<grid_for(nd, 256, 1 << 30), 256, 0, c->stream>>>(m->d_un, 1.0, nd);
+    FUS_LAUNCHED();
     FUS_TRY(launch_mass(c, m->d_un, d_mco, m->d_m, 0, nc, c->stream));
     if (bmass) {
       FUS_CUDA(cudaMemcpyAsync(m->d_vn, bmass, sizeof(double) * nd, cudaMemcpyHostToDevice,

@@ -1257,4 +1257,12 @@ static __global__ void __launch_bounds__(256)
     y[i] += a[i];
 }
 
+// y[i] = value
+static __global__ void __launch_bounds__(256)
+    fill_kernel(double* __restrict__ y, double value, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    y[i] = value;
+}
+
 } // namespace fus
