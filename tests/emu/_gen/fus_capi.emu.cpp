@@ -1810,3 +1810,5 @@ int fus_scatter_rev_dev(fus_ctx* c, double* x) {
 }
 
 } // extern "C"
+
+extern "C" long long fus_emu_graph_launches(void) { return fus_emu::graph_launches(); }

@@ -100,6 +100,9 @@ def build(verbose=False):
         dst = os.path.join(GEN, name.replace(".cu", ".emu.cpp"))
         with open(dst, "w") as f:
             f.write(f"// GENERATED from fenicsx-fus_b200/csrc/{name} by build_emulated_library.py\n" + text)
+            if name == "fus_capi.cu":          # test-only export: how many graph replays ran
+                f.write('\nextern "C" long long fus_emu_graph_launches(void) '
+                        '{ return fus_emu::graph_launches(); }\n')
         gen.append(dst)
     cmd = ["/usr/bin/g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-DFUS_HOST_EMULATION=1",
            "-I" + HERE, "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-o", LIB] + gen + [
