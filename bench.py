@@ -214,7 +214,7 @@ def run_reference_arm(args):
     return 0
 
 
-def child_extras(timeout_s=120.0):
+def child_extras(timeout_s=150.0):
     """Secondary measurements in a CHILD process (scripts/bench_sweep.py), after the headline
     numbers are in hand: the degree sweep of BASELINE config 2 (single operator application, P=2..7,
     ~10 M dofs) with the geometric factors streamed and rebuilt on the fly, and the headline RK4
@@ -222,7 +222,7 @@ def child_extras(timeout_s=120.0):
     time-out -- can cost the headline line."""
     cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_sweep.py"), "--degrees",
            "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,1,2,3", "--rk4-geometry-modes",
-           "0,1,2,3", "--models", "", "--repeats", "20", "--fp32"]
+           "0,1,2,3", "--pipeline-variants", "3,4,5", "--models", "", "--repeats", "20", "--fp32"]
     env = dict(os.environ)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -240,14 +240,20 @@ def child_extras(timeout_s=120.0):
                 rows.append(json.loads(ln))
             except ValueError:
                 pass
-    keep = ("P", "dofs", "geometry_mode", "ms_min", "ms_median", "gdof_per_s",
+    keep = ("P", "dofs", "geometry_mode", "variant", "ms_min", "ms_median", "gdof_per_s",
             "frac_of_measured_peak", "ms_per_step", "dof_updates_per_s", "operator_ms",
-            "rel_l2_vs_first_mode", "rel_l2_vs_fp64")
+            "rel_l2_vs_first_mode", "rel_l2_vs_first_config", "rel_l2_vs_fp64")
     res = {"wall_s": time.perf_counter() - t0, "exit": rc,
            "degree_sweep_operator_apply": [{k: r[k] for k in keep if k in r} for r in rows
                                            if r.get("config") == "degree_sweep"],
            "headline_rk4_by_geometry_mode": [{k: r[k] for k in keep if k in r} for r in rows
                                              if r.get("config") == "headline_rk4_by_geometry_mode"],
+           # stiffness_variant 3/4/5: the line kernel with the software pipelines that remove the
+           # loop-end stall seen in the ncu source view of the default kernel; same
+           # results, first hardware timing here, default unchanged until it is in hand
+           "headline_rk4_by_pipeline_variant": [{k: r[k] for k in keep if k in r} for r in rows
+                                                if r.get("config")
+                                                == "headline_rk4_by_pipeline_variant"],
            # FP32 operator instantiation (float data, 28 B/point + 8 B/dof algorithmic): first
            # hardware run of these kernels -- their logic is covered by the host emulation tests
            "degree_sweep_operator_apply_fp32": [{k: r[k] for k in keep if k in r} for r in rows

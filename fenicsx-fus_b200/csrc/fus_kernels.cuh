@@ -364,9 +364,18 @@ struct LineCfg {
 //   3  the same code as 2 compiled under a 128-register cap (4 blocks/SM for P <= 4 instead of 3:
 //                16 warps/SM at the price of a few spilled values) -- an occupancy experiment that
 //                bench.py's child sweep measures next to mode 2.
+//   4, 5  streamed G like 0 with a different software pipeline (option "stiffness_variant" 3, 4;
+//                experiments for the stall the ncu source view of mode 0 shows):
+//                4 loads the cell coefficient for the CURRENT cell at the top of the iteration
+//                instead of carrying the next cell's across the loop edge (in mode 0 that carried
+//                value becomes a register move at the loop end, which has to wait on a scoreboard
+//                shared with the G loads just issued); 5 additionally prefetches the dofmap rows of
+//                the cell after next into L2 at the loop end; 6 instead loads those rows into
+//                registers a whole iteration ahead (right after the gathers have been issued), so
+//                that the gather addresses of the next iteration never wait on a dofmap load.
 template <int N, bool FUSE2, int GEOM = 0, typename T = double>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS,
-                                  (GEOM == 2 && N <= 5) ? 3 : ((GEOM == 3 && N <= 5) ? 4 : 0))
+                                  (GEOM == 2 && N <= 5) ? 3 : (((GEOM == 3 || GEOM == 5) && N <= 5) ? 4 : 0))
     stiffness_line_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                           const int32_t* __restrict__ dofmap,
                           const typename Vec2<T>::type* __restrict__ G2,
@@ -379,9 +388,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
                 "the trilinear cell map is evaluated in FP64 only");
   constexpr int NN = C::NN, GPF = C::GPF;
   constexpr bool AFFINE = (GEOM == 1), TRI = (GEOM == 2 || GEOM == 3);
+  constexpr bool STREAM = (GEOM == 0 || GEOM >= 4); // G read from memory per point
+  constexpr bool CFNOW = (GEOM >= 4), DMPF = (GEOM == 5), DM2 = (GEOM == 6);
   constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
-  static_assert(GEOM >= 0 && GEOM <= 3, "unknown geometry mode");
+  static_assert(GEOM >= 0 && GEOM <= 6, "unknown geometry mode");
 #ifdef FUS_HOST_EMULATION
   T* smem = reinterpret_cast<T*>(fus_emu::dynamic_shared());
 #else
@@ -425,14 +436,15 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   long long c = cell_begin + (long long)blockIdx.x * C::CPB + slot;
 
   int idx[N], idxn[N];
+  int idxnn[DM2 ? N : 1]; // DM2: dofmap rows of the cell after next
   T xv[N];
-  V2 g[GEOM != 0 ? 1 : GPF][3];
+  V2 g[STREAM ? GPF : 1][3];
   V2 gh[3], ghn[3]; // AFFINE: Ghat of the current and of the next cell
   // TRI: the pieces of J on this thread's line (xi1,xi2) = (x[a],x[b]) for the current cell.  The
   // 192 B of a cell are read by all its threads at the same addresses, so there is nothing to keep
   // in flight: the next cell's two lines are prefetched into L2 and loaded when it becomes current.
   TriLine tl;
-  const T wab = (GEOM != 0) ? D.w[a] * D.w[b] : T(0);
+  const T wab = STREAM ? T(0) : D.w[a] * D.w[b];
   const double xia = TRI ? (double)D.x[a] : 0.0, xib = TRI ? (double)D.x[b] : 0.0;
   T cf = T(0);
   if constexpr (TRI) {
@@ -474,7 +486,10 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     xv[k] = T(0);
   }
 #pragma unroll
-  for (int k = 0; k < (GEOM != 0 ? 1 : GPF); ++k)
+  for (int k = 0; k < (DM2 ? N : 1); ++k)
+    idxnn[k] = 0;
+#pragma unroll
+  for (int k = 0; k < (STREAM ? GPF : 1); ++k)
 #pragma unroll
     for (int p = 0; p < 3; ++p)
       g[k][p] = make_v2<T>(T(0), T(0));
@@ -544,7 +559,9 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
         s = fma(D.d[q * N + k], xv[k], s);
       f0[q] = s;
     }
-    const T cfc = cf;
+    T cfc = cf;
+    if constexpr (CFNOW && !FUSE2)
+      cfc = valid ? __ldg(coeff + c) : T(0); // first used by the G transform, two barriers away
     if (validn) {
       if constexpr (FUSE2) {
         const T ca = __ldg(coeff + cn), cb = __ldg(coeff2 + cn);
@@ -555,7 +572,17 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 #pragma unroll
         for (int k = 0; k < N; ++k)
           xv[k] = __ldg(x + idxn[k]);
-        cf = __ldg(coeff + cn);
+        if constexpr (!CFNOW)
+          cf = __ldg(coeff + cn);
+      }
+    }
+    if constexpr (DM2) {
+      const long long c2 = cn + stride;
+      if (lane_ok && c2 < cell_end) {
+        const int32_t* dm = dofmap + c2 * (N * NN) + t;
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          idxnn[k] = __ldg(dm + k * NN);
       }
     }
     sync();
@@ -622,7 +649,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
         t2 = scale * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
       }
       // refill the ring slot: level i0+GPF of this cell, or of the next cell once past the top
-      if constexpr (GEOM != 0) {
+      if constexpr (!STREAM) {
       } else if (i0 + GPF < N) {
         if (valid) {
 #pragma unroll
@@ -697,7 +724,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
       if (valid)
         tri_setup(c);
     }
-    if (validn) {
+    if constexpr (DM2) { // loaded during phase (1) of this iteration
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        idxn[k] = idxnn[k];
+    } else if (validn) {
       const int32_t* dm = dofmap + cn * (N * NN) + t;
 #pragma unroll
       for (int k = 0; k < N; ++k)
@@ -709,6 +740,14 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
       }
       if constexpr (TRI)
         tri_prefetch(cn);
+    }
+    if constexpr (DMPF) { // dofmap rows of the cell after next: N*N*N int32, touched line by line
+      const long long c2 = cn + stride;
+      if (lane_ok && c2 < cell_end && t * 32 < N * NN) {
+#ifndef FUS_HOST_EMULATION
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dofmap + c2 * (N * NN) + t * 32));
+#endif
+      }
     }
   }
 }

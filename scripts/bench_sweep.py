@@ -84,6 +84,9 @@ def main():
     ap.add_argument("--models", default="linear_het,lossy,westervelt")
     ap.add_argument("--variants", default="0", help="-1 = the library's own choice per degree")
     ap.add_argument("--geometry-modes", default="0")
+    ap.add_argument("--pipeline-variants", default="",
+                    help="extra stiffness variants timed with streamed G only (3,4,5: the line kernel's "
+                         "experimental software pipelines), in the degree sweep and in the RK4 runs")
     ap.add_argument("--rk4-geometry-modes", default="")
     ap.add_argument("--fp32", action="store_true",
                     help="also time the FP32 operator instantiation and report its error vs FP64")
@@ -95,6 +98,7 @@ def main():
     stream = torch.cuda.Stream()        # the legacy default stream cannot be graph-captured
     torch.cuda.set_stream(stream)
     gmodes = [int(s) for s in args.geometry_modes.split(",") if s]
+    pvariants = [int(s) for s in args.pipeline_variants.split(",") if s]
     for P in [int(s) for s in args.degrees.split(",") if s]:
         n = SWEEP[P]
         m = fus.BoxMesh((n, n, n))
@@ -106,7 +110,10 @@ def main():
         y = torch.zeros_like(x)
         coeffs = torch.full((m.ncells,), -1.0 / 1000.0, dtype=torch.float64, device="cuda")
         K = fus.StiffnessSpectral3D(V)
-        for variant, gmode in [(int(s), g) for s in args.variants.split(",") for g in gmodes]:
+        y_first = None
+        pairs = [(int(s), g) for s in args.variants.split(",") for g in gmodes]
+        pairs += [(v, 0) for v in pvariants]
+        for variant, gmode in pairs:
             ctx.set_option("stiffness_variant", variant)
             ctx.set_option("geometry_mode", gmode)
             if ctx.get_option("geometry_compressed") != gmode:
@@ -125,8 +132,14 @@ def main():
             tmin, tmed = min(times), float(np.median(times))
             npts = m.ncells * (P + 1) ** 3
             alg = 52.0 * npts + 16.0 * V.ndofs
+            y1 = K(x, coeffs, torch.zeros_like(x))          # one clean application: same numbers?
+            if y_first is None:
+                y_first = y1
+            err = float((torch.linalg.vector_norm(y1 - y_first)
+                         / torch.linalg.vector_norm(y_first)).item())
             print(json.dumps({"config": "degree_sweep", "P": P, "n": n, "dofs": V.ndofs,
                               "variant": variant, "geometry_mode": gmode,
+                              "rel_l2_vs_first_config": err,
                               "numbering": args.numbering,
                               "y_norm_after_repeats": float(torch.linalg.vector_norm(y).item()),
                               "ms_min": tmin, "ms_median": tmed,
@@ -156,7 +169,8 @@ def main():
         dt0 = 0.65 * np.sqrt(3) * h / (1500.0 * P * P)
         dt = 2e-6 / (int(2e-6 / dt0) + 1)
         K, ref = args.rk4_steps, None
-        for gmode in rk4_modes:
+        for gmode, variant in [(g, -1) for g in rk4_modes] + [(0, v) for v in pvariants]:
+            ctx.set_option("stiffness_variant", variant)
             ctx.set_option("geometry_mode", gmode)
             if ctx.get_option("geometry_compressed") != gmode:
                 continue
@@ -179,7 +193,9 @@ def main():
             u = mdl.u_sol()
             if ref is None:
                 ref = u
-            print(json.dumps({"config": "headline_rk4_by_geometry_mode", "geometry_mode": gmode,
+            print(json.dumps({"config": ("headline_rk4_by_geometry_mode" if variant < 0
+                                         else "headline_rk4_by_pipeline_variant"),
+                              "geometry_mode": gmode, "variant": variant,
                               "P": P, "dofs": V.ndofs, "steps": done, "ms_per_step": ms / done,
                               "dof_updates_per_s": V.ndofs * done / (ms * 1e-3),
                               "operator_ms": ms_st / max(n_st, 1),
@@ -187,6 +203,7 @@ def main():
                                                             / max(np.linalg.norm(ref), 1e-300)),
                               "u_norm": float(np.linalg.norm(u))}), flush=True)
         ctx.set_option("geometry_mode", 0)
+        ctx.set_option("stiffness_variant", -1)
         mdl.destroy()
         V._ctx = None
         ctx.destroy()

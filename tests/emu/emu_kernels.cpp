@@ -37,9 +37,13 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
                 const double* wts, int max_blocks, long long cb, long long ce) {
   const DMat<N> D = make_dmat<N>(dphi, pts, wts);
   const bool fuse = x2 != nullptr;
+  if (variant >= 3) { // stiffness_variant 3/4/5: line kernel, streamed G, kernel GEOM 4/5/6
+    geom = variant + 1;
+    variant = 2;
+  }
   std::vector<double2> G2;
   const double2* gptr = nullptr;
-  if (geom == 0) {
+  if (geom == 0 || geom >= 4) {
     G2 = device_layout<N>(G, ncells);
     gptr = G2.data();
   } else {
@@ -81,8 +85,14 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
     fuse ? run(stiffness_line_kernel<N, true, 1>) : run(stiffness_line_kernel<N, false, 1>);
   else if (geom == 2)
     fuse ? run(stiffness_line_kernel<N, true, 2>) : run(stiffness_line_kernel<N, false, 2>);
-  else
+  else if (geom == 3)
     fuse ? run(stiffness_line_kernel<N, true, 3>) : run(stiffness_line_kernel<N, false, 3>);
+  else if (geom == 4)
+    fuse ? run(stiffness_line_kernel<N, true, 4>) : run(stiffness_line_kernel<N, false, 4>);
+  else if (geom == 5)
+    fuse ? run(stiffness_line_kernel<N, true, 5>) : run(stiffness_line_kernel<N, false, 5>);
+  else
+    fuse ? run(stiffness_line_kernel<N, true, 6>) : run(stiffness_line_kernel<N, false, 6>);
   return 0;
 }
 
@@ -197,7 +207,8 @@ int geometry_quad_n(const double* xg, const int32_t* xdofmap, long long ncells, 
 
 extern "C" {
 
-// y += K x with the production kernels: variant 0 column, 1 point, 2 line; geom 0 streamed G
+// y += K x with the production kernels: variant 0 column, 1 point, 2 line, 3/4/5 line with the
+// experimental software pipelines (as option stiffness_variant); geom 0 streamed G
 // (reference layout in, re-laid-out here), 1 affine (aux = Ghat[cell][6]), 2 trilinear (aux =
 // FUS_TRI_STRIDE doubles per cell).  x2/coeff2 non-NULL selects the fused two-vector gather.
 // Only cells [cell_begin, cell_end) are applied: the split launches of a partitioned stage.

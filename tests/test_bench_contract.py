@@ -306,14 +306,19 @@ def test_child_sweep_script_control_flow_with_a_stub_device(monkeypatch, capsys)
     monkeypatch.setattr(fus, "LinearSpectral3D", Model)
     monkeypatch.setattr(sys, "argv", ["bench_sweep.py", "--degrees", "2,3,4,5,6,7", "--variants=-1",
                                       "--geometry-modes", "0,1,2,3", "--rk4-geometry-modes",
-                                      "0,1,2,3", "--models", "", "--repeats", "2", "--fp32"])
+                                      "0,1,2,3", "--pipeline-variants", "3,4,5", "--models", "",
+                                      "--repeats", "2", "--fp32"])
     sweep.main()
     rows = [json.loads(ln) for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     deg = [r for r in rows if r["config"] == "degree_sweep"]
     rk = [r for r in rows if r["config"] == "headline_rk4_by_geometry_mode"]
-    assert sorted((r["P"], r["geometry_mode"]) for r in deg) == [(P, g) for P in range(2, 8)
-                                                                 for g in (0, 1, 2, 3)]
+    assert sorted((r["P"], r["geometry_mode"]) for r in deg if r["variant"] < 0) == [
+        (P, g) for P in range(2, 8) for g in (0, 1, 2, 3)]
+    assert sorted((r["P"], r["variant"]) for r in deg if r["variant"] >= 0) == [
+        (P, v) for P in range(2, 8) for v in (3, 4, 5)]
     assert [r["geometry_mode"] for r in rk] == [0, 1, 2, 3] and all(r["steps"] == 20 for r in rk)
+    rkv = [r for r in rows if r["config"] == "headline_rk4_by_pipeline_variant"]
+    assert [(r["geometry_mode"], r["variant"]) for r in rkv] == [(0, 3), (0, 4), (0, 5)]
     assert all({"ms_min", "gdof_per_s", "frac_of_measured_peak"} <= set(r) for r in deg)
     f32 = [r for r in rows if r["config"] == "degree_sweep_fp32"]
     assert [r["P"] for r in f32] == list(range(2, 8)) and all("rel_l2_vs_fp64" in r for r in f32)
@@ -380,17 +385,22 @@ def test_child_sweep_script_on_the_emulated_device():
         "sweep.SWEEP = {P: 3 for P in range(2, 8)}\n"
         "sys.argv = ['bench_sweep.py', '--degrees', '2,5', '--variants=-1', '--geometry-modes', "
         "'0,1,2,3', '--rk4-geometry-modes', '0,1,2,3', '--rk4-cells', '3', '--rk4-steps', '3', "
-        "'--models', '', '--repeats', '1', '--fp32']\n"
+        "'--pipeline-variants', '3,5', '--models', '', '--repeats', '1', '--fp32']\n"
         "sweep.main()\n")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1200,
                          cwd=ROOT)
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
     rows = [json.loads(ln) for ln in res.stdout.splitlines() if ln.startswith("{")]
     deg = [r for r in rows if r["config"] == "degree_sweep"]
-    assert sorted((r["P"], r["geometry_mode"]) for r in deg) == [(P, g) for P in (2, 5)
-                                                                 for g in (0, 1, 2, 3)]
+    assert sorted((r["P"], r["geometry_mode"]) for r in deg if r["variant"] < 0) == [
+        (P, g) for P in (2, 5) for g in (0, 1, 2, 3)]
+    assert sorted((r["P"], r["variant"]) for r in deg if r["variant"] >= 0) == [
+        (P, v) for P in (2, 5) for v in (3, 5)]
+    assert all(r["rel_l2_vs_first_config"] < 1e-12 for r in deg)           # same operator in every config
     rk = [r for r in rows if r["config"] == "headline_rk4_by_geometry_mode"]
     assert [r["geometry_mode"] for r in rk] == [0, 1, 2, 3]
-    assert all(r["rel_l2_vs_first_mode"] < 1e-10 for r in rk)              # same fields in every mode
+    rkv = [r for r in rows if r["config"] == "headline_rk4_by_pipeline_variant"]
+    assert [r["variant"] for r in rkv] == [3, 5]
+    assert all(r["rel_l2_vs_first_mode"] < 1e-10 for r in rk + rkv)        # same fields in every mode
     f32 = [r for r in rows if r["config"] == "degree_sweep_fp32"]
     assert [r["P"] for r in f32] == [2, 5] and all(0 < r["rel_l2_vs_fp64"] < 1e-5 for r in f32)

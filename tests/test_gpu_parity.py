@@ -485,6 +485,45 @@ def test_trilinear_geometry_register_capped_build(fus, orc, gpu, P):
     assert rel_l2(k3, k2) < 1e-13 and rel_l2(k3, k0) < TOL_APPLY
 
 
+@pytest.mark.first_hw_run
+@pytest.mark.parametrize("P", [2, 4, 5, 7])
+def test_line_kernel_pipeline_variants(fus, orc, gpu, P):
+    """Option stiffness_variant 3 / 4 / 5: the line kernel with the software pipelines that take the
+    loop-end stall out of the default kernel (coefficient of the current cell; dofmap rows of the
+    cell after next prefetched into L2, or loaded a whole iteration ahead).  Same numbers as the
+    default are required -- one application, the fused two-vector gather, and RK4 steps through the
+    graph -- on warped cells with a ragged cell count."""
+    m = fus.BoxMesh((7, 3, 2), (0.4, -0.3, 1.0), (0.9, 0.0, 1.2),
+                    warp=lambda x: warp_vertices(x, 0.08, 3))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context()
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    rng = np.random.default_rng(500 + P)
+    x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(V.ndofs))
+    mdl = fus.LossySpectral3D(V, 1500.0, 1000.0, 3e-3, 0.5e6, 1e5, 1500.0)
+    u, v = rng.uniform(-1, 1, V.ndofs), 1e6 * rng.uniform(-1, 1, V.ndofs)
+    k0 = mdl.f1(1e-6, u, v)
+    h = 0.1 / 7
+    dt = 0.2 * h / (1500.0 * P * P)
+    mdl.init(u.copy(), v.copy())
+    mdl.rk4(0.0, 4.5 * dt, dt)
+    u_ref = mdl.u_sol()
+    for variant in (3, 4, 5):
+        ctx.set_option("stiffness_variant", variant)
+        assert ctx.get_option("stiffness_variant") == variant
+        y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+        note(f"pipeline_variant{variant}_stiffness_P{P}", rel_l2(y, yo))
+        assert rel_l2(y, yo) < TOL_APPLY
+        assert rel_l2(mdl.f1(1e-6, u, v), k0) < TOL_APPLY
+        mdl.init(u.copy(), v.copy())
+        assert mdl.rk4(0.0, 4.5 * dt, dt) == 5
+        assert rel_l2(mdl.u_sol(), u_ref) < TOL_STEPS
+    ctx.set_option("stiffness_variant", -1)
+    with pytest.raises(fus.FusError):
+        ctx.set_option("stiffness_variant", 6)
+
+
 def test_trilinear_geometry_rk4_and_errors(fus, orc, gpu):
     """geometry_mode=2 inside the captured RK4 loop (linear model, warped mesh) against the oracle;
     a context made from precomputed arrays has no vertices and must refuse the mode."""
