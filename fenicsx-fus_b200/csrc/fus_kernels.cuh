@@ -372,10 +372,14 @@ struct LineCfg {
 //                shared with the G loads just issued); 5 additionally prefetches the dofmap rows of
 //                the cell after next into L2 at the loop end; 6 instead loads those rows into
 //                registers a whole iteration ahead (right after the gathers have been issued), so
-//                that the gather addresses of the next iteration never wait on a dofmap load.
+//                that the gather addresses of the next iteration never wait on a dofmap load; with
+//                FUSE2 it also keeps the two gathered vectors raw and combines them when they are
+//                staged an iteration later (in mode 0 the multiply sits right behind the loads).
 template <int N, bool FUSE2, int GEOM = 0, typename T = double>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS,
-                                  (GEOM == 2 && N <= 5) ? 3 : (((GEOM == 3 || GEOM == 5) && N <= 5) ? 4 : 0))
+                                  (GEOM == 2 && N <= 5)
+                                      ? 3
+                                      : (((GEOM == 3 || GEOM >= 5) && N <= 5) ? 4 : ((GEOM == 6 && N == 6) ? 2 : 0)))
     stiffness_line_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                           const int32_t* __restrict__ dofmap,
                           const typename Vec2<T>::type* __restrict__ G2,
@@ -437,6 +441,9 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
   int idx[N], idxn[N];
   int idxnn[DM2 ? N : 1]; // DM2: dofmap rows of the cell after next
+  constexpr bool RAW2 = DM2 && FUSE2; // second gathered vector kept raw until it is staged
+  T xb[RAW2 ? N : 1];
+  T can = T(0), cbn = T(0);
   T xv[N];
   V2 g[STREAM ? GPF : 1][3];
   V2 gh[3], ghn[3]; // AFFINE: Ghat of the current and of the next cell
@@ -489,6 +496,9 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   for (int k = 0; k < (DM2 ? N : 1); ++k)
     idxnn[k] = 0;
 #pragma unroll
+  for (int k = 0; k < (RAW2 ? N : 1); ++k)
+    xb[k] = T(0);
+#pragma unroll
   for (int k = 0; k < (STREAM ? GPF : 1); ++k)
 #pragma unroll
     for (int p = 0; p < 3; ++p)
@@ -500,7 +510,15 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 #pragma unroll
     for (int k = 0; k < N; ++k)
       idx[k] = __ldg(dm + k * NN);
-    if constexpr (FUSE2) {
+    if constexpr (RAW2) {
+      can = __ldg(coeff + c), cbn = __ldg(coeff2 + c);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        xv[k] = __ldg(x + idx[k]);
+        xb[k] = __ldg(x2 + idx[k]);
+      }
+      cf = T(1);
+    } else if constexpr (FUSE2) {
       const T ca = __ldg(coeff + c), cb = __ldg(coeff2 + c);
 #pragma unroll
       for (int k = 0; k < N; ++k)
@@ -545,6 +563,11 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
   for (int it = 0; it < niter; ++it) {
     // (1) stage x in layout A; direction-0 derivative in registers
+    if constexpr (RAW2) { // gathered one iteration ago
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        xv[k] = can * xv[k] + cbn * xb[k];
+    }
     if (lane_ok) {
 #pragma unroll
       for (int k = 0; k < N; ++k)
@@ -563,7 +586,14 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     if constexpr (CFNOW && !FUSE2)
       cfc = valid ? __ldg(coeff + c) : T(0); // first used by the G transform, two barriers away
     if (validn) {
-      if constexpr (FUSE2) {
+      if constexpr (RAW2) {
+        can = __ldg(coeff + cn), cbn = __ldg(coeff2 + cn);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          xv[k] = __ldg(x + idxn[k]);
+          xb[k] = __ldg(x2 + idxn[k]);
+        }
+      } else if constexpr (FUSE2) {
         const T ca = __ldg(coeff + cn), cb = __ldg(coeff2 + cn);
 #pragma unroll
         for (int k = 0; k < N; ++k)

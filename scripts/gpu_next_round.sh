@@ -3,7 +3,8 @@
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_next_round.sh r2a'
 # 1. full GPU suite (incl. the tests written after the budget ran out: reference 2-D mesh, C ABI from C,
 #    float operator classes), smoke, bench (with the child-process sweep: degree sweep x geometry modes)
-# 2. ncu --set full of the on-the-fly geometry kernel (mode 2) to confirm the latency-bound reading
+# 2. the line kernel's pipeline variants on the three models + ncu of variant 5
+# 2b. ncu --set full of the on-the-fly geometry kernel (mode 2) to confirm the latency-bound reading
 # 3. ncu --set full of the streamed kernel at P=6 and P=7
 # 4. BASELINE config 5 (1.0 G dofs, P=5) on ONE GPU with a lean context
 TAG=${1:-r2a}
@@ -22,6 +23,29 @@ echo "bench exit $?"; tail -c 2500 $OUT/bench_${TAG}.json; tail -n 3 $OUT/bench_
 echo "== probe (all degrees, modes 0 and 2)"
 timeout 300 python scripts/probe_geometry_modes.py 2:107 3:71 4:54 5:43 6:36 7:31 > $OUT/probe_${TAG}.jsonl 2> $OUT/probe_${TAG}.err
 cat $OUT/probe_${TAG}.jsonl
+echo "== line-kernel pipeline variants (stiffness_variant 3/4/5 vs the default 2): headline, lossy, Westervelt"
+for MODEL in linear lossy westervelt; do
+  for V in 2 3 4 5; do
+    FUS_STIFFNESS_VARIANT=$V timeout 300 python bench.py --model $MODEL --steps 20 --warmup 3 --no-cpu-baseline \
+        --no-extras > $OUT/bench_${MODEL}_variant${V}_${TAG}.json 2> $OUT/bench_${MODEL}_variant${V}_${TAG}.err
+    python - "$OUT/bench_${MODEL}_variant${V}_${TAG}.json" $MODEL $V <<'PY'
+import json, sys
+try:
+    d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][0])
+    print(sys.argv[2], "variant", sys.argv[3], "ms/step", round(d["ms_per_step"], 4), "operator ms",
+          round(d["roofline"]["avg_launch_ms"], 4), "frac", round(d["roofline"]["frac"], 3))
+except Exception as e:
+    print("failed", sys.argv[1], e)
+PY
+  done
+done
+echo "== ncu full, variant 5 at P=4 and P=6 (is the loop-end stall gone?)"
+for P in 4 6; do
+  FUS_STIFFNESS_VARIANT=5 timeout 600 ncu --set full --clock-control none --import-source on -k regex:stiffness_line \
+      -s 2 -c 1 -f -o $OUT/prof_stiffness_variant5_P${P}_${TAG} python scripts/bench_sweep.py --degrees $P \
+      --variants=5 --geometry-modes 0 --models "" --repeats 3 > $OUT/ncu_variant5_P${P}_${TAG}.log 2>&1
+  echo "ncu variant 5 P=$P exit $?"
+done
 echo "== ncu full, mode-2 kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:stiffness_line -s 6 -c 2 \
     -f -o $OUT/prof_stiffness_mode2_${TAG} python bench.py --steps 2 --warmup 1 --geometry-mode 2 \
