@@ -364,22 +364,26 @@ struct LineCfg {
 //   3  the same code as 2 compiled under a 128-register cap (4 blocks/SM for P <= 4 instead of 3:
 //                16 warps/SM at the price of a few spilled values) -- an occupancy experiment that
 //                bench.py's child sweep measures next to mode 2.
-//   4, 5  streamed G like 0 with a different software pipeline (option "stiffness_variant" 3, 4;
-//                experiments for the stall the ncu source view of mode 0 shows):
-//                4 loads the cell coefficient for the CURRENT cell at the top of the iteration
-//                instead of carrying the next cell's across the loop edge (in mode 0 that carried
-//                value becomes a register move at the loop end, which has to wait on a scoreboard
-//                shared with the G loads just issued); 5 additionally prefetches the dofmap rows of
-//                the cell after next into L2 at the loop end; 6 instead loads those rows into
-//                registers a whole iteration ahead (right after the gathers have been issued), so
-//                that the gather addresses of the next iteration never wait on a dofmap load; with
-//                FUSE2 it also keeps the two gathered vectors raw and combines them when they are
-//                staged an iteration later (in mode 0 the multiply sits right behind the loads).
+//   4, 5, 6  streamed G like 0 with a different software pipeline (option "stiffness_variant"
+//                3, 4, 5; experiments for the stall the ncu source view of mode 0 shows).
+//                ptxas puts every global load of the cell loop on ONE scoreboard, so the first
+//                consumer of any loaded value waits for all loads in flight; in mode 0 that is a
+//                register move of the carried coefficient at the loop end, a few instructions after
+//                the dofmap rows of the next cell have been requested.
+//                4 folds the coefficient into x when it is staged (K(c) x = K(1)(c x); no carried
+//                copy, no move); 5 additionally prefetches the dofmap rows of the cell after next
+//                into L2 at the loop end; 6 instead loads those rows into registers during phase 3
+//                (with the G refills), so that every wait on the scoreboard finds the youngest load
+//                at least two phases old; with FUSE2 it also keeps the two gathered vectors raw and
+//                combines them when they are staged an iteration later (in mode 0 the multiply sits
+//                right behind the loads).
 template <int N, bool FUSE2, int GEOM = 0, typename T = double>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS,
                                   (GEOM == 2 && N <= 5)
                                       ? 3
-                                      : (((GEOM == 3 || GEOM >= 5) && N <= 5) ? 4 : ((GEOM == 6 && N == 6) ? 2 : 0)))
+                                      : (((GEOM == 3 || GEOM == 5 || (GEOM == 6 && !FUSE2)) && N <= 5)
+                                             ? 4
+                                             : ((GEOM == 6 && N == 6) ? 2 : 0)))
     stiffness_line_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
                           const int32_t* __restrict__ dofmap,
                           const typename Vec2<T>::type* __restrict__ G2,
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   constexpr int NN = C::NN, GPF = C::GPF;
   constexpr bool AFFINE = (GEOM == 1), TRI = (GEOM == 2 || GEOM == 3);
   constexpr bool STREAM = (GEOM == 0 || GEOM >= 4); // G read from memory per point
-  constexpr bool CFNOW = (GEOM >= 4), DMPF = (GEOM == 5), DM2 = (GEOM == 6);
+  constexpr bool CFX = (GEOM >= 4), DMPF = (GEOM == 5), DM2 = (GEOM == 6);
   constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
   static_assert(GEOM >= 0 && GEOM <= 6, "unknown geometry mode");
@@ -567,6 +571,10 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 #pragma unroll
       for (int k = 0; k < N; ++k)
         xv[k] = can * xv[k] + cbn * xb[k];
+    } else if constexpr (CFX && !FUSE2) { // K(c) x = K(1) (c x): the coefficient is constant in a cell
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        xv[k] = cf * xv[k];
     }
     if (lane_ok) {
 #pragma unroll
@@ -582,9 +590,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
         s = fma(D.d[q * N + k], xv[k], s);
       f0[q] = s;
     }
-    T cfc = cf;
-    if constexpr (CFNOW && !FUSE2)
-      cfc = valid ? __ldg(coeff + c) : T(0); // first used by the G transform, two barriers away
+    const T cfc = CFX ? T(1) : cf;
     if (validn) {
       if constexpr (RAW2) {
         can = __ldg(coeff + cn), cbn = __ldg(coeff2 + cn);
@@ -602,17 +608,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 #pragma unroll
         for (int k = 0; k < N; ++k)
           xv[k] = __ldg(x + idxn[k]);
-        if constexpr (!CFNOW)
-          cf = __ldg(coeff + cn);
-      }
-    }
-    if constexpr (DM2) {
-      const long long c2 = cn + stride;
-      if (lane_ok && c2 < cell_end) {
-        const int32_t* dm = dofmap + c2 * (N * NN) + t;
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-          idxnn[k] = __ldg(dm + k * NN);
+        cf = __ldg(coeff + cn);
       }
     }
     sync();
@@ -646,6 +642,16 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
       }
     }
     sync();
+
+    if constexpr (DM2) { // nothing consumes a global load between here and the end of the iteration
+      const long long c2 = cn + stride;
+      if (lane_ok && c2 < cell_end) {
+        const int32_t* dm = dofmap + c2 * (N * NN) + t;
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          idxnn[k] = __ldg(dm + k * NN);
+      }
+    }
 
     // (3) back in layout A: G transform per level, transposed direction 0 in registers
     T yv[N];
