@@ -222,7 +222,7 @@ def child_extras(timeout_s=150.0):
     time-out -- can cost the headline line."""
     cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_sweep.py"), "--degrees",
            "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,1,2,3", "--rk4-geometry-modes",
-           "0,1,2,3", "--pipeline-variants", "3,4,5", "--models", "", "--repeats", "20", "--fp32"]
+           "0,1,2,3", "--pipeline-variants", "3,4,5,6", "--models", "", "--repeats", "20", "--fp32"]
     env = dict(os.environ)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -248,9 +248,10 @@ def child_extras(timeout_s=150.0):
                                            if r.get("config") == "degree_sweep"],
            "headline_rk4_by_geometry_mode": [{k: r[k] for k in keep if k in r} for r in rows
                                              if r.get("config") == "headline_rk4_by_geometry_mode"],
-           # stiffness_variant 3/4/5: the line kernel with the software pipelines that remove the
-           # loop-end stall seen in the ncu source view of the default kernel; same
-           # results, first hardware timing here, default unchanged until it is in hand
+           # stiffness_variant 3..6: the line kernel with the software pipelines that move the
+           # scoreboard wait seen in the ncu source view of the default kernel (6 =
+           # G through a TMA-fed shared-memory ring); same results, first hardware timing here,
+           # default unchanged until it is in hand
            "headline_rk4_by_pipeline_variant": [{k: r[k] for k in keep if k in r} for r in rows
                                                 if r.get("config")
                                                 == "headline_rk4_by_pipeline_variant"],

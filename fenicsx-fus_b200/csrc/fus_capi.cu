@@ -92,8 +92,8 @@ struct fus_ctx {
   bool lean = false;        // neither G nor detJ exist on the device: always mode 2
   int live_models = 0;      // fus_model objects that still point at this context
   // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
-  // profiles/), 0 column kernel, 1 point kernel, 2 line kernel, 3 / 4 / 5 line kernel with the
-  // experimental software pipelines (kernel GEOM 4 / 5 / 6; not yet measured)
+  // profiles/), 0 column kernel, 1 point kernel, 2 line kernel, 3 / 4 / 5 / 6 line kernel with the
+  // experimental software pipelines (kernel GEOM 4 / 5 / 6 / 7; not yet measured)
   int variant = -1;
   int col_blocks_per_sm = 0;
   int reserve_sms = 0;      // SMs left free for the halo kernels while cells overlap with them
@@ -301,11 +301,19 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     return launch(stiffness_line_kernel<N, false, 5>, stiffness_line_kernel<N, true, 5>, L::THREADS,
                   L::SMEM_BYTES, L::CPB, cfg);
   }
-  if (variant == 5) { // ... or the dofmap rows loaded a whole iteration ahead (GEOM 6)
+  if (variant == 5 || (variant == 6 && !LineCfg<N>::RING_FITS)) { // dofmap rows with the G refills
     using L = LineCfg<N>;
     static KernelCfg cfg;
     return launch(stiffness_line_kernel<N, false, 6>, stiffness_line_kernel<N, true, 6>, L::THREADS,
                   L::SMEM_BYTES, L::CPB, cfg);
+  }
+  if constexpr (LineCfg<N>::RING_FITS) {
+    if (variant == 6) { // G through a TMA-fed shared-memory ring (GEOM 7)
+      using L = LineCfg<N>;
+      static KernelCfg cfg;
+      return launch(stiffness_line_kernel<N, false, 7>, stiffness_line_kernel<N, true, 7>,
+                    L::THREADS, L::SMEM_BYTES_RING, L::CPB, cfg);
+    }
   }
   using C = ColCfg<N>;
   static KernelCfg cfg;
@@ -618,7 +626,7 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   gll(P, c->pts, c->wts);
   if (const char* e = std::getenv("FUS_STIFFNESS_VARIANT")) { // A/B runs of bench.py
     const int v = std::atoi(e);
-    if (v >= -1 && v <= 5)
+    if (v >= -1 && v <= 6)
       c->variant = v;
   }
   if (const char* e = std::getenv("FUS_L2_PERSIST"))
@@ -944,8 +952,8 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
     if (!std::strcmp(name, k))
       ++c->config_epoch; // a captured step graph would replay the previous choice
   if (!std::strcmp(name, "stiffness_variant")) {
-    if (value < -1 || value > 5) {
-      set_error("stiffness_variant must be -1 (auto) or 0..5");
+    if (value < -1 || value > 6) {
+      set_error("stiffness_variant must be -1 (auto) or 0..6");
       return FUS_ERR_ARG;
     }
     c->variant = value;

@@ -79,6 +79,78 @@ __device__ __forceinline__ float2 ld_stream(const float2* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA bulk copies into a shared-memory ring (line kernel GEOM 7): one cp.async.bulk per cell brings
+// the cell's whole block of G (48*N^3 contiguous bytes) into a ring stage and signals an mbarrier
+// with the byte count; consumers wait on the barrier's phase.  No registers and no scoreboard are
+// tied up while the copy is in flight.  Waits are bounded: a protocol error gives wrong numbers (which
+// the parity checks see), never a hung device.
+// ------------------------------------------------------------------------------------------------
+#ifdef FUS_HOST_EMULATION
+__device__ __forceinline__ void ring_bar_init(unsigned long long* bar) {
+  std::atomic_ref<unsigned long long>(*bar).store(0ull, std::memory_order_release);
+}
+__device__ __forceinline__ void ring_bar_init_fence() {}
+// the emulated copy is synchronous; the barrier word counts completed phases
+__device__ __forceinline__ void ring_issue(void* dst, const void* src, unsigned bytes,
+                                           unsigned long long* bar) {
+  std::memcpy(dst, src, bytes);
+  std::atomic_ref<unsigned long long>(*bar).fetch_add(1ull, std::memory_order_release);
+}
+__device__ __forceinline__ bool ring_wait(unsigned long long* bar, unsigned phase_index) {
+  for (long long spin = 0; spin < (1ll << 34); ++spin) {
+    if (std::atomic_ref<unsigned long long>(*bar).load(std::memory_order_acquire) > phase_index)
+      return true;
+    std::this_thread::yield();
+  }
+  return false;
+}
+#else
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void ring_bar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ring_bar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// arm the stage's barrier with the byte count, then start the copy that will complete it; the
+// proxy fence orders the generic-proxy reads of the previous contents before the async-proxy write
+__device__ __forceinline__ void ring_issue(void* dst, const void* src, unsigned bytes,
+                                           unsigned long long* bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool ring_wait(unsigned long long* bar, unsigned phase_index) {
+  const unsigned addr = smem_u32(bar), parity = phase_index & 1u;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int spin = 0;; ++spin) { // try_wait suspends for a while by itself
+    unsigned done;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    if (done)
+      return true;
+    if ((spin & 15) == 15) { // a copy lands within microseconds: give up after 20 ms
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000ull)
+        return false;
+    }
+  }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // Stiffness operator, "column" kernel (kernels (1)(2)(3) of the north star in one pass):
 //   y[dof] += sum_cells B^T (coeff_c G_c) B x[dof]        StiffnessSpectral3D::operator(),
 //                                                         spectral_op.hpp:173-243
@@ -350,6 +422,12 @@ struct LineCfg {
   static constexpr int CS = ((X_SZ + B1_SZ + B2_SZ + 7) / 8) * 8 + 8; // all three buffers of a cell
   static constexpr int SMEM_BYTES = CPB * CS * (int)sizeof(double);
   static constexpr int GPF = (N <= 7) ? N : N / 2;
+  // GEOM 7: G of a cell staged in shared memory by TMA bulk copies, RING_STAGES cells deep per slot
+  static constexpr int RING_STAGES = 2;
+  static constexpr int CELLG = 6 * N * NN; // doubles of G per cell (48*N^3 bytes, a multiple of 16)
+  static constexpr int SMEM_BYTES_RING
+      = SMEM_BYTES + CPB * RING_STAGES * (CELLG + 1) * (int)sizeof(double);
+  static constexpr bool RING_FITS = SMEM_BYTES_RING <= 227 * 1024;
 };
 
 // GEOM selects where the geometric factors come from (option "geometry_mode", see DESIGN):
@@ -377,6 +455,10 @@ struct LineCfg {
 //                at least two phases old; with FUSE2 it also keeps the two gathered vectors raw and
 //                combines them when they are staged an iteration later (in mode 0 the multiply sits
 //                right behind the loads).
+//   7  pipeline 6 with the G stream taken off the scoreboard altogether: one TMA bulk copy per cell
+//                (cp.async.bulk, 48*N^3 contiguous bytes) into a two-stage shared-memory ring per
+//                cell slot, completion through an mbarrier, G read back with 16-byte shared loads.
+//                No registers hold G in flight (12*N fewer live registers).  "stiffness_variant" 6.
 template <int N, bool FUSE2, int GEOM = 0, typename T = double>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS,
                                   (GEOM == 2 && N <= 5)
@@ -397,10 +479,13 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   constexpr int NN = C::NN, GPF = C::GPF;
   constexpr bool AFFINE = (GEOM == 1), TRI = (GEOM == 2 || GEOM == 3);
   constexpr bool STREAM = (GEOM == 0 || GEOM >= 4); // G read from memory per point
-  constexpr bool CFX = (GEOM >= 4), DMPF = (GEOM == 5), DM2 = (GEOM == 6);
+  constexpr bool RING = (GEOM == 7);                // ... through a TMA-fed shared-memory ring
+  constexpr bool REGRING = STREAM && !RING;         // ... through the register ring g[][]
+  constexpr bool CFX = (GEOM >= 4), DMPF = (GEOM == 5), DM2 = (GEOM == 6 || GEOM == 7);
+  static_assert(!RING || sizeof(T) == sizeof(double), "the TMA ring is built for FP64 only");
   constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
-  static_assert(GEOM >= 0 && GEOM <= 6, "unknown geometry mode");
+  static_assert(GEOM >= 0 && GEOM <= 7, "unknown geometry mode");
 #ifdef FUS_HOST_EMULATION
   T* smem = reinterpret_cast<T*>(fus_emu::dynamic_shared());
 #else
@@ -438,6 +523,24 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 #endif
   };
 
+  // RING: per cell slot, RING_STAGES stages of CELLG doubles behind the scratch buffers, then one
+  // mbarrier per (slot, stage).  Thread t == 0 of a cell is its producer.
+  constexpr unsigned RING_BYTES = (unsigned)(C::CELLG * sizeof(double));
+  T* const ring = smem + C::CPB * C::CS + slot * (C::RING_STAGES * C::CELLG);
+  unsigned long long* const ring_bar
+      = reinterpret_cast<unsigned long long*>(smem + C::CPB * C::CS
+                                              + C::CPB * C::RING_STAGES * C::CELLG)
+        + slot * C::RING_STAGES;
+  const bool producer = lane_ok && t == 0;
+  bool ring_ok = true;
+  if constexpr (RING) {
+    if (producer)
+      for (int sg = 0; sg < C::RING_STAGES; ++sg)
+        ring_bar_init(ring_bar + sg);
+    ring_bar_init_fence();
+    __syncthreads();
+  }
+
   const long long stride = (long long)gridDim.x * C::CPB;
   const long long ncell = cell_end - cell_begin;
   const int niter = (int)((ncell + stride - 1) / stride);
@@ -449,7 +552,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   T xb[RAW2 ? N : 1];
   T can = T(0), cbn = T(0);
   T xv[N];
-  V2 g[STREAM ? GPF : 1][3];
+  V2 g[REGRING ? GPF : 1][3];
   V2 gh[3], ghn[3]; // AFFINE: Ghat of the current and of the next cell
   // TRI: the pieces of J on this thread's line (xi1,xi2) = (x[a],x[b]) for the current cell.  The
   // 192 B of a cell are read by all its threads at the same addresses, so there is nothing to keep
@@ -503,7 +606,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   for (int k = 0; k < (RAW2 ? N : 1); ++k)
     xb[k] = T(0);
 #pragma unroll
-  for (int k = 0; k < (STREAM ? GPF : 1); ++k)
+  for (int k = 0; k < (REGRING ? GPF : 1); ++k)
 #pragma unroll
     for (int p = 0; p < 3; ++p)
       g[k][p] = make_v2<T>(T(0), T(0));
@@ -540,6 +643,9 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
         gh[p] = __ldg(G2 + c * 3 + p);
     } else if constexpr (TRI) {
       tri_setup(c);
+    } else if constexpr (RING) {
+      if (producer)
+        ring_issue(ring, G2 + c * (3 * N * NN), RING_BYTES, ring_bar);
     } else {
       const V2* gp = G2 + c * (3 * N * NN) + t;
 #pragma unroll
@@ -563,6 +669,10 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     }
     if constexpr (TRI)
       tri_prefetch(cn);
+    if constexpr (RING) {
+      if (producer)
+        ring_issue(ring + C::CELLG, G2 + cn * (3 * N * NN), RING_BYTES, ring_bar + 1);
+    }
   }
 
   for (int it = 0; it < niter; ++it) {
@@ -660,6 +770,13 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
       yv[m] = T(0);
     const V2* gpc = G2 + c * (3 * N * NN) + t;
     const V2* gpn = G2 + cn * (3 * N * NN) + t;
+    // RING: this iteration's stage, filled by the copy issued two iterations ago
+    const int stage = it % C::RING_STAGES;
+    const V2* gring = reinterpret_cast<const V2*>(ring + stage * C::CELLG) + t;
+    if constexpr (RING) { // after one time-out a thread stops waiting (wrong numbers, no stall)
+      if (valid && ring_ok)
+        ring_ok = ring_wait(ring_bar + stage, (unsigned)(it / C::RING_STAGES));
+    }
 #pragma unroll
     for (int i0 = 0; i0 < N; ++i0) {
       T f1 = T(0), f2 = T(0);
@@ -676,6 +793,14 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
         if constexpr (AFFINE) {
           ga = gh[0], gb = gh[1], gc = gh[2];
           scale = cfc * (D.w[i0] * wab);
+        } else if constexpr (RING) {
+          if (valid) {
+            ga = gring[(i0 * 3 + 0) * NN], gb = gring[(i0 * 3 + 1) * NN],
+            gc = gring[(i0 * 3 + 2) * NN];
+          } else {
+            ga = gb = gc = make_v2<T>(T(0), T(0));
+          }
+          scale = cfc;
         } else {
           ga = g[i0 % GPF][0], gb = g[i0 % GPF][1], gc = g[i0 % GPF][2];
           scale = cfc;
@@ -685,7 +810,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
         t2 = scale * (gb.x * f0[i0] + gc.x * f1 + gc.y * f2);
       }
       // refill the ring slot: level i0+GPF of this cell, or of the next cell once past the top
-      if constexpr (!STREAM) {
+      if constexpr (!REGRING) {
       } else if (i0 + GPF < N) {
         if (valid) {
 #pragma unroll
@@ -706,6 +831,12 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
       }
     }
     sync();
+
+    if constexpr (RING) { // every thread of the cell is past its reads of this stage: refill it
+      const long long c2 = cn + stride; // the cell this slot works on two iterations from now
+      if (producer && c2 < cell_end)
+        ring_issue(ring + stage * C::CELLG, G2 + c2 * (3 * N * NN), RING_BYTES, ring_bar + stage);
+    }
 
     // (4) transposed direction 1 and 2 along the thread's own lines, results back in place
     if (lane_ok) {

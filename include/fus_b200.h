@@ -136,7 +136,7 @@ int fus_ctx_set_stream(fus_ctx* ctx, void* cuda_stream);
 /* Tuning/diagnostic knobs (all optional; defaults in brackets):
      "stiffness_variant"  [-1] -1 auto (column kernel for P <= 3, line kernel for P >= 4),
                                0 column, 1 per-point (cross-check), 2 line kernel,
-                               3 / 4 / 5 line kernel with experimental software pipelines (same
+                               3..6 line kernel with experimental software pipelines (same
                                results; kept selectable until measured)
      "geometry_mode"      [0]  0 streamed G, 1 affine compression, 2 trilinear on the fly (below)
      "use_graph"          [1]  replay RK4 steps from a captured CUDA graph when possible

@@ -23,9 +23,9 @@ echo "bench exit $?"; tail -c 2500 $OUT/bench_${TAG}.json; tail -n 3 $OUT/bench_
 echo "== probe (all degrees, modes 0 and 2)"
 timeout 300 python scripts/probe_geometry_modes.py 2:107 3:71 4:54 5:43 6:36 7:31 > $OUT/probe_${TAG}.jsonl 2> $OUT/probe_${TAG}.err
 cat $OUT/probe_${TAG}.jsonl
-echo "== line-kernel pipeline variants (stiffness_variant 3/4/5 vs the default 2): headline, lossy, Westervelt"
+echo "== line-kernel pipeline variants (stiffness_variant 3..6 vs the default 2): headline, lossy, Westervelt"
 for MODEL in linear lossy westervelt; do
-  for V in 2 3 4 5; do
+  for V in 2 3 4 5 6; do
     FUS_STIFFNESS_VARIANT=$V timeout 300 python bench.py --model $MODEL --steps 20 --warmup 3 --no-cpu-baseline \
         --no-extras > $OUT/bench_${MODEL}_variant${V}_${TAG}.json 2> $OUT/bench_${MODEL}_variant${V}_${TAG}.err
     python - "$OUT/bench_${MODEL}_variant${V}_${TAG}.json" $MODEL $V <<'PY'
@@ -39,8 +39,12 @@ except Exception as e:
 PY
   done
 done
-echo "== ncu full, variant 5 at P=4 and P=6 (is the loop-end stall gone?)"
+echo "== ncu full, variants 5 and 6 at P=4 and P=6 (is the loop-end stall gone?)"
 for P in 4 6; do
+  FUS_STIFFNESS_VARIANT=6 timeout 600 ncu --set full --clock-control none --import-source on -k regex:stiffness_line \
+      -s 2 -c 1 -f -o $OUT/prof_stiffness_variant6_P${P}_${TAG} python scripts/bench_sweep.py --degrees $P \
+      --variants=6 --geometry-modes 0 --models "" --repeats 3 > $OUT/ncu_variant6_P${P}_${TAG}.log 2>&1
+  echo "ncu variant 6 P=$P exit $?"
   FUS_STIFFNESS_VARIANT=5 timeout 600 ncu --set full --clock-control none --import-source on -k regex:stiffness_line \
       -s 2 -c 1 -f -o $OUT/prof_stiffness_variant5_P${P}_${TAG} python scripts/bench_sweep.py --degrees $P \
       --variants=5 --geometry-modes 0 --models "" --repeats 3 > $OUT/ncu_variant5_P${P}_${TAG}.log 2>&1

@@ -37,9 +37,11 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
                 const double* wts, int max_blocks, long long cb, long long ce) {
   const DMat<N> D = make_dmat<N>(dphi, pts, wts);
   const bool fuse = x2 != nullptr;
-  if (variant >= 3) { // stiffness_variant 3/4/5: line kernel, streamed G, kernel GEOM 4/5/6
+  if (variant >= 3) { // stiffness_variant 3..6: line kernel, streamed G, kernel GEOM 4..7
     geom = variant + 1;
     variant = 2;
+    if (geom == 7 && !LineCfg<N>::RING_FITS)
+      geom = 6; // as fus_capi.cu: the ring of the largest degree does not fit in shared memory
   }
   std::vector<double2> G2;
   const double2* gptr = nullptr;
@@ -91,8 +93,15 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
     fuse ? run(stiffness_line_kernel<N, true, 4>) : run(stiffness_line_kernel<N, false, 4>);
   else if (geom == 5)
     fuse ? run(stiffness_line_kernel<N, true, 5>) : run(stiffness_line_kernel<N, false, 5>);
-  else
+  else if (geom == 6)
     fuse ? run(stiffness_line_kernel<N, true, 6>) : run(stiffness_line_kernel<N, false, 6>);
+  else if constexpr (LineCfg<N>::RING_FITS) {
+    auto run_ring = [&](auto kern) {
+      fus_emu::launch(blocks_for(L::CPB), L::THREADS, L::SMEM_BYTES_RING,
+                      [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D); });
+    };
+    fuse ? run_ring(stiffness_line_kernel<N, true, 7>) : run_ring(stiffness_line_kernel<N, false, 7>);
+  }
   return 0;
 }
 

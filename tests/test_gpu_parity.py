@@ -521,7 +521,63 @@ def test_line_kernel_pipeline_variants(fus, orc, gpu, P):
         assert rel_l2(mdl.u_sol(), u_ref) < TOL_STEPS
     ctx.set_option("stiffness_variant", -1)
     with pytest.raises(fus.FusError):
-        ctx.set_option("stiffness_variant", 6)
+        ctx.set_option("stiffness_variant", 7)
+
+
+RING_CHECK = r"""
+import os, sys
+import numpy as np
+ROOT = sys.argv[1]
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from fenicsx_fus_b200 import capi
+if os.environ.get("FUS_TEST_LIB"):                      # --emulated-device: tests only
+    capi.LIB_PATH, capi._lib = os.environ["FUS_TEST_LIB"], None
+import fenicsx_fus_b200 as fus
+from oracle.oracle import Oracle
+from conftest import warp_vertices, rel_l2
+orc = Oracle()
+for P in (2, 3, 4, 5, 6):
+    m = fus.BoxMesh((7, 3, 2), (0.4, -0.3, 1.0), (0.9, 0.0, 1.2), warp=lambda x: warp_vertices(x, 0.08, 3))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context()
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    rng = np.random.default_rng(600 + P)
+    x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, np.zeros(V.ndofs))
+    mdl = fus.LossySpectral3D(V, 1500.0, 1000.0, 3e-3, 0.5e6, 1e5, 1500.0)
+    u, v = rng.uniform(-1, 1, V.ndofs), 1e6 * rng.uniform(-1, 1, V.ndofs)
+    k0 = mdl.f1(1e-6, u, v)
+    dt = 0.2 * (0.1 / 7) / (1500.0 * P * P)
+    mdl.init(u.copy(), v.copy()); mdl.rk4(0.0, 4.5 * dt, dt); u_ref = mdl.u_sol()
+    ctx.set_option("stiffness_variant", 6)
+    for rep in range(3):                                  # repeated launches reuse the barriers' phases
+        y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+        assert rel_l2(y, yo) < 1e-12, (P, rep, rel_l2(y, yo))
+    assert rel_l2(mdl.f1(1e-6, u, v), k0) < 1e-12, P
+    mdl.init(u.copy(), v.copy())
+    assert mdl.rk4(0.0, 4.5 * dt, dt) == 5
+    assert rel_l2(mdl.u_sol(), u_ref) < 1e-10, P
+    print("P", P, "ok", rel_l2(y, yo))
+    mdl.destroy()
+print("ring variant ok")
+"""
+
+
+@pytest.mark.first_hw_run
+def test_line_kernel_tma_ring_variant(fus, gpu):
+    """Option stiffness_variant 6: G of a cell arrives by one TMA bulk copy in a shared-memory ring
+    (cp.async.bulk + mbarrier) instead of through registers.  Same checks as the other pipeline
+    variants, in a child process: the first hardware run of the mbarrier protocol must not be able to
+    leave this process with a faulted context (its waits are time-bounded, so it cannot hang either)."""
+    import subprocess
+    import sys
+    from fenicsx_fus_b200 import capi
+    env = exe_env()
+    if capi.LIB_PATH.endswith("libfus_b200_emulated.so"):
+        env["FUS_TEST_LIB"] = capi.LIB_PATH
+    res = subprocess.run([sys.executable, "-c", RING_CHECK, ROOT], capture_output=True, text=True,
+                         timeout=900, env=env, cwd=ROOT)
+    assert res.returncode == 0 and "ring variant ok" in res.stdout, res.stdout[-800:] + res.stderr[-2500:]
 
 
 def test_trilinear_geometry_rk4_and_errors(fus, orc, gpu):

@@ -67,13 +67,14 @@ def _case(fus, orc, P, n=(5, 3, 2), warp=True, numbering=1):
     return m, V, G, dJ, pts, wts
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
 def test_emulated_stiffness_kernels_vs_oracle(fus, orc, emu, P, variant):
     """stiffness_col_kernel / stiffness_point_kernel / stiffness_line_kernel with streamed G, plain
     and fused two-vector gather, 30 warped cells on at most 2 blocks (grid-stride loop, ragged tail,
-    the look-ahead pipeline across cells).  Variants 3-5 are the line kernel's experimental software
-    pipelines (coefficient of the current cell; dofmap prefetched / loaded a whole iteration ahead)."""
+    the look-ahead pipeline across cells).  Variants 3-6 are the line kernel's experimental software
+    pipelines (coefficient folded into x; dofmap prefetched / loaded with the G refills; G through
+    the TMA-fed shared-memory ring, emulated with synchronous copies and phase counters)."""
     m, V, G, dJ, pts, wts = _case(fus, orc, P, numbering=P % 2)
     nd, nc = V.ndofs, m.ncells
     rng = np.random.default_rng(100 * P + variant)
@@ -103,7 +104,8 @@ def test_emulated_stiffness_kernels_vs_oracle(fus, orc, emu, P, variant):
 
 
 @pytest.mark.parametrize("variant,P", [(0, 2), (0, 3), (2, 4), (2, 5), (2, 6), (2, 7), (1, 3),
-                                       (3, 4), (4, 5), (5, 2), (5, 4), (5, 6), (5, 7)])
+                                       (3, 4), (4, 5), (5, 2), (5, 4), (5, 6), (5, 7),
+                                       (6, 1), (6, 3), (6, 4), (6, 5), (6, 6)])
 def test_emulated_split_launches_of_a_partitioned_stage(fus, orc, emu, variant, P):
     """A partitioned stage applies the cells in three launches -- interior A [ni, mid), interface
     [0, ni), interior B [mid, nc) (assemble_rhs in csrc/fus_capi.cu) -- with sub-ranges that are
