@@ -214,19 +214,12 @@ def run_reference_arm(args):
     return 0
 
 
-def child_extras(timeout_s=150.0):
-    """Secondary measurements in a CHILD process (scripts/bench_sweep.py), after the headline
-    numbers are in hand: the degree sweep of BASELINE config 2 (single operator application, P=2..7,
-    ~10 M dofs) with the geometric factors streamed and rebuilt on the fly, and the headline RK4
-    workload per geometry mode.  A child so that nothing it does -- a fault in a newer kernel, a
-    time-out -- can cost the headline line."""
-    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_sweep.py"), "--degrees",
-           "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,1,2,3", "--rk4-geometry-modes",
-           "0,1,2,3", "--pipeline-variants", "3,4,5,6", "--models", "", "--repeats", "20", "--fp32"]
+def _run_sweep(extra_args, timeout_s):
+    """One run of scripts/bench_sweep.py in a child process: (JSON rows, exit code, stderr tail)."""
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_sweep.py")] + extra_args
     env = dict(os.environ)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
-    t0 = time.perf_counter()
     try:
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
         out, rc, err = res.stdout, res.returncode, res.stderr[-400:]
@@ -240,25 +233,39 @@ def child_extras(timeout_s=150.0):
                 rows.append(json.loads(ln))
             except ValueError:
                 pass
+    return rows, rc, err
+
+
+def child_extras(timeout_s=150.0):
+    """Secondary measurements in CHILD processes (scripts/bench_sweep.py), after the headline
+    numbers are in hand: the degree sweep of BASELINE config 2 (single operator application, P=2..7,
+    ~10 M dofs) with the geometric factors streamed and rebuilt on the fly, the headline RK4
+    workload per geometry mode and per pipeline variant, the FP32 operators.  Children so that
+    nothing they do -- a fault in a newer kernel, a time-out -- can cost the headline line; the
+    TMA-ring variant, whose mbarrier protocol has its first hardware run here, gets a child of its
+    own so that it cannot cost the other extras either."""
+    t0 = time.perf_counter()
+    rows, rc, err = _run_sweep(
+        ["--degrees", "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0,1,2,3",
+         "--rk4-geometry-modes", "0,1,2,3", "--pipeline-variants", "3,4,5", "--models", "",
+         "--repeats", "20", "--fp32"], timeout_s)
     keep = ("P", "dofs", "geometry_mode", "variant", "ms_min", "ms_median", "gdof_per_s",
             "frac_of_measured_peak", "ms_per_step", "dof_updates_per_s", "operator_ms",
             "rel_l2_vs_first_mode", "rel_l2_vs_first_config", "rel_l2_vs_fp64")
-    res = {"wall_s": time.perf_counter() - t0, "exit": rc,
-           "degree_sweep_operator_apply": [{k: r[k] for k in keep if k in r} for r in rows
-                                           if r.get("config") == "degree_sweep"],
-           "headline_rk4_by_geometry_mode": [{k: r[k] for k in keep if k in r} for r in rows
-                                             if r.get("config") == "headline_rk4_by_geometry_mode"],
-           # stiffness_variant 3..6: the line kernel with the software pipelines that move the
-           # scoreboard wait seen in the ncu source view of the default kernel (6 =
-           # G through a TMA-fed shared-memory ring); same results, first hardware timing here,
-           # default unchanged until it is in hand
-           "headline_rk4_by_pipeline_variant": [{k: r[k] for k in keep if k in r} for r in rows
-                                                if r.get("config")
-                                                == "headline_rk4_by_pipeline_variant"],
+
+    def pick(rws, config):
+        return [{k: r[k] for k in keep if k in r} for r in rws if r.get("config") == config]
+
+    res = {"exit": rc,
+           "degree_sweep_operator_apply": pick(rows, "degree_sweep"),
+           "headline_rk4_by_geometry_mode": pick(rows, "headline_rk4_by_geometry_mode"),
+           # stiffness_variant 3..5: the line kernel with the software pipelines that move the
+           # scoreboard wait seen in the ncu source view of the default kernel (DESIGN.md 3.1);
+           # same results, first hardware timing here, default unchanged until it is in hand
+           "headline_rk4_by_pipeline_variant": pick(rows, "headline_rk4_by_pipeline_variant"),
            # FP32 operator instantiation (float data, 28 B/point + 8 B/dof algorithmic): first
            # hardware run of these kernels -- their logic is covered by the host emulation tests
-           "degree_sweep_operator_apply_fp32": [{k: r[k] for k in keep if k in r} for r in rows
-                                                if r.get("config") == "degree_sweep_fp32"],
+           "degree_sweep_operator_apply_fp32": pick(rows, "degree_sweep_fp32"),
            "note": ("geometry_mode 0 streams the reference's G (48 B/point; the roofline's bytes), "
                     "1 keeps one Ghat per affine cell (the box qualifies), "
                     "2 rebuilds G per point from the trilinear cell map (192 B/cell), 3 is the same "
@@ -266,6 +273,19 @@ def child_extras(timeout_s=150.0):
                     "frac_of_measured_peak always uses the streamed algorithmic bytes")}
     if rc != 0:
         res["stderr_tail"] = err
+    # stiffness_variant 6: G through a TMA bulk-copy ring in shared memory, next to the default kernel
+    rows6, rc6, err6 = _run_sweep(
+        ["--degrees", "2,3,4,5,6,7", "--variants=-1", "--geometry-modes", "0", "--rk4-geometry-modes",
+         "0", "--pipeline-variants", "6", "--models", "", "--repeats", "20"], 90.0)
+    res["tma_ring_variant"] = {"exit": rc6,
+                               "degree_sweep_operator_apply": pick(rows6, "degree_sweep"),
+                               "headline_rk4": (pick(rows6, "headline_rk4_by_geometry_mode")
+                                                + pick(rows6, "headline_rk4_by_pipeline_variant")),
+                               "note": "variant -1 = the default kernel of the same run; P=7 falls "
+                                       "back to variant 5 (the ring does not fit in shared memory)"}
+    if rc6 != 0:
+        res["tma_ring_variant"]["stderr_tail"] = err6
+    res["wall_s"] = time.perf_counter() - t0
     return res
 
 
