@@ -100,6 +100,7 @@ struct fus_ctx {
   int halo_reserve = 4;     // reserve_sms inside a partitioned stage, NCCL side-stream mode
   int peer_reserve = 0;     // same, peer-direct mode
   int l2_persist = 0;       // keep the rhs accumulator b resident in L2 during rk4 (option)
+  int stage_hints = 0;      // epilogue: streaming vectors marked L2 evict-first (option)
   int use_graph = 1;        // replay RK4 steps from a captured CUDA graph (option "use_graph")
   long long config_epoch = 0; // bumped by anything that changes what a step launches
   Halo* halo = nullptr;
@@ -172,6 +173,8 @@ struct fus_model {
   int64_t nb = 0;
   int32_t* d_bidx = nullptr;
   double *d_bsrc = nullptr, *d_bdsrc = nullptr, *d_babs = nullptr;
+  long long* d_bchunk = nullptr; // first boundary entry of every epilogue chunk (kStageChunk dofs)
+  unsigned int* d_done = nullptr; // stage-3 epilogue: blocks finished
   // state (u0,v0 double as u_n,v_n) and work vectors
   double *d_u0 = nullptr, *d_v0 = nullptr, *d_ua = nullptr, *d_va = nullptr, *d_un = nullptr,
          *d_vn = nullptr, *d_b = nullptr;
@@ -631,6 +634,8 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   }
   if (const char* e = std::getenv("FUS_L2_PERSIST"))
     c->l2_persist = std::atoi(e) != 0;
+  if (const char* e = std::getenv("FUS_STAGE_HINTS"))
+    c->stage_hints = std::atoi(e) != 0;
   if (const char* e = std::getenv("FUS_USE_GRAPH"))
     c->use_graph = std::atoi(e) != 0;
   *out = c;
@@ -1013,6 +1018,11 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
     c->l2_persist = value != 0;
     return FUS_OK;
   }
+  if (!std::strcmp(name, "stage_hints")) {
+    c->stage_hints = value != 0;
+    ++c->config_epoch;
+    return FUS_OK;
+  }
   if (!std::strcmp(name, "use_graph")) {
     c->use_graph = value != 0;
     return FUS_OK;
@@ -1359,28 +1369,62 @@ int fus_model_create(fus_ctx* c, int kind, const double* c0, const double* rho0,
     FUS_CUDA(cudaStreamSynchronize(c->stream));
     FUS_CUDA(cudaMemsetAsync(m->d_un, 0, sizeof(double) * nd, c->stream));
     FUS_CUDA(cudaMemsetAsync(m->d_vn, 0, sizeof(double) * nd, c->stream));
-    // compact the boundary vectors
+    // Boundary terms (facet-lumped vectors of the collocated `ds` forms).  When the mesh is
+    // partitioned every rank has integrated its own facets, so a shared dof carries partial sums:
+    // they are added up on the owner once, here (the term is linear in them and v[d] is the same on
+    // every rank), and the per-stage boundary update then touches owned dofs only.
+    std::vector<double> hs(src ? src : nullptr, src ? src + nd : nullptr),
+        hd(dsrc ? dsrc : nullptr, dsrc ? dsrc + nd : nullptr),
+        ha(absb ? absb : nullptr, absb ? absb + nd : nullptr);
+    if (c->halo) {
+      for (std::vector<double>* hv : {&hs, &hd, &ha}) {
+        // collective: every rank reduces all three vectors, present or not, in the same order
+        if (hv->empty())
+          FUS_CUDA(cudaMemsetAsync(m->d_un, 0, sizeof(double) * nd, c->stream));
+        else
+          FUS_CUDA(cudaMemcpyAsync(m->d_un, hv->data(), sizeof(double) * nd,
+                                   cudaMemcpyHostToDevice, c->stream));
+        FUS_TRY(halo_reverse(c->halo, m->d_un, nullptr, c->stream));
+        hv->resize((size_t)nd);
+        FUS_CUDA(cudaMemcpyAsync(hv->data(), m->d_un, sizeof(double) * nd, cudaMemcpyDeviceToHost,
+                                 c->stream));
+        FUS_CUDA(cudaStreamSynchronize(c->stream));
+      }
+      FUS_CUDA(cudaMemsetAsync(m->d_un, 0, sizeof(double) * nd, c->stream));
+    }
+    // compact them over the owned dofs, in dof order, with the first entry of every epilogue chunk
     std::vector<int32_t> bidx;
     std::vector<double> bs, bd, ba;
-    for (int64_t i = 0; i < nd; ++i) {
-      const double a = src ? src[i] : 0.0, b = dsrc ? dsrc[i] : 0.0, e = absb ? absb[i] : 0.0;
+    const int64_t nchunks = (nd + kStageChunk - 1) / kStageChunk;
+    std::vector<long long> bchunk((size_t)nchunks + 1, 0);
+    for (int64_t i = 0; i < c->nowned; ++i) {
+      const double a = hs.empty() ? 0.0 : hs[i], b = hd.empty() ? 0.0 : hd[i],
+                   e = ha.empty() ? 0.0 : ha[i];
       if (a != 0.0 || b != 0.0 || e != 0.0) {
         bidx.push_back((int32_t)i);
         bs.push_back(a);
         bd.push_back(b);
         ba.push_back(e);
+        ++bchunk[(size_t)(i / kStageChunk) + 1];
       }
     }
+    for (int64_t k = 0; k < nchunks; ++k)
+      bchunk[(size_t)k + 1] += bchunk[(size_t)k];
     m->nb = (int64_t)bidx.size();
+    FUS_CUDA(cudaMalloc(&m->d_done, sizeof(unsigned int)));
+    FUS_CUDA(cudaMemset(m->d_done, 0, sizeof(unsigned int)));
     if (m->nb) {
       FUS_CUDA(cudaMalloc(&m->d_bidx, sizeof(int32_t) * m->nb));
       FUS_CUDA(cudaMalloc(&m->d_bsrc, sizeof(double) * m->nb));
       FUS_CUDA(cudaMalloc(&m->d_bdsrc, sizeof(double) * m->nb));
       FUS_CUDA(cudaMalloc(&m->d_babs, sizeof(double) * m->nb));
+      FUS_CUDA(cudaMalloc(&m->d_bchunk, sizeof(long long) * bchunk.size()));
       FUS_CUDA(cudaMemcpy(m->d_bidx, bidx.data(), sizeof(int32_t) * m->nb, cudaMemcpyHostToDevice));
       FUS_CUDA(cudaMemcpy(m->d_bsrc, bs.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
       FUS_CUDA(cudaMemcpy(m->d_bdsrc, bd.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
       FUS_CUDA(cudaMemcpy(m->d_babs, ba.data(), sizeof(double) * m->nb, cudaMemcpyHostToDevice));
+      FUS_CUDA(cudaMemcpy(m->d_bchunk, bchunk.data(), sizeof(long long) * bchunk.size(),
+                          cudaMemcpyHostToDevice));
     }
     FUS_CUDA(cudaStreamSynchronize(c->stream));
     return FUS_OK;
@@ -1405,6 +1449,7 @@ int fus_model_destroy(fus_model* m) {
   cudaFree(m->d_stepctr);
   for (void* p : {(void*)m->d_lin, (void*)m->d_att, (void*)m->d_m, (void*)m->d_dnl,
                   (void*)m->d_bidx, (void*)m->d_bsrc, (void*)m->d_bdsrc, (void*)m->d_babs,
+                  (void*)m->d_bchunk, (void*)m->d_done,
                   (void*)m->d_u0, (void*)m->d_v0, (void*)m->d_ua, (void*)m->d_va, (void*)m->d_un,
                   (void*)m->d_vn, (void*)m->d_b})
     cudaFree(p);
@@ -1489,24 +1534,30 @@ static void source_scalars(const fus_model* m, double t, double* g, double* dg) 
 // b += K(lin) u [+ K(att) v] + boundary terms, with the halo exchange around it when partitioned:
 // the right-hand side assembly of f1 (Linear.hpp:203-206, Lossy.hpp:229-234, Westervelt.hpp:260-265).
 // u, v must have fresh ghosts on entry.
+// b[d] += g src[d] + dg dsrc[d] - absb[d] v[d] over the (owned) boundary dofs, as a kernel of its
+// own: f1, and the first stage of an rk4 call (every later stage is seeded by the epilogue before it)
+static int launch_boundary(fus_model* m, const double* v, double g, double dg, bool from_table) {
+  fus_ctx* c = m->ctx;
+  if (!m->nb)
+    return FUS_OK;
+  ProfScope prof(c, 2, c->stream);
+  boundary_kernel<<<grid_for(m->nb, 256, 1 << 30), 256, 0, c->stream>>>(
+      m->d_b, v, m->d_bidx, m->d_bsrc, m->d_bdsrc, m->d_babs, m->nb, g, dg,
+      from_table ? m->d_src : nullptr, m->d_stepctr, 0);
+  FUS_LAUNCHED();
+  return FUS_OK;
+}
+
 static int assemble_rhs(fus_model* m, double t, const double* u, const double* v,
-                        bool fwd_pending, int table_stage = -1) {
+                        bool fwd_pending, bool with_boundary) {
   fus_ctx* c = m->ctx;
   double g = 0.0, dg = 0.0;
-  if (table_stage < 0)
+  if (with_boundary)
     source_scalars(m, t, &g, &dg);
-  const double* table = (table_stage >= 0) ? m->d_src : nullptr;
   const double* x2 = (m->kind >= FUS_LOSSY) ? v : nullptr;
   const double* c2 = (m->kind >= FUS_LOSSY) ? m->d_att : nullptr;
   auto boundary = [&]() -> int {
-    if (m->nb) {
-      ProfScope prof(c, 2, c->stream);
-      boundary_kernel<<<grid_for(m->nb, 256, 1 << 30), 256, 0, c->stream>>>(
-          m->d_b, v, m->d_bidx, m->d_bsrc, m->d_bdsrc, m->d_babs, m->nb, g, dg, table,
-          m->d_stepctr, table_stage < 0 ? 0 : table_stage);
-      FUS_LAUNCHED();
-    }
-    return FUS_OK;
+    return with_boundary ? launch_boundary(m, v, g, dg, false) : FUS_OK;
   };
   if (!c->halo) {
     FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, c->ncells, c->stream));
@@ -1553,7 +1604,7 @@ int fus_model_f1(fus_model* m, double t, const double* u, const double* v, doubl
   FUS_CUDA(cudaMemsetAsync(m->d_b, 0, vb, c->stream));
   if (c->halo)
     FUS_TRY(halo_forward(c->halo, m->d_un, m->d_vn, c->stream));
-  FUS_TRY(assemble_rhs(m, t, m->d_un, m->d_vn, false));
+  FUS_TRY(assemble_rhs(m, t, m->d_un, m->d_vn, false, true));
   const int grid = grid_for(nd, 256, 1 << 30);
   if (m->kind == FUS_WESTERVELT)
     f1_finish_kernel<true><<<grid, 256, 0, c->stream>>>(m->d_b, m->d_m, m->d_dnl, m->d_un,
@@ -1574,11 +1625,19 @@ template <int STAGE>
 static int launch_stage(fus_model* m, const StageArgs& A) {
   fus_ctx* c = m->ctx;
   ProfScope prof(c, 1, c->stream);
-  const int grid = grid_for(A.ntotal, 256, c->num_sms * 8);
-  if (m->kind == FUS_WESTERVELT)
-    rk4_stage_kernel<STAGE, true><<<grid, 256, 0, c->stream>>>(A);
-  else
-    rk4_stage_kernel<STAGE, false><<<grid, 256, 0, c->stream>>>(A);
+  const int grid = grid_for(A.ntotal, kStageChunk, c->num_sms * 8);
+  const bool west = m->kind == FUS_WESTERVELT;
+  if (c->stage_hints) {
+    if (west)
+      rk4_stage_kernel<STAGE, true, true><<<grid, kStageThreads, 0, c->stream>>>(A);
+    else
+      rk4_stage_kernel<STAGE, false, true><<<grid, kStageThreads, 0, c->stream>>>(A);
+  } else {
+    if (west)
+      rk4_stage_kernel<STAGE, true, false><<<grid, kStageThreads, 0, c->stream>>>(A);
+    else
+      rk4_stage_kernel<STAGE, false, false><<<grid, kStageThreads, 0, c->stream>>>(A);
+  }
   FUS_LAUNCHED();
   return FUS_OK;
 }
@@ -1587,16 +1646,13 @@ static int launch_stage(fus_model* m, const StageArgs& A) {
 // partitioned.  Issued eagerly or captured into a CUDA graph by fus_model_rk4.
 static int issue_step(fus_model* m, StageArgs& A, double dt) {
   fus_ctx* c = m->ctx;
-  const double a_runge[4] = {0.0, 0.5, 0.5, 1.0};
-  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
   if (c->halo) // scatter_fwd of the step's first stage input (Linear.hpp:196-199)
     FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
   for (int i = 0; i < 4; ++i) {
     const double* u_in = (i == 0) ? m->d_u0 : m->d_un;
     const double* v_in = (i == 0) ? m->d_v0 : m->d_vn;
-    FUS_TRY(assemble_rhs(m, 0.0, u_in, v_in, true, i));
-    A.bw_dt = dt * b_runge[i];
-    A.a_next_dt = (i < 3) ? dt * a_runge[i + 1] : 0.0;
+    FUS_TRY(assemble_rhs(m, 0.0, u_in, v_in, true, false));
+    stage_coefficients(A, i, dt);
     switch (i) {
     case 0: FUS_TRY(launch_stage<0>(m, A)); break;
     case 1: FUS_TRY(launch_stage<1>(m, A)); break;
@@ -1635,6 +1691,12 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
       }
       dts.push_back(dt);
       t += dt;
+      if (t >= tf) { // row read by the last stage-3 epilogue when it seeds a step that is not taken
+        double g, dg;
+        source_scalars(m, t, &g, &dg);
+        table.push_back(g);
+        table.push_back(dg);
+      }
       if (dts.size() > (size_t)100000000) {
         set_error("fus_model_rk4: more than 1e8 steps requested");
         return FUS_ERR_ARG;
@@ -1678,7 +1740,17 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   A.nowned = c->nowned;
   A.ntotal = c->ndofs;
   A.step_ctr = m->d_stepctr;
+  A.done_ctr = m->d_done;
+  A.nb = m->nb;
+  A.bidx = m->d_bidx;
+  A.bsrc = m->d_bsrc;
+  A.bdsrc = m->d_bdsrc;
+  A.babs = m->d_babs;
+  A.bchunk = m->d_bchunk;
+  A.src_table = m->d_src;
+  // boundary terms of the first stage; every later stage is seeded by the epilogue before it
   FUS_CUDA(cudaMemsetAsync(m->d_b, 0, sizeof(double) * c->ndofs, c->stream));
+  FUS_TRY(launch_boundary(m, m->d_v0, 0.0, 0.0, true));
   // Optional: pin b in the persisting part of the 126 MB L2 (measured slower overall, off).
   bool l2_window = false;
   if (c->l2_persist) {

@@ -1366,26 +1366,99 @@ static __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// 32-byte global accesses with an L2 eviction priority (sm_100: LDG/STG.E.256 carry EFL2 / ELL2
+// directly).  Streaming vectors that are not needed again soon are marked evict-first so that the
+// lines the NEXT kernel wants (b, the next stage input) stay in the 126 MB L2.
+// ------------------------------------------------------------------------------------------------
+struct D4 {
+  double v[4];
+};
+enum L2Pol { L2_NORMAL = 0, L2_FIRST = 1, L2_LAST = 2 };
+
+template <int POL>
+__device__ __forceinline__ D4 ld4(const double* p) {
+  D4 r;
+#ifdef FUS_HOST_EMULATION
+  for (int k = 0; k < 4; ++k)
+    r.v[k] = p[k];
+#else
+  if constexpr (POL == L2_FIRST)
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+                 : "l"(p)
+                 : "memory");
+  else if constexpr (POL == L2_LAST)
+    asm volatile("ld.global.L1::no_allocate.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+                 : "l"(p)
+                 : "memory");
+  else
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+                 : "l"(p)
+                 : "memory");
+#endif
+  return r;
+}
+
+template <int POL>
+__device__ __forceinline__ void st4(double* p, const D4& r) {
+#ifdef FUS_HOST_EMULATION
+  for (int k = 0; k < 4; ++k)
+    p[k] = r.v[k];
+#else
+  if constexpr (POL == L2_FIRST)
+    asm volatile("st.global.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.v[0]),
+                 "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3])
+                 : "memory");
+  else if constexpr (POL == L2_LAST)
+    asm volatile("st.global.L2::evict_last.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.v[0]),
+                 "d"(r.v[1]), "d"(r.v[2]), "d"(r.v[3])
+                 : "memory");
+  else
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]),
+                 "d"(r.v[2]), "d"(r.v[3])
+                 : "memory");
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused RK4 stage epilogue (kernels (4)(5) of the north star).  After the operator has
 // accumulated b = K(un[,vn]) + boundary terms, one pass does, per owned dof,
 //     kv     = b / m                                   (Linear.hpp:212-221; Westervelt: m = m0 - dnl*un,
 //                                                       b += dnl*vn^2, Westervelt.hpp:249-265)
 //     ku     = vn                                      (f0, Linear.hpp:171-174)
-//     uacc  += bw*dt*ku ; vacc += bw*dt*kv             (:293-294)
 //     un'    = u0 + a'*dt*ku ; vn' = v0 + a'*dt*kv     (:279-283 of the NEXT stage)
-//     b      = 0                                       (:203 of the NEXT stage)
-// STAGE 0: the stage input is (u0,v0) itself and uacc/vacc are written, not read-modified.
-// STAGE 3: the new state is written straight into (u0,v0), which is also the next step's stage-0
-//          input, so no un'/vn' are produced.
-// Every vector crosses HBM at most once per stage: 9 / 12 / 12 / 8 passes for stages 0..3.
+//     b      = boundary terms of the NEXT stage        (:203,205 of the NEXT stage; 0 off the boundary)
+// and the solution update u += b_i dt ku, v += b_i dt kv (:293-294) WITHOUT a read-modify-write of
+// the accumulators in every stage.  Because ku_i = vn_i and the stage inputs are themselves
+// vn_1 = v0 + a_1 dt kv_0, vn_3 = v0 + a_3 dt kv_2, the classical tableau gives
+//     u_new = [u0 + b_0 dt v0 + b_1 dt vn_1 + b_2 dt vn_2]            + b_3 dt vn_3
+//     v_new = [(1 - b_0/a_1 - b_2/a_3) v0 + (b_0/a_1) vn_1 + b_1 dt kv_1] + (b_2/a_3) vn_3 + b_3 dt kv_3
+// where both brackets are known in the stage-1 epilogue (vn_2 is produced there) and the rest in
+// the stage-3 epilogue.  So ua, va are WRITTEN once (stage 1) and READ once (stage 3); the
+// arithmetic differs from the reference's running sums by rounding only (b_0/a_1 = b_2/a_3 = 1/3).
+// STAGE 0: the stage input is (u0,v0) itself.  STAGE 3: the new state goes straight into (u0,v0),
+// the next step's stage-0 input.  Vector passes per stage: 7 / 10 / 8 / 8 (was 9 / 12 / 12 / 8).
+//
+// Boundary terms.  The collocated `ds` forms reduce to g*src[d] + dg*dsrc[d] - absb[d]*v[d] on
+// boundary dofs (fem::assemble_vector(b_, *L), Linear.hpp:205).  v of the next stage is produced
+// right here, so instead of zero-filling b and launching a boundary kernel, the block seeds b with
+// the next stage's boundary terms: the compacted, dof-sorted boundary list is indexed per chunk of
+// kStageChunk dofs (bchunk).  The source scalars come from the host-computed table of
+// fus_model_rk4, row (step, stage) with the step counter on the device.
 // ------------------------------------------------------------------------------------------------
+constexpr int kStageThreads = 256;
+constexpr int kStageVec = 4;                              // doubles per access (32 bytes)
+constexpr int kStageChunk = kStageThreads * kStageVec;    // dofs per block pass
+
 struct StageArgs {
-  double* b;         // rhs accumulator, zeroed on exit (owned + ghosts)
+  double* b;         // rhs accumulator; seeded for the next stage on exit (owned + ghosts)
   const double* m;   // lumped mass (m0 for Westervelt)
   const double* dnl; // Westervelt: D^(2 beta / rho^2 c^4) assembled; else nullptr
   double* u0;        // state at step start (stage-3 output)
   double* v0;
-  double* ua; // accumulators
+  double* ua; // partial sums of the update: written by stage 1, read by stage 3
   double* va;
   double* un; // stage inputs of stages 1..3 (read as ku = vn, rewritten for the next stage)
   double* vn;
@@ -1393,49 +1466,171 @@ struct StageArgs {
   long long ntotal;
   double a_next_dt; // a_{i+1} * dt
   double bw_dt;     // b_i * dt
+  double bw0_dt;    // stage 1: b_0 * dt
+  double bw2_dt;    // stage 1: b_2 * dt
+  double c_v0;      // stage 1: 1 - b_0/a_1 - b_2/a_3
+  double c_vn;      // stage 1: b_0/a_1 ; stage 3: b_2/a_3
   int* step_ctr;    // advanced by the stage-3 epilogue (index into the source-scalar table)
+  unsigned int* done_ctr; // stage 3: blocks finished (the last one advances step_ctr)
+  // boundary terms of the next stage (nb == 0: b is zero-filled)
+  long long nb;
+  const int32_t* bidx;
+  const double* bsrc;
+  const double* bdsrc;
+  const double* babs;
+  const long long* bchunk;    // [nchunks + 1] first boundary entry of every chunk of kStageChunk dofs
+  const double* src_table;    // (g, dg) per (step, stage)
 };
 
+// Classical RK4 tableau (Linear.hpp:263-265) -> the coefficients of stage `i` with step size dt
+inline void stage_coefficients(StageArgs& A, int i, double dt) {
+  const double a_runge[4] = {0.0, 0.5, 0.5, 1.0};
+  const double b_runge[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
+  A.bw_dt = dt * b_runge[i];
+  A.a_next_dt = (i < 3) ? dt * a_runge[i + 1] : 0.0;
+  A.bw0_dt = dt * b_runge[0];
+  A.bw2_dt = dt * b_runge[2];
+  A.c_vn = (i == 1) ? b_runge[0] / a_runge[1] : b_runge[2] / a_runge[3];
+  A.c_v0 = 1.0 - b_runge[0] / a_runge[1] - b_runge[2] / a_runge[3];
+}
+
+// one dof of one stage
 template <int STAGE, bool WESTERVELT>
-__global__ void __launch_bounds__(256) rk4_stage_kernel(const StageArgs A) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (long long i = i0; i < A.nowned; i += stride) {
-    double b = A.b[i];
-    const double u0 = (STAGE < 3) ? A.u0[i] : 0.0;
-    const double v0 = (STAGE < 3) ? A.v0[i] : 0.0;
-    const double vn = (STAGE == 0) ? v0 : A.vn[i];
-    double m = A.m[i];
-    if constexpr (WESTERVELT) {
-      const double un = (STAGE == 0) ? u0 : A.un[i];
-      const double d = A.dnl[i];
-      m = m - d * un;
-      b = b + d * (vn * vn);
-    }
-    const double kv = b / m;
-    double ua, va;
-    if constexpr (STAGE == 0) {
-      ua = fma(vn, A.bw_dt, u0);
-      va = fma(kv, A.bw_dt, v0);
-    } else {
-      ua = fma(vn, A.bw_dt, A.ua[i]);
-      va = fma(kv, A.bw_dt, A.va[i]);
-    }
-    if constexpr (STAGE < 3) {
-      A.ua[i] = ua;
-      A.va[i] = va;
-      A.un[i] = fma(vn, A.a_next_dt, u0);
-      A.vn[i] = fma(kv, A.a_next_dt, v0);
-    } else {
-      A.u0[i] = ua;
-      A.v0[i] = va;
-    }
-    A.b[i] = 0.0;
+__device__ __forceinline__ void stage_dof(const StageArgs& A, double b, double m, double dnl,
+                                          double u0, double v0, double un, double vn, double ua,
+                                          double va, double& o_un, double& o_vn, double& o_ua,
+                                          double& o_va) {
+  // STAGE 0: un == u0, vn == v0 are passed by the caller
+  if constexpr (WESTERVELT) {
+    m = m - dnl * un;
+    b = b + dnl * (vn * vn);
   }
-  for (long long i = A.nowned + i0; i < A.ntotal; i += stride)
-    A.b[i] = 0.0; // ghost partial sums have been sent to their owners
-  if (STAGE == 3 && A.step_ctr && i0 == 0)
-    *A.step_ctr += 1; // nothing else in this kernel reads it
+  const double kv = b / m;
+  if constexpr (STAGE < 3) {
+    o_un = fma(vn, A.a_next_dt, u0);
+    o_vn = fma(kv, A.a_next_dt, v0);
+  }
+  if constexpr (STAGE == 1) {
+    o_ua = fma(o_vn, A.bw2_dt, fma(vn, A.bw_dt, fma(v0, A.bw0_dt, u0)));
+    o_va = fma(kv, A.bw_dt, fma(vn, A.c_vn, A.c_v0 * v0));
+  }
+  if constexpr (STAGE == 3) {
+    o_un = fma(vn, A.bw_dt, ua);                    // u_new
+    o_vn = fma(kv, A.bw_dt, fma(vn, A.c_vn, va));   // v_new
+  }
+}
+
+template <int STAGE, bool WESTERVELT, bool HINTS = false>
+__global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArgs A) {
+  constexpr int STREAM = HINTS ? L2_FIRST : L2_NORMAL; // vectors not needed by the next kernel
+  const int tid = threadIdx.x;
+  const long long nchunks = (A.ntotal + kStageChunk - 1) / kStageChunk;
+  double g = 0.0, dg = 0.0;
+  if (A.nb) {
+    const int s = *A.step_ctr; // stage 3 advances it only after every block has read it
+    const int row = (STAGE < 3) ? (s * 4 + STAGE + 1) : ((s + 1) * 4);
+    g = A.src_table[2 * row];
+    dg = A.src_table[2 * row + 1];
+  }
+  double* const vnext = (STAGE < 3) ? A.vn : A.v0;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long i = ch * kStageChunk + (long long)tid * kStageVec;
+    if (i + kStageVec <= A.nowned) {
+      D4 b = ld4<L2_NORMAL>(A.b + i), m = ld4<STREAM>(A.m + i);
+      D4 u0, v0, un, vn, ua, va, dnl;
+      if constexpr (STAGE < 3) {
+        u0 = ld4<STREAM>(A.u0 + i);
+        v0 = ld4<STREAM>(A.v0 + i);
+      }
+      if constexpr (STAGE == 0) {
+        un = u0;
+        vn = v0;
+      } else {
+        vn = ld4<L2_NORMAL>(A.vn + i);
+        if constexpr (WESTERVELT)
+          un = ld4<L2_NORMAL>(A.un + i);
+      }
+      if constexpr (STAGE == 3) {
+        ua = ld4<STREAM>(A.ua + i);
+        va = ld4<STREAM>(A.va + i);
+      }
+      if constexpr (WESTERVELT)
+        dnl = ld4<STREAM>(A.dnl + i);
+      D4 oun, ovn, oua, ova, zero;
+#pragma unroll
+      for (int k = 0; k < kStageVec; ++k) {
+        stage_dof<STAGE, WESTERVELT>(A, b.v[k], m.v[k], WESTERVELT ? dnl.v[k] : 0.0,
+                                     STAGE < 3 ? u0.v[k] : 0.0, STAGE < 3 ? v0.v[k] : 0.0,
+                                     (WESTERVELT || STAGE == 0) ? un.v[k] : 0.0, vn.v[k],
+                                     STAGE == 3 ? ua.v[k] : 0.0, STAGE == 3 ? va.v[k] : 0.0,
+                                     oun.v[k], ovn.v[k], oua.v[k], ova.v[k]);
+        zero.v[k] = 0.0;
+      }
+      if constexpr (STAGE < 3) {
+        st4<L2_NORMAL>(A.un + i, oun);
+        st4<L2_NORMAL>(A.vn + i, ovn);
+      } else {
+        st4<L2_NORMAL>(A.u0 + i, oun);
+        st4<L2_NORMAL>(A.v0 + i, ovn);
+      }
+      if constexpr (STAGE == 1) {
+        st4<STREAM>(A.ua + i, oua);
+        st4<STREAM>(A.va + i, ova);
+      }
+      st4<L2_NORMAL>(A.b + i, zero);
+    } else {
+      // the chunk that straddles the owned / ghost boundary, and the ghost chunks: entry by entry
+#pragma unroll
+      for (int k = 0; k < kStageVec; ++k) {
+        const long long j = i + k;
+        if (j < A.nowned) {
+          const double u0 = (STAGE < 3) ? A.u0[j] : 0.0, v0 = (STAGE < 3) ? A.v0[j] : 0.0;
+          const double vn = (STAGE == 0) ? v0 : A.vn[j];
+          const double un = (STAGE == 0) ? u0 : (WESTERVELT ? A.un[j] : 0.0);
+          double oun = 0.0, ovn = 0.0, oua = 0.0, ova = 0.0;
+          stage_dof<STAGE, WESTERVELT>(A, A.b[j], A.m[j], WESTERVELT ? A.dnl[j] : 0.0, u0, v0, un,
+                                       vn, STAGE == 3 ? A.ua[j] : 0.0, STAGE == 3 ? A.va[j] : 0.0,
+                                       oun, ovn, oua, ova);
+          if constexpr (STAGE < 3) {
+            A.un[j] = oun;
+            A.vn[j] = ovn;
+          } else {
+            A.u0[j] = oun;
+            A.v0[j] = ovn;
+          }
+          if constexpr (STAGE == 1) {
+            A.ua[j] = oua;
+            A.va[j] = ova;
+          }
+          A.b[j] = 0.0;
+        } else if (j < A.ntotal) {
+          A.b[j] = 0.0; // ghost partial sums have been sent to their owners
+        }
+      }
+    }
+    if (A.nb) { // uniform over the block
+      const long long kb = A.bchunk[ch], ke = A.bchunk[ch + 1];
+      if (ke > kb) {
+        __syncthreads(); // the block's own stores of v' and of the zeros are ordered before this
+        for (long long k = kb + tid; k < ke; k += kStageThreads) {
+          const int d = A.bidx[k];
+          A.b[d] = g * A.bsrc[k] + dg * A.bdsrc[k] - A.babs[k] * __ldcg(vnext + d);
+        }
+      }
+    }
+  }
+  if constexpr (STAGE == 3) {
+    if (A.step_ctr && A.done_ctr) { // the last block to finish advances the step counter
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(A.done_ctr, 1u) == gridDim.x - 1) {
+          *A.done_ctr = 0u;
+          *A.step_ctr += 1;
+        }
+      }
+    }
+  }
 }
 
 // out = b / m (Westervelt: with the solution-dependent terms) -- single f1 evaluation for tests

@@ -267,27 +267,49 @@ int emu_mass(const double* x, double* y, const int32_t* dofmap, const double* de
   return 0;
 }
 
-// one fused RK4 stage epilogue; vectors are updated in place
+// one fused RK4 stage epilogue; vectors are updated in place.  The boundary terms of the NEXT stage
+// are seeded into b from the compacted list (nb entries, bchunk = first entry per chunk of
+// kStageChunk dofs) with the source scalars (g_next, dg_next); nb == 0 zero-fills b.
 int emu_rk4_stage(int stage, int westervelt, double* b, const double* m, const double* dnl,
                   double* u0, double* v0, double* ua, double* va, double* un, double* vn,
-                  long long nowned, long long ntotal, double a_next_dt, double bw_dt) {
+                  long long nowned, long long ntotal, double dt, long long nb, const int32_t* bidx,
+                  const double* bsrc, const double* bdsrc, const double* babs,
+                  const long long* bchunk, double g_next, double dg_next, int hints, int grid) {
   StageArgs A;
   A.b = b, A.m = m, A.dnl = dnl, A.u0 = u0, A.v0 = v0, A.ua = ua, A.va = va, A.un = un, A.vn = vn;
-  A.nowned = nowned, A.ntotal = ntotal, A.a_next_dt = a_next_dt, A.bw_dt = bw_dt;
-  A.step_ctr = nullptr;
-  auto go = [&](auto kern) { fus_emu::launch(2, 256, 0, [&] { kern(A); }); };
-  switch (stage * 2 + (westervelt ? 1 : 0)) {
-  case 0: go(rk4_stage_kernel<0, false>); break;
-  case 1: go(rk4_stage_kernel<0, true>); break;
-  case 2: go(rk4_stage_kernel<1, false>); break;
-  case 3: go(rk4_stage_kernel<1, true>); break;
-  case 4: go(rk4_stage_kernel<2, false>); break;
-  case 5: go(rk4_stage_kernel<2, true>); break;
-  case 6: go(rk4_stage_kernel<3, false>); break;
-  case 7: go(rk4_stage_kernel<3, true>); break;
+  A.nowned = nowned, A.ntotal = ntotal;
+  stage_coefficients(A, stage, dt);
+  int step_ctr = 0;
+  unsigned done = 0;
+  double table[10];
+  for (int r = 0; r < 5; ++r)
+    table[2 * r] = g_next, table[2 * r + 1] = dg_next;
+  A.step_ctr = &step_ctr, A.done_ctr = &done;
+  A.nb = nb, A.bidx = bidx, A.bsrc = bsrc, A.bdsrc = bdsrc, A.babs = babs, A.bchunk = bchunk;
+  A.src_table = table;
+  auto go = [&](auto kern) { fus_emu::launch((unsigned)grid, kStageThreads, 0, [&] { kern(A); }); };
+  switch (stage * 4 + (westervelt ? 2 : 0) + (hints ? 1 : 0)) {
+  case 0: go(rk4_stage_kernel<0, false, false>); break;
+  case 1: go(rk4_stage_kernel<0, false, true>); break;
+  case 2: go(rk4_stage_kernel<0, true, false>); break;
+  case 3: go(rk4_stage_kernel<0, true, true>); break;
+  case 4: go(rk4_stage_kernel<1, false, false>); break;
+  case 5: go(rk4_stage_kernel<1, false, true>); break;
+  case 6: go(rk4_stage_kernel<1, true, false>); break;
+  case 7: go(rk4_stage_kernel<1, true, true>); break;
+  case 8: go(rk4_stage_kernel<2, false, false>); break;
+  case 9: go(rk4_stage_kernel<2, false, true>); break;
+  case 10: go(rk4_stage_kernel<2, true, false>); break;
+  case 11: go(rk4_stage_kernel<2, true, true>); break;
+  case 12: go(rk4_stage_kernel<3, false, false>); break;
+  case 13: go(rk4_stage_kernel<3, false, true>); break;
+  case 14: go(rk4_stage_kernel<3, true, false>); break;
+  case 15: go(rk4_stage_kernel<3, true, true>); break;
   default: return -1;
   }
-  return 0;
+  if (stage == 3 && (step_ctr != 1 || done != 0))
+    return -2; // the last block advances the step counter exactly once
+  return kStageChunk;
 }
 
 int emu_boundary(double* b, const double* v, const int32_t* bidx, const double* bsrc,

@@ -141,6 +141,7 @@ inline long long clock64() {
 }
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <typename T>
 inline T __ldcg(const T* p) {
   return *p;

@@ -53,7 +53,7 @@ def emu():
     L.emu_geometry.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64, _f64, C.POINTER(_int)]
     L.emu_geometry_quad.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64]
     L.emu_rk4_stage.argtypes = [_int, _int, _f64, _f64, _p, _f64, _f64, _f64, _f64, _f64, _f64, _ll,
-                                _ll, _dbl, _dbl]
+                                _ll, _dbl, _ll, _p, _p, _p, _p, _p, _dbl, _dbl, _int, _int]
     L.emu_boundary.argtypes = [_f64, _f64, _i32, _f64, _f64, _f64, _ll, _dbl, _dbl]
     return L
 
@@ -228,11 +228,22 @@ def test_emulated_mass_boundary_and_rk4_stage_kernels(fus, orc, emu):
     want[bidx] += 0.7 * bs + (-0.3) * bd - ba * v[bidx]
     emu.emu_boundary(b, v, bidx, bs, bd, ba, nb, 0.7, -0.3)
     assert np.allclose(b, want, rtol=1e-15, atol=0)
-    # RK4 epilogues: owned entries updated, every entry of b zeroed, ghosts untouched elsewhere
+    # RK4 epilogues against the reference's running sums (Linear.hpp:278-295): stage inputs after
+    # every stage, the new state after stage 3; b re-seeded with the next stage's boundary terms on
+    # the owned boundary dofs and zero elsewhere (ghost entries included); ghosts of the state
+    # vectors untouched.  Odd owned count and a grid smaller than the chunk count: the straddling
+    # chunk and the grid-stride loop are exercised.  hints: the L2 evict-first build of the kernel.
     nowned = nd - 37
     dt = 1e-3
     a_r, b_r = (0.0, 0.5, 0.5, 1.0), (1 / 6, 1 / 3, 1 / 3, 1 / 6)
-    for west in (0, 1):
+    chunk = emu.emu_rk4_stage(0, 0, np.zeros(8), np.ones(8), None, np.zeros(8), np.zeros(8),
+                              np.zeros(8), np.zeros(8), np.zeros(8), np.zeros(8), 0, 8, dt, 0, None,
+                              None, None, None, None, 0.0, 0.0, 0, 1)
+    assert chunk > 0
+    bown = bidx[bidx < nowned]
+    nbo = bown.size
+    bchunk = np.searchsorted(bown, np.arange(0, (nd + chunk - 1) // chunk + 1) * chunk).astype(np.int64)
+    for west, hints in ((0, 0), (1, 0), (0, 1), (1, 1)):
         mvec, dnl = rng.uniform(1, 2, nd), rng.uniform(0.01, 0.02, nd)
         u0, v0 = rng.uniform(-1, 1, nd), rng.uniform(-1, 1, nd)
         st = dict(u0=u0.copy(), v0=v0.copy(), ua=np.zeros(nd), va=np.zeros(nd), un=np.zeros(nd),
@@ -256,12 +267,29 @@ def test_emulated_mass_boundary_and_rk4_stage_kernels(fus, orc, emu):
                 ref["ua"][o], ref["va"][o] = ua, va
             else:
                 ref["u0"][o], ref["v0"][o] = ua, va
-            emu.emu_rk4_stage(i, west, b, mvec, _opt(dnl) if west else None, st["u0"], st["v0"],
-                              st["ua"], st["va"], st["un"], st["vn"], nowned, nd,
-                              a_r[i + 1] * dt if i < 3 else 0.0, b_r[i] * dt)
-            assert not b.any()
-            for k in st:
+            gn, dgn = 0.3 + i, -0.2 * (i + 1)
+            rc = emu.emu_rk4_stage(i, west, b, mvec, _opt(dnl) if west else None, st["u0"], st["v0"],
+                                   st["ua"], st["va"], st["un"], st["vn"], nowned, nd, dt, nbo,
+                                   _opt(bown), _opt(bs), _opt(bd), _opt(ba), _opt(bchunk), gn, dgn,
+                                   hints, 3)
+            assert rc == chunk
+            vnext = st["vn"] if i < 3 else st["v0"]
+            want_b = np.zeros(nd)
+            want_b[bown] = gn * bs[:nbo] + dgn * bd[:nbo] - ba[:nbo] * vnext[bown]
+            assert np.allclose(b, want_b, rtol=1e-15, atol=0), (west, i)
+            # the accumulators are internal now (written in stage 1, read in stage 3): compare the
+            # stage inputs and the state
+            for k in ("u0", "v0", "un", "vn"):
                 assert np.allclose(st[k], ref[k], rtol=1e-14, atol=1e-15), (west, i, k)
+            for k in st:                    # ghost entries are never written
+                assert np.array_equal(st[k][nowned:], (u0 if k == "u0" else v0 if k == "v0"
+                                                       else np.zeros(nd))[nowned:]), (west, i, k)
+        # without a boundary list b is zero-filled
+        b = rng.uniform(-1, 1, nd)
+        emu.emu_rk4_stage(2, west, b, mvec, _opt(dnl) if west else None, st["u0"], st["v0"],
+                          st["ua"], st["va"], st["un"], st["vn"], nowned, nd, dt, 0, None, None, None,
+                          None, None, 0.0, 0.0, hints, 2)
+        assert not b.any()
 
 
 @pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7])
@@ -347,7 +375,8 @@ def test_emulation_with_scheduling_jitter(fus, orc, emu):
 @pytest.mark.parametrize("kind", ["linear", "westervelt"])
 def test_emulated_fused_rk4_step_vs_reference_flow(fus, orc, emu, kind):
     """The fused stage flow of fus_model_rk4 (csrc/fus_capi.cu: operator with the fused two-vector
-    gather, boundary_kernel, rk4_stage_kernel<STAGE,WESTERVELT>; 41 vector passes per step) executed
+    gather, rk4_stage_kernel<STAGE,WESTERVELT> seeding the next stage's boundary terms; 33 vector
+    passes per step) executed
     with the emulated kernels, against the oracle's literal restatement of the reference loop
     (Linear.hpp:228-314, Westervelt.hpp:216-373; ~30 passes per stage).  Same fields after 3 steps."""
     from fenicsx_fus_b200 import capi
@@ -391,32 +420,45 @@ def test_emulated_fused_rk4_step_vs_reference_flow(fus, orc, emu, kind):
     att = (-delta / rho0 / c0 ** 2) if west else None
     bidx = np.flatnonzero((src != 0) | (dsrc != 0) | (absb != 0)).astype(np.int32)
     bs, bd, ba = src[bidx].copy(), dsrc[bidx].copy(), absb[bidx].copy()
+    chunk = emu.emu_rk4_stage(0, 0, np.zeros(8), np.ones(8), None, np.zeros(8), np.zeros(8),
+                              np.zeros(8), np.zeros(8), np.zeros(8), np.zeros(8), 0, 8, 1.0, 0, None,
+                              None, None, None, None, 0.0, 0.0, 0, 1)
+    bchunk = np.searchsorted(bidx, np.arange(0, (nd + chunk - 1) // chunk + 1) * chunk).astype(np.int64)
     # ---- the time loop as fus_model_rk4 / issue_step issue it
     st = dict(u0=u0.copy(), v0=v0.copy(), ua=np.zeros(nd), va=np.zeros(nd), un=np.zeros(nd),
               vn=np.zeros(nd))
+    a_r = (0.0, 0.5, 0.5, 1.0)
+    w0, kappa = 2 * np.pi * f0, (2.0 if west else 1.0)
+
+    def scalars(tn):                       # Linear.hpp:185-192, Lossy.hpp:199-220
+        win = 0.5 * (1 - np.cos(f0 * np.pi * tn / 4.0)) if tn < 4.0 / f0 else 1.0
+        dwin = 0.5 * np.pi * f0 / 4.0 * np.sin(f0 * np.pi * tn / 4.0) if tn < 4.0 / f0 else 0.0
+        g = kappa * win * p0 * w0 / s0 * np.cos(w0 * tn)
+        dg = (kappa * (dwin * p0 * w0 / s0 * np.cos(w0 * tn) - win * p0 * w0 * w0 / s0 * np.sin(w0 * tn))
+              if west else 0.0)
+        return g, dg
+
+    # the boundary terms of the first stage come from boundary_kernel; every later stage's are
+    # seeded into b by the epilogue before it, with the scalars of that (step, stage)
     b = np.zeros(nd)
-    a_r, b_r = (0.0, 0.5, 0.5, 1.0), (1 / 6, 1 / 3, 1 / 3, 1 / 6)
+    g, dg = scalars(0.0)
+    emu.emu_boundary(b, st["v0"], bidx, bs, bd, ba, bidx.size, g, dg)
     t, dt_full = 0.0, dt
     while t < tf:                          # Linear.hpp:270-298, as fus_model_rk4 tabulates it
         dt = min(dt_full, tf - t)
+        dt_next = min(dt_full, tf - (t + dt))
         for i in range(4):
             u_in = st["u0"] if i == 0 else st["un"]
             v_in = st["v0"] if i == 0 else st["vn"]
-            tn = t + a_r[i] * dt
-            win = 0.5 * (1 - np.cos(f0 * np.pi * tn / 4.0)) if tn < 4.0 / f0 else 1.0
-            dwin = 0.5 * np.pi * f0 / 4.0 * np.sin(f0 * np.pi * tn / 4.0) if tn < 4.0 / f0 else 0.0
-            w0 = 2 * np.pi * f0
-            kappa = 2.0 if west else 1.0
-            g = kappa * win * p0 * w0 / s0 * np.cos(w0 * tn)
-            dg = (kappa * (dwin * p0 * w0 / s0 * np.cos(w0 * tn) - win * p0 * w0 * w0 / s0 * np.sin(w0 * tn))
-                  if west else 0.0)
             emu.emu_stiffness(P + 1, 0, 0, u_in, _opt(v_in) if west else None, b, V.dofmap, _opt(G),
                               None, lin, _opt(att), nc, dphi, pts, wts, 2, 0, nc)
-            emu.emu_boundary(b, v_in, bidx, bs, bd, ba, bidx.size, g, dg)
-            emu.emu_rk4_stage(i, int(west), b, mvec, _opt(dnl), st["u0"], st["v0"], st["ua"],
-                              st["va"], st["un"], st["vn"], nd, nd,
-                              a_r[i + 1] * dt if i < 3 else 0.0, b_r[i] * dt)
+            gn, dgn = scalars(t + a_r[i + 1] * dt) if i < 3 else scalars(t + dt)
+            rc = emu.emu_rk4_stage(i, int(west), b, mvec, _opt(dnl), st["u0"], st["v0"], st["ua"],
+                                   st["va"], st["un"], st["vn"], nd, nd, dt, bidx.size, _opt(bidx),
+                                   _opt(bs), _opt(bd), _opt(ba), _opt(bchunk), gn, dgn, 0, 2)
+            assert rc == chunk
         t += dt
+        del dt_next
     assert rel_l2(st["u0"], u_ref) < 1e-12 and rel_l2(st["v0"], v_ref) < 1e-12
 
 
