@@ -137,10 +137,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU side: the reference kernels on the host cores (oracle/_ref)
 # --------------------------------------------------------------------------------------------
-def cpu_linear_rk4(n_cells, steps, warmup, threads=None, budget_s=None):
+def cpu_linear_rk4(n_cells, steps, warmup, threads=None, budget_s=None, mesh=None, fields=False):
     """LinearSpectral3D RK4 on a P=4 box of n_cells^3 cells, with the cell loops running on the
     reference's own sum_factorisation.hpp (oracle/_ref), one OpenMP thread per contiguous cell
-    range.  Returns (dof_updates_per_s, cores, steps_done, ndofs, kind)."""
+    range.  `mesh` = (x, xdofmap, dofmap, facets, ndofs) runs the same model on exactly these arrays
+    (the GPU arm's own mesh and numbering: the parity check), else on the oracle's box generator.
+    Returns (dof_updates_per_s, cores, steps_done, ndofs, kind, seconds[, u, v, apply])."""
     from oracle.oracle import Oracle, ref_available
     use_ref = ref_available() or os.path.isdir("/root/reference/cpp/fenicsx-sf/common")
     orc = Oracle(ref=use_ref)
@@ -153,15 +155,19 @@ def cpu_linear_rk4(n_cells, steps, warmup, threads=None, budget_s=None):
     else:
         cores = 1
     P, n = P_BENCH, (n_cells,) * 3
-    h = BOX_LEN / N_BENCH                      # same cell size as the GPU workload
-    xg, xd = orc.box_mesh(n, (0, 0, 0), (h * n_cells,) * 3)
-    dm = orc.box_dofmap(P, n, 0)
-    nd = int(dm.max()) + 1
+    h = BOX_LEN / 54                           # same cell size as the GPU workload
+    if mesh is None:
+        xg, xd = orc.box_mesh(n, (0, 0, 0), (h * n_cells,) * 3)
+        dm = orc.box_dofmap(P, n, 0)
+        nd = int(dm.max()) + 1
+        facets = orc.box_facets(n)
+    else:
+        xg, xd, dm, facets, nd = mesh
     G, dJ = orc.geometry(P, xg, xd)
-    facets = orc.box_facets(n)
     fn, fs = orc.facet_data(P, xg, xd, facets)
     nc = dm.shape[0]
-    mdl = orc.model("linear", P, nd, dm, G, dJ, orc.dphi(P), np.full(nc, C0), np.full(nc, RHO0),
+    dphi = orc.dphi(P)
+    mdl = orc.model("linear", P, nd, dm, G, dJ, dphi, np.full(nc, C0), np.full(nc, RHO0),
                     None, None, facets, fn, fs, FREQ, P0, C0, use_ref_kernels=use_ref)
     dt = timestep(P, h, C0)
     u, v = np.zeros(nd), np.zeros(nd)
@@ -179,7 +185,20 @@ def cpu_linear_rk4(n_cells, steps, warmup, threads=None, budget_s=None):
             t += dt
     el = time.perf_counter() - t0
     assert np.isfinite(u).all()
-    return nd * done / el, cores, done, nd, kind, el
+    if not fields:
+        return nd * done / el, cores, done, nd, kind, el
+
+    def apply(x, coeffs):
+        return orc.stiffness_apply(P, dm, G, dphi, coeffs, x, np.zeros(nd), use_ref_kernels=use_ref)
+    return nd * done / el, cores, done, nd, kind, el, u, v, apply
+
+
+def rel_l2(a, b):
+    nb = float(np.linalg.norm(b))
+    return float(np.linalg.norm(a - b)) / (nb if nb > 0 else 1.0)
+
+
+PARITY_TOL = {"apply_rel_l2": 1e-12, "u_rel_l2": 1e-10, "v_rel_l2": 1e-10}   # BASELINE.json north_star
 
 
 def run_reference_arm(args):
@@ -204,8 +223,8 @@ def run_reference_arm(args):
         "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * el / max(done, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"linear_rk4_P{P_BENCH}_box{n_cells}", "dofs": nd,
-                   "full_size": n_cells == N_BENCH},
+        "config": {"workload": f"linear_rk4_P{P_BENCH}_box{N_BENCH}", "degree": P_BENCH,
+                   "cells_per_direction": n_cells, "dofs": nd, "full_size": n_cells == N_BENCH},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

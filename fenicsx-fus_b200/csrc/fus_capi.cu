@@ -212,7 +212,13 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   std::memcpy(D.w, c->wts, sizeof(double) * N);
   std::memcpy(D.x, c->pts, sizeof(double) * N);
   const bool fuse = (x2 != nullptr);
-  const int variant = (c->variant >= 0) ? c->variant : (N >= 5 ? 2 : 0);
+  // Kernel per degree, from the measured sweep of every variant at every degree on a B200
+  // (profiles/r2a_variant_sweep.jsonl, one application on ~10 M dofs, fraction of the measured HBM
+  // peak): P<=3 column kernel (0.82 / 0.94), P=4 line kernel (0.91), P=5 and P=6 the line kernel
+  // with the dofmap rows loaded next to the G refills (0.89 / 0.81; the default pipeline gives
+  // 0.83 / 0.70), P=7 the pipeline with the coefficient folded into x (0.76 vs 0.73).
+  const int variant = (c->variant >= 0) ? c->variant
+                                        : (N <= 4 ? 0 : (N == 5 ? 2 : (N <= 7 ? 5 : 3)));
   if (variant == 1 && c->geom_active == 0) {
     ProfScope prof(c, 0, st);
     const int blocks = (int)std::min<long long>(ce - cb, (long long)c->num_sms * 16);
