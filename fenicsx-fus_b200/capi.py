@@ -85,9 +85,11 @@ SIGNATURES = {
     "fus_ctx_profile": (_int, [_p, C.c_char_p, C.POINTER(_ll), C.POINTER(_dbl)]),
     "fus_comm_unique_id": (_int, [_p]),
     "fus_halo_setup": (_int, [_p, _int, _int, _p, _int, _p, _p, _p, _p, _p, _ll]),
-    "fus_halo_peer_export": (_int, [_p, _p, _p]),
+    "fus_halo_peer_export": (_int, [_p, _p, _p, C.POINTER(_p)]),
     "fus_halo_mailbox_layout": (_int, [_ll, _ll, _int, _i64]),
+    "fus_halo_peer_offsets": (_int, [_i64, _i64, _i64, _int, _i64]),
     "fus_halo_peer_connect": (_int, [_p, _p, _p]),
+    "fus_halo_peer_connect_local": (_int, [_p, _p, _p, _p]),
     "fus_box_partition_create": (_int, [_int, _i32, _i32, _int, _int, C.POINTER(_p)]),
     "fus_box_partition_info": (_int, [_p, _i64, _i32, _i32]),
     "fus_box_partition_arrays": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

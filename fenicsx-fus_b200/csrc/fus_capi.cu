@@ -98,7 +98,6 @@ struct fus_ctx {
   int col_blocks_per_sm = 0;
   int reserve_sms = 0;      // SMs left free for the halo kernels while cells overlap with them
   int halo_reserve = 4;     // reserve_sms inside a partitioned stage, NCCL side-stream mode
-  int peer_reserve = 0;     // same, peer-direct mode
   int l2_persist = 0;       // keep the rhs accumulator b resident in L2 during rk4 (option)
   int stage_hints = 0;      // epilogue: streaming vectors marked L2 evict-first (option)
   int use_graph = 1;        // replay RK4 steps from a captured CUDA graph (option "use_graph")
@@ -204,7 +203,7 @@ int select_device(fus_ctx* c) {
 template <int N>
 int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const double* coeff,
                        const double* coeff2, double* y, long long cb, long long ce,
-                       cudaStream_t st) {
+                       cudaStream_t st, const FusedHalo* fh) {
   if (ce <= cb)
     return FUS_OK;
   DMat<N> D;
@@ -212,6 +211,58 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
   std::memcpy(D.w, c->wts, sizeof(double) * N);
   std::memcpy(D.x, c->pts, sizeof(double) * N);
   const bool fuse = (x2 != nullptr);
+  if (fh) { // partitioned mesh, fused peer transport: the cells that touch shared dofs
+    using L = LineCfg<N>;
+    const int v = (c->variant >= 0) ? c->variant : (N <= 5 ? 2 : (N <= 7 ? 5 : 3));
+    auto go = [&](auto kern_plain, auto kern_fuse, KernelCfg& cfg) -> int {
+      std::atomic<bool>& configured = cfg.configured[c->device];
+      int &bps_plain = cfg.blocks_plain[c->device], &bps_fuse = cfg.blocks_fuse[c->device];
+      if (!configured.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(cfg.mu);
+        if (!configured.load(std::memory_order_relaxed)) {
+          FUS_CUDA(cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        L::SMEM_BYTES));
+          FUS_CUDA(cudaFuncSetAttribute(kern_fuse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        L::SMEM_BYTES));
+          FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_plain, kern_plain, L::THREADS,
+                                                                L::SMEM_BYTES));
+          FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_fuse, kern_fuse, L::THREADS,
+                                                                L::SMEM_BYTES));
+          if (bps_plain < 1 || bps_fuse < 1) {
+            set_error("stiffness kernel <N=%d> does not fit on an SM", N);
+            return FUS_ERR_CUDA;
+          }
+          configured.store(true, std::memory_order_release);
+        }
+      }
+      const int bps = fuse ? bps_fuse : bps_plain;
+      const long long want = (ce - cb + L::CPB - 1) / L::CPB;
+      const int blocks = (int)std::min<long long>(want, (long long)c->num_sms * bps);
+      const HaloLaunch HL = halo_fused_launch(c->halo);
+      ProfScope prof(c, 0, st);
+      if (fuse)
+        kern_fuse<<<blocks, L::THREADS, L::SMEM_BYTES, st>>>(x, x2, y, c->d_dofmap, c->d_G2, coeff,
+                                                             coeff2, cb, ce, D, HL);
+      else
+        kern_plain<<<blocks, L::THREADS, L::SMEM_BYTES, st>>>(x, x2, y, c->d_dofmap, c->d_G2, coeff,
+                                                              coeff2, cb, ce, D, HL);
+      FUS_LAUNCHED();
+      return FUS_OK;
+    };
+    if (v >= 5) { // dofmap rows loaded next to the G refills (kernel GEOM 6)
+      static KernelCfg cfg;
+      return go(stiffness_line_kernel<N, false, 6, double, true>,
+                stiffness_line_kernel<N, true, 6, double, true>, cfg);
+    }
+    if (v >= 3) { // coefficient folded into x (kernel GEOM 4)
+      static KernelCfg cfg;
+      return go(stiffness_line_kernel<N, false, 4, double, true>,
+                stiffness_line_kernel<N, true, 4, double, true>, cfg);
+    }
+    static KernelCfg cfg;
+    return go(stiffness_line_kernel<N, false, 0, double, true>,
+              stiffness_line_kernel<N, true, 0, double, true>, cfg);
+  }
   // Kernel per degree, from the measured sweep of every variant at every degree on a B200
   // (profiles/r2a_variant_sweep.jsonl, one application on ~10 M dofs, fraction of the measured HBM
   // peak): P<=3 column kernel (0.82 / 0.94), P=4 line kernel (0.91), P=5 and P=6 the line kernel
@@ -264,10 +315,10 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     const int blocks = (int)std::min<long long>(want, (long long)sms * bps);
     if (fuse)
       kern_fuse<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, Gptr, coeff, coeff2,
-                                                     cb, ce, D);
+                                                     cb, ce, D, HaloLaunch{});
     else
       kern_plain<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, Gptr, coeff, coeff2,
-                                                      cb, ce, D);
+                                                      cb, ce, D, HaloLaunch{});
     FUS_LAUNCHED();
     return FUS_OK;
   };
@@ -356,7 +407,7 @@ int launch_stiffness_quad_n(fus_ctx* c, const double* x, const double* x2, const
 
 int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double* coeff,
                      const double* coeff2, double* y, long long cb, long long ce,
-                     cudaStream_t st) {
+                     cudaStream_t st, const FusedHalo* fh = nullptr) {
   if (c->dim == 2) {
     if (!c->d_Gq) {
       set_error("context was created without G: stiffness operator unavailable");
@@ -379,13 +430,13 @@ int launch_stiffness(fus_ctx* c, const double* x, const double* x2, const double
     return FUS_ERR_STATE;
   }
   switch (c->N) {
-  case 2: return launch_stiffness_n<2>(c, x, x2, coeff, coeff2, y, cb, ce, st);
-  case 3: return launch_stiffness_n<3>(c, x, x2, coeff, coeff2, y, cb, ce, st);
-  case 4: return launch_stiffness_n<4>(c, x, x2, coeff, coeff2, y, cb, ce, st);
-  case 5: return launch_stiffness_n<5>(c, x, x2, coeff, coeff2, y, cb, ce, st);
-  case 6: return launch_stiffness_n<6>(c, x, x2, coeff, coeff2, y, cb, ce, st);
-  case 7: return launch_stiffness_n<7>(c, x, x2, coeff, coeff2, y, cb, ce, st);
-  case 8: return launch_stiffness_n<8>(c, x, x2, coeff, coeff2, y, cb, ce, st);
+  case 2: return launch_stiffness_n<2>(c, x, x2, coeff, coeff2, y, cb, ce, st, fh);
+  case 3: return launch_stiffness_n<3>(c, x, x2, coeff, coeff2, y, cb, ce, st, fh);
+  case 4: return launch_stiffness_n<4>(c, x, x2, coeff, coeff2, y, cb, ce, st, fh);
+  case 5: return launch_stiffness_n<5>(c, x, x2, coeff, coeff2, y, cb, ce, st, fh);
+  case 6: return launch_stiffness_n<6>(c, x, x2, coeff, coeff2, y, cb, ce, st, fh);
+  case 7: return launch_stiffness_n<7>(c, x, x2, coeff, coeff2, y, cb, ce, st, fh);
+  case 8: return launch_stiffness_n<8>(c, x, x2, coeff, coeff2, y, cb, ce, st, fh);
   }
   set_error("unsupported degree P=%d", c->P);
   return FUS_ERR_UNSUPPORTED;
@@ -453,7 +504,7 @@ int launch_stiffness_f32_n(fus_ctx* c, const float* x, const float* coeff, float
       = (int)std::min<long long>(want, (long long)c->num_sms * cfg.blocks_plain[c->device]);
   kern<<<blocks, L::THREADS, L::SMEM_BYTES, c->stream>>>(
       x, nullptr, y, c->d_dofmap, reinterpret_cast<const float2*>(c->d_G2f), coeff, nullptr, 0,
-      c->ncells, D);
+      c->ncells, D, HaloLaunch{});
   FUS_LAUNCHED();
   return FUS_OK;
 }
@@ -1555,7 +1606,7 @@ static int launch_boundary(fus_model* m, const double* v, double g, double dg, b
 }
 
 static int assemble_rhs(fus_model* m, double t, const double* u, const double* v,
-                        bool fwd_pending, bool with_boundary) {
+                        bool fwd_pending, bool with_boundary, bool fused = false) {
   fus_ctx* c = m->ctx;
   double g = 0.0, dg = 0.0;
   if (with_boundary)
@@ -1569,18 +1620,27 @@ static int assemble_rhs(fus_model* m, double t, const double* u, const double* v
     FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, c->ncells, c->stream));
     return boundary();
   }
-  // Partitioned stage.  Cells are ordered [interface | interior]; the interior is split in two so
-  // that BOTH exchanges hide behind cells that touch no shared dof:
+  if (fused) {
+    // The stage kernels exchange themselves (fus_halo_kernels.cuh).  The cells that touch shared
+    // dofs first, in a launch that ends by shipping the ghost partial sums to their owners; then
+    // everything else through the plain kernel while they travel.
+    const long long ni = halo_fused_interface_cells(c->halo);
+    FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, ni, c->stream, halo_fused(c->halo)));
+    if (ni == 0) // no cell to run: the exchange number still has to advance
+      FUS_TRY(halo_fused_operator_skipped(c->halo, c->stream));
+    return launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, c->ncells, c->stream);
+  }
+  // NCCL transport.  In order (default): all cells, boundary terms, then the ghost -> owner sum.
+  // Overlapped (option halo_overlap): cells are ordered [interface | interior] and the interior is
+  // split in two so that BOTH exchanges hide behind cells that touch no shared dof:
   //   interior A  ||  owner->ghost update of (u,v) started by the caller (halo_forward_begin)
   //   interface cells + boundary terms (need the fresh ghosts)
   //   interior B  ||  ghost->owner sum of b
-  // A few SMs are left free so that the exchange kernels can start while a cell kernel runs.
+  // A few SMs are left free so that NCCL's kernels can start while a cell kernel runs.
   const bool ov = halo_overlap(c->halo) != 0;
   const long long ni = halo_interface_cells(c->halo);
   const long long mid = ov ? ni + (c->ncells - ni) / 2 : c->ncells;
-  // SMs kept free for the exchange kernels: only the NCCL side-stream mode needs them (NCCL's
-  // kernels are wide); the peer-direct puts are small and measured best with none reserved.
-  c->reserve_sms = (halo_mode(c->halo) == 1) ? c->halo_reserve : c->peer_reserve;
+  c->reserve_sms = ov ? c->halo_reserve : 0;
   int rc = launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, ni, mid, c->stream);
   if (rc == FUS_OK && fwd_pending)
     rc = halo_forward_end(c->halo, const_cast<double*>(u), const_cast<double*>(v), c->stream);
@@ -1633,7 +1693,12 @@ static int launch_stage(fus_model* m, const StageArgs& A) {
   ProfScope prof(c, 1, c->stream);
   const int grid = grid_for(A.ntotal, kStageChunk, c->num_sms * 8);
   const bool west = m->kind == FUS_WESTERVELT;
-  if (c->stage_hints) {
+  if (A.halo) {
+    if (west)
+      rk4_stage_kernel<STAGE, true, false, true><<<grid, kStageThreads, 0, c->stream>>>(A);
+    else
+      rk4_stage_kernel<STAGE, false, false, true><<<grid, kStageThreads, 0, c->stream>>>(A);
+  } else if (c->stage_hints) {
     if (west)
       rk4_stage_kernel<STAGE, true, true><<<grid, kStageThreads, 0, c->stream>>>(A);
     else
@@ -1652,12 +1717,13 @@ static int launch_stage(fus_model* m, const StageArgs& A) {
 // partitioned.  Issued eagerly or captured into a CUDA graph by fus_model_rk4.
 static int issue_step(fus_model* m, StageArgs& A, double dt) {
   fus_ctx* c = m->ctx;
-  if (c->halo) // scatter_fwd of the step's first stage input (Linear.hpp:196-199)
+  const bool fused = A.halo != nullptr;
+  if (c->halo && !fused) // scatter_fwd of the step's first stage input (Linear.hpp:196-199)
     FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
   for (int i = 0; i < 4; ++i) {
     const double* u_in = (i == 0) ? m->d_u0 : m->d_un;
     const double* v_in = (i == 0) ? m->d_v0 : m->d_vn;
-    FUS_TRY(assemble_rhs(m, 0.0, u_in, v_in, true, false));
+    FUS_TRY(assemble_rhs(m, 0.0, u_in, v_in, true, false, fused));
     stage_coefficients(A, i, dt);
     switch (i) {
     case 0: FUS_TRY(launch_stage<0>(m, A)); break;
@@ -1665,7 +1731,7 @@ static int issue_step(fus_model* m, StageArgs& A, double dt) {
     case 2: FUS_TRY(launch_stage<2>(m, A)); break;
     case 3: FUS_TRY(launch_stage<3>(m, A)); break;
     }
-    if (c->halo && i < 3) // next stage input; joined inside the next assemble_rhs
+    if (c->halo && !fused && i < 3) // next stage input; joined inside the next assemble_rhs
       FUS_TRY(halo_forward_begin(c->halo, m->d_un, m->d_vn, c->stream));
   }
   return FUS_OK;
@@ -1754,6 +1820,12 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   A.babs = m->d_babs;
   A.bchunk = m->d_bchunk;
   A.src_table = m->d_src;
+  // Fused peer transport: streamed G only (the HALO kernels are built for it); otherwise this call
+  // runs on NCCL in stream order.
+  const bool fused = c->halo && halo_mode(c->halo) == 2 && c->geom_active == 0 && c->dim == 3;
+  A.halo = fused ? halo_fused(c->halo) : nullptr;
+  if (fused) // handshake with the neighbours + owner -> ghost update of (u_n, v_n)
+    FUS_TRY(halo_fused_entry(c->halo, m->d_u0, m->d_v0, c->stream));
   // boundary terms of the first stage; every later stage is seeded by the epilogue before it
   FUS_CUDA(cudaMemsetAsync(m->d_b, 0, sizeof(double) * c->ndofs, c->stream));
   FUS_TRY(launch_boundary(m, m->d_v0, 0.0, 0.0, true));
@@ -1780,9 +1852,9 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   }
 
   // CUDA graph: steps are identical launches once the scalars come from the table, so one step
-  // is captured (both streams of the peer-direct halo included) and replayed.  Not used while
+  // is captured (with the fused peer transport it is still a single stream) and replayed.  Not used while
   // per-kernel profiling is on (event pairs), with the NCCL transport, or for the odd last step.
-  const int hmode = c->halo ? halo_mode(c->halo) : -1;
+  const int hmode = c->halo ? (fused ? 2 : halo_mode(c->halo) % 2) : -1;
   const bool graph_ok = m->use_graph && c->use_graph && !c->profile && !l2_window
                         && (hmode == -1 || hmode == 2);
   if (m->step_graph
@@ -1844,7 +1916,9 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   }
   if (rc != FUS_OK)
     return rc;
-  if (c->halo) { // u_n, v_n leave with fresh ghosts (Linear.hpp:312-313)
+  if (fused) { // u_n, v_n leave with fresh ghosts (Linear.hpp:312-313): sent by the last epilogue
+    FUS_TRY(halo_fused_exit(c->halo, m->d_u0, m->d_v0, c->stream));
+  } else if (c->halo) {
     FUS_TRY(halo_forward_begin(c->halo, m->d_u0, m->d_v0, c->stream));
     FUS_TRY(halo_forward_end(c->halo, m->d_u0, m->d_v0, c->stream));
   }
@@ -1880,25 +1954,38 @@ int fus_halo_setup(fus_ctx* c, int rank, int nranks, const void* uid, int nneigh
     if (const char* e = std::getenv("FUS_HALO_OVERLAP"))
       halo_set_overlap(c->halo, std::atoi(e));
     if (const char* e = std::getenv("FUS_HALO_RESERVE"))
-      c->halo_reserve = c->peer_reserve = std::max(0, std::min(c->num_sms - 1, std::atoi(e)));
+      c->halo_reserve = std::max(0, std::min(c->num_sms - 1, std::atoi(e)));
   }
   return rc;
 }
 
-int fus_halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout4) {
-  if (nsend < 0 || nrecv < 0 || nneigh < 0 || !layout4)
+int fus_halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout6) {
+  if (nsend < 0 || nrecv < 0 || nneigh < 0 || !layout6)
     return FUS_ERR_ARG;
-  halo_mailbox_layout(nsend, nrecv, nneigh, layout4);
+  halo_mailbox_layout(nsend, nrecv, nneigh, layout6);
   return FUS_OK;
 }
 
-int fus_halo_peer_export(fus_ctx* c, void* ipc_handle64, int64_t* layout3) {
+int fus_halo_peer_offsets(const int64_t* q_layout6, const int64_t* q_send_off,
+                          const int64_t* q_recv_off, int j, int64_t* out6) {
+  if (!q_layout6 || !q_send_off || !q_recv_off || j < 0 || !out6)
+    return FUS_ERR_ARG;
+  out6[0] = 8 * q_recv_off[j];
+  out6[1] = q_layout6[0] + 8 * q_recv_off[j];
+  out6[2] = q_layout6[1] + 8 * q_send_off[j];
+  out6[3] = q_layout6[2] + 8 * (int64_t)j;
+  out6[4] = q_layout6[3] + 8 * (int64_t)j;
+  out6[5] = q_layout6[4] + 8 * (int64_t)j;
+  return FUS_OK;
+}
+
+int fus_halo_peer_export(fus_ctx* c, void* ipc_handle64, int64_t* layout6, void** base) {
   if (!c || !c->halo) {
     set_error("fus_halo_peer_export: call fus_halo_setup first");
     return FUS_ERR_STATE;
   }
   FUS_TRY(select_device(c));
-  return halo_peer_export(c->halo, ipc_handle64, layout3);
+  return halo_peer_export(c->halo, ipc_handle64, layout6, base);
 }
 
 int fus_halo_peer_connect(fus_ctx* c, const void* handles, const int64_t* byte_off) {
@@ -1907,6 +1994,15 @@ int fus_halo_peer_connect(fus_ctx* c, const void* handles, const int64_t* byte_o
   FUS_TRY(select_device(c));
   ++c->config_epoch;
   return halo_peer_connect(c->halo, handles, byte_off);
+}
+
+int fus_halo_peer_connect_local(fus_ctx* c, void* const* bases, const int* devices,
+                                const int64_t* byte_off) {
+  if (!c || !c->halo)
+    return FUS_ERR_STATE;
+  FUS_TRY(select_device(c));
+  ++c->config_epoch;
+  return halo_peer_connect_local(c->halo, bases, devices, byte_off);
 }
 
 int fus_scatter_fwd_dev(fus_ctx* c, double* x) {

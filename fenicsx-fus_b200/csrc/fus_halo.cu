@@ -98,10 +98,8 @@ struct PhaseProf {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
 };
 bool g_prof = std::getenv("FUS_HALO_PROF") != nullptr;
-// FUS_HALO_LIGHTFENCE=1: one system fence per block (thread 0, after the block barrier)
-bool g_lightfence = std::getenv("FUS_HALO_LIGHTFENCE") != nullptr;
-PhaseProf g_phase[6] = {{"put_fwd", {}}, {"wait_fwd", {}}, {"put_rev", {}},
-                        {"wait_rev", {}}, {"nccl_fwd", {}}, {"nccl_rev", {}}};
+PhaseProf g_phase[6] = {{"unused0", {}}, {"unused1", {}}, {"unused2", {}},
+                        {"unused3", {}}, {"nccl_fwd", {}}, {"nccl_rev", {}}};
 struct PhaseScope {
   cudaEvent_t stop = nullptr;
   cudaStream_t st;
@@ -155,17 +153,23 @@ struct Halo {
   int overlap = 0; // NCCL on a side stream: measured slower than in-order beyond 2 ranks (profiles/)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_fwd_ready = nullptr, ev_fwd_done = nullptr;
-  // ---- peer-direct transport: one-sided puts into the neighbours' mailboxes over NVLink ----
-  // mailbox = [fwd data: 2*nrecv doubles][rev data: nsend doubles][fwd flags][rev flags]
+  // ---- fused peer transport (fus_halo_kernels.cuh): the stage kernels exchange over NVLink ----
+  // mailbox = [fwd_u: nghost][fwd_v: nghost][rev: nsend][fwd flags][rev flags][ready flags]
   bool peer = false;
+  bool ipc = false;                          // peer_base[] were opened with cudaIpcOpenMemHandle
   char* d_mbox = nullptr;
-  size_t off_rev = 0, off_fflag = 0, off_rflag = 0, mbox_bytes = 0;
-  std::vector<void*> peer_base;              // opened mailboxes (one per neighbour)
-  struct PeerTable* d_tab = nullptr;         // device copy of the per-neighbour destination table
-  unsigned int* d_counter = nullptr;         // block-completion counters (fwd, rev)
+  int64_t lay[6] = {0, 0, 0, 0, 0, 0};       // byte offsets {fwd_v, rev, fwd flags, rev flags, ready, total}
+  std::vector<void*> peer_base;              // the neighbours' mailboxes
+  FusedHalo* d_fh = nullptr;                 // device copy of the transport state
+  FusedHalo h_fh;                            // host copy (options rewrite single fields)
+  int64_t nshared = 0;
+  int32_t* d_spos_off = nullptr;
+  int32_t* d_spos = nullptr;
+  signed char* d_spos_nb = nullptr;
+  unsigned int* d_ctr = nullptr;
   int* d_error = nullptr;
-  unsigned long long* d_epoch = nullptr;     // [fwd, rev] exchange counters, advanced on the device
-                                             // so that a captured CUDA graph can replay the step
+  unsigned long long* d_seq = nullptr;       // exchange numbers, advanced on the device so that a
+                                             // captured CUDA graph can replay the step
 };
 
 int halo_unique_id(void* id128) {
@@ -260,13 +264,17 @@ void halo_destroy(Halo* h) {
     cudaStreamSynchronize(h->comm_stream);
   if (h->comm && g_nccl.CommDestroy)
     g_nccl.CommDestroy(h->comm);
-  for (void* pb : h->peer_base)
-    if (pb)
-      cudaIpcCloseMemHandle(pb);
+  if (h->ipc)
+    for (void* pb : h->peer_base)
+      if (pb)
+        cudaIpcCloseMemHandle(pb);
   cudaFree(h->d_mbox);
-  cudaFree(h->d_tab);
-  cudaFree(h->d_counter);
-  cudaFree(h->d_epoch);
+  cudaFree(h->d_fh);
+  cudaFree(h->d_spos_off);
+  cudaFree(h->d_spos);
+  cudaFree(h->d_spos_nb);
+  cudaFree(h->d_ctr);
+  cudaFree(h->d_seq);
   cudaFree(h->d_error);
   cudaFree(h->d_soff);
   cudaFree(h->d_roff);
@@ -288,11 +296,9 @@ void halo_destroy(Halo* h) {
 }
 
 void halo_set_overlap(Halo* h, int on) { h->overlap = on; }
-int halo_overlap(const Halo* h) { return h->overlap || h->peer; }
+int halo_overlap(const Halo* h) { return h->overlap; }
 int halo_mode(const Halo* h) { return h->peer ? 2 : (h->overlap ? 1 : 0); }
-long long halo_interface_cells(const Halo* h) {
-  return (h->overlap || h->peer) ? h->ninterface : 0;
-}
+long long halo_interface_cells(const Halo* h) { return h->overlap ? h->ninterface : 0; }
 
 // One grouped exchange.  `fwd`: owners send send_idx entries, ghosts receive; otherwise reversed.
 // nv vectors are concatenated per neighbour: [neighbour k][vector][entry].
@@ -341,68 +347,26 @@ int halo_forward(Halo* h, double* a, double* b, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Peer-direct transport.  A put kernel gathers the interface values and stores them straight into
-// the neighbours' mailboxes (IPC-mapped peer memory, NVLink); the last block to finish raises one
-// epoch flag per neighbour with system-scope release ordering.  The receiving side's wait kernel
-// spins on its own flags (acquire, bounded), then unpacks with L1-bypassing loads.
-// Puts are one-sided, so they are issued as early as possible and the waits as late as possible:
-// the cells that touch no shared dof run in between on the same stream.
-// A mailbox segment is never overwritten before it is consumed because every exchanging pair
-// alternates forward (owner -> ghost) and reverse (ghost -> owner) messages: the owner cannot put
-// stage s+1 before it has received the reverse message of stage s, which the ghost side only
-// sends after it has unpacked the forward message of stage s (and symmetrically).
+// Fused peer transport: set-up.  Every rank owns a mailbox in device memory that its neighbours map
+// (CUDA IPC across processes, plain peer access between the devices of one process); the exchange
+// itself happens inside the stage kernels (fus_halo_kernels.cuh, fus_kernels.cuh).
 // ---------------------------------------------------------------------------------------------
-static int peer_put(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
-  if (fwd && !b) {
-    set_error("peer transport: the forward update always carries two vectors");
-    return FUS_ERR_ARG;
-  }
-  const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
-  const OffTables T = tables(h);
-  const long long n = fwd ? h->nsend : h->nrecv;
-  // launched even with nothing to send: the kernel also advances the exchange counter
-  PhaseScope ps(fwd ? 0 : 2, st);
-  peer_put_kernel<<<blocks_for(n), 256, 0, st>>>(a, b, fwd ? h->d_send_idx : h->d_recv_idx,
-                                                 fwd ? T.d_soff : T.d_roff, nn, n, nv, h->d_tab,
-                                                 fwd ? 1 : 0, h->d_counter + (fwd ? 0 : 1),
-                                                 h->d_epoch + (fwd ? 0 : 1), g_lightfence ? 1 : 0);
-  FUS_CUDA_H(cudaGetLastError());
-  return FUS_OK;
-}
-
-static int peer_wait(Halo* h, bool fwd, double* a, double* b, cudaStream_t st) {
-  const int nv = fwd ? 2 : 1, nn = (int)h->neigh.size();
-  const OffTables T = tables(h);
-  const long long n = fwd ? h->nrecv : h->nsend;
-  const unsigned long long* epoch = h->d_epoch + (fwd ? 0 : 1);
-  if (n == 0)
-    return FUS_OK;
-  const double* data = (const double*)(h->d_mbox + (fwd ? 0 : h->off_rev));
-  const unsigned long long* flags
-      = (const unsigned long long*)(h->d_mbox + (fwd ? h->off_fflag : h->off_rflag));
-  PhaseScope ps(fwd ? 1 : 3, st);
-  if (fwd)
-    peer_wait_kernel<false><<<blocks_for(n), 256, 0, st>>>(a, b, h->d_recv_idx, T.d_roff, nn, n,
-                                                           nv, data, flags, epoch, h->d_error);
-  else
-    peer_wait_kernel<true><<<blocks_for(n), 256, 0, st>>>(a, nullptr, h->d_send_idx, T.d_soff, nn,
-                                                          n, 1, data, flags, epoch, h->d_error);
-  FUS_CUDA_H(cudaGetLastError());
-  return FUS_OK;
-}
-
-// mailbox = [fwd data: 2*nrecv doubles][rev data: nsend doubles][fwd flags][rev flags];
-// layout4 = byte offsets {reverse data, forward flags, reverse flags, total size}
-void halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout4) {
+// mailbox = [fwd_u: nrecv doubles][fwd_v: nrecv][rev: nsend][fwd flags][rev flags][ready flags];
+// layout6 = byte offsets {fwd_v, rev, forward flags, reverse flags, ready flags, total size}
+void halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout6) {
+  auto up = [](int64_t v) { return (v + 127) / 128 * 128; };
   const int64_t nn = std::max(1, nneigh);
-  layout4[0] = (int64_t)sizeof(double) * 2 * std::max<int64_t>(1, nrecv);
-  layout4[1] = layout4[0] + (int64_t)sizeof(double) * std::max<int64_t>(1, nsend);
-  layout4[2] = layout4[1] + (int64_t)sizeof(unsigned long long) * nn;
-  layout4[3] = layout4[2] + (int64_t)sizeof(unsigned long long) * nn;
+  const int64_t vec = up((int64_t)sizeof(double) * std::max<int64_t>(1, nrecv));
+  layout6[0] = vec;
+  layout6[1] = 2 * vec;
+  layout6[2] = layout6[1] + up((int64_t)sizeof(double) * std::max<int64_t>(1, nsend));
+  layout6[3] = layout6[2] + up((int64_t)sizeof(unsigned long long) * nn);
+  layout6[4] = layout6[3] + up((int64_t)sizeof(unsigned long long) * nn);
+  layout6[5] = layout6[4] + up((int64_t)sizeof(unsigned long long) * nn);
 }
 
-int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3) {
-  if (!h || !ipc_handle64 || !layout3)
+int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout6, void** base) {
+  if (!h || !layout6)
     return FUS_ERR_ARG;
   if ((int)h->neigh.size() > kMaxNeigh) {
     set_error("peer transport supports at most %d neighbours", kMaxNeigh);
@@ -411,38 +375,103 @@ int halo_peer_export(Halo* h, void* ipc_handle64, int64_t* layout3) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   FUS_CUDA_H(cudaSetDevice(h->device));
   if (!h->d_mbox) {
-    int64_t lay[4];
-    halo_mailbox_layout(h->nsend, h->nrecv, (int)h->neigh.size(), lay);
-    h->off_rev = (size_t)lay[0];
-    h->off_fflag = (size_t)lay[1];
-    h->off_rflag = (size_t)lay[2];
-    h->mbox_bytes = (size_t)lay[3];
-    FUS_CUDA_H(cudaMalloc(&h->d_mbox, h->mbox_bytes));
-    FUS_CUDA_H(cudaMemset(h->d_mbox, 0, h->mbox_bytes));
-    FUS_CUDA_H(cudaMalloc(&h->d_counter, 2 * sizeof(unsigned int)));
-    FUS_CUDA_H(cudaMemset(h->d_counter, 0, 2 * sizeof(unsigned int)));
-    FUS_CUDA_H(cudaMalloc(&h->d_epoch, 2 * sizeof(unsigned long long)));
-    FUS_CUDA_H(cudaMemset(h->d_epoch, 0, 2 * sizeof(unsigned long long)));
+    halo_mailbox_layout(h->nsend, h->nrecv, (int)h->neigh.size(), h->lay);
+    FUS_CUDA_H(cudaMalloc(&h->d_mbox, (size_t)h->lay[5]));
+    FUS_CUDA_H(cudaMemset(h->d_mbox, 0, (size_t)h->lay[5]));
+    FUS_CUDA_H(cudaMalloc(&h->d_ctr, CTR_COUNT * sizeof(unsigned int)));
+    FUS_CUDA_H(cudaMemset(h->d_ctr, 0, CTR_COUNT * sizeof(unsigned int)));
+    FUS_CUDA_H(cudaMalloc(&h->d_seq, SEQ_COUNT * sizeof(unsigned long long)));
+    FUS_CUDA_H(cudaMemset(h->d_seq, 0, SEQ_COUNT * sizeof(unsigned long long)));
     FUS_CUDA_H(cudaMalloc(&h->d_error, sizeof(int)));
     FUS_CUDA_H(cudaMemset(h->d_error, 0, sizeof(int)));
     FUS_CUDA_H(cudaDeviceSynchronize());
   }
-  cudaIpcMemHandle_t hd;
-  FUS_CUDA_H(cudaIpcGetMemHandle(&hd, h->d_mbox));
-  std::memcpy(ipc_handle64, &hd, sizeof(hd));
-  layout3[0] = (int64_t)h->off_rev;
-  layout3[1] = (int64_t)h->off_fflag;
-  layout3[2] = (int64_t)h->off_rflag;
+  if (ipc_handle64) {
+    cudaIpcMemHandle_t hd;
+    FUS_CUDA_H(cudaIpcGetMemHandle(&hd, h->d_mbox));
+    std::memcpy(ipc_handle64, &hd, sizeof(hd));
+  }
+  if (base)
+    *base = h->d_mbox;
+  std::memcpy(layout6, h->lay, sizeof(h->lay));
   return FUS_OK;
 }
 
-// handles: one 64-byte IPC handle per neighbour (same order as the neighbour list);
-// byte_off[k][4]: byte offsets inside neighbour k's mailbox of {my forward data segment, my forward
-// flag, my reverse data segment, my reverse flag}.  The caller derives them from the layout triple
-// that halo_peer_export returned on that neighbour and from its offset tables:
-//   fwd data  = 8 * 2 * recv_off_q[j]            fwd flag = off_fflag_q + 8 * j
-//   rev data  = off_rev_q + 8 * send_off_q[j]    rev flag = off_rflag_q + 8 * j
-// with j = this rank's position in neighbour q's neighbour list.
+// bases[k]: neighbour k's mailbox as mapped into this process (IPC) or its device pointer (same
+// process); byte_off[k][6]: byte offsets inside it of {my forward-u run, my forward-v run, my reverse
+// run, my forward flag, my reverse flag, my ready flag}.  From neighbour q's layout6 = L, its offset
+// tables and j = this rank's position in q's neighbour list:
+//   fwd_u = 8 roff_q[j]   fwd_v = L[0] + 8 roff_q[j]   rev = L[1] + 8 soff_q[j]
+//   flags = L[2] + 8 j,  L[3] + 8 j,  L[4] + 8 j
+static int peer_connect_bases(Halo* h, const int64_t* byte_off) {
+  const size_t nn = h->neigh.size();
+  std::vector<int32_t> sidx((size_t)h->nsend), ridx((size_t)h->nrecv);
+  if (h->nsend)
+    FUS_CUDA_H(cudaMemcpy(sidx.data(), h->d_send_idx, sizeof(int32_t) * h->nsend,
+                          cudaMemcpyDeviceToHost));
+  if (h->nrecv)
+    FUS_CUDA_H(cudaMemcpy(ridx.data(), h->d_recv_idx, sizeof(int32_t) * h->nrecv,
+                          cudaMemcpyDeviceToHost));
+  std::vector<int32_t> spos_off, spos;
+  std::vector<signed char> spos_nb;
+  const std::string why = fused_halo_lists(h->nowned, (int)nn, h->send_off.data(), sidx.data(),
+                                           ridx.data(), h->nrecv, &h->nshared, spos_off, spos, spos_nb);
+  if (!why.empty()) {
+    set_error("fused halo: %s", why.c_str());
+    return FUS_ERR_UNSUPPORTED;
+  }
+  FUS_CUDA_H(cudaMalloc(&h->d_spos_off, sizeof(int32_t) * spos_off.size()));
+  FUS_CUDA_H(cudaMalloc(&h->d_spos, sizeof(int32_t) * std::max<size_t>(1, spos.size())));
+  FUS_CUDA_H(cudaMalloc(&h->d_spos_nb, std::max<size_t>(1, spos_nb.size())));
+  FUS_CUDA_H(cudaMemcpy(h->d_spos_off, spos_off.data(), sizeof(int32_t) * spos_off.size(),
+                        cudaMemcpyHostToDevice));
+  if (!spos.empty()) {
+    FUS_CUDA_H(cudaMemcpy(h->d_spos, spos.data(), sizeof(int32_t) * spos.size(),
+                          cudaMemcpyHostToDevice));
+    FUS_CUDA_H(cudaMemcpy(h->d_spos_nb, spos_nb.data(), spos_nb.size(), cudaMemcpyHostToDevice));
+  }
+  FusedHalo& F = h->h_fh;
+  std::memset(&F, 0, sizeof(F));
+  F.nneigh = (int)nn;
+  F.nowned = h->nowned;
+  F.nghost = h->nrecv;
+  F.nshared = h->nshared;
+  F.nsend = h->nsend;
+  F.fwd_u = (const double*)h->d_mbox;
+  F.fwd_v = (const double*)(h->d_mbox + h->lay[0]);
+  F.rev = (const double*)(h->d_mbox + h->lay[1]);
+  F.fwd_flag = (const unsigned long long*)(h->d_mbox + h->lay[2]);
+  F.rev_flag = (const unsigned long long*)(h->d_mbox + h->lay[3]);
+  F.ready_flag = (const unsigned long long*)(h->d_mbox + h->lay[4]);
+  for (size_t k = 0; k < nn; ++k) {
+    char* cb = (char*)h->peer_base[k];
+    F.r_fwd_u[k] = (double*)(cb + byte_off[6 * k + 0]);
+    F.r_fwd_v[k] = (double*)(cb + byte_off[6 * k + 1]);
+    F.r_rev[k] = (double*)(cb + byte_off[6 * k + 2]);
+    F.r_fwd_flag[k] = (unsigned long long*)(cb + byte_off[6 * k + 3]);
+    F.r_rev_flag[k] = (unsigned long long*)(cb + byte_off[6 * k + 4]);
+    F.r_ready_flag[k] = (unsigned long long*)(cb + byte_off[6 * k + 5]);
+  }
+  F.soff = h->d_soff;
+  F.roff = h->d_roff;
+  F.sidx = h->d_send_idx;
+  F.spos_off = h->d_spos_off;
+  F.spos = h->d_spos;
+  F.spos_nb = h->d_spos_nb;
+  F.seq = h->d_seq;
+  F.ctr = h->d_ctr;
+  F.error = h->d_error;
+  double timeout_s = 30.0; // a neighbour that is this late is taken for dead (FUS_HALO_TIMEOUT_S)
+  if (const char* e = std::getenv("FUS_HALO_TIMEOUT_S"))
+    timeout_s = std::max(0.001, std::atof(e));
+  F.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  if (!h->d_fh)
+    FUS_CUDA_H(cudaMalloc(&h->d_fh, sizeof(FusedHalo)));
+  FUS_CUDA_H(cudaMemcpy(h->d_fh, &F, sizeof(F), cudaMemcpyHostToDevice));
+  h->peer = true;
+  return FUS_OK;
+}
+
 int halo_peer_connect(Halo* h, const void* handles, const int64_t* byte_off) {
   if (!h || !h->d_mbox || (!h->neigh.empty() && (!handles || !byte_off))) {
     set_error("halo_peer_connect: export first, then pass the neighbours' handles and offsets");
@@ -450,26 +479,48 @@ int halo_peer_connect(Halo* h, const void* handles, const int64_t* byte_off) {
   }
   FUS_CUDA_H(cudaSetDevice(h->device));
   const size_t nn = h->neigh.size();
-  PeerTable tab;
-  std::memset(&tab, 0, sizeof(tab));
   h->peer_base.assign(nn, nullptr);
+  h->ipc = true;
   for (size_t k = 0; k < nn; ++k) {
     cudaIpcMemHandle_t hd;
     std::memcpy(&hd, (const char*)handles + 64 * k, sizeof(hd));
     void* base = nullptr;
     FUS_CUDA_H(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
     h->peer_base[k] = base;
-    char* cb = (char*)base;
-    tab.fwd_dst[k] = (double*)(cb + byte_off[4 * k + 0]);
-    tab.fwd_flag[k] = (unsigned long long*)(cb + byte_off[4 * k + 1]);
-    tab.rev_dst[k] = (double*)(cb + byte_off[4 * k + 2]);
-    tab.rev_flag[k] = (unsigned long long*)(cb + byte_off[4 * k + 3]);
   }
-  if (!h->d_tab)
-    FUS_CUDA_H(cudaMalloc(&h->d_tab, sizeof(PeerTable)));
-  FUS_CUDA_H(cudaMemcpy(h->d_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice));
-  h->peer = true;
-  return FUS_OK;
+  return peer_connect_bases(h, byte_off);
+}
+
+// Same transport between the devices of ONE process (one host thread per GPU): the neighbours'
+// mailboxes are plain device pointers; peer access is enabled here.
+int halo_peer_connect_local(Halo* h, void* const* bases, const int* devices,
+                            const int64_t* byte_off) {
+  if (!h || !h->d_mbox || (!h->neigh.empty() && (!bases || !devices || !byte_off))) {
+    set_error("halo_peer_connect_local: export first, then pass the neighbours' mailboxes");
+    return FUS_ERR_ARG;
+  }
+  FUS_CUDA_H(cudaSetDevice(h->device));
+  const size_t nn = h->neigh.size();
+  h->peer_base.assign(nn, nullptr);
+  h->ipc = false;
+  for (size_t k = 0; k < nn; ++k) {
+    if (devices[k] != h->device) {
+      int can = 0;
+      FUS_CUDA_H(cudaDeviceCanAccessPeer(&can, h->device, devices[k]));
+      if (!can) {
+        set_error("device %d cannot access device %d", h->device, devices[k]);
+        return FUS_ERR_UNSUPPORTED;
+      }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devices[k], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        set_error("cudaDeviceEnablePeerAccess(%d): %s", devices[k], cudaGetErrorString(e));
+        return FUS_ERR_CUDA;
+      }
+      cudaGetLastError();
+    }
+    h->peer_base[k] = bases[k];
+  }
+  return peer_connect_bases(h, byte_off);
 }
 
 int halo_peer_error(Halo* h) {
@@ -481,18 +532,46 @@ int halo_peer_error(Halo* h) {
   return e;
 }
 
+const FusedHalo* halo_fused(const Halo* h) { return (h && h->peer) ? h->d_fh : nullptr; }
+
+// The by-value halo parameter of the stiffness launch over the interface cells [0, ninterface)
+HaloLaunch halo_fused_launch(const Halo* h) {
+  HaloLaunch L;
+  std::memset(&L, 0, sizeof(L));
+  if (!h || !h->peer)
+    return L;
+  L.H = h->d_fh;
+  L.nown = h->nowned;
+  L.mbu = h->h_fh.fwd_u - h->nowned;
+  L.mbv = h->h_fh.fwd_v - h->nowned;
+  return L;
+}
+long long halo_fused_interface_cells(const Halo* h) { return h ? h->ninterface : 0; }
+int halo_fused_operator_skipped(Halo* h, cudaStream_t st) {
+  halo_operator_skipped_kernel<<<1, 32, 0, st>>>(h->d_fh);
+  FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
+// Entry of an rk4 call in fused mode: handshake with the neighbours, then the owner -> ghost update
+// of the state with the protocol the epilogues continue (see fus_halo_kernels.cuh).
+int halo_fused_entry(Halo* h, const double* u, const double* v, cudaStream_t st) {
+  halo_ready_kernel<<<1, 32, 0, st>>>(h->d_fh, 3);
+  halo_entry_put_kernel<<<blocks_for(h->nsend), 256, 0, st>>>(h->d_fh, u, v, 0);
+  FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
+// Exit: the new state's ghost values, sent by the last epilogue, into the ghost entries of (u, v).
+int halo_fused_exit(Halo* h, double* u, double* v, cudaStream_t st) {
+  halo_exit_unpack_kernel<<<blocks_for(h->nrecv), 256, 0, st>>>(h->d_fh, u, v);
+  FUS_CUDA_H(cudaGetLastError());
+  return FUS_OK;
+}
+
 int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
   if (h->neigh.empty())
     return FUS_OK;
-  if (h->peer) { // one-sided put on the side stream, concurrent with the next cells on `st`
-    FUS_CUDA_H(cudaEventRecord(h->ev_fwd_ready, st));
-    FUS_CUDA_H(cudaStreamWaitEvent(h->comm_stream, h->ev_fwd_ready, 0));
-    int r = peer_put(h, true, a, b, h->comm_stream);
-    if (r != FUS_OK)
-      return r;
-    FUS_CUDA_H(cudaEventRecord(h->ev_fwd_done, h->comm_stream));
-    return FUS_OK;
-  }
   if (!h->overlap)
     return halo_forward(h, a, b, st);
   FUS_CUDA_H(cudaEventRecord(h->ev_fwd_ready, st));
@@ -507,11 +586,6 @@ int halo_forward_begin(Halo* h, double* a, double* b, cudaStream_t st) {
 int halo_forward_end(Halo* h, double* a, double* b, cudaStream_t st) {
   if (h->neigh.empty())
     return FUS_OK;
-  if (h->peer) {
-    // our own put has read a/b before anything later on `st` may overwrite them
-    FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_fwd_done, 0));
-    return peer_wait(h, true, a, b, st);
-  }
   if (!h->overlap)
     return FUS_OK;
   FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_fwd_done, 0));
@@ -543,15 +617,6 @@ int halo_reverse(Halo* h, double* a, double* b, cudaStream_t st) {
 int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
   if (h->neigh.empty())
     return FUS_OK;
-  if (h->peer) {
-    FUS_CUDA_H(cudaEventRecord(h->ev_ready, st));
-    FUS_CUDA_H(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
-    int r = peer_put(h, false, a, nullptr, h->comm_stream);
-    if (r != FUS_OK)
-      return r;
-    FUS_CUDA_H(cudaEventRecord(h->ev_done, h->comm_stream));
-    return FUS_OK;
-  }
   if (!h->overlap)
     return FUS_OK; // whole exchange happens in _end, after all cells
   FUS_CUDA_H(cudaEventRecord(h->ev_ready, st));
@@ -566,10 +631,6 @@ int halo_reverse_begin(Halo* h, double* a, cudaStream_t st) {
 int halo_reverse_end(Halo* h, double* a, cudaStream_t st) {
   if (h->neigh.empty())
     return FUS_OK;
-  if (h->peer) {
-    FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_done, 0)); // ghost partial sums have been read
-    return peer_wait(h, false, a, nullptr, st);
-  }
   if (!h->overlap)
     return reverse_on(h, a, nullptr, st);
   FUS_CUDA_H(cudaStreamWaitEvent(st, h->ev_done, 0));

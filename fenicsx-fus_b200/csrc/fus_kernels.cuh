@@ -12,6 +12,7 @@
 // threads so that their indexing, staging and barrier logic is exercised by the CPU test suite).
 // The guarded alternatives replace inline PTX and CUDA-only declarations; device builds never see
 // them.
+#include "fus_halo_kernels.cuh"
 #include "fus_trilinear.hpp"
 
 #ifndef FUS_HOST_EMULATION
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(ColCfg<N>::THREADS)
                          double* __restrict__ y, const int32_t* __restrict__ dofmap,
                          const double2* __restrict__ G2, const double* __restrict__ coeff,
                          const double* __restrict__ coeff2, long long cell_begin,
-                         long long cell_end, const __grid_constant__ DMat<N> D) {
+                         long long cell_end, const __grid_constant__ DMat<N> D,
+                         const HaloLaunch = HaloLaunch{}) {
   using C = ColCfg<N>;
   constexpr int NN = C::NN, NS = C::NS, PL = C::PL;
 #ifdef FUS_HOST_EMULATION
@@ -390,6 +392,90 @@ __global__ void __launch_bounds__(ColCfg<N>::THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// The tail of a HALO launch of the line kernel (fused peer transport, fus_halo_kernels.cuh).
+// A HALO launch covers only the cells that touch a dof shared with a neighbour (stored first,
+// [0, ninterface)); the rest of the mesh runs through the plain kernel in a second launch.  The
+// exchange code sits AFTER the cell loop, so the loop is the plain kernel's (anything with waits or
+// calls in front of or inside the loop cost ~150-300 B of spills per thread in the loop itself --
+// measured with ptxas -v -- hence also: no forward wait here, the epilogue does it).
+// A "group" is the set of warps that works on a cell slot: one warp (WARP) or GTHREADS/32 warps
+// synchronising on the named barrier group + 1.
+// ------------------------------------------------------------------------------------------------
+template <bool WARP, int GTHREADS>
+__device__ __forceinline__ void halo_group_sync(int group) {
+  if constexpr (WARP)
+    __syncwarp();
+  else
+#ifdef FUS_HOST_EMULATION
+    fus_emu::named_barrier(group + 1, GTHREADS);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(GTHREADS) : "memory");
+#endif
+}
+
+// After the last cell: the group reports in; once every group of the grid has (they all finish
+// within a few microseconds of each other, and all are resident: the grid is sized by occupancy),
+// the ghost part of y is final and the groups ship it to the owners' mailboxes, one 2 KB chunk at a
+// time; the group that completes the last chunk raises the reverse flags.  The emulation runs
+// blocks one after another, so there a group looks once and the last one ships everything.
+template <bool WARP, int GTHREADS>
+__device__ __forceinline__ void halo_group_report_and_ship(const FusedHalo* Hp, const double* y,
+                                                        long long nown, int* word, int lg,
+                                                        int group, unsigned int total) {
+  const FusedHalo& H = *Hp;
+  const long long nchunks = (H.nghost + kRevChunk - 1) / kRevChunk;
+  __threadfence();
+  halo_group_sync<WARP, GTHREADS>(group);
+  if (lg == 0) {
+    const unsigned int before = atomicAdd(H.ctr + CTR_GROUPS_PAST, 1u);
+    if (before == total - 1 && nchunks == 0)
+      halo_raise(H, false); // nothing to send: the exchange number advances all the same
+    int all = ld_acquire_gpu(H.ctr + CTR_GROUPS_PAST) >= total ? 1 : 0;
+#ifndef FUS_HOST_EMULATION
+    if (!all && nchunks > 0) {
+      const unsigned long long t0 = halo_time_ns();
+      while (!(all = ld_acquire_gpu(H.ctr + CTR_GROUPS_PAST) >= total ? 1 : 0)) {
+        __nanosleep(100);
+        if (halo_time_ns() - t0 > H.timeout_ns || *(volatile int*)H.error) {
+          atomicExch(H.error, 1);
+          break;
+        }
+      }
+    }
+#endif
+    *word = all;
+  }
+  halo_group_sync<WARP, GTHREADS>(group);
+  const bool all_past = *word != 0;
+  halo_group_sync<WARP, GTHREADS>(group);
+  if (!all_past)
+    return;
+  for (;;) {
+    if (lg == 0)
+      *word = (int)atomicAdd(H.ctr + CTR_NEXT_CHUNK, 1u);
+    halo_group_sync<WARP, GTHREADS>(group);
+    const long long ch = *word;
+    halo_group_sync<WARP, GTHREADS>(group);
+    if (ch >= nchunks)
+      break;
+    const long long e1 = (ch + 1) * kRevChunk < H.nghost ? (ch + 1) * kRevChunk : H.nghost;
+    for (long long e = ch * kRevChunk + lg; e < e1; e += GTHREADS) {
+      int kq = 0;
+      while (kq + 1 < H.nneigh && e >= H.roff[kq + 1])
+        ++kq;
+      H.r_rev[kq][e - H.roff[kq]] = __ldcg(y + nown + e);
+    }
+    __threadfence_system();
+    halo_group_sync<WARP, GTHREADS>(group);
+    if (lg == 0) {
+      const unsigned int done = atomicAdd(H.ctr + CTR_CHUNKS_DONE, 1u) + 1u;
+      if ((long long)done == nchunks)
+        halo_raise(H, false);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Stiffness operator, "line" kernel: same work split as the column kernel (N*N threads per cell, G
 // streamed to registers with whole-cell look-ahead, RED scatter) but every contraction runs in
 // registers.  Thread (a,b) owns one line of the cell in each of three layouts
@@ -459,11 +545,19 @@ struct LineCfg {
 //                (cp.async.bulk, 48*N^3 contiguous bytes) into a two-stage shared-memory ring per
 //                cell slot, completion through an mbarrier, G read back with 16-byte shared loads.
 //                No registers hold G in flight (12*N fewer live registers).  "stiffness_variant" 6.
-template <int N, bool FUSE2, int GEOM = 0, typename T = double>
+// HALO (mesh partitioned, fused peer transport, fus_halo_kernels.cuh): the launch covers the cells
+// that touch a dof shared with a neighbour.  Ghost values of the stage input are gathered straight
+// from the mailbox the owners' epilogues write into (the epilogue BEFORE this launch has already
+// waited for the owners' flags, so there is no wait here); after the last cell the groups ship the
+// ghost part of y -- the partial sums the owners need -- into the owners' mailboxes and raise the
+// reverse flags (halo_group_report_and_ship above, outside the cell loop).
+template <int N, bool FUSE2, int GEOM = 0, typename T = double, bool HALO = false>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS,
                                   (GEOM == 2 && N <= 5)
                                       ? 3
-                                      : (((GEOM == 3 || GEOM == 5 || (GEOM == 6 && !FUSE2)) && N <= 5)
+                                      : (((GEOM == 3 || GEOM == 5 || (GEOM == 6 && !FUSE2)
+                                           || (HALO && GEOM != 6))
+                                          && N <= 5)
                                              ? 4
                                              : ((GEOM == 6 && N == 6) ? 2 : 0)))
     stiffness_line_kernel(const T* __restrict__ x, const T* __restrict__ x2, T* __restrict__ y,
@@ -471,7 +565,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
                           const typename Vec2<T>::type* __restrict__ G2,
                           const T* __restrict__ coeff, const T* __restrict__ coeff2,
                           long long cell_begin, long long cell_end,
-                          const __grid_constant__ DMatT<T, N> D) {
+                          const __grid_constant__ DMatT<T, N> D,
+                          const __grid_constant__ HaloLaunch HL) {
   using C = LineCfg<N>;
   using V2 = typename Vec2<T>::type;
   static_assert(GEOM < 2 || sizeof(T) == sizeof(double),
@@ -483,6 +578,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   constexpr bool REGRING = STREAM && !RING;         // ... through the register ring g[][]
   constexpr bool CFX = (GEOM >= 4), DMPF = (GEOM == 5), DM2 = (GEOM == 6 || GEOM == 7);
   static_assert(!RING || sizeof(T) == sizeof(double), "the TMA ring is built for FP64 only");
+  static_assert(!HALO || (sizeof(T) == sizeof(double) && STREAM), "fused halo: FP64, streamed G");
   constexpr int TQ = FUS_TRI_STRIDE / 2; // double2 per cell of trilinear coefficients
   static_assert(N % GPF == 0, "G look-ahead depth must divide N");
   static_assert(GEOM >= 0 && GEOM <= 7, "unknown geometry mode");
@@ -544,6 +640,30 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   const long long stride = (long long)gridDim.x * C::CPB;
   const long long ncell = cell_end - cell_begin;
   const int niter = (int)((ncell + stride - 1) / stride);
+  int* h_word = nullptr; // one word per group for broadcasts of the group leader's findings
+  if constexpr (HALO) {
+    __shared__ int h_words[C::GROUPS];
+    h_word = h_words + group;
+    if (*(volatile int*)HL.H->error)
+      return; // an earlier wait timed out: the run is being aborted
+    if (blockIdx.x == 0 && tid == 0) { // state for the NEXT epilogue; nothing here reads it
+      HL.H->seq[SEQ_REV_EXPECT] += 1ull;
+      HL.H->ctr[CTR_SHARED_DONE] = 0u;
+    }
+  }
+  // owned entries from the vector, ghost entries from the mailbox
+  auto gx = [&](int i) -> T {
+    if constexpr (HALO)
+      return __ldg((i < HL.nown ? x : reinterpret_cast<const T*>(HL.mbu)) + i);
+    else
+      return __ldg(x + i);
+  };
+  auto gx2 = [&](int i) -> T {
+    if constexpr (HALO)
+      return __ldg((i < HL.nown ? x2 : reinterpret_cast<const T*>(HL.mbv)) + i);
+    else
+      return __ldg(x2 + i);
+  };
   long long c = cell_begin + (long long)blockIdx.x * C::CPB + slot;
 
   int idx[N], idxn[N];
@@ -621,20 +741,20 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
       can = __ldg(coeff + c), cbn = __ldg(coeff2 + c);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        xv[k] = __ldg(x + idx[k]);
-        xb[k] = __ldg(x2 + idx[k]);
+        xv[k] = gx(idx[k]);
+        xb[k] = gx2(idx[k]);
       }
       cf = T(1);
     } else if constexpr (FUSE2) {
       const T ca = __ldg(coeff + c), cb = __ldg(coeff2 + c);
 #pragma unroll
       for (int k = 0; k < N; ++k)
-        xv[k] = ca * __ldg(x + idx[k]) + cb * __ldg(x2 + idx[k]);
+        xv[k] = ca * gx(idx[k]) + cb * gx2(idx[k]);
       cf = T(1);
     } else {
 #pragma unroll
       for (int k = 0; k < N; ++k)
-        xv[k] = __ldg(x + idx[k]);
+        xv[k] = gx(idx[k]);
       cf = __ldg(coeff + c);
     }
     if constexpr (AFFINE) {
@@ -706,18 +826,18 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
         can = __ldg(coeff + cn), cbn = __ldg(coeff2 + cn);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-          xv[k] = __ldg(x + idxn[k]);
-          xb[k] = __ldg(x2 + idxn[k]);
+          xv[k] = gx(idxn[k]);
+          xb[k] = gx2(idxn[k]);
         }
       } else if constexpr (FUSE2) {
         const T ca = __ldg(coeff + cn), cb = __ldg(coeff2 + cn);
 #pragma unroll
         for (int k = 0; k < N; ++k)
-          xv[k] = ca * __ldg(x + idxn[k]) + cb * __ldg(x2 + idxn[k]);
+          xv[k] = ca * gx(idxn[k]) + cb * gx2(idxn[k]);
       } else {
 #pragma unroll
         for (int k = 0; k < N; ++k)
-          xv[k] = __ldg(x + idxn[k]);
+          xv[k] = gx(idxn[k]);
         cf = __ldg(coeff + cn);
       }
     }
@@ -917,6 +1037,9 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
       }
     }
   }
+  if constexpr (HALO)
+    halo_group_report_and_ship<C::WARP, C::GW * 32>(HL.H, reinterpret_cast<const double*>(y), HL.nown,
+                                                    h_word, lg, group, gridDim.x * C::GROUPS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1480,6 +1603,8 @@ struct StageArgs {
   const double* babs;
   const long long* bchunk;    // [nchunks + 1] first boundary entry of every chunk of kStageChunk dofs
   const double* src_table;    // (g, dg) per (step, stage)
+  const FusedHalo* halo;      // fused exchange (HALO instantiations), else nullptr
+  int halo_defer_wait;        // tests/emu only: the closing wait runs as a kernel of its own
 };
 
 // Classical RK4 tableau (Linear.hpp:263-265) -> the coefficients of stage `i` with step size dt
@@ -1520,11 +1645,36 @@ __device__ __forceinline__ void stage_dof(const StageArgs& A, double b, double m
   }
 }
 
-template <int STAGE, bool WESTERVELT, bool HINTS = false>
+// HALO (mesh partitioned, fused peer transport; see fus_halo_kernels.cuh): the chunks that hold the
+// dofs shared with neighbours, [0, nshared), come first.  Their blocks wait for the neighbours'
+// partial sums of b, add them in a fixed order (send-list order: reproducible, unlike atomics), and
+// store the next stage input straight into the neighbours' mailboxes; the block that finishes the
+// last shared chunk raises the forward flags while the other ~99 % of the kernel is still running.
+template <int STAGE, bool WESTERVELT, bool HINTS = false, bool HALO = false>
 __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArgs A) {
   constexpr int STREAM = HINTS ? L2_FIRST : L2_NORMAL; // vectors not needed by the next kernel
   const int tid = threadIdx.x;
   const long long nchunks = (A.ntotal + kStageChunk - 1) / kStageChunk;
+  long long nshared = 0, shared_chunks = 0;
+  unsigned int my_shared_chunks = 0;
+  if constexpr (HALO) {
+    if (*(volatile int*)A.halo->error)
+      return; // an earlier wait timed out: the run is being aborted
+    nshared = A.halo->nshared;
+    shared_chunks = (nshared + kStageChunk - 1) / kStageChunk;
+    if (blockIdx.x == 0 && tid == 0) { // state for the NEXT operator; nothing here reads it
+      for (int q = CTR_GROUPS_PAST; q <= CTR_CHUNKS_DONE; ++q)
+        A.halo->ctr[q] = 0u;
+    }
+    if ((long long)blockIdx.x < shared_chunks) { // this block's first chunk holds shared dofs
+      __shared__ int rev_ok;
+      if (tid == 0)
+        rev_ok = halo_wait_all(*A.halo, false) ? 1 : 0;
+      __syncthreads();
+      if (!rev_ok)
+        return;
+    }
+  }
   double g = 0.0, dg = 0.0;
   if (A.nb) {
     const int s = *A.step_ctr; // stage 3 advances it only after every block has read it
@@ -1535,7 +1685,7 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
   double* const vnext = (STAGE < 3) ? A.vn : A.v0;
   for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const long long i = ch * kStageChunk + (long long)tid * kStageVec;
-    if (i + kStageVec <= A.nowned) {
+    if (i + kStageVec <= A.nowned && (!HALO || i >= nshared)) {
       D4 b = ld4<L2_NORMAL>(A.b + i), m = ld4<STREAM>(A.m + i);
       D4 u0, v0, un, vn, ua, va, dnl;
       if constexpr (STAGE < 3) {
@@ -1588,9 +1738,28 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
           const double vn = (STAGE == 0) ? v0 : A.vn[j];
           const double un = (STAGE == 0) ? u0 : (WESTERVELT ? A.un[j] : 0.0);
           double oun = 0.0, ovn = 0.0, oua = 0.0, ova = 0.0;
-          stage_dof<STAGE, WESTERVELT>(A, A.b[j], A.m[j], WESTERVELT ? A.dnl[j] : 0.0, u0, v0, un,
+          double bj = A.b[j];
+          if constexpr (HALO) {
+            if (j < nshared) { // ghost -> owner: the neighbours' partial sums, in send-list order
+              const FusedHalo& H = *A.halo;
+              for (int e = H.spos_off[j]; e < H.spos_off[j + 1]; ++e)
+                bj += __ldcg(H.rev + H.spos[e]);
+            }
+          }
+          stage_dof<STAGE, WESTERVELT>(A, bj, A.m[j], WESTERVELT ? A.dnl[j] : 0.0, u0, v0, un,
                                        vn, STAGE == 3 ? A.ua[j] : 0.0, STAGE == 3 ? A.va[j] : 0.0,
                                        oun, ovn, oua, ova);
+          if constexpr (HALO) {
+            if (j < nshared) { // owner -> ghost: the next stage input into the neighbours' mailboxes
+              const FusedHalo& H = *A.halo;
+              for (int e = H.spos_off[j]; e < H.spos_off[j + 1]; ++e) {
+                const int pos = H.spos[e], k = H.spos_nb[e];
+                const long long slot = pos - H.soff[k];
+                H.r_fwd_u[k][slot] = oun;
+                H.r_fwd_v[k][slot] = ovn;
+              }
+            }
+          }
           if constexpr (STAGE < 3) {
             A.un[j] = oun;
             A.vn[j] = ovn;
@@ -1608,6 +1777,21 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
         }
       }
     }
+    if constexpr (HALO) {
+      if (ch < shared_chunks) { // uniform over the block
+        ++my_shared_chunks;
+        __threadfence_system(); // this thread's stores into the neighbours' mailboxes
+        __syncthreads();
+        if (tid == 0 && (ch + gridDim.x >= shared_chunks)) { // the block's last shared chunk
+          const unsigned int done = atomicAdd(A.halo->ctr + CTR_SHARED_DONE, my_shared_chunks)
+                                    + my_shared_chunks;
+          if ((long long)done == shared_chunks) {
+            __threadfence();
+            halo_raise(*A.halo, true);
+          }
+        }
+      }
+    }
     if (A.nb) { // uniform over the block
       const long long kb = A.bchunk[ch], ke = A.bchunk[ch + 1];
       if (ke > kb) {
@@ -1617,6 +1801,18 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
           A.b[d] = g * A.bsrc[k] + dg * A.bdsrc[k] - A.babs[k] * __ldcg(vnext + d);
         }
       }
+    }
+  }
+  if constexpr (HALO) {
+    if (blockIdx.x == 0 && tid == 0) {
+      if (shared_chunks == 0) // nothing to send: the exchange number advances all the same
+        halo_raise(*A.halo, true);
+      // The next operator gathers ghost values from the mailbox without waiting: this kernel does
+      // not end before the neighbours' forward data of this exchange have landed.  Their epilogues
+      // send first thing, as this one did above, so the wait is over long before the private part
+      // of this kernel is -- and every rank raises its own flags before it waits: no cycle.
+      if (!A.halo_defer_wait)
+        halo_forward_landed(*A.halo);
     }
   }
   if constexpr (STAGE == 3) {

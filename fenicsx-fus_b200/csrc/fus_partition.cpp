@@ -8,8 +8,10 @@
 // numpy implementation that the tests compare against array by array):
 //   * an interface node is owned by the block with the lowest grid coordinates sharing it, so a
 //     block's ghosts sit on its lower faces;
-//   * local numbering: owned dofs in the order of the block's own cell-blocked numbering, then
-//     ghosts grouped by owner rank and sorted by global node id;
+//   * local numbering: owned dofs that some neighbour ghosts ("shared") first, then the other owned
+//     dofs, both in the order of the block's own cell-blocked numbering, then ghosts grouped by
+//     owner rank and sorted by global node id (so that the fused epilogue + exchange kernels find
+//     the dofs they send at [0, nshared) and every neighbour's ghosts in one contiguous run);
 //   * receive list of neighbour q: its ghosts in that order; send list to an upper neighbour: the
 //     owned nodes on the shared top planes, sorted by global node id (matching orders on both sides);
 //   * cells touching a shared dof come first (the reverse exchange overlaps with the rest).
@@ -24,7 +26,7 @@ struct fus_partition {
   int P = 0, rank = 0;
   int n_global[3] = {0, 0, 0}, pgrid[3] = {1, 1, 1}, rcoord[3] = {0, 0, 0};
   int32_t n_local[3] = {0, 0, 0}, cell_lo[3] = {0, 0, 0};
-  int64_t ncells = 0, ndofs = 0, nowned = 0, ninterface = 0, ndofs_global = 0;
+  int64_t ncells = 0, ndofs = 0, nowned = 0, nshared = 0, ninterface = 0, ndofs_global = 0;
   std::vector<int32_t> dofmap, xdofmap, facets, neigh, send_idx, recv_idx;
   std::vector<int64_t> cell_global, global_key, send_off, recv_off;
 };
@@ -143,7 +145,17 @@ int fus_box_partition_create(int P, const int n_global[3], const int pgrid[3], i
     };
     std::vector<Ghost> ghosts;
     std::vector<int32_t> new_of_raw((size_t)nraw);
-    int32_t nowned = 0;
+    const int top[3] = {nl[0] * P, nl[1] * P, nl[2] * P};
+    // an owned node on a top plane that an upper neighbour shares is ghosted there: those come
+    // first in the local numbering (the fused epilogue + exchange handles [0, nshared) specially)
+    auto shared_owned = [&](int64_t r) {
+      for (int d = 0; d < 3; ++d)
+        if (g[d][r] == top[d] && has_upper[d])
+          return true;
+      return false;
+    };
+    int32_t nowned = 0, nshared = 0;
+    std::vector<char> kind((size_t)nraw, 0); // 0 private, 1 shared owned, 2 ghost
     for (int64_t r = 0; r < nraw; ++r) {
       bool ghost = false;
       int owner = 0;
@@ -152,11 +164,27 @@ int fus_box_partition_create(int P, const int n_global[3], const int pgrid[3], i
         ghost = ghost || on_low;
         owner += mult[d] * (p->rcoord[d] - (on_low ? 1 : 0));
       }
-      if (ghost)
+      if (ghost) {
         ghosts.push_back({(int32_t)owner, key_of(r), (int32_t)r});
-      else
-        new_of_raw[r] = nowned++;
+        kind[r] = 2;
+      } else {
+        ++nowned;
+        if (shared_owned(r)) {
+          kind[r] = 1;
+          ++nshared;
+        }
+      }
     }
+    {
+      int32_t next_shared = 0, next_private = nshared;
+      for (int64_t r = 0; r < nraw; ++r) {
+        if (kind[r] == 1)
+          new_of_raw[r] = next_shared++;
+        else if (kind[r] == 0)
+          new_of_raw[r] = next_private++;
+      }
+    }
+    p->nshared = nshared;
     std::sort(ghosts.begin(), ghosts.end(), [](const Ghost& a, const Ghost& b) {
       return a.owner != b.owner ? a.owner < b.owner : a.key < b.key;
     });
@@ -184,7 +212,6 @@ int fus_box_partition_create(int P, const int n_global[3], const int pgrid[3], i
       lists_of(ghosts[k].owner).recv.push_back(nowned + (int32_t)k);
 
     // send lists: owned nodes on the top planes shared with each upper neighbour
-    const int top[3] = {nl[0] * P, nl[1] * P, nl[2] * P};
     std::vector<std::pair<int64_t, int32_t>> cand[8]; // per delta mask: (global key, new index)
     for (int64_t r = 0; r < nraw; ++r) {
       const int32_t nw = new_of_raw[r];

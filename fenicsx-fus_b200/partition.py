@@ -28,12 +28,15 @@ def _split(n, parts, r):
 
 
 def peer_byte_offsets(q_neigh, q_soff, q_roff, q_layout, my_rank):
-    """Where this rank's messages go inside neighbour q's mailbox (bytes): {forward data, forward
-    flag, reverse data, reverse flag}, from q's neighbour list, offset tables and mailbox layout
-    {off_rev, off_fflag, off_rflag} (fus_halo_peer_connect in include/fus_b200.h)."""
+    """Where this rank's data go inside neighbour q's mailbox (bytes): {forward-u run, forward-v run,
+    reverse run, forward flag, reverse flag, ready flag}, from q's neighbour list, offset tables and
+    mailbox layout (fus_halo_peer_offsets in include/fus_b200.h)."""
     j = list(q_neigh).index(my_rank)
-    off_rev, off_fflag, off_rflag = (int(v) for v in q_layout[:3])
-    return (8 * 2 * int(q_roff[j]), off_fflag + 8 * j, off_rev + 8 * int(q_soff[j]), off_rflag + 8 * j)
+    out = np.zeros(6, dtype=np.int64)
+    capi.check(capi.load().fus_halo_peer_offsets(
+        np.ascontiguousarray(q_layout, dtype=np.int64), np.ascontiguousarray(q_soff, dtype=np.int64),
+        np.ascontiguousarray(q_roff, dtype=np.int64), j, out), "fus_halo_peer_offsets")
+    return tuple(int(v) for v in out)
 
 
 class _PartitionBase:
@@ -91,14 +94,15 @@ class _PartitionBase:
                                       self.ninterface_cells), "fus_halo_setup")
 
     def connect_peers(self, ctx, dist):
-        """Switch the context's in-loop exchanges to the peer-direct transport: every rank exports
-        its mailbox (CUDA IPC handle + layout), all ranks gather them, each rank opens its
-        neighbours' mailboxes.  Returns False (and leaves NCCL in place) if IPC is unavailable."""
+        """Switch the exchanges inside rk4 to the fused peer transport: every rank exports its
+        mailbox (CUDA IPC handle + layout), all ranks gather them, each rank opens its neighbours'
+        mailboxes.  Returns False (and leaves NCCL in place) if IPC is unavailable or the local
+        numbering does not have the shape the fused kernels need."""
         lib = capi.load()
         handle = np.zeros(64, dtype=np.uint8)
-        layout = np.zeros(3, dtype=np.int64)
+        layout = np.zeros(6, dtype=np.int64)
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        rc = lib.fus_halo_peer_export(ctx.h, p(handle), p(layout))
+        rc = lib.fus_halo_peer_export(ctx.h, p(handle), p(layout), None)
         neigh, soff, _, roff, _ = self.halo_arrays()
         mine = dict(ok=(rc == 0), handle=handle.tobytes(), layout=layout.tolist(),
                     neigh=[int(q) for q in neigh], soff=soff.tolist(), roff=roff.tolist())
@@ -108,7 +112,7 @@ class _PartitionBase:
             return False
         nn = len(self.neigh)
         handles = np.zeros((max(nn, 1), 64), dtype=np.uint8)
-        boff = np.zeros((max(nn, 1), 4), dtype=np.int64)
+        boff = np.zeros((max(nn, 1), 6), dtype=np.int64)
         for k, q in enumerate(self.neigh):
             info = allinfo[q]
             handles[k] = np.frombuffer(info["handle"], dtype=np.uint8)
@@ -117,6 +121,8 @@ class _PartitionBase:
         rc = lib.fus_halo_peer_connect(ctx.h, p(handles), p(boff))
         flags = [None] * self.nranks
         dist.all_gather_object(flags, rc == 0)
+        if not any(flags):
+            return False
         if not all(flags):
             raise capi.FusError("peer transport connected on some ranks only: "
                                 + lib.fus_last_error().decode(errors="replace"))
@@ -230,12 +236,19 @@ class BoxPartition(_PartitionBase):
         key *= M[2]
         key += g[2] + self.cell_lo[2] * P_                           # global node id
 
-        # ---- local numbering: owned (raw order), then ghosts grouped by owner, by global key --
-        owned_raw = np.flatnonzero(~ghost)
+        # ---- local numbering: owned dofs that a neighbour ghosts first, then the other owned dofs
+        # (raw order within each), then ghosts grouped by owner, by global key --------------------
+        shared_owned = np.zeros(nraw, dtype=bool)
+        for d in range(3):
+            if self.has_upper[d]:
+                shared_owned |= g[d] == top[d]
+        shared_owned &= ~ghost
+        owned_raw = np.concatenate([np.flatnonzero(shared_owned), np.flatnonzero(~ghost & ~shared_owned)])
         ghost_raw = np.flatnonzero(ghost)
         order = np.lexsort((key[ghost_raw], owner_rank[ghost_raw]))
         ghost_raw = ghost_raw[order]
         self.nowned = int(owned_raw.size)
+        self.nshared = int(shared_owned.sum())
         self.ndofs = nraw
         new_of_raw = np.empty(nraw, dtype=np.int32)
         new_of_raw[owned_raw] = np.arange(self.nowned, dtype=np.int32)
@@ -348,6 +361,7 @@ class BoxPartition(_PartitionBase):
         self.neigh = [int(q) for q in neigh]
         self.send_lists = [sidx[soff[k]:soff[k + 1]] for k in range(nn)]
         self.recv_lists = [ridx[roff[k]:roff[k + 1]] for k in range(nn)]
+        self.nshared = int(np.unique(sidx).size)
         # vertex coordinates from the GLOBAL formula (bitwise identical to the unpartitioned box)
         lo, hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
         nv = self.n_local + 1
@@ -390,6 +404,11 @@ class HexPartition(_PartitionBase):
         uniq = uniq[np.argsort(first, kind="stable")]                 # first appearance order
         is_owned = owner[uniq] == self.rank
         owned = uniq[is_owned]
+        # owned dofs that another rank touches ("shared": ghosted there) come first
+        nranks_touching = np.bincount(pairs[:, 0], minlength=V.ndofs)
+        sh = nranks_touching[owned] > 1
+        owned = np.concatenate([owned[sh], owned[~sh]])
+        self.nshared = int(sh.sum())
         ghosts = uniq[~is_owned]
         ghosts = ghosts[np.lexsort((ghosts, owner[ghosts]))]
         self.nowned, self.ndofs = int(owned.size), int(uniq.size)

@@ -144,6 +144,9 @@ int fus_ctx_set_stream(fus_ctx* ctx, void* cuda_stream);
      "l2_persist"         [0]  L2 persistence window on the rhs accumulator (measured slower)
      "halo_overlap"       [0]  NCCL transport: run the exchanges on a side stream
      "halo_reserve_sms"   [4]  SMs left free for NCCL kernels in that mode
+     "halo_interior_first" [25] fused peer transport: percentage of the interior cells the
+                               stiffness kernel visits before the cells that touch shared dofs
+     "stage_hints"        [0]  epilogue: streaming vectors marked L2 evict-first (measured slower)
      "col_blocks_per_sm"  [0]  cap on resident blocks of the stiffness kernels (0 = occupancy) */
 int fus_ctx_set_option(fus_ctx* ctx, const char* name, int value);
 /* "geometry_mode" 1 asks for affine compression: if every cell is a parallelepiped the operator
@@ -269,25 +272,44 @@ int fus_comm_unique_id(void* id128);
 int fus_halo_setup(fus_ctx* ctx, int rank, int nranks, const void* nccl_unique_id, int nneigh,
                    const int* neigh, const int64_t* send_off, const int32_t* send_idx,
                    const int64_t* recv_off, const int32_t* recv_idx, int64_t ninterface_cells);
-/* Optional peer-direct transport for the exchanges inside fus_model_rk4 (after fus_halo_setup):
- * one-sided stores into the neighbours' mailboxes over NVLink peer memory instead of NCCL
- * send/recv.  Export this rank's mailbox (64-byte cudaIpcMemHandle_t + its layout triple
- * {off_rev, off_fflag, off_rflag} in bytes), distribute both, then connect with one handle per
- * neighbour and byte_off[nneigh][4] = offsets inside neighbour q's mailbox of
- *   {8*2*recv_off_q[j], off_fflag_q + 8*j, off_rev_q + 8*send_off_q[j], off_rflag_q + 8*j}
- * where j is this rank's position in q's neighbour list. */
-int fus_halo_peer_export(fus_ctx* ctx, void* ipc_handle64, int64_t* layout3);
-/* Byte layout of a rank's mailbox for given list sizes (host arithmetic, no device): layout4 =
- * {off_rev, off_fflag, off_rflag, total bytes}; the first three are what fus_halo_peer_export
- * reports. */
-int fus_halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout4);
+/* Optional FUSED PEER transport for the exchanges inside fus_model_rk4 (after fus_halo_setup).
+ * There is no exchange kernel: the RK4 epilogue adds the neighbours' partial sums of the right-hand
+ * side for the dofs it shares (scatter_rev) and stores the next stage input straight into the
+ * neighbours' mailboxes over NVLink peer memory (scatter_fwd); the stiffness kernel gathers ghost
+ * values from the mailbox and ships its ghost partial sums to the owners' mailboxes between two of
+ * its own cells.  Flags with device-side sequence numbers order everything, so a captured CUDA
+ * graph replays whole steps; every wait on a neighbour is bounded (FUS_HALO_TIMEOUT_S, default 30 s)
+ * and a time-out aborts the run: the remaining kernels return at once and fus_ctx_sync /
+ * fus_model_get_state report FUS_ERR_COMM.  fus_model_rk4 begins with a handshake between
+ * neighbours, so ranks may enter it at different times (as with the reference's MPI scatters).
+ * Requirements on the local numbering (fus_box_partition_* and the Python partitioners provide it;
+ * FUS_ERR_UNSUPPORTED otherwise, and the context stays on NCCL): the owned dofs that appear in the
+ * send lists are exactly [0, nshared), and recv_idx = nowned + 0, 1, 2, ...
+ * Set-up: export this rank's mailbox -- a 64-byte cudaIpcMemHandle_t (other processes) and/or its
+ * device pointer (other contexts of this process), plus layout6 = byte offsets {fwd_v, rev, forward
+ * flags, reverse flags, ready flags, total size} -- distribute it together with the offset tables,
+ * then connect with one handle (or pointer + device) per neighbour and byte_off[nneigh][6] from
+ * fus_halo_peer_offsets. */
+int fus_halo_peer_export(fus_ctx* ctx, void* ipc_handle64, int64_t* layout6, void** base);
+/* Byte layout of a rank's mailbox for given list sizes (host arithmetic, no device). */
+int fus_halo_mailbox_layout(int64_t nsend, int64_t nrecv, int nneigh, int64_t* layout6);
+/* Where this rank's data go inside neighbour q's mailbox: out6 = byte offsets of {forward-u run,
+ * forward-v run, reverse run, forward flag, reverse flag, ready flag}, from q's layout6, q's offset
+ * tables and j = this rank's position in q's neighbour list. */
+int fus_halo_peer_offsets(const int64_t* q_layout6, const int64_t* q_send_off,
+                          const int64_t* q_recv_off, int j, int64_t* out6);
 int fus_halo_peer_connect(fus_ctx* ctx, const void* handles, const int64_t* byte_off);
+/* The same between contexts of ONE process (one host thread per GPU): bases[k] / devices[k] are
+ * neighbour k's mailbox pointer (from its fus_halo_peer_export) and CUDA device. */
+int fus_halo_peer_connect_local(fus_ctx* ctx, void* const* bases, const int* devices,
+                                const int64_t* byte_off);
 
 /* Partition of the structured box over a pgrid[0] x pgrid[1] x pgrid[2] process grid for rank
  * `rank` (host, once per rank): what DOLFINx's mesh partitioner and common::IndexMap provide to the
  * reference.  Cells are split in contiguous blocks without ghost cells; an interface node is owned
  * by the block with the lowest grid coordinates sharing it; local numbering is owned entries first,
- * then ghosts grouped by owner rank; cells touching a shared dof come first.
+ * (those that a neighbour ghosts before the others), then ghosts grouped by owner rank; cells
+ * touching a shared dof come first.
  * fus_box_partition_info: sizes = {ncells, ndofs, nowned, nfacets, nneigh, nsend, nrecv,
  * ninterface_cells, ndofs_global}.  fus_box_partition_arrays copies out (any pointer may be NULL):
  * dofmap[ncells][Nd], xdofmap[ncells][8] (vertex numbering of fus_box_mesh on the local block),

@@ -37,7 +37,10 @@ def norm(n):
     n = re.sub(r"\(.*", "", n).replace("void fus::", "")
     # bool template arguments print as true/false, ints as digits: make them comparable; a trailing
     # default scalar type (added when the line kernel was templated on it) is not part of the name
-    return n.replace("true", "1").replace("false", "0").replace(", double>", ">")
+    n = n.replace("true", "1").replace("false", "0")
+    # ... nor is the trailing HALO = false added with the fused halo exchange
+    n = re.sub(r"(stiffness_line_kernel<[^>]*), double, 0>", r"\1>", n)
+    return n.replace(", double>", ">")
 
 
 a, b = kernels(sys.argv[1]), kernels(sys.argv[2])

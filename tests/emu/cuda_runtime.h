@@ -22,6 +22,7 @@
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;
 constexpr cudaError_t cudaErrorEmulated = 999;
+constexpr cudaError_t cudaErrorPeerAccessAlreadyEnabled = 704;
 typedef struct emu_stream* cudaStream_t;
 struct emu_graph {
   std::vector<std::function<void()>> ops;
@@ -89,6 +90,11 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) {
+  *can = 1;
+  return cudaSuccess;
+}
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 inline cudaError_t cudaCtxResetPersistingL2Cache() { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) {

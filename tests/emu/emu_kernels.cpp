@@ -68,7 +68,7 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
     using C = ColCfg<N>;
     auto run = [&](auto kern) {
       fus_emu::launch(blocks_for(C::CPB), C::THREADS, C::SMEM_BYTES,
-                      [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D); });
+                      [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D, HaloLaunch{}); });
     };
     if (fuse)
       run(stiffness_col_kernel<N, true>);
@@ -79,7 +79,7 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
   using L = LineCfg<N>;
   auto run = [&](auto kern) {
     fus_emu::launch(blocks_for(L::CPB), L::THREADS, L::SMEM_BYTES,
-                    [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D); });
+                    [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D, HaloLaunch{}); });
   };
   if (geom == 0)
     fuse ? run(stiffness_line_kernel<N, true, 0>) : run(stiffness_line_kernel<N, false, 0>);
@@ -98,9 +98,57 @@ int stiffness_n(int variant, int geom, const double* x, const double* x2, double
   else if constexpr (LineCfg<N>::RING_FITS) {
     auto run_ring = [&](auto kern) {
       fus_emu::launch(blocks_for(L::CPB), L::THREADS, L::SMEM_BYTES_RING,
-                      [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D); });
+                      [&] { kern(x, x2, y, dofmap, gptr, coeff, coeff2, cb, ce, D, HaloLaunch{}); });
     };
     fuse ? run_ring(stiffness_line_kernel<N, true, 7>) : run_ring(stiffness_line_kernel<N, false, 7>);
+  }
+  return 0;
+}
+
+// the HALO instantiations of the line kernel (fused peer transport): one launch over all cells
+template <int N>
+int stiffness_halo_n(int geom, const double* x, const double* x2, double* y, const int32_t* dofmap,
+                     const double* G, const double* coeff, const double* coeff2, long long ncells,
+                     const double* dphi, const double* pts, const double* wts, int max_blocks,
+                     FusedHalo* H, long long ninterface) {
+  using L = LineCfg<N>;
+  const DMat<N> D = make_dmat<N>(dphi, pts, wts);
+  const std::vector<double2> G2 = device_layout<N>(G, ncells);
+  // as assemble_rhs (fus_capi.cu) issues a fused stage: the interface cells [0, ninterface) with
+  // the HALO kernel (or its bookkeeping alone when there are none), then the rest with the plain one
+  if (ninterface == 0) {
+    fus_emu::launch(1, 32, 0, [&] { halo_operator_skipped_kernel(H); });
+  }
+  auto blocks_of = [&](long long nc) {
+    return (unsigned)std::max<long long>(1, std::min<long long>((nc + L::CPB - 1) / L::CPB, max_blocks));
+  };
+  HaloLaunch HL; // as halo_fused_launch (fus_halo.cu) builds it
+  HL.H = H, HL.nown = H->nowned, HL.mbu = H->fwd_u - H->nowned, HL.mbv = H->fwd_v - H->nowned;
+  auto run = [&](auto kern) {
+    if (ninterface > 0)
+      fus_emu::launch(blocks_of(ninterface), L::THREADS, L::SMEM_BYTES, [&] {
+        kern(x, x2, y, dofmap, G2.data(), coeff, coeff2, 0, ninterface, D, HL);
+      });
+  };
+  const bool fuse = x2 != nullptr;
+  if (geom == 0)
+    fuse ? run(stiffness_line_kernel<N, true, 0, double, true>)
+         : run(stiffness_line_kernel<N, false, 0, double, true>);
+  else if (geom == 4)
+    fuse ? run(stiffness_line_kernel<N, true, 4, double, true>)
+         : run(stiffness_line_kernel<N, false, 4, double, true>);
+  else if (geom == 6)
+    fuse ? run(stiffness_line_kernel<N, true, 6, double, true>)
+         : run(stiffness_line_kernel<N, false, 6, double, true>);
+  else
+    return -1;
+  if (ncells > ninterface) {
+    auto rest = [&](auto kern) {
+      fus_emu::launch(blocks_of(ncells - ninterface), L::THREADS, L::SMEM_BYTES, [&] {
+        kern(x, x2, y, dofmap, G2.data(), coeff, coeff2, ninterface, ncells, D, HaloLaunch{});
+      });
+    };
+    fuse ? rest(stiffness_line_kernel<N, true, 0>) : rest(stiffness_line_kernel<N, false, 0>);
   }
   return 0;
 }
@@ -164,7 +212,7 @@ int f32_n(const float* x, float* y, float* ym, const int32_t* dofmap, const doub
   fus_emu::launch(blocks, L::THREADS, L::SMEM_BYTES, [&] {
     stiffness_line_kernel<N, false, 0, float>(x, nullptr, y, dofmap,
                                               reinterpret_cast<const float2*>(G2f.data()), coeff,
-                                              nullptr, 0, ncells, D);
+                                              nullptr, 0, ncells, D, HaloLaunch{});
   });
   fus_emu::launch(3, 256, 0, [&] {
     mass_kernel_f32(x, ym, dofmap, dJf.data(), coeff, ncells * Nd, Nd);
@@ -274,7 +322,8 @@ int emu_rk4_stage(int stage, int westervelt, double* b, const double* m, const d
                   double* u0, double* v0, double* ua, double* va, double* un, double* vn,
                   long long nowned, long long ntotal, double dt, long long nb, const int32_t* bidx,
                   const double* bsrc, const double* bdsrc, const double* babs,
-                  const long long* bchunk, double g_next, double dg_next, int hints, int grid) {
+                  const long long* bchunk, double g_next, double dg_next, int hints, int grid,
+                  void* fused) {
   StageArgs A;
   A.b = b, A.m = m, A.dnl = dnl, A.u0 = u0, A.v0 = v0, A.ua = ua, A.va = va, A.un = un, A.vn = vn;
   A.nowned = nowned, A.ntotal = ntotal;
@@ -287,7 +336,22 @@ int emu_rk4_stage(int stage, int westervelt, double* b, const double* m, const d
   A.step_ctr = &step_ctr, A.done_ctr = &done;
   A.nb = nb, A.bidx = bidx, A.bsrc = bsrc, A.bdsrc = bdsrc, A.babs = babs, A.bchunk = bchunk;
   A.src_table = table;
+  A.halo = static_cast<FusedHalo*>(fused);
+  A.halo_defer_wait = 1; // see emu_fused_forward_landed
   auto go = [&](auto kern) { fus_emu::launch((unsigned)grid, kStageThreads, 0, [&] { kern(A); }); };
+  if (fused) {
+    switch (stage * 2 + (westervelt ? 1 : 0)) {
+    case 0: go(rk4_stage_kernel<0, false, false, true>); break;
+    case 1: go(rk4_stage_kernel<0, true, false, true>); break;
+    case 2: go(rk4_stage_kernel<1, false, false, true>); break;
+    case 3: go(rk4_stage_kernel<1, true, false, true>); break;
+    case 4: go(rk4_stage_kernel<2, false, false, true>); break;
+    case 5: go(rk4_stage_kernel<2, true, false, true>); break;
+    case 6: go(rk4_stage_kernel<3, false, false, true>); break;
+    case 7: go(rk4_stage_kernel<3, true, false, true>); break;
+    }
+    return kStageChunk;
+  }
   switch (stage * 4 + (westervelt ? 2 : 0) + (hints ? 1 : 0)) {
   case 0: go(rk4_stage_kernel<0, false, false>); break;
   case 1: go(rk4_stage_kernel<0, false, true>); break;
@@ -320,6 +384,108 @@ int emu_boundary(double* b, const double* v, const int32_t* bidx, const double* 
   return 0;
 }
 
+// ---- fused peer transport (fus_halo_kernels.cuh): one emulated rank's state ------------------------
+struct EmuFused {
+  FusedHalo H;
+  std::vector<int64_t> soff, roff;
+  std::vector<int32_t> sidx, spos_off, spos;
+  std::vector<signed char> spos_nb;
+  unsigned long long seq[SEQ_COUNT];
+  unsigned int ctr[CTR_COUNT];
+  int error;
+};
+
+// mailbox: this rank's own, laid out by fus_halo_mailbox_layout (layout6).  Returns NULL when the
+// numbering does not have the shape the fused kernels need.
+void* emu_fused_create(long long nowned, int nneigh, const int64_t* send_off, const int32_t* sidx,
+                       const int64_t* recv_off, const int32_t* ridx, char* mailbox,
+                       const int64_t* layout6, double timeout_s) {
+  EmuFused* e = new EmuFused();
+  const int64_t nsend = nneigh ? send_off[nneigh] : 0, nrecv = nneigh ? recv_off[nneigh] : 0;
+  e->soff.assign(send_off, send_off + nneigh + 1);
+  e->roff.assign(recv_off, recv_off + nneigh + 1);
+  e->sidx.assign(sidx, sidx + nsend);
+  int64_t nshared = 0;
+  const std::string why = fused_halo_lists(nowned, nneigh, send_off, sidx, ridx, nrecv, &nshared,
+                                           e->spos_off, e->spos, e->spos_nb);
+  if (!why.empty()) {
+    delete e;
+    return nullptr;
+  }
+  std::memset(e->seq, 0, sizeof(e->seq));
+  std::memset(e->ctr, 0, sizeof(e->ctr));
+  e->error = 0;
+  FusedHalo& F = e->H;
+  std::memset(&F, 0, sizeof(F));
+  F.nneigh = nneigh, F.nowned = nowned, F.nghost = nrecv, F.nshared = nshared, F.nsend = nsend;
+  F.fwd_u = (const double*)mailbox;
+  F.fwd_v = (const double*)(mailbox + layout6[0]);
+  F.rev = (const double*)(mailbox + layout6[1]);
+  F.fwd_flag = (const unsigned long long*)(mailbox + layout6[2]);
+  F.rev_flag = (const unsigned long long*)(mailbox + layout6[3]);
+  F.ready_flag = (const unsigned long long*)(mailbox + layout6[4]);
+  F.soff = e->soff.data(), F.roff = e->roff.data(), F.sidx = e->sidx.data();
+  F.spos_off = e->spos_off.data(), F.spos = e->spos.data(), F.spos_nb = e->spos_nb.data();
+  F.seq = e->seq, F.ctr = e->ctr, F.error = &e->error;
+  F.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  return e;
+}
+// neighbour k's mailbox and the byte offsets of this rank's runs inside it (fus_halo_peer_offsets)
+int emu_fused_connect(void* h, int k, char* base, const int64_t* off6) {
+  FusedHalo& F = static_cast<EmuFused*>(h)->H;
+  F.r_fwd_u[k] = (double*)(base + off6[0]);
+  F.r_fwd_v[k] = (double*)(base + off6[1]);
+  F.r_rev[k] = (double*)(base + off6[2]);
+  F.r_fwd_flag[k] = (unsigned long long*)(base + off6[3]);
+  F.r_rev_flag[k] = (unsigned long long*)(base + off6[4]);
+  F.r_ready_flag[k] = (unsigned long long*)(base + off6[5]);
+  return 0;
+}
+long long emu_fused_nshared(void* h) { return static_cast<EmuFused*>(h)->H.nshared; }
+int emu_fused_state(void* h, unsigned long long* seq, unsigned int* ctr) {
+  EmuFused* e = static_cast<EmuFused*>(h);
+  std::memcpy(seq, e->seq, sizeof(e->seq));
+  std::memcpy(ctr, e->ctr, sizeof(e->ctr));
+  return e->error;
+}
+void emu_fused_destroy(void* h) { delete static_cast<EmuFused*>(h); }
+int emu_fused_ready(void* h, int phase) {
+  FusedHalo* H = &static_cast<EmuFused*>(h)->H;
+  fus_emu::launch(1, 32, 0, [&] { halo_ready_kernel(H, phase); });
+  return 0;
+}
+// the closing wait of the entry put and of the epilogues runs as a kernel of its own here: ranks
+// are emulated one after another, so a rank cannot wait for a neighbour that has not run yet
+int emu_fused_entry_put(void* h, const double* u, const double* v) {
+  FusedHalo* H = &static_cast<EmuFused*>(h)->H;
+  fus_emu::launch((unsigned)std::max<long long>(1, (H->nsend + 255) / 256), 256, 0,
+                  [&] { halo_entry_put_kernel(H, u, v, 1); });
+  return 0;
+}
+int emu_fused_forward_landed(void* h) {
+  FusedHalo* H = &static_cast<EmuFused*>(h)->H;
+  fus_emu::launch(1, 32, 0, [&] { halo_forward_landed_kernel(H); });
+  return 0;
+}
+int emu_fused_exit(void* h, double* u, double* v) {
+  FusedHalo* H = &static_cast<EmuFused*>(h)->H;
+  fus_emu::launch((unsigned)std::max<long long>(1, (H->nghost + 255) / 256), 256, 0,
+                  [&] { halo_exit_unpack_kernel(H, u, v); });
+  return 0;
+}
+// y += K x over all local cells as a fused stage issues it: the interface cells with the HALO line
+// kernel (geom 0, 4 or 6; ghost values from the mailbox, ghost partial sums of y shipped to the
+// owners), the rest with the plain kernel.
+int emu_stiffness_fused(int N, int geom, const double* x, const double* x2, double* y,
+                        const int32_t* dofmap, const double* G, const double* coeff,
+                        const double* coeff2, long long ncells, const double* dphi,
+                        const double* pts, const double* wts, int max_blocks, void* h,
+                        long long ninterface) {
+  FusedHalo* H = &static_cast<EmuFused*>(h)->H;
+  EMU_DISPATCH(N, stiffness_halo_n, geom, x, x2, y, dofmap, G, coeff, coeff2, ncells, dphi, pts, wts,
+               max_blocks, H, ninterface);
+}
+
 // ---- halo kernels (fus_halo_kernels.cuh) ----------------------------------------------------------
 // NCCL transport: pack the interface values of one or two vectors / unpack (insert or add)
 int emu_halo_pack(const double* a, const double* b, const int32_t* idx, const int64_t* off,
@@ -335,37 +501,6 @@ int emu_halo_unpack(int add, double* a, double* b, const int32_t* idx, const int
       halo_unpack_kernel<true>(a, b, idx, off, nneigh, buf, n, nv);
     else
       halo_unpack_kernel<false>(a, b, idx, off, nneigh, buf, n, nv);
-  });
-  return 0;
-}
-
-// peer-direct transport: one rank's put into its neighbours' mailboxes (dst[4*k..] = addresses of
-// {forward data, forward flag, reverse data, reverse flag} inside neighbour k's mailbox), and one
-// rank's wait + unpack from its own mailbox
-int emu_peer_put(const double* a, const double* b, const int32_t* idx, const int64_t* off,
-                 int nneigh, long long n, int nv, const unsigned long long* dst, int forward,
-                 unsigned* counter, unsigned long long* epoch_ctr, int lightfence) {
-  PeerTable tab;
-  std::memset(&tab, 0, sizeof(tab));
-  for (int k = 0; k < nneigh; ++k) {
-    tab.fwd_dst[k] = reinterpret_cast<double*>(dst[4 * k + 0]);
-    tab.fwd_flag[k] = reinterpret_cast<unsigned long long*>(dst[4 * k + 1]);
-    tab.rev_dst[k] = reinterpret_cast<double*>(dst[4 * k + 2]);
-    tab.rev_flag[k] = reinterpret_cast<unsigned long long*>(dst[4 * k + 3]);
-  }
-  fus_emu::launch((unsigned)std::max<long long>(1, (n + 255) / 256), 256, 0, [&] {
-    peer_put_kernel(a, b, idx, off, nneigh, n, nv, &tab, forward, counter, epoch_ctr, lightfence);
-  });
-  return 0;
-}
-int emu_peer_wait(int add, double* a, double* b, const int32_t* idx, const int64_t* off, int nneigh,
-                  long long n, int nv, const double* mbox_data, const unsigned long long* flags,
-                  const unsigned long long* epoch_ctr, int* error) {
-  fus_emu::launch((unsigned)((n + 255) / 256), 256, 0, [&] {
-    if (add)
-      peer_wait_kernel<true>(a, b, idx, off, nneigh, n, nv, mbox_data, flags, epoch_ctr, error);
-    else
-      peer_wait_kernel<false>(a, b, idx, off, nneigh, n, nv, mbox_data, flags, epoch_ctr, error);
   });
   return 0;
 }

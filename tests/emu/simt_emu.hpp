@@ -45,6 +45,7 @@ inline emu_dim3 blockDim, gridDim; // one launch at a time
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __grid_constant__
 #define __launch_bounds__(...)

@@ -62,6 +62,9 @@ def test_child_extras_never_raise():
     assert res["headline_rk4_by_geometry_mode"] == [] and "stderr_tail" in res
     short = bench.child_extras(timeout_s=0.05)
     assert short["exit"] == -9 and "timed out" in short["stderr_tail"]
+    # the other BASELINE configs are child runs of bench.py itself: same guarantee
+    cfg = bench.config_extras(1, 2, 1, 29999)
+    assert set(cfg) == {"linear_het", "lossy", "westervelt"} and all(v["exit"] != 0 for v in cfg.values())
 
 
 class _FakeEvent:
@@ -222,7 +225,7 @@ def test_gpu_arm_control_flow_with_a_stub_device(monkeypatch, capsys, model, ext
     for name in ("LinearSpectral3D", "LossySpectral3D", "WesterveltSpectral3D"):
         monkeypatch.setattr(fus, name, Model)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "2", "--warmup", "1", "--cells", "3",
-                                      "--model", model] + extra)
+                                      "--no-parity", "--model", model] + extra)
     assert bench.main() == 0
     lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -230,15 +233,14 @@ def test_gpu_arm_control_flow_with_a_stub_device(monkeypatch, capsys, model, ext
     need = (REQUIRED - {"impl"}) | {"roofline", "clocks", "gpu_launches", "extras"}
     assert need <= set(d), need - set(d)
     assert d["steps"] == 2 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["value"] > 0
-    assert d["config"]["workload"] == f"{model}_rk4_P4_box3_per_gpu"
+    assert d["config"]["workload"] == f"{model}_rk4_P4_box3"
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
     assert calls["lean"] == ("--lean" in extra)
     if "--geometry-mode" in extra:
         assert ("geometry_mode", 2) in calls["options"] and "trilinear" in d["config"]["geometry"]
         assert d["roofline"]["kernel"].endswith(",2>")
-    if model == "linear":
-        assert ("geometry_mode", 1) in calls["options"]          # the affine extra was attempted
+    assert "parity" in d
 
 
 def test_child_sweep_script_control_flow_with_a_stub_device(monkeypatch, capsys):
@@ -346,7 +348,7 @@ def test_gpu_arm_on_the_emulated_device(extra):
         "for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'): os.environ.pop(k, None)\n"
         "spec = importlib.util.spec_from_file_location('bench_emu', os.path.join(ROOT, 'bench.py'))\n"
         "bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)\n"
-        f"sys.argv = ['bench.py', '--steps', '3', '--warmup', '1', '--cells', '3'] + {extra!r}\n"
+        f"sys.argv = ['bench.py', '--steps', '3', '--warmup', '1', '--cells', '3', '--no-extras'] + {extra!r}\n"
         "sys.exit(bench.main())\n")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900,
                          cwd=ROOT)
@@ -356,8 +358,12 @@ def test_gpu_arm_on_the_emulated_device(extra):
     d = json.loads(lines[0])
     assert d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] > 0
     assert d["roofline"]["launches"] == 12 and d["roofline"]["operator_applications"] == 12
-    if not extra:                               # headline geometry: the affine extra ran as well
-        assert "affine_compressed_geometry" in d["extras"]
+    if "--lean" not in extra:
+        # the oracle ran the same steps on the same mesh: the parity block of the JSON line
+        par = d["parity"]
+        assert par["steps"] == 3 and par["apply_rel_l2"] < 1e-12
+        assert par["u_rel_l2"] < 1e-10 and par["v_rel_l2"] < 1e-10
+        assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     if "--lean" in extra or "--geometry-mode" in extra:
         assert d["roofline"]["kernel"].endswith(",2>")
 

@@ -48,12 +48,24 @@ def emu():
     i64 = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
     L.emu_halo_pack.argtypes = [_f64, _p, _i32, i64, _int, _f64, _ll, _int]
     L.emu_halo_unpack.argtypes = [_int, _f64, _p, _i32, i64, _int, _f64, _ll, _int]
-    L.emu_peer_put.argtypes = [_f64, _p, _i32, i64, _int, _ll, _int, u64, _int, _p, _p, _int]
-    L.emu_peer_wait.argtypes = [_int, _f64, _p, _i32, i64, _int, _ll, _int, _p, _p, _p, _p]
+    L.emu_fused_create.argtypes = [_ll, _int, i64, _i32, i64, _i32, _p, i64, _dbl]
+    L.emu_fused_create.restype = _p
+    L.emu_fused_connect.argtypes = [_p, _int, _p, i64]
+    L.emu_fused_nshared.argtypes = [_p]
+    L.emu_fused_nshared.restype = _ll
+    L.emu_fused_state.argtypes = [_p, u64, np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")]
+    L.emu_fused_destroy.argtypes = [_p]
+    L.emu_fused_destroy.restype = None
+    L.emu_fused_ready.argtypes = [_p, _int]
+    L.emu_fused_entry_put.argtypes = [_p, _f64, _f64]
+    L.emu_fused_exit.argtypes = [_p, _f64, _f64]
+    L.emu_stiffness_fused.argtypes = [_int, _int, _f64, _p, _f64, _i32, _f64, _f64, _p, _ll, _f64,
+                                      _f64, _f64, _int, _p, _ll]
+    L.emu_fused_forward_landed.argtypes = [_p]
     L.emu_geometry.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64, _f64, C.POINTER(_int)]
     L.emu_geometry_quad.argtypes = [_int, _f64, _i32, _ll, _f64, _f64, _f64, _f64]
     L.emu_rk4_stage.argtypes = [_int, _int, _f64, _f64, _p, _f64, _f64, _f64, _f64, _f64, _f64, _ll,
-                                _ll, _dbl, _ll, _p, _p, _p, _p, _p, _dbl, _dbl, _int, _int]
+                                _ll, _dbl, _ll, _p, _p, _p, _p, _p, _dbl, _dbl, _int, _int, _p]
     L.emu_boundary.argtypes = [_f64, _f64, _i32, _f64, _f64, _f64, _ll, _dbl, _dbl]
     return L
 
@@ -238,7 +250,7 @@ def test_emulated_mass_boundary_and_rk4_stage_kernels(fus, orc, emu):
     a_r, b_r = (0.0, 0.5, 0.5, 1.0), (1 / 6, 1 / 3, 1 / 3, 1 / 6)
     chunk = emu.emu_rk4_stage(0, 0, np.zeros(8), np.ones(8), None, np.zeros(8), np.zeros(8),
                               np.zeros(8), np.zeros(8), np.zeros(8), np.zeros(8), 0, 8, dt, 0, None,
-                              None, None, None, None, 0.0, 0.0, 0, 1)
+                              None, None, None, None, 0.0, 0.0, 0, 1, None)
     assert chunk > 0
     bown = bidx[bidx < nowned]
     nbo = bown.size
@@ -271,7 +283,7 @@ def test_emulated_mass_boundary_and_rk4_stage_kernels(fus, orc, emu):
             rc = emu.emu_rk4_stage(i, west, b, mvec, _opt(dnl) if west else None, st["u0"], st["v0"],
                                    st["ua"], st["va"], st["un"], st["vn"], nowned, nd, dt, nbo,
                                    _opt(bown), _opt(bs), _opt(bd), _opt(ba), _opt(bchunk), gn, dgn,
-                                   hints, 3)
+                                   hints, 3, None)
             assert rc == chunk
             vnext = st["vn"] if i < 3 else st["v0"]
             want_b = np.zeros(nd)
@@ -288,7 +300,7 @@ def test_emulated_mass_boundary_and_rk4_stage_kernels(fus, orc, emu):
         b = rng.uniform(-1, 1, nd)
         emu.emu_rk4_stage(2, west, b, mvec, _opt(dnl) if west else None, st["u0"], st["v0"],
                           st["ua"], st["va"], st["un"], st["vn"], nowned, nd, dt, 0, None, None, None,
-                          None, None, 0.0, 0.0, hints, 2)
+                          None, None, 0.0, 0.0, hints, 2, None)
         assert not b.any()
 
 
@@ -422,7 +434,7 @@ def test_emulated_fused_rk4_step_vs_reference_flow(fus, orc, emu, kind):
     bs, bd, ba = src[bidx].copy(), dsrc[bidx].copy(), absb[bidx].copy()
     chunk = emu.emu_rk4_stage(0, 0, np.zeros(8), np.ones(8), None, np.zeros(8), np.zeros(8),
                               np.zeros(8), np.zeros(8), np.zeros(8), np.zeros(8), 0, 8, 1.0, 0, None,
-                              None, None, None, None, 0.0, 0.0, 0, 1)
+                              None, None, None, None, 0.0, 0.0, 0, 1, None)
     bchunk = np.searchsorted(bidx, np.arange(0, (nd + chunk - 1) // chunk + 1) * chunk).astype(np.int64)
     # ---- the time loop as fus_model_rk4 / issue_step issue it
     st = dict(u0=u0.copy(), v0=v0.copy(), ua=np.zeros(nd), va=np.zeros(nd), un=np.zeros(nd),
@@ -455,105 +467,236 @@ def test_emulated_fused_rk4_step_vs_reference_flow(fus, orc, emu, kind):
             gn, dgn = scalars(t + a_r[i + 1] * dt) if i < 3 else scalars(t + dt)
             rc = emu.emu_rk4_stage(i, int(west), b, mvec, _opt(dnl), st["u0"], st["v0"], st["ua"],
                                    st["va"], st["un"], st["vn"], nd, nd, dt, bidx.size, _opt(bidx),
-                                   _opt(bs), _opt(bd), _opt(ba), _opt(bchunk), gn, dgn, 0, 2)
+                                   _opt(bs), _opt(bd), _opt(ba), _opt(bchunk), gn, dgn, 0, 2, None)
             assert rc == chunk
         t += dt
         del dt_next
     assert rel_l2(st["u0"], u_ref) < 1e-12 and rel_l2(st["v0"], v_ref) < 1e-12
 
 
-class _EmuRank:
-    """One rank of an emulated peer-direct halo: its partition, its mailbox (laid out by
-    fus_halo_mailbox_layout, the function halo_peer_export uses) and its device-side counters."""
+class _FusedRank:
+    """One rank of an emulated partitioned run on the fused peer transport: its partition, its
+    mailbox (laid out by fus_halo_mailbox_layout, as halo_peer_export does), its transport state
+    (tests/emu: emu_fused_*, the host mirror of halo_peer_connect) and its model vectors."""
 
-    def __init__(self, part):
+    def __init__(self, emu, part):
         from fenicsx_fus_b200 import capi
-        self.p = part
+        self.emu, self.p = emu, part
         self.neigh, self.soff, self.sidx, self.roff, self.ridx = part.halo_arrays()
-        self.nsend, self.nrecv = int(self.sidx.size), int(self.ridx.size)
-        self.layout = np.zeros(4, dtype=np.int64)
-        assert capi.load().fus_halo_mailbox_layout(self.nsend, self.nrecv, len(self.neigh),
+        self.layout = np.zeros(6, dtype=np.int64)
+        assert capi.load().fus_halo_mailbox_layout(self.sidx.size, self.ridx.size, len(self.neigh),
                                                    self.layout) == 0
-        self.mbox = np.zeros(int(self.layout[3]) // 8 + 1, dtype=np.uint64)      # 8-byte aligned
-        self.counter = np.zeros(2, dtype=np.uint32)
-        self.epoch = np.zeros(2, dtype=np.uint64)
-        self.error = np.zeros(1, dtype=np.int32)
+        self.mbox = np.zeros(int(self.layout[5]) // 8 + 1, dtype=np.uint64)      # 8-byte aligned
+        z = np.zeros(1, np.int32)
+        self.h = emu.emu_fused_create(part.nowned, len(self.neigh), self.soff,
+                                      self.sidx if self.sidx.size else z, self.roff,
+                                      self.ridx if self.ridx.size else z,
+                                      self.mbox.ctypes.data_as(_p), self.layout, 5.0)
+        assert self.h, "the partitioner's numbering must have the shape the fused kernels need"
+        assert emu.emu_fused_nshared(self.h) == part.nshared
 
     def connect(self, ranks):
         from fenicsx_fus_b200.partition import peer_byte_offsets
-        self.dst = np.zeros(4 * max(1, len(self.neigh)), dtype=np.uint64)
         for k, q in enumerate(self.neigh):
             o = ranks[int(q)]
-            offs = peer_byte_offsets(o.neigh, o.soff, o.roff, o.layout, self.p.rank)
-            assert all(0 <= b < o.layout[3] for b in offs)
-            self.dst[4 * k:4 * k + 4] = [o.mbox.ctypes.data + b for b in offs]
+            offs = np.array(peer_byte_offsets(o.neigh, o.soff, o.roff, o.layout, self.p.rank),
+                            dtype=np.int64)
+            assert all(0 <= b < o.layout[5] for b in offs)
+            self.emu.emu_fused_connect(self.h, k, o.mbox.ctypes.data_as(_p), offs)
 
-    def put(self, emu, fwd, a, b, lightfence=0):
-        idx, off = (self.sidx, self.soff) if fwd else (self.ridx, self.roff)
-        emu.emu_peer_put(a, _opt(b), idx if idx.size else np.zeros(1, np.int32), off, len(self.neigh),
-                         idx.size, 2 if fwd else 1, self.dst, int(fwd),
-                         self.counter[0 if fwd else 1:].ctypes.data_as(_p),
-                         self.epoch[0 if fwd else 1:].ctypes.data_as(_p), lightfence)
+    def state(self):
+        seq, ctr = np.zeros(8, dtype=np.uint64), np.zeros(8, dtype=np.uint32)
+        err = self.emu.emu_fused_state(self.h, seq, ctr)
+        return err, seq, ctr
 
-    def wait(self, emu, fwd, a, b):
-        idx, off = (self.ridx, self.roff) if fwd else (self.sidx, self.soff)
-        if not idx.size:
-            return
-        base = self.mbox.ctypes.data
-        emu.emu_peer_wait(0 if fwd else 1, a, _opt(b), idx, off, len(self.neigh), idx.size,
-                          2 if fwd else 1, C.c_void_p(base + (0 if fwd else int(self.layout[0]))),
-                          C.c_void_p(base + int(self.layout[1 if fwd else 2])),
-                          self.epoch[0 if fwd else 1:].ctypes.data_as(_p),
-                          self.error.ctypes.data_as(_p))
-        assert self.error[0] == 0
+    def close(self):
+        self.emu.emu_fused_destroy(self.h)
 
 
-@pytest.mark.parametrize("P,n,pg", [(2, (4, 3, 2), (2, 1, 1)), (2, (5, 2, 2), (3, 1, 1)),
-                                    (1, (4, 4, 2), (4, 1, 1)), (2, (3, 3, 2), (2, 2, 1)),
-                                    (1, (2, 2, 2), (2, 2, 2)), (1, (2, 3, 4), (1, 3, 2))])
-def test_emulated_peer_direct_halo_exchange(fus, emu, P, n, pg):
-    """peer_put_kernel / peer_wait_kernel (csrc/fus_halo_kernels.cuh) for every rank of a process
-    grid, with the partition lists of the native partitioner, the mailbox layout of
-    fus_halo_mailbox_layout and the byte offsets of partition.peer_byte_offsets -- the pieces the
-    multi-GPU runs connect over CUDA IPC.  Three stages of forward (owner -> ghost, two vectors)
-    and reverse (ghost -> owner, add) exchanges; slabs (a middle rank with two neighbours), 2x2
-    (edge neighbours) and 2x2x2 (corner neighbours) grids."""
+def _reduce_to_owners(ranks, vecs):
+    """Host stand-in for scatter_rev at set-up: the sum over all ranks that hold a dof."""
+    total = {}
+    for rk, v in zip(ranks, vecs):
+        for k, val in zip(rk.p.global_key, v):
+            total[int(k)] = total.get(int(k), 0.0) + val
+    return [np.array([total[int(k)] for k in rk.p.global_key]) for rk in ranks]
+
+
+@pytest.mark.parametrize("P,n,pg,geom,kind", [
+    (2, (4, 3, 2), (2, 1, 1), 0, "linear"), (2, (8, 2, 2), (3, 1, 1), 0, "westervelt"),
+    (1, (4, 4, 2), (2, 2, 1), 6, "linear"), (1, (2, 2, 2), (2, 2, 2), 4, "westervelt"),
+    (3, (2, 6, 2), (1, 3, 1), 6, "westervelt"), (4, (6, 2, 1), (2, 1, 1), 0, "linear")])
+def test_emulated_fused_halo_rk4(fus, orc, emu, P, n, pg, geom, kind):
+    """The partitioned RK4 flow on the fused peer transport, every rank of a process grid emulated:
+    handshake and owner -> ghost update at entry (halo_ready_kernel, halo_entry_put_kernel), then per
+    stage the HALO line kernel over the interface cells (ghost values gathered from the mailbox, ghost
+    partial sums of b shipped to the owners after the last cell), the plain kernel over the rest, and
+    the HALO epilogue (neighbours' partial sums added in send-list order, next stage input stored
+    into the neighbours' mailboxes, flags raised by the block that finishes the last shared chunk,
+    closing wait for the neighbours' forward data), and
+    halo_exit_unpack_kernel -- with the native partitioner's lists, fus_halo_mailbox_layout and
+    fus_halo_peer_offsets, i.e. what the multi-GPU runs connect over CUDA IPC.  Ranks advance in
+    lockstep, kernel by kernel, so no wait may ever block (5 s time-out = failure).  Every rank's
+    whole state, ghosts included, equals the single-domain oracle; the device-side sequence numbers
+    end where the protocol says; slabs (a middle rank with interior cells and two neighbours), 2x2,
+    2x2x2 and 1x3 grids; all three HALO pipelines; the fused two-vector gather (Westervelt)."""
+    from fenicsx_fus_b200 import capi
     from fenicsx_fus_b200.partition import BoxPartition
+    lib = capi.load()
+    west = kind == "westervelt"
+    h = 0.002
+    hi = tuple(h * k for k in n)
     R = int(np.prod(pg))
-    ranks = [_EmuRank(BoxPartition(P, n, pg, r)) for r in range(R)]
+    parts = [BoxPartition(P, n, pg, r, lo=(0, 0, 0), hi=hi) for r in range(R)]
+    ranks = [_FusedRank(emu, p) for p in parts]
     for rk in ranks:
         rk.connect(ranks)
-    for stage in range(3):
-        # forward: owners hold f(global id, stage), ghosts hold garbage
-        us, vs = [], []
+    pts, wts = orc.gll(P + 1)
+    dphi = orc.dphi(P)
+    Nd = (P + 1) ** 3
+    ncg = int(np.prod(n))
+    gid = np.arange(ncg)
+    c0g, rho0g = 1500.0 + 60.0 * np.sin(gid), 1000.0 + 40.0 * np.cos(2.0 * gid)
+    deltag = (2e-3 + 1e-3 * np.sin(3.0 * gid)) if west else None
+    betag = (3.5 + 0.3 * np.cos(gid)) if west else None
+    f0, p0, s0 = 0.5e6, 6.0e4, 1500.0
+    # ---- single-domain oracle
+    xg, xd = orc.box_mesh(n, (0, 0, 0), hi)
+    dmg = orc.box_dofmap(P, n, 0)
+    ndg = int(dmg.max()) + 1
+    Gg, dJg = orc.geometry(P, xg, xd)
+    fg = orc.box_facets(n)
+    fng, fsg = orc.facet_data(P, xg, xd, fg)
+    om = orc.model(kind, P, ndg, dmg, Gg, dJg, dphi, c0g, rho0g, deltag, betag, fg, fng, fsg, f0, p0, s0)
+    rng = np.random.default_rng(11)
+    u0g, v0g = 1e3 * rng.uniform(-1, 1, ndg), 1e9 * rng.uniform(-1, 1, ndg)
+    dt = 0.2 * np.sqrt(3) * h / (1600.0 * P * P)
+    # ---- per-rank set-up as fus_model_create does it (partial sums reduced to the owners once)
+    S = []
+    for rk in ranks:
+        p = rk.p
+        cg = p.cell_global
+        d = dict(c0=c0g[cg].copy(), rho0=rho0g[cg].copy())
+        d["G"], d["dJ"] = orc.geometry(P, p.x, p.xdofmap)
+        src, dsrc, absb, bmass = (np.zeros(p.ndofs) for _ in range(4))
+        dl = deltag[cg].copy() if west else None
+        assert lib.fus_boundary_vectors(capi.KINDS[kind], P, p.ncells, p.ndofs, p.x, p.xdofmap,
+                                        p.dofmap, p.facets.shape[0], p.facets, d["c0"], d["rho0"],
+                                        _opt(dl), capi.optional(src), capi.optional(dsrc),
+                                        capi.optional(absb), capi.optional(bmass)) == 0
+        dmf, dJf = np.ascontiguousarray(p.dofmap.reshape(-1)), np.ascontiguousarray(d["dJ"].reshape(-1))
+        mvec = np.zeros(p.ndofs)
+        emu.emu_mass(np.ones(p.ndofs), mvec, dmf, dJf, 1.0 / d["rho0"] / d["c0"] ** 2, p.ncells * Nd, Nd)
+        d["m"] = mvec + bmass
+        d["dnl"] = np.zeros(p.ndofs)
+        if west:
+            emu.emu_mass(np.ones(p.ndofs), d["dnl"], dmf, dJf,
+                         2.0 * betag[cg] / d["rho0"] ** 2 / d["c0"] ** 4, p.ncells * Nd, Nd)
+        d.update(src=src, dsrc=dsrc, absb=absb, lin=-1.0 / d["rho0"],
+                 att=(-dl / d["rho0"] / d["c0"] ** 2) if west else None)
+        S.append(d)
+    for key in ("m", "dnl", "src", "dsrc", "absb"):
+        for d, red in zip(S, _reduce_to_owners(ranks, [d[key] for d in S])):
+            d[key] = red
+    chunk = emu.emu_rk4_stage(0, 0, np.zeros(8), np.ones(8), None, np.zeros(8), np.zeros(8),
+                              np.zeros(8), np.zeros(8), np.zeros(8), np.zeros(8), 0, 8, 1.0, 0, None,
+                              None, None, None, None, 0.0, 0.0, 0, 1, None)
+    for rk, d in zip(ranks, S):
+        p = rk.p
+        own = np.arange(p.nowned)
+        sel = own[(d["src"][own] != 0) | (d["dsrc"][own] != 0) | (d["absb"][own] != 0)].astype(np.int32)
+        d["bidx"], d["bs"], d["bd"], d["ba"] = sel, d["src"][sel].copy(), d["dsrc"][sel].copy(), d["absb"][sel].copy()
+        d["bchunk"] = np.searchsorted(sel, np.arange(0, (p.ndofs + chunk - 1) // chunk + 1) * chunk).astype(np.int64)
+        d["st"] = dict(u0=u0g[p.global_key].copy(), v0=v0g[p.global_key].copy(), ua=np.zeros(p.ndofs),
+                       va=np.zeros(p.ndofs), un=np.zeros(p.ndofs), vn=np.zeros(p.ndofs))
+        d["st"]["u0"][p.nowned:] = -5.0          # stale ghosts: the entry exchange must not need them
+        d["st"]["v0"][p.nowned:] = 7.0
+        d["b"] = np.zeros(p.ndofs)
+    w0, kappa = 2 * np.pi * f0, (2.0 if west else 1.0)
+
+    def scalars(tn):
+        win = 0.5 * (1 - np.cos(f0 * np.pi * tn / 4.0)) if tn < 4.0 / f0 else 1.0
+        dwin = 0.5 * np.pi * f0 / 4.0 * np.sin(f0 * np.pi * tn / 4.0) if tn < 4.0 / f0 else 0.0
+        g = kappa * win * p0 * w0 / s0 * np.cos(w0 * tn)
+        dg = (kappa * (dwin * p0 * w0 / s0 * np.cos(w0 * tn) - win * p0 * w0 * w0 / s0 * np.sin(w0 * tn))
+              if west else 0.0)
+        return g, dg
+
+    a_r = (0.0, 0.5, 0.5, 1.0)
+    for call in range(2):                      # two rk4 calls: the handshake and the exit/entry pairing
         for rk in ranks:
-            key = rk.p.global_key.astype(np.float64)
-            u, v = np.full(rk.p.ndofs, -7.0), np.full(rk.p.ndofs, -9.0)
-            u[:rk.p.nowned] = np.sin(key[:rk.p.nowned] + stage)
-            v[:rk.p.nowned] = 3.0 * key[:rk.p.nowned] - stage
-            us.append(u)
-            vs.append(v)
-        for rk, u, v in zip(ranks, us, vs):
-            rk.put(emu, True, u, v, lightfence=stage % 2)
-        for rk, u, v in zip(ranks, us, vs):
-            rk.wait(emu, True, u, v)
-            key = rk.p.global_key.astype(np.float64)
-            assert np.array_equal(u, np.sin(key + stage)) and np.array_equal(v, 3.0 * key - stage)
-        # reverse: every rank contributes 1 + rank to each of its dofs; owners end with the sum over
-        # all ranks that hold the dof
-        bs = [np.full(rk.p.ndofs, 1.0 + rk.p.rank) for rk in ranks]
-        for rk, b in zip(ranks, bs):
-            rk.put(emu, False, b, None)
-        for rk, b in zip(ranks, bs):
-            rk.wait(emu, False, b, None)
-        total = {}
+            emu.emu_fused_ready(rk.h, 1)
         for rk in ranks:
-            for k in rk.p.global_key:
-                total[int(k)] = total.get(int(k), 0.0) + 1.0 + rk.p.rank
-        for rk, b in zip(ranks, bs):
-            want = np.array([total[int(k)] for k in rk.p.global_key[:rk.p.nowned]])
-            assert np.array_equal(b[:rk.p.nowned], want)
-        assert all(int(rk.epoch[0]) == stage + 1 and int(rk.epoch[1]) == stage + 1 for rk in ranks)
+            emu.emu_fused_ready(rk.h, 2)
+        for rk, d in zip(ranks, S):
+            emu.emu_fused_entry_put(rk.h, d["st"]["u0"], d["st"]["v0"])
+        for rk in ranks:                       # the put's closing wait (in-kernel on the device)
+            emu.emu_fused_forward_landed(rk.h)
+        t = call * dt
+        g, dg = scalars(t)
+        for rk, d in zip(ranks, S):
+            d["b"][:] = 0.0
+            emu.emu_boundary(d["b"], d["st"]["v0"], d["bidx"], d["bs"], d["bd"], d["ba"],
+                             d["bidx"].size, g, dg)
+        for i in range(4):
+            for rk, d in zip(ranks, S):
+                p, st = rk.p, d["st"]
+                u_in = st["u0"] if i == 0 else st["un"]
+                v_in = st["v0"] if i == 0 else st["vn"]
+                assert emu.emu_stiffness_fused(P + 1, geom, u_in, _opt(v_in) if west else None, d["b"],
+                                               p.dofmap, d["G"], d["lin"], _opt(d["att"]), p.ncells,
+                                               dphi, pts, wts, 2, rk.h, p.ninterface_cells) == 0
+            gn, dgn = scalars(t + a_r[i + 1] * dt) if i < 3 else scalars(t + dt)
+            for rk, d in zip(ranks, S):
+                p, st = rk.p, d["st"]
+                rc = emu.emu_rk4_stage(i, int(west), d["b"], d["m"], _opt(d["dnl"]), st["u0"], st["v0"],
+                                       st["ua"], st["va"], st["un"], st["vn"], p.nowned, p.ndofs, dt,
+                                       d["bidx"].size, _opt(d["bidx"]), _opt(d["bs"]), _opt(d["bd"]),
+                                       _opt(d["ba"]), _opt(d["bchunk"]), gn, dgn, 0, 3, rk.h)
+                assert rc == chunk
+            for rk in ranks:                   # the epilogue's closing wait (in-kernel on the device)
+                emu.emu_fused_forward_landed(rk.h)
+        for rk, d in zip(ranks, S):
+            emu.emu_fused_exit(rk.h, d["st"]["u0"], d["st"]["v0"])
+        for rk in ranks:
+            err, seq, ctr = rk.state()
+            assert err == 0
+            # entry + 4 epilogues per call sent forward; 4 operators per call sent reverse
+            assert (int(seq[0]), int(seq[1]), int(seq[2]), int(seq[3]), int(seq[4])) == (
+                5 * (call + 1), 5 * (call + 1), 4 * (call + 1), 4 * (call + 1), call + 1)
+    u_ref2, v_ref2 = u0g.copy(), v0g.copy()
+    # two calls of one step each == the reference loop over two (full) steps
+    assert om.rk4(0.0, 2.0 * dt, dt, u_ref2, v_ref2) == 2
+    for rk, d in zip(ranks, S):
+        key = rk.p.global_key
+        assert rel_l2(d["st"]["u0"], u_ref2[key]) < 1e-12, (rk.p.rank, "u")      # ghosts included
+        assert rel_l2(d["st"]["v0"], v_ref2[key]) < 1e-12, (rk.p.rank, "v")
+        rk.close()
+
+
+def test_fused_halo_refuses_other_numberings(fus, emu):
+    """The fused kernels rely on (P1) shared owned dofs numbered first and (P2) ghosts numbered
+    neighbour by neighbour: lists that break either are refused (the context then stays on NCCL)."""
+    from fenicsx_fus_b200.partition import BoxPartition
+    p = BoxPartition(2, (4, 2, 2), (2, 1, 1), 0)
+    neigh, soff, sidx, roff, ridx = p.halo_arrays()
+    assert sidx.size and np.array_equal(np.unique(sidx), np.arange(p.nshared))
+    mbox = np.zeros(1 << 16, dtype=np.uint64)
+    lay = np.zeros(6, dtype=np.int64)
+    z = np.zeros(1, np.int32)
+    ok = emu.emu_fused_create(p.nowned, len(neigh), soff, sidx, roff, z, mbox.ctypes.data_as(_p), lay,
+                              1.0)
+    assert ok
+    emu.emu_fused_destroy(ok)
+    bad = sidx.copy()
+    bad[0] = p.nowned - 1                      # an owned dof that is not among the first nshared
+    assert not emu.emu_fused_create(p.nowned, len(neigh), soff, bad, roff, z, mbox.ctypes.data_as(_p),
+                                    lay, 1.0)
+    p1 = BoxPartition(2, (4, 2, 2), (2, 1, 1), 1)
+    neigh, soff, sidx, roff, ridx = p1.halo_arrays()
+    assert np.array_equal(ridx, p1.nowned + np.arange(ridx.size))
+    assert not emu.emu_fused_create(p1.nowned, len(neigh), soff, z, roff, ridx[::-1].copy(),
+                                    mbox.ctypes.data_as(_p), lay, 1.0)
 
 
 def test_emulated_nccl_pack_unpack(fus, emu):
