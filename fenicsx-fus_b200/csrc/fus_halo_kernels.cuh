@@ -124,7 +124,7 @@ __device__ __forceinline__ unsigned long long halo_time_ns() {
 enum HaloSeq { SEQ_FWD_SENT = 0, SEQ_FWD_EXPECT = 1, SEQ_REV_SENT = 2, SEQ_REV_EXPECT = 3,
                SEQ_CALLS = 4, SEQ_COUNT = 8 };
 enum HaloCtr { CTR_GROUPS_PAST = 0, CTR_NEXT_CHUNK = 1, CTR_CHUNKS_DONE = 2, CTR_SHARED_DONE = 3,
-               CTR_COUNT = 8 };
+               CTR_EPI_NEXT = 4, CTR_COUNT = 8 };
 constexpr int kRevChunk = 256; // ghost entries of b copied per helper step (2 KB)
 
 struct FusedHalo {
@@ -254,6 +254,45 @@ __device__ __forceinline__ bool halo_forward_landed(const FusedHalo& H) {
   return ok;
 }
 
+// The same two steps with one thread per neighbour (called by ALL threads of a block, or of a warp
+// group with its own barrier): waiting for, or raising, seven flags one after the other costs seven
+// NVLink round trips in a row, and both sit on the critical path of a stage.
+template <typename Sync>
+__device__ __forceinline__ bool halo_wait_parallel(const FusedHalo& H, bool forward,
+                                                   unsigned long long want, int lane, int* word,
+                                                   Sync sync) {
+  if (lane == 0)
+    *word = 1;
+  sync();
+  const int64_t* off = forward ? H.roff : H.soff; // forward data fill my ghost runs
+  const unsigned long long* flags = forward ? H.fwd_flag : H.rev_flag;
+  if (lane < H.nneigh && off[lane + 1] > off[lane])
+    if (!halo_wait_flag(flags + lane, want, H.timeout_ns, H.error))
+      *word = 0;
+  sync();
+  const bool ok = *word != 0;
+  sync();
+  return ok;
+}
+
+// all data stores have been fenced system-wide by their writers and ordered before this call
+template <typename Sync>
+__device__ __forceinline__ void halo_raise_parallel(const FusedHalo& H, bool forward, int lane,
+                                                    unsigned long long* word, Sync sync) {
+  if (lane == 0) {
+    unsigned long long* sent = H.seq + (forward ? SEQ_FWD_SENT : SEQ_REV_SENT);
+    *word = *sent + 1ull;
+    *sent = *word;
+  }
+  sync();
+  const int64_t* off = forward ? H.soff : H.roff;
+  if (lane < H.nneigh && off[lane + 1] > off[lane]) {
+    __threadfence_system();
+    st_release_sys(forward ? H.r_fwd_flag[lane] : H.r_rev_flag[lane], *word);
+  }
+  sync();
+}
+
 // Raise this rank's flag of one direction on every neighbour it has sent to (one thread; all the
 // data stores have been fenced system-wide and ordered before this call by the caller).
 __device__ __forceinline__ void halo_raise(const FusedHalo& H, bool forward) {
@@ -331,6 +370,7 @@ static __global__ void __launch_bounds__(32) halo_operator_skipped_kernel(const 
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     Hp->seq[SEQ_REV_EXPECT] += 1ull;
     Hp->ctr[CTR_SHARED_DONE] = 0u;
+    Hp->ctr[CTR_EPI_NEXT] = 0u;
     halo_raise(*Hp, false);
   }
 }

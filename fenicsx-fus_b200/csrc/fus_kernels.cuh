@@ -467,10 +467,14 @@ __device__ __forceinline__ void halo_group_report_and_ship(const FusedHalo* Hp, 
     }
     __threadfence_system();
     halo_group_sync<WARP, GTHREADS>(group);
-    if (lg == 0) {
-      const unsigned int done = atomicAdd(H.ctr + CTR_CHUNKS_DONE, 1u) + 1u;
-      if ((long long)done == nchunks)
-        halo_raise(H, false);
+    if (lg == 0)
+      *word = (long long)(atomicAdd(H.ctr + CTR_CHUNKS_DONE, 1u) + 1u) == nchunks ? 1 : 0;
+    halo_group_sync<WARP, GTHREADS>(group);
+    const bool last = *word != 0;
+    halo_group_sync<WARP, GTHREADS>(group);
+    if (last) { // one lane per neighbour raises its flag
+      __shared__ unsigned long long raise_word;
+      halo_raise_parallel(H, false, lg, &raise_word, [group] { halo_group_sync<WARP, GTHREADS>(group); });
     }
   }
 }
@@ -649,6 +653,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     if (blockIdx.x == 0 && tid == 0) { // state for the NEXT epilogue; nothing here reads it
       HL.H->seq[SEQ_REV_EXPECT] += 1ull;
       HL.H->ctr[CTR_SHARED_DONE] = 0u;
+      HL.H->ctr[CTR_EPI_NEXT] = 0u;
     }
   }
   // owned entries from the vector, ghost entries from the mailbox
@@ -1656,7 +1661,6 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
   const int tid = threadIdx.x;
   const long long nchunks = (A.ntotal + kStageChunk - 1) / kStageChunk;
   long long nshared = 0, shared_chunks = 0;
-  unsigned int my_shared_chunks = 0;
   if constexpr (HALO) {
     if (*(volatile int*)A.halo->error)
       return; // an earlier wait timed out: the run is being aborted
@@ -1666,15 +1670,11 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
       for (int q = CTR_GROUPS_PAST; q <= CTR_CHUNKS_DONE; ++q)
         A.halo->ctr[q] = 0u;
     }
-    if ((long long)blockIdx.x < shared_chunks) { // this block's first chunk holds shared dofs
-      __shared__ int rev_ok;
-      if (tid == 0)
-        rev_ok = halo_wait_all(*A.halo, false) ? 1 : 0;
-      __syncthreads();
-      if (!rev_ok)
-        return;
-    }
   }
+  __shared__ int s_word;
+  __shared__ unsigned long long s_raise;
+  auto block_sync = [] { __syncthreads(); };
+  bool rev_waited = false;
   double g = 0.0, dg = 0.0;
   if (A.nb) {
     const int s = *A.step_ctr; // stage 3 advances it only after every block has read it
@@ -1683,7 +1683,18 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
     dg = A.src_table[2 * row + 1];
   }
   double* const vnext = (STAGE < 3) ? A.vn : A.v0;
-  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+  // HALO: every block starts with chunk blockIdx.x and then takes the next free one from a counter:
+  // the blocks that begin with a shared chunk (scalar work, remote stores, flags) are slower there
+  // and must not be left with as many private chunks as everybody else.
+  long long ch = blockIdx.x;
+  while (ch < nchunks) {
+    if constexpr (HALO) {
+      if (ch < shared_chunks && !rev_waited) { // uniform over the block
+        rev_waited = true;
+        if (!halo_wait_parallel(*A.halo, false, A.halo->seq[SEQ_REV_EXPECT], tid, &s_word, block_sync))
+          return; // timed out: the run is being aborted
+      }
+    }
     const long long i = ch * kStageChunk + (long long)tid * kStageVec;
     if (i + kStageVec <= A.nowned && (!HALO || i >= nshared)) {
       D4 b = ld4<L2_NORMAL>(A.b + i), m = ld4<STREAM>(A.m + i);
@@ -1779,17 +1790,19 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
     }
     if constexpr (HALO) {
       if (ch < shared_chunks) { // uniform over the block
-        ++my_shared_chunks;
         __threadfence_system(); // this thread's stores into the neighbours' mailboxes
         __syncthreads();
-        if (tid == 0 && (ch + gridDim.x >= shared_chunks)) { // the block's last shared chunk
-          const unsigned int done = atomicAdd(A.halo->ctr + CTR_SHARED_DONE, my_shared_chunks)
-                                    + my_shared_chunks;
-          if ((long long)done == shared_chunks) {
+        if (tid == 0) {
+          const unsigned int done = atomicAdd(A.halo->ctr + CTR_SHARED_DONE, 1u) + 1u;
+          s_word = (long long)done == shared_chunks ? 1 : 0;
+          if (s_word)
             __threadfence();
-            halo_raise(*A.halo, true);
-          }
         }
+        __syncthreads();
+        const bool last = s_word != 0;
+        __syncthreads();
+        if (last) // one thread per neighbour raises its forward flag
+          halo_raise_parallel(*A.halo, true, tid, &s_raise, block_sync);
       }
     }
     if (A.nb) { // uniform over the block
@@ -1802,17 +1815,30 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
         }
       }
     }
+    if constexpr (HALO) { // next chunk: first come, first served
+      __syncthreads();
+      if (tid == 0)
+        s_word = (int)atomicAdd(A.halo->ctr + CTR_EPI_NEXT, 1u);
+      __syncthreads();
+      ch = (long long)gridDim.x + s_word;
+    } else {
+      ch += gridDim.x;
+    }
   }
   if constexpr (HALO) {
-    if (blockIdx.x == 0 && tid == 0) {
-      if (shared_chunks == 0) // nothing to send: the exchange number advances all the same
-        halo_raise(*A.halo, true);
+    if (blockIdx.x == 0 && tid == 0 && shared_chunks == 0)
+      halo_raise(*A.halo, true); // nothing to send: the exchange number advances all the same
+    if (blockIdx.x == 0) {
       // The next operator gathers ghost values from the mailbox without waiting: this kernel does
       // not end before the neighbours' forward data of this exchange have landed.  Their epilogues
       // send first thing, as this one did above, so the wait is over long before the private part
       // of this kernel is -- and every rank raises its own flags before it waits: no cycle.
-      if (!A.halo_defer_wait)
-        halo_forward_landed(*A.halo);
+      if (!A.halo_defer_wait) {
+        __syncthreads();
+        halo_wait_parallel(*A.halo, true, A.halo->seq[SEQ_FWD_EXPECT] + 1ull, tid, &s_word, block_sync);
+        if (tid == 0)
+          A.halo->seq[SEQ_FWD_EXPECT] += 1ull;
+      }
     }
   }
   if constexpr (STAGE == 3) {
