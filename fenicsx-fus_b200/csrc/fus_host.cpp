@@ -461,15 +461,16 @@ int boundary_vectors_2d(int kind, int P, int64_t ncells, int64_t ndofs, const do
       const int32_t d = dm[c * Nd + id[0] * N + id[1]];
       if (tag == 1 && src)
         src[d] += s / rho;
-      if (kind == FUS_LINEAR) {
-        if (tag == 2 && absb)
-          absb[d] += s / rho / cc;
-      } else {
-        if (absb)
-          absb[d] += s / rho / cc;
+      // the 2-D forms of cpp/fenicsx-sf-naive integrate the absorbing term and its mass-like
+      // counterpart over ds(2) for every model (examples/lossy_planewave2d_1/forms.py:37-42,
+      // westervelt_planewave2d_1/forms.py:37-42) -- unlike the 3-D forms of cpp/fenicsx-sf, which
+      // use `ds` without an id for the lossy and Westervelt models (boundary_vectors above)
+      if (tag == 2 && absb)
+        absb[d] += s / rho / cc;
+      if (kind != FUS_LINEAR) {
         if (tag == 1 && dsrc)
           dsrc[d] += s * del / rho / cc / cc;
-        if (bmass)
+        if (tag == 2 && bmass)
           bmass[d] += s * del / rho / cc / cc / cc;
       }
     }

@@ -245,6 +245,11 @@ int fus_rect_dofmap(int P, const int n[2], int32_t* tensor_dofmap); /* lexicogra
 int64_t fus_rect_num_dofs(int P, const int n[2]);
 /* exterior edges {cell, local facet, tag}: tag 1 on x=lo, 2 on x=hi, 0 elsewhere */
 int64_t fus_rect_facets(const int n[2], int32_t* facets);
+/* As fus_boundary_vectors, with the facet sets of the 2-D forms of cpp/fenicsx-sf-naive
+   (examples/lossy_planewave2d_1/forms.py:37-42, westervelt_planewave2d_1/forms.py:37-42): the
+   absorbing term and its mass-like counterpart over ds(2) for EVERY model kind
+     absb  S^(1/rho c)(tag 2)     bmass  S^(delta/rho c^3)(tag 2)   [lossy, westervelt]
+   -- the 3-D forms of cpp/fenicsx-sf use `ds` without an id for the lossy and Westervelt models. */
 int fus_boundary_vectors_2d(int kind, int P, int64_t ncells, int64_t ndofs, const double* xg,
                             const int32_t* xdofmap, const int32_t* tensor_dofmap, int64_t nfacets,
                             const int32_t* facets, const double* c0, const double* rho0,

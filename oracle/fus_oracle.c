@@ -510,11 +510,20 @@ static void vzero(double* dst, int64_t n) {
 
 static double* vec(int64_t n) { return (double*)calloc((size_t)n, sizeof(double)); }
 
-/* facet part of the bilinear form a (mass-like, applied to u==1) and of L */
+/* facet part of the bilinear form a (mass-like, applied to u==1) and of L.
+   Which facets carry the absorbing term and its mass-like counterpart differs between the two
+   variants of the reference: the 3-D forms of cpp/fenicsx-sf integrate them with `ds` WITHOUT an id,
+   i.e. over every exterior facet (benchmarks/PH1/BM7-SC1/forms.py:37-42), the 2-D forms of
+   cpp/fenicsx-sf-naive over ds(2) only (examples/lossy_planewave2d_1/forms.py:37-42,
+   westervelt_planewave2d_1/forms.py:37-42). */
+static int absorbing_facet(const fo_model* M, int tag) { return M->dim == 3 || tag == 2; }
+
 static void assemble_facets_a(const fo_model* M, double* out) {
   int NN = M->nfn;
   for (int64_t f = 0; f < M->nfacets; ++f) {
     int32_t c = M->facets[3 * f];
+    if (!absorbing_facet(M, M->facets[3 * f + 2]))
+      continue;
     double coef = M->delta0[c] / M->rho0[c] / M->c0[c] / M->c0[c] / M->c0[c];
     for (int k = 0; k < NN; ++k) {
       int32_t d = M->dofmap[(int64_t)c * M->Nd + M->fnodes[f * NN + k]];
@@ -538,7 +547,8 @@ static void assemble_facets_L(const fo_model* M, double* b) {
         if (tag == 2)
           b[d] -= 1.0 / rho / cc * M->v_n[d] * s;
       } else {
-        b[d] -= 1.0 / rho / cc * M->v_n[d] * s; /* ds without id: every exterior facet */
+        if (absorbing_facet(M, tag)) /* 3-D: ds without id, every exterior facet; 2-D: ds(2) */
+          b[d] -= 1.0 / rho / cc * M->v_n[d] * s;
         if (tag == 1)
           b[d] += M->delta0[c] / rho / cc / cc * M->dg[d] * s;
       }

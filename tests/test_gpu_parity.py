@@ -206,7 +206,8 @@ def test_models_vs_oracle_from_rest(fus, orc, gpu, kind, P):
 @pytest.mark.emu_skip
 def test_full_size_properties(fus, gpu):
     """BASELINE config (P=4, 54^3 cells, 10.2 M dofs): size-independent properties of the operator
-    on the device -- K 1 = 0, symmetry, linearity, accumulate -- since the oracle would take minutes."""
+    on the device -- K 1 = 0, symmetry, linearity, accumulate -- next to the oracle comparisons at
+    the same size in tests/test_gpu_baseline_configs.py."""
     import torch
     P, n = 4, (54, 54, 54)
     m = fus.BoxMesh(n)

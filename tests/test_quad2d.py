@@ -106,12 +106,14 @@ def test_host_setup_2d_vs_oracle(fus, orc, kind):
         d = V.dofmap[c, fn[f]]
         if tag == 1:
             np.add.at(r_src, d, fs[f] / rho0[c])
-        if kind == "linear":
-            if tag == 2:
-                np.add.at(r_abs, d, fs[f] / rho0[c] / c0[c])
-        else:
+        # the 2-D forms integrate the absorbing term and its mass-like counterpart over ds(2) for
+        # every model (cpp/fenicsx-sf-naive/examples/lossy_planewave2d_1/forms.py:37-42) -- not over
+        # all exterior facets as the 3-D lossy / Westervelt forms do
+        if tag == 2:
             np.add.at(r_abs, d, fs[f] / rho0[c] / c0[c])
-            np.add.at(r_bm, d, fs[f] * delta[c] / rho0[c] / c0[c] ** 3)
+        if kind != "linear":
+            if tag == 2:
+                np.add.at(r_bm, d, fs[f] * delta[c] / rho0[c] / c0[c] ** 3)
             if tag == 1:
                 np.add.at(r_ds, d, fs[f] * delta[c] / rho0[c] / c0[c] ** 2)
     for a, b in ((src, r_src), (absb, r_abs), (dsrc, r_ds), (bmass, r_bm)):
@@ -439,7 +441,13 @@ def test_reference_analytic_tests_on_the_2d_solvers(fus, orc):
     dt, tend = 0.5 * (L / nx) / (c0 * P * P), L / c0 + 16 / f0
     u, v = np.zeros(nd), np.zeros(nd)
     mdl.rk4(0.0, tend, dt, u, v)
-    exact = p0 * np.exp(-aNp * xs) * np.sin(w0 * tend - w0 / c0 * xs)
+    # As committed, the 2-D lossy / Westervelt solvers drive with the doubled source of their
+    # "heterogeneous domain" branch (fenicsx-sf-naive Lossy.hpp:216-219, Westervelt.hpp:235-238)
+    # while their forms absorb on ds(2) only (examples/lossy_planewave2d_1/forms.py:37-42): nothing
+    # on the source edge takes half of it away, as the all-facet `ds` of the 3-D forms does, so the
+    # wave that leaves is the analytic one for the amplitude 2 p0.
+    p_eff = 2.0 * p0
+    exact = p_eff * np.exp(-aNp * xs) * np.sin(w0 * tend - w0 / c0 * xs)
     assert np.linalg.norm(u - exact) / np.linalg.norm(exact) < 1e-2
     # Westervelt: Fubini solution
     rho0, beta0, p0 = 1.0, 0.01, 1.0
@@ -451,8 +459,14 @@ def test_reference_analytic_tests_on_the_2d_solvers(fus, orc):
     dt, tend = 0.9 * (L / nx) / (c0 * P * P), L / c0 + 8 / f0
     u, v = np.zeros(nd), np.zeros(nd)
     mdl.rk4(0.0, tend, dt, u, v)
-    sigma = (xs + 1e-7) / (c0 ** 2 / w0 / beta0 / (p0 / rho0 / c0))
+    p_eff = 2.0 * p0
+    sigma = (xs + 1e-7) / (c0 ** 2 / w0 / beta0 / (p_eff / rho0 / c0))
     exact = np.zeros(nd)
     for term in range(1, 50):
         exact += 2 / term / sigma * jv(term, term * sigma) * np.sin(term * w0 * (tend - xs / c0))
-    assert np.linalg.norm(u - p0 * exact) / np.linalg.norm(p0 * exact) < 1e-2
+    # the doubled amplitude halves the shock-formation distance (sigma = 1 at x = 0.8 L): Fubini's
+    # series is the solution up to there only, so compare where sigma < 0.75
+    pre = sigma < 0.75
+    assert pre.sum() > nd // 2
+    err = np.linalg.norm((u - p_eff * exact)[pre]) / np.linalg.norm(p_eff * exact[pre])
+    assert err < 5e-2, err           # the reference's own threshold for this test is 1e-1
