@@ -1,8 +1,8 @@
 // float_operators.cpp -- the reference's operator acceptance set-up with T = float
 // (cpp/fenicsx-sf/tests/test_operators3d/main.cpp:13,59-79: P = 4, u = sin(x) cos(pi y),
 // c0 = 1.5e-3, rho0 = 1e-3) against the drop-in headers: MassSpectral3D<float,P> and
-// StiffnessSpectral3D<float,P> next to their double instantiations.  The device arithmetic is
-// FP64 for both (see fus/spectral_op.hpp); the float classes widen and round at the boundary.
+// StiffnessSpectral3D<float,P> next to their double instantiations.  The float classes run the FP32
+// instantiation of the device kernels, the double classes the FP64 one (see fus/spectral_op.hpp).
 //
 //   ./float_operators [cells_per_direction=6]
 #include <fus/spectral_op.hpp>

@@ -297,8 +297,8 @@ def test_cpp_dropin_driver(fus, gpu):
 def test_cpp_float_operator_instantiation(fus, gpu):
     """examples/float_operators.cpp: MassSpectral3D<float,P> / StiffnessSpectral3D<float,P> (the
     scalar type of the reference's tests/test_operators3d/main.cpp:13) next to the double classes.
-    The float classes widen at the boundary and run the FP64 device path, so they agree with the
-    double result to float rounding of the inputs and of the output."""
+    The float classes run the FP32 instantiation of the kernels (fus_*_apply_f32_host), so they
+    agree with the double result to float accuracy."""
     import subprocess
     exe = os.path.join(ROOT, "examples", "float_operators")
     if not os.path.exists(exe):
@@ -309,7 +309,7 @@ def test_cpp_float_operator_instantiation(fus, gpu):
     vals = {ln.split(":")[0]: float(ln.split(":")[1]) for ln in res.stdout.splitlines() if ":" in ln}
     for op in ("mass", "stiffness"):
         f, d = vals[f"float_{op}_l2"], vals[f"double_{op}_l2"]
-        assert d > 0 and abs(f - d) < 1e-5 * d, (op, f, d)
+        assert d > 0 and abs(f - d) < 2e-5 * d, (op, f, d)
 
 
 @pytest.mark.first_hw_run
@@ -568,8 +568,8 @@ print("ring variant ok")
 def test_line_kernel_tma_ring_variant(fus, gpu):
     """Option stiffness_variant 6: G of a cell arrives by one TMA bulk copy in a shared-memory ring
     (cp.async.bulk + mbarrier) instead of through registers.  Same checks as the other pipeline
-    variants, in a child process: the first hardware run of the mbarrier protocol must not be able to
-    leave this process with a faulted context (its waits are time-bounded, so it cannot hang either)."""
+    variants, in a child process (a protocol error there cannot leave this process with a faulted
+    context; its waits are time-bounded, so it cannot hang either)."""
     import subprocess
     import sys
     from fenicsx_fus_b200 import capi
@@ -579,13 +579,7 @@ def test_line_kernel_tma_ring_variant(fus, gpu):
     res = subprocess.run([sys.executable, "-c", RING_CHECK, ROOT], capture_output=True, text=True,
                          timeout=900, env=env, cwd=ROOT)
     ok = res.returncode == 0 and "ring variant ok" in res.stdout
-    note("tma_ring_variant_first_hw_run", 0.0 if ok else 1.0)
-    if not ok and "FUS_TEST_LIB" not in env:
-        # Experimental, opt-in, never selected by the library itself, and its mbarrier protocol has
-        # only been through ptxas and the host emulation so far: a failure of its FIRST hardware run
-        # is reported (xfail + the parity report) instead of turning the suite of the product path red.
-        pytest.xfail("stiffness_variant 6 (TMA ring) failed its first hardware run: "
-                     + res.stdout[-400:] + res.stderr[-1200:])
+    note("tma_ring_variant", 0.0 if ok else 1.0)
     assert ok, res.stdout[-800:] + res.stderr[-2500:]
 
 
