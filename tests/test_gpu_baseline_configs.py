@@ -70,23 +70,35 @@ def test_configs_3_and_4_at_full_size(fus, gpu, bench, model):
 @pytest.mark.parametrize("P", [2, 3, 4, 5, 6, 7])
 def test_config2_operator_apply_at_sweep_size(fus, gpu, orc_ref, P):
     """One application of the kernel the library picks for the degree, on the box of the degree
-    sweep (9.8 - 10.4 M dofs), against the reference kernels; u = sin(x) cos(pi y) at the nodes and
-    coefficient -1/1000 as in measure_fraction_of_peak_performance/main.cpp:75-104."""
+    sweep (9.8 - 10.4 M dofs), against the reference kernels, coefficient -1/1000 as in
+    measure_fraction_of_peak_performance/main.cpp:97-104:
+      * a seeded uniform(-1, 1) vector (SURVEY.md section 8d) at BASELINE.json's 1e-12;
+      * the experiment's own input u = sin(x) cos(pi y) (main.cpp:75-82) at 1e-11.  For that smooth
+        field ||K u|| is ~3e3 times smaller against ||u|| than for a random one (K u = O(h^2)), and
+        every implementation's rounding is amplified accordingly: the reference's own kernels
+        (-Ofast) and the plain-C restatement of them differ by 5e-14 / 1.6e-13 at 12^3 / 24^3 cells
+        on this input and by 1.5e-16 on the random one (measured in the build container)."""
     n = {2: 107, 3: 71, 4: 54, 5: 43, 6: 36, 7: 31}[P]
     m = fus.BoxMesh((n, n, n))
     V = fus.FunctionSpace(m, P, numbering=1)
     X = V.tabulate_dof_coordinates()
-    x = np.sin(X[:, 0]) * np.cos(np.pi * X[:, 1])
+    smooth = np.sin(X[:, 0]) * np.cos(np.pi * X[:, 1])
     del X
+    rnd = np.random.default_rng(12345).uniform(-1.0, 1.0, V.ndofs)
     coeffs = np.full(m.ncells, -1.0 / 1000.0)
-    y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+    K = fus.StiffnessSpectral3D(V)
+    y_rnd = K(rnd, coeffs, np.zeros(V.ndofs))
+    y_smooth = K(smooth, coeffs, np.zeros(V.ndofs))
     ctx = V.context()
     V._ctx = None
     ctx.destroy()
     orc_ref.lib.fr_set_threads(os.cpu_count() or 1)
     G, _ = orc_ref.geometry(P, m.x, m.xdofmap, want_detJ=False)
-    yo = orc_ref.stiffness_apply(P, V.dofmap, G, orc_ref.dphi(P), coeffs, x, np.zeros(V.ndofs),
-                                 use_ref_kernels=True)
-    err = rel_l2(y, yo)
-    print(f"P={P}: {V.ndofs} dofs, apply rel L2 {err:.2e}")
-    assert err < 1e-12
+    dphi = orc_ref.dphi(P)
+    e_rnd = rel_l2(y_rnd, orc_ref.stiffness_apply(P, V.dofmap, G, dphi, coeffs, rnd, np.zeros(V.ndofs),
+                                                  use_ref_kernels=True))
+    e_smooth = rel_l2(y_smooth, orc_ref.stiffness_apply(P, V.dofmap, G, dphi, coeffs, smooth,
+                                                        np.zeros(V.ndofs), use_ref_kernels=True))
+    print(f"P={P}: {V.ndofs} dofs, apply rel L2: random {e_rnd:.2e}, sin(x)cos(pi y) {e_smooth:.2e}")
+    assert e_rnd < 1e-12
+    assert e_smooth < 1e-11
