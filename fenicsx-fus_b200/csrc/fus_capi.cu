@@ -100,6 +100,8 @@ struct fus_ctx {
   int halo_reserve = 4;     // reserve_sms inside a partitioned stage, NCCL side-stream mode
   int l2_persist = 0;       // keep the rhs accumulator b resident in L2 during rk4 (option)
   int stage_hints = 0;      // epilogue: streaming vectors marked L2 evict-first (option)
+  int reverse_op = 1;       // RK4 loop: the operator walks the cells backwards (option "reverse_operator")
+  int reverse_cells = 0;    // what the next stiffness launch does (set by assemble_rhs)
   int use_graph = 1;        // replay RK4 steps from a captured CUDA graph (option "use_graph")
   long long config_epoch = 0; // bumped by anything that changes what a step launches
   Halo* halo = nullptr;
@@ -313,12 +315,14 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     const long long want = (ce - cb + cpb - 1) / cpb;
     const int sms = std::max(1, c->num_sms - c->reserve_sms);
     const int blocks = (int)std::min<long long>(want, (long long)sms * bps);
+    HaloLaunch HL{};
+    HL.reverse = c->reverse_cells; // set by the RK4 loop around its operator launches
     if (fuse)
       kern_fuse<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, Gptr, coeff, coeff2,
-                                                     cb, ce, D, HaloLaunch{});
+                                                     cb, ce, D, HL);
     else
       kern_plain<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, Gptr, coeff, coeff2,
-                                                      cb, ce, D, HaloLaunch{});
+                                                      cb, ce, D, HL);
     FUS_LAUNCHED();
     return FUS_OK;
   };
@@ -691,6 +695,8 @@ int ctx_common(int P, int64_t ncells, int64_t ndofs, int64_t nowned, const int32
   }
   if (const char* e = std::getenv("FUS_L2_PERSIST"))
     c->l2_persist = std::atoi(e) != 0;
+  if (const char* e = std::getenv("FUS_REVERSE_OPERATOR"))
+    c->reverse_op = std::atoi(e) != 0;
   if (const char* e = std::getenv("FUS_STAGE_HINTS"))
     c->stage_hints = std::atoi(e) != 0;
   if (const char* e = std::getenv("FUS_USE_GRAPH"))
@@ -1073,6 +1079,11 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
   }
   if (!std::strcmp(name, "l2_persist")) {
     c->l2_persist = value != 0;
+    return FUS_OK;
+  }
+  if (!std::strcmp(name, "reverse_operator")) {
+    c->reverse_op = value != 0;
+    ++c->config_epoch;
     return FUS_OK;
   }
   if (!std::strcmp(name, "stage_hints")) {
@@ -1616,6 +1627,12 @@ static int assemble_rhs(fus_model* m, double t, const double* u, const double* v
   auto boundary = [&]() -> int {
     return with_boundary ? launch_boundary(m, v, g, dg, false) : FUS_OK;
   };
+  // inside the RK4 loop the operator walks the cells backwards (see stiffness_line_kernel)
+  struct Rev {
+    fus_ctx* c;
+    Rev(fus_ctx* c_, bool on) : c(c_) { c->reverse_cells = on ? 1 : 0; }
+    ~Rev() { c->reverse_cells = 0; }
+  } rev(c, !with_boundary && c->reverse_op);
   if (!c->halo) {
     FUS_TRY(launch_stiffness(c, u, x2, m->d_lin, c2, m->d_b, 0, c->ncells, c->stream));
     return boundary();
@@ -1663,6 +1680,10 @@ int fus_model_f1(fus_model* m, double t, const double* u, const double* v, doubl
     return FUS_ERR_ARG;
   fus_ctx* c = m->ctx;
   FUS_TRY(select_device(c));
+  if (c->nowned < c->ndofs && !c->halo) {
+    set_error("fus_model_f1: the context has ghost dofs but no halo (fus_halo_setup)");
+    return FUS_ERR_STATE;
+  }
   const int64_t nd = c->ndofs;
   const size_t vb = sizeof(double) * nd;
   FUS_CUDA(cudaMemcpyAsync(m->d_un, u, vb, cudaMemcpyHostToDevice, c->stream));
@@ -1747,6 +1768,10 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
   }
   fus_ctx* c = m->ctx;
   FUS_TRY(select_device(c));
+  if (c->nowned < c->ndofs && !c->halo) {
+    set_error("fus_model_rk4: the context has ghost dofs but no halo (fus_halo_setup)");
+    return FUS_ERR_STATE;
+  }
   // Same host-side time arithmetic as the reference loop (Linear.hpp:231-298), run ahead of the
   // device: the step sizes and the source scalars of every (step, stage) are tabulated first.
   const double c_runge[4] = {0.0, 0.5, 0.5, 1.0};
@@ -1948,8 +1973,17 @@ int fus_halo_setup(fus_ctx* c, int rank, int nranks, const void* uid, int nneigh
     halo_destroy(c->halo);
     c->halo = nullptr;
   }
+  if (c->live_models > 0) { // their lumped mass and boundary vectors were reduced over the old halo
+    set_error("fus_halo_setup: %d model(s) built on this context are alive; set the halo up first",
+              c->live_models);
+    return FUS_ERR_STATE;
+  }
   int rc = halo_create(&c->halo, c->device, rank, nranks, uid, nneigh, neigh, send_off, send_idx,
                        recv_off, recv_idx, c->nowned, c->ndofs, ninterface_cells);
+  if (rc != FUS_OK && c->halo) { // nothing half-built stays attached to the context
+    halo_destroy(c->halo);
+    c->halo = nullptr;
+  }
   if (rc == FUS_OK) { // experiment knobs
     if (const char* e = std::getenv("FUS_HALO_OVERLAP"))
       halo_set_overlap(c->halo, std::atoi(e));

@@ -195,6 +195,25 @@ int halo_create(Halo** out, int device, int rank, int nranks, const void* uid, i
     set_error("halo_create: bad argument");
     return FUS_ERR_ARG;
   }
+  // validate everything that can be validated on this rank before anything is allocated or any
+  // collective is entered (a rank that returned early would leave the others in ncclCommInitRank)
+  if (nneigh > 0) {
+    const int64_t ns = send_off[nneigh], nr = recv_off[nneigh];
+    if (ns < 0 || nr < 0 || (ns > 0 && !send_idx) || (nr > 0 && !recv_idx)) {
+      set_error("halo_create: bad lists");
+      return FUS_ERR_ARG;
+    }
+    for (int64_t i = 0; i < ns; ++i)
+      if (send_idx[i] < 0 || send_idx[i] >= nowned) {
+        set_error("halo_create: send index %d is not an owned dof", send_idx[i]);
+        return FUS_ERR_ARG;
+      }
+    for (int64_t i = 0; i < nr; ++i)
+      if (recv_idx[i] < nowned || recv_idx[i] >= ndofs) {
+        set_error("halo_create: recv index %d is not a ghost dof", recv_idx[i]);
+        return FUS_ERR_ARG;
+      }
+  }
   Halo* h = new Halo();
   *out = h;
   h->device = device;
@@ -213,16 +232,6 @@ int halo_create(Halo** out, int device, int rank, int nranks, const void* uid, i
   }
   h->nsend = nneigh ? send_off[nneigh] : 0;
   h->nrecv = nneigh ? recv_off[nneigh] : 0;
-  for (int64_t i = 0; i < h->nsend; ++i)
-    if (send_idx[i] < 0 || send_idx[i] >= nowned) {
-      set_error("halo_create: send index %d is not an owned dof", send_idx[i]);
-      return FUS_ERR_ARG;
-    }
-  for (int64_t i = 0; i < h->nrecv; ++i)
-    if (recv_idx[i] < nowned || recv_idx[i] >= ndofs) {
-      set_error("halo_create: recv index %d is not a ghost dof", recv_idx[i]);
-      return FUS_ERR_ARG;
-    }
   FUS_CUDA_H(cudaSetDevice(device));
   FUS_CUDA_H(cudaMalloc(&h->d_send_idx, sizeof(int32_t) * std::max<int64_t>(1, h->nsend)));
   FUS_CUDA_H(cudaMalloc(&h->d_recv_idx, sizeof(int32_t) * std::max<int64_t>(1, h->nrecv)));

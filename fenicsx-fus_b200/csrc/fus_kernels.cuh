@@ -641,9 +641,17 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     __syncthreads();
   }
 
-  const long long stride = (long long)gridDim.x * C::CPB;
+  // HL.reverse: the launch walks its cells from the last to the first.  Inside the RK4 loop the
+  // epilogue before this kernel has written the stage input and the zeroed b in ascending dof order,
+  // so their TAILS are what is still in L2 when this kernel starts, and the epilogue after it
+  // starts at the dofs this kernel touched last.
   const long long ncell = cell_end - cell_begin;
-  const int niter = (int)((ncell + stride - 1) / stride);
+  const long long pass = (long long)gridDim.x * C::CPB;
+  const int niter = (int)((ncell + pass - 1) / pass);
+  const long long stride = HL.reverse ? -pass : pass;
+  auto in_range = [&](long long cell) {
+    return (unsigned long long)(cell - cell_begin) < (unsigned long long)ncell;
+  };
   int* h_word = nullptr; // one word per group for broadcasts of the group leader's findings
   if constexpr (HALO) {
     __shared__ int h_words[C::GROUPS];
@@ -669,7 +677,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     else
       return __ldg(x2 + i);
   };
-  long long c = cell_begin + (long long)blockIdx.x * C::CPB + slot;
+  long long c = HL.reverse ? cell_end - 1 - ((long long)blockIdx.x * C::CPB + slot)
+                           : cell_begin + (long long)blockIdx.x * C::CPB + slot;
 
   int idx[N], idxn[N];
   int idxnn[DM2 ? N : 1]; // DM2: dofmap rows of the cell after next
@@ -736,7 +745,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     for (int p = 0; p < 3; ++p)
       g[k][p] = make_v2<T>(T(0), T(0));
 
-  bool valid = lane_ok && (c < cell_end);
+  bool valid = lane_ok && in_range(c);
   if (valid) {
     const int32_t* dm = dofmap + c * (N * NN) + t;
 #pragma unroll
@@ -781,7 +790,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     }
   }
   long long cn = c + stride;
-  bool validn = lane_ok && (cn < cell_end);
+  bool validn = lane_ok && in_range(cn);
   if (validn) {
     const int32_t* dm = dofmap + cn * (N * NN) + t;
 #pragma unroll
@@ -880,7 +889,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
     if constexpr (DM2) { // nothing consumes a global load between here and the end of the iteration
       const long long c2 = cn + stride;
-      if (lane_ok && c2 < cell_end) {
+      if (lane_ok && in_range(c2)) {
         const int32_t* dm = dofmap + c2 * (N * NN) + t;
 #pragma unroll
         for (int k = 0; k < N; ++k)
@@ -959,7 +968,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
     if constexpr (RING) { // every thread of the cell is past its reads of this stage: refill it
       const long long c2 = cn + stride; // the cell this slot works on two iterations from now
-      if (producer && c2 < cell_end)
+      if (producer && in_range(c2))
         ring_issue(ring + stage * C::CELLG, G2 + c2 * (3 * N * NN), RING_BYTES, ring_bar + stage);
     }
 
@@ -1006,7 +1015,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     valid = validn;
     c = cn;
     cn += stride;
-    validn = lane_ok && (cn < cell_end);
+    validn = lane_ok && in_range(cn);
     if constexpr (AFFINE) {
 #pragma unroll
       for (int p = 0; p < 3; ++p)
@@ -1035,7 +1044,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     }
     if constexpr (DMPF) { // dofmap rows of the cell after next: N*N*N int32, touched line by line
       const long long c2 = cn + stride;
-      if (lane_ok && c2 < cell_end && t * 32 < N * NN) {
+      if (lane_ok && in_range(c2) && t * 32 < N * NN) {
 #ifndef FUS_HOST_EMULATION
         asm volatile("prefetch.global.L2 [%0];" ::"l"(dofmap + c2 * (N * NN) + t * 32));
 #endif
