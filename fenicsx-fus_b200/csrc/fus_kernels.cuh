@@ -1695,9 +1695,16 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
   // HALO: every block starts with chunk blockIdx.x and then takes the next free one from a counter:
   // the blocks that begin with a shared chunk (scalar work, remote stores, flags) are slower there
   // and must not be left with as many private chunks as everybody else.
+  // The next chunk is claimed while the current one is being processed (one atomic per 1 024 dofs,
+  // its latency hidden behind the chunk's own loads) and handed to the block through one of two
+  // shared words, so a chunk ends with a single barrier.
+  __shared__ int s_next[2];
+  int parity = 0;
   long long ch = blockIdx.x;
   while (ch < nchunks) {
     if constexpr (HALO) {
+      if (tid == 0)
+        s_next[parity] = (int)atomicAdd(A.halo->ctr + CTR_EPI_NEXT, 1u);
       if (ch < shared_chunks && !rev_waited) { // uniform over the block
         rev_waited = true;
         if (!halo_wait_parallel(*A.halo, false, A.halo->seq[SEQ_REV_EXPECT], tid, &s_word, block_sync))
@@ -1826,10 +1833,8 @@ __global__ void __launch_bounds__(kStageThreads) rk4_stage_kernel(const StageArg
     }
     if constexpr (HALO) { // next chunk: first come, first served
       __syncthreads();
-      if (tid == 0)
-        s_word = (int)atomicAdd(A.halo->ctr + CTR_EPI_NEXT, 1u);
-      __syncthreads();
-      ch = (long long)gridDim.x + s_word;
+      ch = (long long)gridDim.x + s_next[parity];
+      parity ^= 1;
     } else {
       ch += gridDim.x;
     }
