@@ -15,7 +15,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfus_b200.so")
 SOURCES = ["fus_capi.cu", "fus_halo.cu", "fus_host.cpp", "fus_partition.cpp"]
 HEADERS = ["fus_kernels.cuh", "fus_internal.hpp", "fus_halo.hpp", "fus_trilinear.hpp",
-           "fus_halo_kernels.cuh"]
+           "fus_halo_kernels.cuh", "fus_cell_kernel.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

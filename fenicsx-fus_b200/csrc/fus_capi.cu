@@ -6,6 +6,7 @@
 #include "fus_halo.hpp"
 #include "fus_internal.hpp"
 #include "fus_kernels.cuh"
+#include "fus_cell_kernel.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -88,12 +89,16 @@ struct fus_ctx {
   // float copies of G2 / detJ for the FP32 operator entry points, made on first use
   float* d_G2f = nullptr;
   float* d_detJf = nullptr;
+  // cell data in blocks of 32 cells, lane-minor, for the cell-per-thread kernel (P = 2), made on
+  // first use (fus_cell_kernel.cuh)
+  double2* d_Gt = nullptr;
+  int32_t* d_dmt = nullptr;
   int geom_active = 0;      // what the stiffness operator currently uses: 0 streamed G, 1, 2, 3
   bool lean = false;        // neither G nor detJ exist on the device: always mode 2
   int live_models = 0;      // fus_model objects that still point at this context
   // -1 auto (column kernel for P <= 3, line kernel for P >= 4: measured crossover, see
   // profiles/), 0 column kernel, 1 point kernel, 2 line kernel, 3 / 4 / 5 / 6 line kernel with the
-  // experimental software pipelines (kernel GEOM 4 / 5 / 6 / 7; not yet measured)
+  // software pipelines (kernel GEOM 4 / 5 / 6 / 7), 7 cell-per-thread kernel (P = 2 only)
   int variant = -1;
   int col_blocks_per_sm = 0;
   int reserve_sms = 0;      // SMs left free for the halo kernels while cells overlap with them
@@ -202,6 +207,40 @@ int select_device(fus_ctx* c) {
 
 // ---- per-degree dispatch ---------------------------------------------------------------------
 
+// Kernel per degree, from the measured sweep of every variant at every degree on a B200
+// (profiles/r2a_variant_sweep.jsonl, one application on ~10 M dofs, fraction of the measured HBM
+// peak): P<=3 column kernel (0.82 / 0.94), P=4 line kernel (0.91), P=5 and P=6 the line kernel
+// with the dofmap rows loaded next to the G refills (0.89 / 0.81; the default pipeline gives
+// 0.83 / 0.70), P=7 the pipeline with the coefficient folded into x (0.76 vs 0.73).
+int resolved_variant(const fus_ctx* c) {
+  const int N = c->N;
+  int v = (c->variant >= 0) ? c->variant : (N <= 4 ? 0 : (N == 5 ? 2 : (N <= 7 ? 5 : 3)));
+  if (v == 7 && (N != 3 || c->geom_active != 0 || c->dim != 3))
+    v = 0; // the cell-per-thread kernel exists for P = 2 with streamed G only
+  return v;
+}
+
+// Lane-minor copies of G and of the dofmap for the cell-per-thread kernel.  Allocates: must not
+// run while the stream is being captured (fus_model_rk4 calls it before it captures).
+int ensure_cell_layout(fus_ctx* c) {
+  if (c->d_Gt || resolved_variant(c) != 7 || !c->d_G2)
+    return FUS_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  FUS_CUDA(cudaStreamIsCapturing(c->stream, &cap));
+  if (cap != cudaStreamCaptureStatusNone) {
+    set_error("cell-per-thread kernel: its cell data must be made before a stream capture");
+    return FUS_ERR_STATE;
+  }
+  const long long nblk = (c->ncells + kCellLanes - 1) / kCellLanes;
+  FUS_CUDA(cudaMalloc(&c->d_Gt, sizeof(double2) * 3 * c->Nd * kCellLanes * nblk));
+  FUS_CUDA(cudaMalloc(&c->d_dmt, sizeof(int32_t) * c->Nd * kCellLanes * nblk));
+  transpose_cells_kernel<<<grid_for(nblk * 3 * c->Nd * kCellLanes, 256, c->num_sms * 8), 256, 0,
+                           c->stream>>>(c->d_G2, c->d_dofmap, c->d_Gt, c->d_dmt, c->ncells, c->Nd);
+  FUS_LAUNCHED();
+  FUS_CUDA(cudaStreamSynchronize(c->stream)); // once; later launches may use another stream
+  return FUS_OK;
+}
+
 template <int N>
 int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const double* coeff,
                        const double* coeff2, double* y, long long cb, long long ce,
@@ -265,13 +304,50 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     return go(stiffness_line_kernel<N, false, 0, double, true>,
               stiffness_line_kernel<N, true, 0, double, true>, cfg);
   }
-  // Kernel per degree, from the measured sweep of every variant at every degree on a B200
-  // (profiles/r2a_variant_sweep.jsonl, one application on ~10 M dofs, fraction of the measured HBM
-  // peak): P<=3 column kernel (0.82 / 0.94), P=4 line kernel (0.91), P=5 and P=6 the line kernel
-  // with the dofmap rows loaded next to the G refills (0.89 / 0.81; the default pipeline gives
-  // 0.83 / 0.70), P=7 the pipeline with the coefficient folded into x (0.76 vs 0.73).
-  const int variant = (c->variant >= 0) ? c->variant
-                                        : (N <= 4 ? 0 : (N == 5 ? 2 : (N <= 7 ? 5 : 3)));
+  const int variant = resolved_variant(c);
+  if constexpr (N == 3) {
+    if (variant == 7) { // a thread per cell, cell data in lane-minor blocks of 32 cells
+      FUS_TRY(ensure_cell_layout(c));
+      auto go = [&](auto kern_plain, auto kern_fuse, KernelCfg& cfg) -> int {
+        std::atomic<bool>& configured = cfg.configured[c->device];
+        int& bps = cfg.blocks_plain[c->device];
+        if (!configured.load(std::memory_order_acquire)) {
+          std::lock_guard<std::mutex> lock(cfg.mu);
+          int bf = 0;
+          FUS_CUDA(cudaFuncSetAttribute(kern_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kCellSmemBytes));
+          FUS_CUDA(cudaFuncSetAttribute(kern_fuse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kCellSmemBytes));
+          FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern_plain, kCellThreads,
+                                                                kCellSmemBytes));
+          FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bf, kern_fuse, kCellThreads,
+                                                                kCellSmemBytes));
+          bps = std::min(bps, bf);
+          if (bps < 1) {
+            set_error("cell-per-thread stiffness kernel does not fit on an SM");
+            return FUS_ERR_CUDA;
+          }
+          configured.store(true, std::memory_order_release);
+        }
+        ProfScope prof(c, 0, st);
+        const long long nblk = (ce - 1) / kCellLanes - cb / kCellLanes + 1;
+        const long long want = (nblk * 32 + kCellThreads - 1) / kCellThreads;
+        const int sms = std::max(1, c->num_sms - c->reserve_sms);
+        const int per_sm = c->col_blocks_per_sm > 0 ? std::min(bps, c->col_blocks_per_sm) : bps;
+        const int blocks = (int)std::min<long long>(want, (long long)sms * per_sm);
+        if (fuse)
+          kern_fuse<<<blocks, kCellThreads, kCellSmemBytes, st>>>(x, x2, y, c->d_dmt, c->d_Gt, coeff, coeff2, cb,
+                                                     ce, D, c->reverse_cells ? 1 : 0);
+        else
+          kern_plain<<<blocks, kCellThreads, kCellSmemBytes, st>>>(x, x2, y, c->d_dmt, c->d_Gt, coeff, coeff2, cb,
+                                                      ce, D, c->reverse_cells ? 1 : 0);
+        FUS_LAUNCHED();
+        return FUS_OK;
+      };
+      static KernelCfg cfg;
+      return go(stiffness_cell_kernel<false>, stiffness_cell_kernel<true>, cfg);
+    }
+  }
   if (variant == 1 && c->geom_active == 0) {
     ProfScope prof(c, 0, st);
     const int blocks = (int)std::min<long long>(ce - cb, (long long)c->num_sms * 16);
@@ -990,6 +1066,8 @@ int fus_ctx_destroy(fus_ctx* c) {
   cudaFree(c->d_tri);
   cudaFree(c->d_G2f);
   cudaFree(c->d_detJf);
+  cudaFree(c->d_Gt);
+  cudaFree(c->d_dmt);
   cudaFree(c->d_G2);
   cudaFree(c->d_Gq);
   cudaFree(c->d_detJ);
@@ -1020,8 +1098,8 @@ int fus_ctx_set_option(fus_ctx* c, const char* name, int value) {
     if (!std::strcmp(name, k))
       ++c->config_epoch; // a captured step graph would replay the previous choice
   if (!std::strcmp(name, "stiffness_variant")) {
-    if (value < -1 || value > 6) {
-      set_error("stiffness_variant must be -1 (auto) or 0..6");
+    if (value < -1 || value > 7) {
+      set_error("stiffness_variant must be -1 (auto) or 0..7");
       return FUS_ERR_ARG;
     }
     c->variant = value;
@@ -1772,6 +1850,7 @@ int fus_model_rk4(fus_model* m, double startTime, double finalTime, double timeS
     set_error("fus_model_rk4: the context has ghost dofs but no halo (fus_halo_setup)");
     return FUS_ERR_STATE;
   }
+  FUS_TRY(ensure_cell_layout(c)); // allocates: ahead of any stream capture
   // Same host-side time arithmetic as the reference loop (Linear.hpp:231-298), run ahead of the
   // device: the step sizes and the source scalars of every (step, stage) are tabulated first.
   const double c_runge[4] = {0.0, 0.5, 0.5, 1.0};

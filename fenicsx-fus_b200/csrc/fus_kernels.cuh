@@ -97,6 +97,11 @@ __device__ __forceinline__ void ring_issue(void* dst, const void* src, unsigned 
   std::memcpy(dst, src, bytes);
   std::atomic_ref<unsigned long long>(*bar).fetch_add(1ull, std::memory_order_release);
 }
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() { return 0ull; }
+__device__ __forceinline__ void ring_issue_hint(void* dst, const void* src, unsigned bytes,
+                                                unsigned long long* bar, unsigned long long) {
+  ring_issue(dst, src, bytes, bar);
+}
 __device__ __forceinline__ bool ring_wait(unsigned long long* bar, unsigned phase_index) {
   for (long long spin = 0; spin < (1ll << 34); ++spin) {
     if (std::atomic_ref<unsigned long long>(*bar).load(std::memory_order_acquire) > phase_index)
@@ -125,6 +130,24 @@ __device__ __forceinline__ void ring_issue(void* dst, const void* src, unsigned 
                : "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// the same with an L2 eviction policy on the source lines (createpolicy): for a stream that is read
+// once and must not push the vectors out of L2
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void ring_issue_hint(void* dst, const void* src, unsigned bytes,
+                                                unsigned long long* bar, unsigned long long pol) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+               "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ bool ring_wait(unsigned long long* bar, unsigned phase_index) {

@@ -134,18 +134,24 @@ int fus_ctx_destroy(fus_ctx* ctx);
 /* Launch all work of this context on the given cudaStream_t (default: a private stream). */
 int fus_ctx_set_stream(fus_ctx* ctx, void* cuda_stream);
 /* Tuning/diagnostic knobs (all optional; defaults in brackets):
-     "stiffness_variant"  [-1] -1 auto (column kernel for P <= 3, line kernel for P >= 4),
+     "stiffness_variant"  [-1] -1 auto: the fastest kernel per degree from the hardware sweep of
+                               DESIGN.md 3.1 (column kernel for P <= 3, line kernel for P = 4,
+                               its software pipelines 5 / 5 / 3 for P = 5 / 6 / 7),
                                0 column, 1 per-point (cross-check), 2 line kernel,
-                               3..6 line kernel with experimental software pipelines (same
-                               results; kept selectable until measured)
+                               3..6 line kernel with software pipelines (same results),
+                               7 cell-per-thread kernel (P = 2 only, other degrees keep their
+                               own; a measured alternative, slower than the column kernel)
      "geometry_mode"      [0]  0 streamed G, 1 affine compression, 2 trilinear on the fly (below)
      "use_graph"          [1]  replay RK4 steps from a captured CUDA graph when possible
      "profile_kernels"    [0]  CUDA event pair around every launch (disables graph replay)
      "l2_persist"         [0]  L2 persistence window on the rhs accumulator (measured slower)
      "halo_overlap"       [0]  NCCL transport: run the exchanges on a side stream
      "halo_reserve_sms"   [4]  SMs left free for NCCL kernels in that mode
-     "halo_interior_first" [25] fused peer transport: percentage of the interior cells the
-                               stiffness kernel visits before the cells that touch shared dofs
+     "reverse_operator"   [1]  inside fus_model_rk4 the stiffness kernel walks the cells from the
+                               last to the first, so that the epilogue after it (which streams the
+                               vectors from the front) finds the part of the right-hand side written
+                               last still in L2, and the operator after that the tail of the stage
+                               input (same results up to the order of the atomic sums)
      "stage_hints"        [0]  epilogue: streaming vectors marked L2 evict-first (measured slower)
      "col_blocks_per_sm"  [0]  cap on resident blocks of the stiffness kernels (0 = occupancy) */
 int fus_ctx_set_option(fus_ctx* ctx, const char* name, int value);
@@ -281,8 +287,9 @@ int fus_halo_setup(fus_ctx* ctx, int rank, int nranks, const void* nccl_unique_i
  * There is no exchange kernel: the RK4 epilogue adds the neighbours' partial sums of the right-hand
  * side for the dofs it shares (scatter_rev) and stores the next stage input straight into the
  * neighbours' mailboxes over NVLink peer memory (scatter_fwd); the stiffness kernel gathers ghost
- * values from the mailbox and ships its ghost partial sums to the owners' mailboxes between two of
- * its own cells.  Flags with device-side sequence numbers order everything, so a captured CUDA
+ * values from the mailbox and, in a launch of its own over the cells that touch shared dofs, ships
+ * its ghost partial sums to the owners' mailboxes after its last cell, while the launch over the
+ * other cells runs.  Flags with device-side sequence numbers order everything, so a captured CUDA
  * graph replays whole steps; every wait on a neighbour is bounded (FUS_HALO_TIMEOUT_S, default 30 s)
  * and a time-out aborts the run: the remaining kernels return at once and fus_ctx_sync /
  * fus_model_get_state report FUS_ERR_COMM.  fus_model_rk4 begins with a handshake between

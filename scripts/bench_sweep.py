@@ -84,6 +84,8 @@ def main():
     ap.add_argument("--models", default="linear_het,lossy,westervelt")
     ap.add_argument("--variants", default="0", help="-1 = the library's own choice per degree")
     ap.add_argument("--geometry-modes", default="0")
+    ap.add_argument("--col-blocks-per-sm", type=int, default=0,
+                    help="option col_blocks_per_sm for the degree sweep (0 = occupancy)")
     ap.add_argument("--pipeline-variants", default="",
                     help="extra stiffness variants timed with streamed G only (3,4,5: the line kernel's "
                          "experimental software pipelines), in the degree sweep and in the RK4 runs")
@@ -116,6 +118,7 @@ def main():
         for variant, gmode in pairs:
             ctx.set_option("stiffness_variant", variant)
             ctx.set_option("geometry_mode", gmode)
+            ctx.set_option("col_blocks_per_sm", args.col_blocks_per_sm)
             if ctx.get_option("geometry_compressed") != gmode:
                 continue
             y.zero_()
@@ -139,6 +142,7 @@ def main():
                          / torch.linalg.vector_norm(y_first)).item())
             print(json.dumps({"config": "degree_sweep", "P": P, "n": n, "dofs": V.ndofs,
                               "variant": variant, "geometry_mode": gmode,
+                              "col_blocks_per_sm": args.col_blocks_per_sm,
                               "rel_l2_vs_first_config": err,
                               "numbering": args.numbering,
                               "y_norm_after_repeats": float(torch.linalg.vector_norm(y).item()),

@@ -15,6 +15,10 @@ rows = list(csv.reader(io.StringIO(text[start:]))) if start >= 0 else []
 if len(rows) < 2:
     print("no source page in the report")
     sys.exit(0)
+# the dump may open with metadata rows ("Kernel Name", ...): the header is the first row naming a
+# sampling column
+hrow = next((i for i, r in enumerate(rows) if any("Sampl" in c for c in r)), 0)
+rows = rows[hrow:]
 head = rows[0]
 scol = next((i for i, h in enumerate(head) if "Sampling" in h and "All" in h), None)
 if scol is None:

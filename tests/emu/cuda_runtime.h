@@ -57,6 +57,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cu
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaStreamCaptureMode { cudaStreamCaptureModeThreadLocal = 1 };
+enum cudaStreamCaptureStatus { cudaStreamCaptureStatusNone = 0, cudaStreamCaptureStatusActive = 1 };
 enum cudaLimit { cudaLimitPersistingL2CacheSize = 6 };
 enum cudaStreamAttrID { cudaStreamAttributeAccessPolicyWindow = 1 };
 enum cudaAccessProperty { cudaAccessPropertyStreaming = 1, cudaAccessPropertyPersisting = 2 };
@@ -149,6 +150,10 @@ inline cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode)
   if (!s || fus_emu::capturing() || std::getenv("FUS_EMU_NO_GRAPH"))
     return cudaErrorEmulated; // the library then stays on eager issue (fus_model_rk4)
   fus_emu::capturing() = new emu_graph();
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus* st) {
+  *st = fus_emu::capturing() ? cudaStreamCaptureStatusActive : cudaStreamCaptureStatusNone;
   return cudaSuccess;
 }
 inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) {

@@ -13,6 +13,7 @@
 #define FUS_HOST_EMULATION 1
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <barrier>
 #include <chrono>
@@ -59,6 +60,7 @@ struct BlockState {
   std::map<int, std::unique_ptr<std::barrier<>>> named;
   std::mutex mu;
   std::vector<double> dyn;
+  std::vector<std::array<unsigned long long, 32>> shfl; // one exchange row per warp
 };
 inline BlockState* g_block = nullptr;
 
@@ -86,6 +88,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
     for (unsigned w = 0; w < (block + 31) / 32; ++w)
       st.warps.push_back(std::make_unique<std::barrier<>>(std::min(32u, block - 32 * w)));
     st.dyn.assign(smem_bytes / sizeof(double) + 1, 0.0);
+    st.shfl.resize((block + 31) / 32);
     g_block = &st;
     std::vector<std::thread> th;
     th.reserve(block);
@@ -125,6 +128,38 @@ inline void __syncthreads() {
 inline void __syncwarp() {
   fus_emu::g_block->warps[threadIdx.x / 32]->arrive_and_wait();
   fus_emu::jitter();
+}
+// warp shuffles: every lane of the warp must call (mask is not interpreted); values up to 8 bytes
+namespace fus_emu {
+template <typename T>
+inline T shfl_from(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+  auto& row = g_block->shfl[threadIdx.x / 32];
+  const int lane = threadIdx.x % 32;
+  unsigned long long bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  row[lane] = bits;
+  g_block->warps[threadIdx.x / 32]->arrive_and_wait();
+  const unsigned long long got = row[(src_lane >= 0 && src_lane < 32) ? src_lane : lane];
+  g_block->warps[threadIdx.x / 32]->arrive_and_wait();
+  T out;
+  std::memcpy(&out, &got, sizeof(T));
+  return out;
+}
+} // namespace fus_emu
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int m) {
+  return fus_emu::shfl_from(v, (int)(threadIdx.x % 32) ^ m);
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, int d) {
+  const int lane = threadIdx.x % 32;
+  return fus_emu::shfl_from(v, lane >= d ? lane - d : lane);
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned, T v, int d) {
+  const int lane = threadIdx.x % 32;
+  return fus_emu::shfl_from(v, lane + d < 32 ? lane + d : lane);
 }
 template <typename T>
 inline T __ldg(const T* p) {

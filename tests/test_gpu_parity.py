@@ -522,7 +522,66 @@ def test_line_kernel_pipeline_variants(fus, orc, gpu, P):
         assert rel_l2(mdl.u_sol(), u_ref) < TOL_STEPS
     ctx.set_option("stiffness_variant", -1)
     with pytest.raises(fus.FusError):
-        ctx.set_option("stiffness_variant", 7)
+        ctx.set_option("stiffness_variant", 8)
+
+
+@pytest.mark.parametrize("n", [(1, 1, 1), (7, 3, 2), (5, 5, 3), (11, 4, 3)])
+def test_cell_per_thread_kernel(fus, orc, gpu, n):
+    """Option stiffness_variant 7 (P = 2): one thread per cell on lane-minor blocks of 32 cells
+    (fus_cell_kernel.cuh).  Cell counts below, at and above one block with ragged tails; warped cells
+    (all six entries of G); integer data bit-exact; the fused two-vector gather; RK4 through the
+    captured graph, where the kernel walks the blocks backwards; sub-ranges of cells as the
+    partitioned flow launches them; other degrees fall back to their own kernel."""
+    P = 2
+    m = fus.BoxMesh(n, (0.4, -0.3, 1.0), (0.9, 0.0, 1.2), warp=lambda x: warp_vertices(x, 0.08, 3))
+    V = fus.FunctionSpace(m, P, numbering=1)
+    ctx = V.context()
+    G, dJ = orc.geometry(P, m.x, m.xdofmap)
+    rng = np.random.default_rng(700 + m.ncells)
+    x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2, m.ncells)
+    y0 = rng.uniform(-1, 1, V.ndofs)
+    yo = orc.stiffness_apply(P, V.dofmap, G, orc.dphi(P), coeffs, x, y0.copy())
+    mdl = fus.LossySpectral3D(V, 1500.0, 1000.0, 3e-3, 0.5e6, 1e5, 1500.0)
+    u, v = rng.uniform(-1, 1, V.ndofs), 1e6 * rng.uniform(-1, 1, V.ndofs)
+    k0 = mdl.f1(1e-6, u, v)
+    dt = 0.2 * (0.1 / 7) / (1500.0 * P * P)
+    mdl.init(u.copy(), v.copy())
+    mdl.rk4(0.0, 4.5 * dt, dt)
+    u_ref = mdl.u_sol()
+    ctx.set_option("stiffness_variant", 7)
+    for rep in range(2):
+        y = fus.StiffnessSpectral3D(V)(x, coeffs, y0.copy())
+        note(f"cell_kernel_stiffness_{m.ncells}cells", rel_l2(y - y0, yo - y0))
+        assert rel_l2(y - y0, yo - y0) < TOL_APPLY
+    assert rel_l2(mdl.f1(1e-6, u, v), k0) < TOL_APPLY
+    mdl.init(u.copy(), v.copy())
+    assert mdl.rk4(0.0, 4.5 * dt, dt) == 5
+    assert rel_l2(mdl.u_sol(), u_ref) < TOL_STEPS
+    # integers: any indexing error in the transposed cell data, the gather or the scatter shows
+    dm = V.dofmap
+    nc, Nd = dm.shape
+    Gi = rng.integers(-3, 4, (nc, Nd, 6)).astype(np.float64)
+    dJi = rng.integers(1, 5, (nc, Nd)).astype(np.float64)
+    dphi = rng.integers(-2, 3, (P + 1) ** 2).astype(np.float64)
+    xi = rng.integers(-4, 5, V.ndofs).astype(np.float64)
+    ci = rng.integers(1, 4, nc).astype(np.float64)
+    yi = rng.integers(-9, 10, V.ndofs).astype(np.float64)
+    ctx2 = fus.Context.from_arrays(P, dm, V.ndofs, Gi, dJi, dphi)
+    ctx2.set_option("stiffness_variant", 7)
+    assert np.array_equal(fus.StiffnessSpectral3D(ctx2)(xi, ci, yi.copy()),
+                          orc.stiffness_apply(P, dm, Gi, dphi, ci, xi, yi.copy()))
+    ctx2.destroy()
+
+
+def test_cell_per_thread_kernel_other_degrees_fall_back(fus, orc, gpu):
+    m, V, G, dJ = make_case(fus, orc, 3, (3, 2, 2), 1)
+    ctx = V.context()
+    ctx.set_option("stiffness_variant", 7)
+    rng = np.random.default_rng(3)
+    x, coeffs = rng.uniform(-1, 1, V.ndofs), rng.uniform(0.5, 2.0, m.ncells)
+    y = fus.StiffnessSpectral3D(V)(x, coeffs, np.zeros(V.ndofs))
+    yo = orc.stiffness_apply(3, V.dofmap, G, orc.dphi(3), coeffs, x, np.zeros(V.ndofs))
+    assert rel_l2(y, yo) < TOL_APPLY
 
 
 RING_CHECK = r"""
