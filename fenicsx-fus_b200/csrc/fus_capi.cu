@@ -247,6 +247,10 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
                        cudaStream_t st, const FusedHalo* fh) {
   if (ce <= cb)
     return FUS_OK;
+  if (ce - cb >= (1ll << 30)) { // the kernels count their walk through the cells in 32 bits
+    set_error("stiffness operator: more than 2^30 cells in one launch");
+    return FUS_ERR_UNSUPPORTED;
+  }
   DMat<N> D;
   std::memcpy(D.d, c->dphi, sizeof(double) * N * N);
   std::memcpy(D.w, c->wts, sizeof(double) * N);

@@ -672,9 +672,9 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
   const long long pass = (long long)gridDim.x * C::CPB;
   const int niter = (int)((ncell + pass - 1) / pass);
   const long long stride = HL.reverse ? -pass : pass;
-  auto in_range = [&](long long cell) {
-    return (unsigned long long)(cell - cell_begin) < (unsigned long long)ncell;
-  };
+  // validity is decided on the position in the walk (32-bit; the launch refuses >= 2^30 cells),
+  // not on the cell number: one int per thread instead of 64-bit range checks
+  const int ncell32 = (int)ncell, pass32 = (int)pass;
   int* h_word = nullptr; // one word per group for broadcasts of the group leader's findings
   if constexpr (HALO) {
     __shared__ int h_words[C::GROUPS];
@@ -768,7 +768,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     for (int p = 0; p < 3; ++p)
       g[k][p] = make_v2<T>(T(0), T(0));
 
-  bool valid = lane_ok && in_range(c);
+  int vn = (int)blockIdx.x * C::CPB + slot; // position of cn in the walk (of c until cn is set)
+  bool valid = lane_ok && vn < ncell32;
   if (valid) {
     const int32_t* dm = dofmap + c * (N * NN) + t;
 #pragma unroll
@@ -813,7 +814,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     }
   }
   long long cn = c + stride;
-  bool validn = lane_ok && in_range(cn);
+  vn += pass32;
+  bool validn = lane_ok && vn < ncell32;
   if (validn) {
     const int32_t* dm = dofmap + cn * (N * NN) + t;
 #pragma unroll
@@ -912,7 +914,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
     if constexpr (DM2) { // nothing consumes a global load between here and the end of the iteration
       const long long c2 = cn + stride;
-      if (lane_ok && in_range(c2)) {
+      if (lane_ok && vn + pass32 < ncell32) {
         const int32_t* dm = dofmap + c2 * (N * NN) + t;
 #pragma unroll
         for (int k = 0; k < N; ++k)
@@ -991,7 +993,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
     if constexpr (RING) { // every thread of the cell is past its reads of this stage: refill it
       const long long c2 = cn + stride; // the cell this slot works on two iterations from now
-      if (producer && in_range(c2))
+      if (producer && vn + pass32 < ncell32)
         ring_issue(ring + stage * C::CELLG, G2 + c2 * (3 * N * NN), RING_BYTES, ring_bar + stage);
     }
 
@@ -1038,7 +1040,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     valid = validn;
     c = cn;
     cn += stride;
-    validn = lane_ok && in_range(cn);
+    vn += pass32;
+    validn = lane_ok && vn < ncell32;
     if constexpr (AFFINE) {
 #pragma unroll
       for (int p = 0; p < 3; ++p)
@@ -1067,7 +1070,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     }
     if constexpr (DMPF) { // dofmap rows of the cell after next: N*N*N int32, touched line by line
       const long long c2 = cn + stride;
-      if (lane_ok && in_range(c2) && t * 32 < N * NN) {
+      if (lane_ok && vn + pass32 < ncell32 && t * 32 < N * NN) {
 #ifndef FUS_HOST_EMULATION
         asm volatile("prefetch.global.L2 [%0];" ::"l"(dofmap + c2 * (N * NN) + t * 32));
 #endif
