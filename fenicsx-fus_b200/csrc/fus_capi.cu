@@ -395,8 +395,7 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     const long long want = (ce - cb + cpb - 1) / cpb;
     const int sms = std::max(1, c->num_sms - c->reserve_sms);
     const int blocks = (int)std::min<long long>(want, (long long)sms * bps);
-    HaloLaunch HL{};
-    HL.reverse = c->reverse_cells; // set by the RK4 loop around its operator launches
+    const HaloLaunch HL{};
     if (fuse)
       kern_fuse<<<blocks, threads, smem_bytes, st>>>(x, x2, y, c->d_dofmap, Gptr, coeff, coeff2,
                                                      cb, ce, D, HL);
@@ -426,6 +425,29 @@ int launch_stiffness_n(fus_ctx* c, const double* x, const double* x2, const doub
     Gptr = reinterpret_cast<const double2*>(c->d_tri);
     return launch(stiffness_line_kernel<N, false, 3>, stiffness_line_kernel<N, true, 3>,
                   L::THREADS, L::SMEM_BYTES, L::CPB, cfg);
+  }
+  // Inside the RK4 loop (reverse_cells, set by assemble_rhs) the operator walks the cells backwards,
+  // for the L2 reuse with the epilogues on either side.  The direction is a template flag of the
+  // line kernel, instantiated for the kernels the library picks at P = 4, 5, 6; any other choice
+  // walks forward (it is a hint).  P = 7 stays forward: its kernel has no register to spare.
+  if (c->reverse_cells) {
+    using L = LineCfg<N>;
+    if constexpr (N == 5) {
+      if (variant == 2) {
+        static KernelCfg cfg;
+        return launch(stiffness_line_kernel<N, false, 0, double, false, true>,
+                      stiffness_line_kernel<N, true, 0, double, false, true>, L::THREADS,
+                      L::SMEM_BYTES, L::CPB, cfg);
+      }
+    }
+    if constexpr (N == 6 || N == 7) {
+      if (variant == 5) {
+        static KernelCfg cfg;
+        return launch(stiffness_line_kernel<N, false, 6, double, false, true>,
+                      stiffness_line_kernel<N, true, 6, double, false, true>, L::THREADS,
+                      L::SMEM_BYTES, L::CPB, cfg);
+      }
+    }
   }
   if (variant == 2) {
     using L = LineCfg<N>;

@@ -164,7 +164,6 @@ struct HaloLaunch {
   const double* mbu;    // fwd_u - nowned: ghost dof d of the first gathered vector is mbu[d]
   const double* mbv;    // same for the second gathered vector
   long long nown;       // owned dofs
-  int reverse;          // any launch: walk the cells from the last to the first (see the line kernel)
 };
 
 // Host side: checks (P1) and (P2) on the lists given to fus_halo_setup and builds the CSR over the

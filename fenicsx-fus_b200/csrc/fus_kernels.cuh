@@ -578,7 +578,8 @@ struct LineCfg {
 // waited for the owners' flags, so there is no wait here); after the last cell the groups ship the
 // ghost part of y -- the partial sums the owners need -- into the owners' mailboxes and raise the
 // reverse flags (halo_group_report_and_ship above, outside the cell loop).
-template <int N, bool FUSE2, int GEOM = 0, typename T = double, bool HALO = false>
+template <int N, bool FUSE2, int GEOM = 0, typename T = double, bool HALO = false,
+          bool REV = false>
 __global__ void __launch_bounds__(LineCfg<N>::THREADS,
                                   (GEOM == 2 && N <= 5)
                                       ? 3
@@ -664,17 +665,17 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     __syncthreads();
   }
 
-  // HL.reverse: the launch walks its cells from the last to the first.  Inside the RK4 loop the
-  // epilogue before this kernel has written the stage input and the zeroed b in ascending dof order,
-  // so their TAILS are what is still in L2 when this kernel starts, and the epilogue after it
-  // starts at the dofs this kernel touched last.
+  // REV: the launch walks its cells from the last to the first.  Inside the RK4 loop the epilogue
+  // before this kernel has written the stage input and the zeroed b in ascending dof order, so their
+  // TAILS are what is still in L2 when this kernel starts, and the epilogue after it starts at the
+  // dofs this kernel touched last.  A compile-time flag: as a run-time one it cost the cell loops
+  // of P = 5 and P = 7 registers they do not have (spills inside the loop, -10 %).  Only the
+  // instantiations the RK4 loop uses exist (fus_capi.cu); the direction is a hint, never needed.
   const long long ncell = cell_end - cell_begin;
   const long long pass = (long long)gridDim.x * C::CPB;
   const int niter = (int)((ncell + pass - 1) / pass);
-  const long long stride = HL.reverse ? -pass : pass;
-  // validity is decided on the position in the walk (32-bit; the launch refuses >= 2^30 cells),
-  // not on the cell number: one int per thread instead of 64-bit range checks
-  const int ncell32 = (int)ncell, pass32 = (int)pass;
+  const long long stride = REV ? -pass : pass;
+  auto in_range = [&](long long cell) { return REV ? cell >= cell_begin : cell < cell_end; };
   int* h_word = nullptr; // one word per group for broadcasts of the group leader's findings
   if constexpr (HALO) {
     __shared__ int h_words[C::GROUPS];
@@ -700,8 +701,8 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     else
       return __ldg(x2 + i);
   };
-  long long c = HL.reverse ? cell_end - 1 - ((long long)blockIdx.x * C::CPB + slot)
-                           : cell_begin + (long long)blockIdx.x * C::CPB + slot;
+  long long c = REV ? cell_end - 1 - ((long long)blockIdx.x * C::CPB + slot)
+                    : cell_begin + (long long)blockIdx.x * C::CPB + slot;
 
   int idx[N], idxn[N];
   int idxnn[DM2 ? N : 1]; // DM2: dofmap rows of the cell after next
@@ -768,8 +769,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     for (int p = 0; p < 3; ++p)
       g[k][p] = make_v2<T>(T(0), T(0));
 
-  int vn = (int)blockIdx.x * C::CPB + slot; // position of cn in the walk (of c until cn is set)
-  bool valid = lane_ok && vn < ncell32;
+  bool valid = lane_ok && in_range(c);
   if (valid) {
     const int32_t* dm = dofmap + c * (N * NN) + t;
 #pragma unroll
@@ -814,8 +814,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     }
   }
   long long cn = c + stride;
-  vn += pass32;
-  bool validn = lane_ok && vn < ncell32;
+  bool validn = lane_ok && in_range(cn);
   if (validn) {
     const int32_t* dm = dofmap + cn * (N * NN) + t;
 #pragma unroll
@@ -914,7 +913,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
     if constexpr (DM2) { // nothing consumes a global load between here and the end of the iteration
       const long long c2 = cn + stride;
-      if (lane_ok && vn + pass32 < ncell32) {
+      if (lane_ok && in_range(c2)) {
         const int32_t* dm = dofmap + c2 * (N * NN) + t;
 #pragma unroll
         for (int k = 0; k < N; ++k)
@@ -993,7 +992,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
 
     if constexpr (RING) { // every thread of the cell is past its reads of this stage: refill it
       const long long c2 = cn + stride; // the cell this slot works on two iterations from now
-      if (producer && vn + pass32 < ncell32)
+      if (producer && in_range(c2))
         ring_issue(ring + stage * C::CELLG, G2 + c2 * (3 * N * NN), RING_BYTES, ring_bar + stage);
     }
 
@@ -1040,8 +1039,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     valid = validn;
     c = cn;
     cn += stride;
-    vn += pass32;
-    validn = lane_ok && vn < ncell32;
+    validn = lane_ok && in_range(cn);
     if constexpr (AFFINE) {
 #pragma unroll
       for (int p = 0; p < 3; ++p)
@@ -1070,7 +1068,7 @@ __global__ void __launch_bounds__(LineCfg<N>::THREADS,
     }
     if constexpr (DMPF) { // dofmap rows of the cell after next: N*N*N int32, touched line by line
       const long long c2 = cn + stride;
-      if (lane_ok && vn + pass32 < ncell32 && t * 32 < N * NN) {
+      if (lane_ok && in_range(c2) && t * 32 < N * NN) {
 #ifndef FUS_HOST_EMULATION
         asm volatile("prefetch.global.L2 [%0];" ::"l"(dofmap + c2 * (N * NN) + t * 32));
 #endif
