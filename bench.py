@@ -168,6 +168,13 @@ class ClockSampler:
         self.index, self.samples, self.reason_bits = index, [], 0
         self.stop_flag = threading.Event()
         self.thread, self.h, self.nv, self.max_mhz = None, None, None, None
+        self.t_begin, self.t_end = None, None     # the timed region, on the clock of the samples
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def start(self):
         try:
@@ -187,8 +194,11 @@ class ClockSampler:
         nv = self.nv
         while not self.stop_flag.is_set():
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                t0 = time.perf_counter()
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((t0, time.perf_counter(), mhz, bits))
+                self.reason_bits |= bits
             except Exception:
                 pass
             time.sleep(0.002)
@@ -207,12 +217,27 @@ class ClockSampler:
                         "reasons": ["clock query unavailable"]}
         self.stop_flag.set()
         self.thread.join(timeout=2)
+        # An NVML query takes milliseconds under load, so a 24 ms timed region sees one or two of
+        # them: the poller also runs through the warm-up before it and the two passes after it that
+        # repeat the same K steps (per-kernel events, end to end).  Reported: the samples that
+        # overlap the timed region (`samples`, and their median when there are any) and all samples
+        # under this workload; throttle reasons are the union over all of them (conservative).
+        def overlaps(smp):
+            return (self.t_begin is not None and self.t_end is not None
+                    and smp[1] >= self.t_begin and smp[0] <= self.t_end)
+        timed = [smp for smp in self.samples if overlaps(smp)]
+        use = timed if timed else self.samples
         reasons = [nm for nm, bit in (("hw_slowdown", self.HW), ("hw_thermal_slowdown", self.HW_THERM),
                                       ("sw_thermal_slowdown", self.SW_THERM),
                                       ("sw_power_cap", self.SW_POWER)) if self.reason_bits & bit]
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "samples": len(self.samples), "reasons": reasons,
-                "source": "NVML polled every 2 ms during the timed region"}
+        allmhz = [smp[2] for smp in self.samples]
+        return {"sm_mhz": float(np.median([smp[2] for smp in use])) if use else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(timed), "reasons": reasons,
+                "samples_same_workload": len(allmhz),
+                "sm_mhz_min_same_workload": float(min(allmhz)) if allmhz else None,
+                "source": ("NVML polled during the timed region (`samples`) and, for more samples, "
+                           "through the warm-up before it and the two repeat passes of the same K "
+                           "steps after it; reasons = union over all of them")}
 
 
 # --------------------------------------------------------------------------------------------
@@ -642,14 +667,15 @@ def run_gpu_arm(args):
     sync_all()
     launches0 = fus.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     ev0.record(stream)
     t_enq0 = time.perf_counter()
     done = mdl.rk4(t, t + (K - 0.5) * dt, dt)
     host_enqueue_ms = 1e3 * (time.perf_counter() - t_enq0)
     ev1.record(stream)
     sync_all()
+    sampler.mark_end()
     launches = fus.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     assert done == K, (done, K)
     t += K * dt
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
@@ -698,6 +724,7 @@ def run_gpu_arm(args):
     ms_e2e = max(float(ms2.item()), 0.0)
     e2e_value = ndofs_global * K / (ms_e2e * 1e-3)
     bytes_state = 2 * 8 * nloc
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- step with a host round trip of the state around EVERY step (extra information) ----
     kr = min(K, 5)
